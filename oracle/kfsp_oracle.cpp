@@ -1,0 +1,1245 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+//
+// Single-threaded CPU restatement of the hot path of voduchuy/KrylovFspSsa, used by
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// as the checker.  Nothing in the product path (krylovfspssa_b200/) links, loads or
+// calls this file.
+//
+// PARITY STATUS: the reference ships no golden vector, known-answer test or fixture for
+// the solver path and cannot be built here (no Fortran compiler), so
+// against the *reference's own outputs* this oracle is "parity unpinned".  It is pinned
+// instead by (tests/test_oracle_*.py): the closed-form PROP grid of
+// test/TestModelParser.f90:80-102, scipy.linalg.expm for the Pade kernel, the Poisson
+// closed form of the birth-death network in models/bursting_gene_model.input, and the
+// invariants the reference prints (W >= 0, 1 - FSPTOL*t/T <= WSUM <= 1).
+//
+// Each routine cites the reference lines it follows (paths relative to /root/reference).
+// Deliberate deviations, all documented in DESIGN.md:
+//   * keys are unsigned __int128 instead of 140-byte BIG_INTEGERs (same arithmetic,
+//     same saturation at 0; max key is 80 bits for 6 species);
+//   * the hash table is an exact map; Brent's slot layout (HashTable.f90:61-236) is not
+//     observable and is not restated;
+//   * RANDOM_NUMBER is behind an interface: mode 0 = the gfortran xoshiro stream through
+//     libgfortran's _gfortran_random_r8 (seeded by PUT), mode 1 = one counter-based
+//     Philox4x32-10 sub-stream per SSA trajectory (what the device path implements);
+//   * STOP becomes an error code.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <unordered_map>
+#include <algorithm>
+#include <dlfcn.h>
+#include <time.h>
+
+typedef unsigned __int128 u128;
+
+// ------------------------------------------------------------------------------------
+// Fortran intrinsics with gfortran semantics
+// ------------------------------------------------------------------------------------
+static inline int f_nint(double x) {            // NINT: round half away from zero
+    long long r = llround(x);
+    return (int)(int32_t)(uint32_t)(uint64_t)r;
+}
+static inline int f_int_trunc(double x) {       // INT()/CEILING() result conversion (cvttsd2si)
+    if (!(x > -2147483649.0 && x < 2147483648.0)) return INT32_MIN;
+    return (int)x;
+}
+static inline int f_ceiling(double x) { return f_int_trunc(ceil(x)); }
+static inline int32_t wrap32(int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; }
+// real**integer: libgcc __powidf2
+static double f_powi(double x, int m) {
+    unsigned n = m < 0 ? 0u - (unsigned)m : (unsigned)m;
+    double y = (n % 2) ? x : 1.0;
+    while (n >>= 1) {
+        x = x * x;
+        if (n % 2) y *= x;
+    }
+    return m < 0 ? 1.0 / y : y;
+}
+
+// ------------------------------------------------------------------------------------
+// BLAS level 1/2/3 and DGESV, netlib reference semantics (the reference links an
+// unpinned system libblas/liblapack: CMakeLists.txt:8, README.md:9-13)
+// ------------------------------------------------------------------------------------
+static double b_ddot(int n, const double* x, const double* y) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += x[i] * y[i];
+    return t;
+}
+static void b_daxpy(int n, double a, const double* x, double* y) {
+    if (a == 0.0) return;
+    for (int i = 0; i < n; ++i) y[i] += a * x[i];
+}
+static void b_dscal(int n, double a, double* x) {
+    for (int i = 0; i < n; ++i) x[i] = a * x[i];
+}
+static double b_dnrm2(int n, const double* x) {
+    if (n < 1) return 0.0;
+    if (n == 1) return fabs(x[0]);
+    double scale = 0.0, ssq = 1.0;
+    for (int i = 0; i < n; ++i) {
+        if (x[i] != 0.0) {
+            double a = fabs(x[i]);
+            if (scale < a) {
+                double r = scale / a;
+                ssq = 1.0 + ssq * r * r;
+                scale = a;
+            } else {
+                double r = a / scale;
+                ssq += r * r;
+            }
+        }
+    }
+    return scale * sqrt(ssq);
+}
+static double b_dasum(int n, const double* x) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += fabs(x[i]);
+    return t;
+}
+// y = alpha*A*x  (trans='N', beta=0), A is n x m column-major with leading dimension lda
+static void b_dgemv_n(int n, int m, double alpha, const double* A, long lda, const double* x, double* y) {
+    for (int i = 0; i < n; ++i) y[i] = 0.0;
+    for (int j = 0; j < m; ++j) {
+        double t = alpha * x[j];
+        const double* col = A + (long)j * lda;
+        for (int i = 0; i < n; ++i) y[i] += t * col[i];
+    }
+}
+// C = alpha*A*B, all m x m, C has leading dimension m
+static void b_dgemm_nn(int m, double alpha, const double* A, int lda, const double* B, int ldb, double* C) {
+    for (int j = 0; j < m; ++j) {
+        double* cj = C + (long)j * m;
+        for (int i = 0; i < m; ++i) cj[i] = 0.0;
+        for (int l = 0; l < m; ++l) {
+            double t = alpha * B[(long)j * ldb + l];
+            const double* al = A + (long)l * lda;
+            for (int i = 0; i < m; ++i) cj[i] += t * al[i];
+        }
+    }
+}
+// Solve A X = B in place (LU, partial pivoting), A and B m x m, ld = m.  Returns info.
+static int b_dgesv(int m, double* A, double* B) {
+    std::vector<int> piv(m);
+    for (int k = 0; k < m; ++k) {
+        int p = k;
+        double best = fabs(A[(long)k * m + k]);
+        for (int i = k + 1; i < m; ++i) {
+            double v = fabs(A[(long)k * m + i]);
+            if (v > best) { best = v; p = i; }
+        }
+        piv[k] = p;
+        if (A[(long)k * m + p] == 0.0) return k + 1;
+        if (p != k)
+            for (int j = 0; j < m; ++j) std::swap(A[(long)j * m + k], A[(long)j * m + p]);
+        double inv = 1.0 / A[(long)k * m + k];
+        for (int i = k + 1; i < m; ++i) A[(long)k * m + i] *= inv;
+        for (int j = k + 1; j < m; ++j) {
+            double akj = A[(long)j * m + k];
+            if (akj != 0.0)
+                for (int i = k + 1; i < m; ++i) A[(long)j * m + i] -= A[(long)k * m + i] * akj;
+        }
+    }
+    for (int k = 0; k < m; ++k)
+        if (piv[k] != k)
+            for (int j = 0; j < m; ++j) std::swap(B[(long)j * m + k], B[(long)j * m + piv[k]]);
+    for (int j = 0; j < m; ++j) {
+        double* b = B + (long)j * m;
+        for (int k = 0; k < m; ++k)           // L y = b (unit lower)
+            if (b[k] != 0.0)
+                for (int i = k + 1; i < m; ++i) b[i] -= b[k] * A[(long)k * m + i];
+        for (int k = m - 1; k >= 0; --k) {    // U x = y
+            if (b[k] != 0.0) {
+                b[k] /= A[(long)k * m + k];
+                for (int i = 0; i < k; ++i) b[i] -= b[k] * A[(long)k * m + i];
+            }
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// DGPADM / DGPADMnorm -- src/expokit/dgpadm.f:2-169 and :171-339
+// out (m x m, ld m) receives exp(t*H).  Returns iflag (0 ok).
+// ------------------------------------------------------------------------------------
+static int o_dgpadm(int ideg, int m, double t, const double* H, int ldh, double* out, int* ns_out, double* hnorm_out) {
+    const long mm = (long)m * m;
+    std::vector<double> coef(ideg + 1), rows(m, 0.0);
+    std::vector<double> h2(mm), bufp(mm), bufq(mm), buff(mm);
+    // scaling (dgpadm.f:241-257): infinity norm by row sums
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) rows[i] += fabs(H[(long)j * ldh + i]);
+    double hnorm = 0.0;
+    for (int i = 0; i < m; ++i) hnorm = std::max(hnorm, rows[i]);
+    hnorm = fabs(t * hnorm);
+    if (hnorm_out) *hnorm_out = hnorm;
+    if (hnorm == 0.0) return -3;                 // 'Error - null H in input of DGPADM.'
+    int ns = std::max(0, f_int_trunc(log(hnorm) / log(2.0)) + 2);
+    if (ns > 30) return -4;                      // 2**ns overflows a default integer
+    double scale = t / (double)(1 << ns);
+    double scale2 = scale * scale;
+    // Pade coefficients (dgpadm.f:261-266)
+    {
+        int i = ideg + 1, j = 2 * ideg + 1;
+        coef[0] = 1.0;
+        for (int k = 1; k <= ideg; ++k) coef[k] = (coef[k - 1] * (double)(i - k)) / (double)(k * (j - k));
+    }
+    b_dgemm_nn(m, scale2, H, ldh, H, ldh, h2.data());          // :270
+    double* p = bufp.data();
+    double* q = bufq.data();
+    double* fr = buff.data();
+    double cp = coef[ideg - 1], cq = coef[ideg];
+    for (long x = 0; x < mm; ++x) { p[x] = 0.0; q[x] = 0.0; }
+    for (int j = 0; j < m; ++j) { p[(long)j * (m + 1)] = cp; q[(long)j * (m + 1)] = cq; }
+    // Horner (dgpadm.f:287-301)
+    int iodd = 1;
+    int k = ideg - 1;
+    do {
+        double* used = iodd ? q : p;
+        b_dgemm_nn(m, 1.0, used, m, h2.data(), m, fr);
+        for (int j = 0; j < m; ++j) fr[(long)j * (m + 1)] += coef[k - 1];
+        if (iodd) { q = fr; } else { p = fr; }
+        fr = used;
+        iodd = 1 - iodd;
+        --k;
+    } while (k > 0);
+    // (+/-)(I + 2*(p\q)) (dgpadm.f:305-325)
+    if (iodd == 1) {
+        b_dgemm_nn(m, scale, q, m, H, ldh, fr);
+        std::swap(q, fr);
+    } else {
+        b_dgemm_nn(m, scale, p, m, H, ldh, fr);
+        std::swap(p, fr);
+    }
+    for (long x = 0; x < mm; ++x) q[x] += -1.0 * p[x];            // DAXPY(mm,-1,p,q)
+    int info = b_dgesv(m, q, p);
+    if (info != 0) return -5;                    // 'Problem in DGESV (within DGPADM)'
+    for (long x = 0; x < mm; ++x) p[x] = 2.0 * p[x];
+    for (int j = 0; j < m; ++j) p[(long)j * (m + 1)] += 1.0;
+    double* put = p;
+    if (ns == 0 && iodd == 1) {
+        for (long x = 0; x < mm; ++x) p[x] = -1.0 * p[x];
+    } else {
+        int io = 1;
+        for (int kk = 1; kk <= ns; ++kk) {
+            double* get = io ? p : q;
+            put = io ? q : p;
+            b_dgemm_nn(m, 1.0, get, m, get, m, put);
+            io = 1 - io;
+        }
+    }
+    memcpy(out, put, sizeof(double) * mm);
+    if (ns_out) *ns_out = ns;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// Propensity programs -- evaluate: src/parser/FortranParser.f90:187-302
+// ------------------------------------------------------------------------------------
+enum { cImmed = 1, cNeg, cAdd, cSub, cMul, cDiv, cPow, cAbs, cExp, cLog10, cLog, cSqrt, cSinh, cCosh, cTanh,
+       cSin, cCos, cTan, cAsin, cAcos, cAtan, VarBegin };
+
+struct Program {
+    std::vector<int> code;
+    std::vector<double> immed;
+};
+
+static double prog_eval(const Program& pr, const double* val) {
+    double st[64];
+    int sp = -1;
+    size_t dp = 0;
+    for (size_t ip = 0; ip < pr.code.size(); ++ip) {
+        int op = pr.code[ip];
+        switch (op) {
+        case cImmed: st[++sp] = pr.immed[dp++]; break;
+        case cNeg: st[sp] = -st[sp]; break;
+        case cAdd: st[sp - 1] = st[sp - 1] + st[sp]; --sp; break;
+        case cSub: st[sp - 1] = st[sp - 1] - st[sp]; --sp; break;
+        case cMul: st[sp - 1] = st[sp - 1] * st[sp]; --sp; break;
+        case cDiv:
+            if (st[sp] == 0.0) return 0.0;       // EvalErrType=1, res=zero (:219-223)
+            st[sp - 1] = st[sp - 1] / st[sp]; --sp; break;
+        case cPow: st[sp - 1] = pow(st[sp - 1], st[sp]); --sp; break;
+        case cAbs: st[sp] = fabs(st[sp]); break;
+        case cExp: st[sp] = exp(st[sp]); break;
+        case cLog10: if (st[sp] <= 0.0) return 0.0; st[sp] = log10(st[sp]); break;
+        case cLog: if (st[sp] <= 0.0) return 0.0; st[sp] = log(st[sp]); break;
+        case cSqrt: if (st[sp] < 0.0) return 0.0; st[sp] = sqrt(st[sp]); break;
+        case cSinh: st[sp] = sinh(st[sp]); break;
+        case cCosh: st[sp] = cosh(st[sp]); break;
+        case cTanh: st[sp] = tanh(st[sp]); break;
+        case cSin: st[sp] = sin(st[sp]); break;
+        case cCos: st[sp] = cos(st[sp]); break;
+        case cTan: st[sp] = tan(st[sp]); break;
+        case cAsin: if (st[sp] < -1.0 || st[sp] > 1.0) return 0.0; st[sp] = asin(st[sp]); break;
+        case cAcos: if (st[sp] < -1.0 || st[sp] > 1.0) return 0.0; st[sp] = acos(st[sp]); break;
+        case cAtan: st[sp] = atan(st[sp]); break;
+        default: st[++sp] = val[op - VarBegin]; break;
+        }
+    }
+    return st[0];
+}
+
+typedef double (*prop_callback)(const int32_t* state, int32_t reaction /*1-based*/, const double* params, void* ctx);
+
+// Hard-coded CUSTOMPROP functions of the reference's drivers.
+enum { CUSTOM_NONE = 0, CUSTOM_GOUTSIAS = 1, CUSTOM_REPRESSILATOR = 2, CUSTOM_TOGGLE = 3, CUSTOM_PARSER_TEST = 4,
+       CUSTOM_CALLBACK = 100 };
+
+struct Model {
+    int S = 0, R = 0, P = 0;
+    std::vector<int> stoich;       // S x R column-major: stoich[k*S + s]   (ModelModule.f90:24-25)
+    std::vector<double> params;
+    std::vector<Program> prog;
+    int custom = CUSTOM_NONE;
+    prop_callback cb = nullptr;
+    void* cb_ctx = nullptr;
+};
+
+// MODEL%PROPENSITY -- src/model/ModelModule.f90:163-199 (reaction is 1-based)
+static double model_propensity(const Model& m, const int32_t* st, int reaction) {
+    const double* p = m.params.data();
+    switch (m.custom) {
+    case CUSTOM_GOUTSIAS: {  // examples/transcr6d.f90:63-89 (M=1,D=2,RNA=3,DNA=4,DNAD=5,DNA2D=6)
+        const int M = 0, D = 1, RNA = 2, DNA = 3, DNAD = 4, DNA2D = 5;
+        switch (reaction) {
+        case 1: return p[0] * st[RNA];
+        case 2: return p[1] * st[M];
+        case 3: return p[2] * st[DNAD];
+        case 4: return p[3] * st[RNA];
+        case 5: return p[4] * st[DNA] * st[D];
+        case 6: return p[5] * st[DNAD];
+        case 7: return p[6] * st[DNAD] * st[D];
+        case 8: return p[7] * st[DNA2D];
+        case 9: return p[8] * (double)wrap32((int64_t)st[M] * (st[M] - 1) / 2);   // integer M*(M-1)/2
+        case 10: return p[9] * st[D];
+        }
+        return 0.0;
+    }
+    case CUSTOM_REPRESSILATOR: {  // examples/repressilator.f90:50-69
+        switch (reaction) {
+        case 1: return p[0] / (1.0 + p[1] * pow((double)st[1], 6.0));
+        case 2: return p[2] * st[0];
+        case 3: return p[0] / (1.0 + p[1] * pow((double)st[2], 6.0));
+        case 4: return p[2] * st[1];
+        case 5: return p[0] / (1.0 + p[1] * pow((double)st[0], 6.0));
+        case 6: return p[2] * st[2];
+        }
+        return 0.0;
+    }
+    case CUSTOM_TOGGLE: {  // examples/toggle.f90:60-74
+        switch (reaction) {
+        case 1: return p[0] + p[1] / (1.0 + pow((double)st[1], 1.5));
+        case 2: return p[2] * st[0];
+        case 3: return p[3] + p[4] / (1.0 + pow((double)st[0], 3.5));
+        case 4: return p[5] * st[1];
+        }
+        return 0.0;
+    }
+    case CUSTOM_PARSER_TEST: {  // test/TestModelParser.f90:80-102
+        switch (reaction) {
+        case 1: return 5000.0 / (1.0 + pow((double)st[1], 2.5));
+        case 2: return 1600.0 / (1.0 + pow((double)st[0], 1.5));
+        case 3: return 1.0 * (double)st[0];
+        case 4: return 1.0 * (double)st[1];
+        }
+        return 0.0;
+    }
+    case CUSTOM_CALLBACK:
+        return m.cb(st, reaction, p, m.cb_ctx);
+    default: {
+        double val[64];
+        for (int i = 0; i < m.S; ++i) val[i] = (double)st[i];
+        for (int i = 0; i < m.P; ++i) val[m.S + i] = p[i];
+        return prog_eval(m.prog[reaction - 1], val);
+    }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// RNG behind an interface
+// ------------------------------------------------------------------------------------
+static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+struct Rng {
+    int mode = 1;                  // 0 gfortran stream, 1 philox per trajectory
+    uint64_t seed = 0;
+    uint32_t call_no = 0;          // SSA_EXTENDER invocation counter (philox)
+    void (*gf_random_r8)(double*) = nullptr;
+    // two uniforms for jump `jump` of the walk started at 1-based index j0
+    void draw2(uint32_t j0, uint32_t jump, double* r1, double* r2) {
+        if (mode == 0) {
+            gf_random_r8(r1);
+            gf_random_r8(r2);
+        } else {
+            uint32_t c[4] = { jump, j0, call_no, 0u };
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            uint64_t a = ((uint64_t)c[1] << 32) | c[0];
+            uint64_t b = ((uint64_t)c[3] << 32) | c[2];
+            *r1 = (double)(a >> 11) * (1.0 / 9007199254740992.0);
+            *r2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// State space -- src/state_space/StateSpace.f90, src/hash_table/HashTable.f90
+// ------------------------------------------------------------------------------------
+struct KeyHash {
+    size_t operator()(const u128& k) const {
+        uint64_t lo = (uint64_t)k, hi = (uint64_t)(k >> 64);
+        uint64_t x = lo * 0x9E3779B97F4A7C15ull ^ (hi + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+        x ^= x >> 29;
+        return (size_t)x;
+    }
+};
+
+struct Fsp {
+    const Model* model = nullptr;
+    int S = 0, R = 0;
+    long max_size = 0;
+    int maxmol = 10000;            // MAXNUMBERMOLECULES (StateSpace.f90:11)
+    long size = 0;
+    std::vector<int32_t> state;    // S x size
+    std::vector<u128> key;
+    std::vector<int32_t> adj;      // R x size, Fortran values: >0 1-based index, 0 unexplored, -1 illegal
+    std::vector<double> offdiag;   // R x size
+    std::vector<double> diag;
+    std::vector<double> vec;       // FSP%VECTOR (aliased with W inside the solver)
+    std::unordered_map<u128, int32_t, KeyHash> table;   // key -> 1-based index
+    std::vector<u128> rkey;        // REACTIONKEY
+    std::vector<int> rsign;        // RKEYSIGN
+    int error = 0;
+    // stats
+    long n_hash = 0;
+
+    void reserve(long n) {
+        if ((long)diag.size() >= n) return;
+        long c = std::max(n, (long)diag.size() * 2);
+        c = std::min(c, max_size + 8);
+        c = std::max(c, n);
+        state.resize((size_t)c * S); key.resize(c); adj.resize((size_t)c * R);
+        offdiag.resize((size_t)c * R); diag.resize(c); vec.resize(c, 0.0);
+    }
+    int lookup(u128 k) {
+        ++n_hash;
+        if (k < 2) return 0;       // 0 = empty flag, 1 = DELKEY: never found (HashTable.f90:139,154-156)
+        auto it = table.find(k);
+        return it == table.end() ? 0 : it->second;
+    }
+};
+
+// STATE2KEY -- HashTable.f90:39-59
+static u128 state2key(const int32_t* st, int S, int B) {
+    u128 j = 2, mul = 1;
+    bool bad = false;
+    for (int k = 0; k < S; ++k) {
+        if (st[k] < 0 || st[k] > B) bad = true;
+        else j += (u128)(uint32_t)st[k] * mul;
+        mul *= (u128)(B + 1);
+    }
+    return bad ? (u128)0 : j;
+}
+// COMPUTE_RKEY -- StateSpace.f90:635-669
+static void compute_rkey(Fsp& f) {
+    const Model& m = *f.model;
+    f.rkey.assign(f.R, 0);
+    f.rsign.assign(f.R, 1);
+    for (int j = 0; j < f.R; ++j) {
+        int sgn = 1;
+        u128 rk = 0, mul = 1;
+        for (int i = 0; i < f.S; ++i) {
+            int rs = m.stoich[(size_t)j * f.S + i];
+            u128 term = (u128)(uint32_t)abs(rs) * mul;
+            if (sgn * rs < 0) {
+                sgn = -sgn;
+                rk = term >= rk ? term - rk : 0;     // BIG '-' saturates at 0 (big_integer_module.f90:550-572)
+            } else {
+                rk = term + rk;
+            }
+            mul *= (u128)(f.maxmol + 1);
+        }
+        f.rkey[j] = rk;
+        f.rsign[j] = sgn;
+    }
+}
+// KEY2KEY -- HashTable.f90:7-19 (k 0-based)
+static inline u128 key2key(const Fsp& f, u128 key, int k) {
+    if (f.rsign[k] > 0) return key + f.rkey[k];
+    return key >= f.rkey[k] ? key - f.rkey[k] : 0;
+}
+// KEY2KEYBW -- HashTable.f90:21-37
+static inline u128 key2keybw(const Fsp& f, u128 key, int k) {
+    if (f.rsign[k] > 0) return key < f.rkey[k] ? 0 : key - f.rkey[k];
+    return key + f.rkey[k];
+}
+
+// ADD_STATE -- StateSpace.f90:136-246
+static void add_state(Fsp& f, const int32_t* st, u128 key) {
+    const Model& m = *f.model;
+    if (key < 2) return;                               // HASH mode 2 returns KA=0 for key 0 / DELKEY
+    ++f.n_hash;
+    if (f.table.find(key) != f.table.end()) return;    // FOUND -> nothing happens
+    if (f.size >= f.max_size) return;                  // table full: KA = 0
+    f.reserve(f.size + 1);
+    long n = f.size;                                   // 0-based slot of the new state
+    f.size += 1;
+    int32_t idx = (int32_t)f.size;                     // 1-based
+    memcpy(&f.state[(size_t)n * f.S], st, sizeof(int32_t) * f.S);
+    f.key[n] = key;
+    f.table.emplace(key, idx);
+    f.vec[n] = 0.0;
+    f.diag[n] = 0.0;
+    std::vector<int32_t> rs(f.S);
+    for (int k = 0; k < f.R; ++k) {
+        double aij = model_propensity(m, st, k + 1);
+        f.diag[n] = f.diag[n] + aij;
+        f.offdiag[(size_t)n * f.R + k] = aij;
+        for (int s = 0; s < f.S; ++s) rs[s] = st[s] + m.stoich[(size_t)k * f.S + s];
+        for (int s = 0; s < f.S; ++s) if (rs[s] < 0) rs[0] = -1;
+        if (rs[0] >= 0) {
+            int j = f.lookup(key2key(f, key, k));
+            f.adj[(size_t)n * f.R + k] = j > 0 ? j : 0;
+        } else {
+            f.adj[(size_t)n * f.R + k] = -1;
+        }
+    }
+    for (int k = 0; k < f.R; ++k) {
+        int j = f.lookup(key2keybw(f, key, k));
+        if (j > 0) f.adj[(size_t)(j - 1) * f.R + k] = idx;
+    }
+}
+
+// MATRIX_STARTER -- StateSpace.f90:248-345.  f.state[0..size) already holds the caller's states.
+static int matrix_starter(Fsp& f) {
+    const Model& m = *f.model;
+    std::vector<int32_t> rs(f.S);
+    for (long i = 0; i < f.size; ++i) {
+        const int32_t* st = &f.state[(size_t)i * f.S];
+        u128 key = state2key(st, f.S, f.maxmol);
+        if (key == 0) return -11;                      // reference would write KVTAB(0): invalid initial state
+        ++f.n_hash;
+        f.table[key] = (int32_t)(i + 1);               // KVTAB(KA) = I (duplicates: last one wins)
+        f.key[i] = key;
+        f.diag[i] = 0.0;
+        for (int k = 0; k < f.R; ++k) {
+            for (int s = 0; s < f.S; ++s) rs[s] = st[s] + m.stoich[(size_t)k * f.S + s];
+            for (int s = 0; s < f.S; ++s) if (rs[s] < 0) rs[0] = -1;
+            f.diag[i] = f.diag[i] + model_propensity(m, st, k + 1);
+            f.offdiag[(size_t)i * f.R + k] = model_propensity(m, st, k + 1);
+            if (rs[0] >= 0) {
+                int j = f.lookup(state2key(rs.data(), f.S, f.maxmol));
+                f.adj[(size_t)i * f.R + k] = j > 0 ? j : 0;
+            } else {
+                f.adj[(size_t)i * f.R + k] = -1;
+            }
+        }
+        for (int k = 0; k < f.R; ++k) {
+            for (int s = 0; s < f.S; ++s) rs[s] = st[s] - m.stoich[(size_t)k * f.S + s];
+            for (int s = 0; s < f.S; ++s) if (rs[s] < 0) rs[0] = -1;
+            if (rs[0] >= 0) {
+                int j = f.lookup(state2key(rs.data(), f.S, f.maxmol));
+                if (j > 0) f.adj[(size_t)(j - 1) * f.R + k] = (int32_t)(i + 1);
+            }
+        }
+    }
+    return 0;
+}
+
+// ONESTEP_EXTENDER -- StateSpace.f90:347-396
+static int onestep_extender(Fsp& f) {
+    const Model& m = *f.model;
+    long lsize_copy = f.size;
+    std::vector<int32_t> rs(f.S);
+    for (long j = 0; j < lsize_copy; ++j) {
+        for (int k = 0; k < f.R; ++k) {
+            if (f.adj[(size_t)j * f.R + k] == 0) {
+                for (int s = 0; s < f.S; ++s) rs[s] = f.state[(size_t)j * f.S + s] + m.stoich[(size_t)k * f.S + s];
+                u128 key = key2key(f, f.key[j], k);
+                int found = f.lookup(key);
+                if (found > 0) {
+                    f.adj[(size_t)j * f.R + k] = found;
+                } else {
+                    add_state(f, rs.data(), key);
+                    if (f.size >= f.max_size) return -10;   // STOP 'OVERFLOW ERROR: FSP SIZE EXCEEDS MEMORY LIMIT.'
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// SSA_EXTENDER -- StateSpace.f90:550-630
+static void ssa_extender(Fsp& f, double timestep, Rng& rng) {
+    const Model& m = *f.model;
+    long lsize_old = f.size;
+    std::vector<int32_t> st(f.S), rs(f.S);
+    rng.call_no += 1;
+    for (long j0 = 1; j0 <= lsize_old; ++j0) {
+        long j = j0;                                       // 1-based
+        memcpy(st.data(), &f.state[(size_t)(j - 1) * f.S], sizeof(int32_t) * f.S);
+        double t = 0.0;
+        uint32_t jump = 0;
+        for (;;) {
+            double r1, r2;
+            rng.draw2((uint32_t)j0, jump++, &r1, &r2);
+            const double dg = f.diag[j - 1];
+            t = std::min(timestep, t + (-log(r1) / dg));
+            if (!(t <= timestep)) break;
+            double tmp = f.offdiag[(size_t)(j - 1) * f.R + 0];
+            int k = 1;
+            double r2a = std::min(r2 * dg, dg);
+            while (tmp < r2a && k < f.R) {
+                k += 1;
+                tmp = tmp + f.offdiag[(size_t)(j - 1) * f.R + (k - 1)];
+            }
+            for (int s = 0; s < f.S; ++s) rs[s] = st[s] + m.stoich[(size_t)(k - 1) * f.S + s];
+            for (int s = 0; s < f.S; ++s) if (rs[s] < 0) rs[0] = -1;
+            if (rs[0] < 0) {
+                f.adj[(size_t)(j - 1) * f.R + (k - 1)] = -1;
+                break;
+            }
+            int32_t a = f.adj[(size_t)(j - 1) * f.R + (k - 1)];
+            if (a == 0) {
+                u128 key = key2key(f, f.key[j - 1], k - 1);
+                int found = f.lookup(key);
+                if (found > 0) {
+                    j = found;
+                } else {
+                    if (f.size >= f.max_size) return;       // silent return on overflow (:612-616)
+                    add_state(f, rs.data(), key);
+                    j = f.size;
+                }
+            } else {
+                j = a;
+            }
+            memcpy(st.data(), &f.state[(size_t)(j - 1) * f.S], sizeof(int32_t) * f.S);
+            if (!(t < timestep && j >= j0)) break;
+        }
+    }
+}
+
+// FMATVEC -- src/fsp/KrylovSolver.f90:577-607
+static void fmatvec(const Fsp& f, const double* x, double* y) {
+    long n = f.size;
+    for (long i = 0; i < n; ++i) y[i] = 0.0;
+    for (long i = 0; i < n; ++i) {
+        for (int j = 0; j < f.R; ++j) {
+            int32_t k = f.adj[(size_t)i * f.R + j];
+            if (k >= 1) y[k - 1] = y[k - 1] + f.offdiag[(size_t)i * f.R + j] * x[i];
+        }
+        y[i] = y[i] - f.diag[i] * x[i];
+    }
+}
+
+// FIND_DROPTOL -- StateSpace.f90:398-427
+static double find_droptol(long n, const double* w, double dsum) {
+    double droptol = 1.0e-8;
+    for (;;) {
+        double sum1 = 0.0;
+        for (long i = 0; i < n; ++i)
+            if (w[i] < droptol && w[i] > 0) sum1 = sum1 + w[i];
+        if (sum1 < dsum) break;
+        droptol = droptol / 10.0;
+        if (droptol == 0.0) break;                     // guard: cannot loop forever once the threshold underflows
+    }
+    return droptol;
+}
+
+// DROP_STATES -- StateSpace.f90:431-548.  Returns 1 if the state space was compacted.
+static int drop_states(Fsp& f, double* w, double dsum, double* droptol_out, long* dropcount_out) {
+    long lsize = f.size;
+    std::vector<char> drop(lsize);
+    std::vector<double> wtmp(lsize);
+    double droptol = find_droptol(lsize, w, dsum);
+    long drop_count = 0;
+    for (long i = 0; i < lsize; ++i) {
+        if (w[i] < droptol) { drop[i] = 1; drop_count += 1; } else drop[i] = 0;
+    }
+    fmatvec(f, w, wtmp.data());
+    for (long i = 0; i < lsize; ++i) {
+        if (wtmp[i] > 1.0e-8) { drop[i] = 0; drop_count -= 1; }   // decremented even if it was not marked (:490-494)
+    }
+    if (droptol_out) *droptol_out = droptol;
+    if (dropcount_out) *dropcount_out = drop_count;
+    if (!((double)drop_count * 1.0 / ((double)lsize * 1.0) > 0.1)) return 0;
+    std::vector<int32_t> new_index(lsize);
+    long q = 0;
+    for (long j = 0; j < lsize; ++j) {
+        if (!drop[j]) {
+            if (q != j) {
+                w[q] = w[j];
+                memcpy(&f.state[(size_t)q * f.S], &f.state[(size_t)j * f.S], sizeof(int32_t) * f.S);
+                f.diag[q] = f.diag[j];
+                memcpy(&f.offdiag[(size_t)q * f.R], &f.offdiag[(size_t)j * f.R], sizeof(double) * f.R);
+                memcpy(&f.adj[(size_t)q * f.R], &f.adj[(size_t)j * f.R], sizeof(int32_t) * f.R);
+                f.key[q] = f.key[j];
+            }
+            q += 1;
+            new_index[j] = (int32_t)q;
+            f.table[f.key[q - 1]] = (int32_t)q;
+        } else {
+            new_index[j] = 0;
+            f.table.erase(f.key[j]);
+        }
+    }
+    for (long j = q; j < lsize; ++j) w[j] = 0.0;
+    f.size = q;
+    for (long j = 0; j < q; ++j)
+        for (int k = 0; k < f.R; ++k) {
+            int32_t i = f.adj[(size_t)j * f.R + k];
+            if (i > 0) f.adj[(size_t)j * f.R + k] = new_index[i - 1];
+        }
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------
+// DGEXPV_FSP -- src/fsp/KrylovSolver.f90:40-573
+// ------------------------------------------------------------------------------------
+struct Options {
+    int m_max = 100, m_min = 10;   // :47
+    int qiop = 2;                  // :137
+    int ideg = 6;                  // :82
+    double delta = 1.2, gamma = 0.9;   // :85-87
+    double break_tol = 1.0e-7;     // :173
+    int n_init_onestep = 5;        // :132
+    int fsp_reject_limit = 5;      // :466
+    int mxstep = 0, mxreject = 0;  // :77-79
+    int enable_drop = 1, enable_expand = 1;
+};
+
+struct TraceRow {                  // one pass of the label-100 loop
+    double t_now, t_step, t_new, wsum, err_loc, beta;
+    int32_t m, n_step, n_after, flags, nmult, nexph;   // flags: 1 expanded, 2 dropped, 4 fsp 5-reject path, 8 happy breakdown
+};
+
+struct Stats {
+    int32_t nmult, nexph, nscale, nstep, nreject, ibrkflag, mbrkdwn, iflag;
+    double step_min, step_max, x_error, s_error, tbrkdwn, t_now, hump, beta_ratio;
+    int64_t n_expand, n_drop;
+    double wall_seconds;
+};
+
+static double now_s() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+struct Solver {
+    Options opt;
+    std::vector<TraceRow> trace;
+    Stats stats{};
+    int nnz = 0;                   // default INTEGER NNZ (:112)
+
+    // KRYLOV_COST -- :618-639; default-integer products, result goes through REAL
+    float krylov_cost(double t_now, double t_out, double tau, int m, int n, double hnorm) const {
+        const int q = opt.qiop;
+        double nom = 25.0 / 3.0 + (double)std::max(0, 2 + f_int_trunc(log(tau * hnorm) / log(2.0)));
+        int32_t i1 = wrap32((int64_t)wrap32((int64_t)(2 * (m + 1)) * nnz) +
+                            (int64_t)wrap32((int64_t)(5 * m + 4 * q * m + 2 * q - 2 * q * q + 7) * n));
+        double inner = (double)i1 + 2 * nom * (m + 2) * (m + 2) * (m + 2);
+        double c = (double)f_nint((t_out - t_now) / tau) * inner;
+        return (float)c;
+    }
+
+    int solve(Fsp& fsp, double T, const double* v_in, long n_in, double fsptol, double krytol, int itrace, Rng& rng) {
+        const int M_MAX = opt.m_max, M_MIN = opt.m_min, IDEG = opt.ideg, QIOP = opt.qiop;
+        const double DELTA = opt.delta, GAMMA = opt.gamma;
+        double t0 = now_s();
+        trace.clear();
+        int iflag = 0;
+        const double ANORM = 1.0;
+        int rc = matrix_starter(fsp);                                    // :130
+        if (rc) return rc;
+        for (int i = 0; i < opt.n_init_onestep; ++i) {                   // :132-134
+            rc = onestep_extender(fsp);
+            if (rc) return rc;
+        }
+        int M = M_MIN, ISTART = 1;
+        long N = fsp.max_size;
+        if ((M >= N) || (M <= 0)) return -3;
+        int IBRKFLAG = 0, NMULT = 0, NREJECT = 0, NEXPH = 0, NSCALE = 0, NSTEP = 0;
+        double T_OUT = fabs(T), TBRKDWN = 0.0, STEP_MIN = T_OUT, STEP_MAX = 0.0;
+        double S_ERROR = 0.0, X_ERROR = 0.0, T_NOW = 0.0, T_NEW = 0.0;
+        double P1 = 4.0 / 3.0, P2, P3, EPS;
+        do {                                                             // :166-170
+            P2 = P1 - 1.0;
+            P3 = P2 + P2 + P2;
+            EPS = fabs(P3 - 1.0);
+        } while (EPS == 0.0);
+        if (krytol <= EPS) krytol = sqrt(EPS);
+        const double KRYTOL = krytol;
+        const double RNDOFF = EPS * ANORM;
+        const double BREAK_TOL = opt.break_tol;
+        const double SGN = T < 0 ? -1.0 : 1.0;
+
+        // W aliases FSP%VECTOR (CME_SOLVE passes FSP_OUT%VECTOR as W, :33)
+        fsp.reserve(fsp.size);
+        for (long i = 0; i < fsp.size; ++i) fsp.vec[i] = i < n_in ? v_in[i] : 0.0;     // DCOPY (:176), zero padded
+        double BETA = b_dnrm2((int)fsp.size, fsp.vec.data());
+        const double VNORM = BETA;
+        double HUMP = BETA;
+        const double SQR1 = sqrt(0.1);
+        double XM = 1.0 / (double)M;
+        P1 = KRYTOL * f_powi((M + 1) / 2.72, M + 1) * sqrt(2.0 * 3.14 * (M + 1));
+        T_NEW = (1.0 / ANORM) * pow(P1 / (4.0 * BETA * ANORM), XM);
+        P1 = f_powi(10.0, f_nint(log10(T_NEW) - SQR1) - 1);
+        T_NEW = trunc(T_NEW / P1 + 0.55) * P1;
+
+        long N_NOW = fsp.size;
+        int IEXPAND = 0;
+        double WSUM_OLD = 1.0;
+        int IREJECTFSP = 0;
+        nnz = wrap32((int64_t)(fsp.R + 1) * fsp.size);
+        int IMREJECT = 0, JOLD = 1, M_NEW = M;
+        bool ORDEROLD = true, KESTOLD = true, M_CHANGED = false;
+        // locals the reference leaves uninitialised on the first pass
+        double OMEGA = 0.0, OMEGA_OLD = 0.0, T_OLD = 0.0, ORDER = 0.0, K_FACTOR = 2.0, T_OPT = 0.0;
+        int M_OLD = -1, M_OPT = 0;
+        double HNORM = 0.0, ERR_LOC = 0.0, AVNORM = 0.0, T_STEP = 0.0, WSUM = 0.0;
+        double ERROR_ = 0.0, ERROROLD = 1.0, TAU_OLD = 1.0, FSPORDER = 2.0, TFSP = 0.0, T_SSA = 0.0;
+        int MBRKDWN = M, K1 = 2, MH = 0, MX = 0, NS = 0, IREJECT = 0;
+        std::vector<double> V, H, HTMP, EXPH;
+        long n_expand = 0, n_drop = 0;
+
+        while (T_NOW < T_OUT) {                                          // label 100
+            T_STEP = std::min(T_OUT - T_NOW, T_NEW);
+            N = N_NOW;
+            M = (int)std::min((long)(N - 1), (long)M_NEW);
+            MBRKDWN = M;
+            K1 = 2;
+            MH = M + 2;
+            NSTEP += 1;
+            int flags = 0;
+            if ((long)V.size() < N * (long)(M_MAX + 2)) V.resize((size_t)N * (M_MAX + 2));
+            H.assign((size_t)MH * MH, 0.0);
+            double* W = fsp.vec.data();
+            P1 = 1.0 / BETA;
+            for (long i = 0; i < N; ++i) V[i] = P1 * W[i];
+            IREJECT = 0;
+            bool to_404 = false;
+        L101:
+            {
+                bool broke = false;
+                for (int J = JOLD; J <= M; ++J) {                         // DO 200
+                    NMULT += 1;
+                    double* vj = &V[(size_t)(J - 1) * N];
+                    double* vn = &V[(size_t)J * N];
+                    fmatvec(fsp, vj, vn);
+                    if (QIOP > 0) ISTART = std::max(1, J - QIOP + 1);
+                    for (int I = ISTART; I <= J; ++I) {
+                        double HIJ = b_ddot((int)N, &V[(size_t)(I - 1) * N], vn);
+                        b_daxpy((int)N, -HIJ, &V[(size_t)(I - 1) * N], vn);
+                        H[(size_t)(J - 1) * MH + (I - 1)] = HIJ;
+                    }
+                    double HJ1J = b_dnrm2((int)N, vn);
+                    if (HJ1J <= BREAK_TOL) {                              // happy breakdown (:249-256)
+                        K1 = 0;
+                        IBRKFLAG = 1;
+                        MBRKDWN = J;
+                        TBRKDWN = T_NOW;
+                        T_STEP = T_OUT - T_NOW;
+                        broke = true;
+                        flags |= 8;
+                        break;
+                    }
+                    H[(size_t)(J - 1) * MH + J] = HJ1J;
+                    b_dscal((int)N, 1.0 / HJ1J, vn);
+                }
+                if (!broke) {
+                    NMULT += 1;
+                    fmatvec(fsp, &V[(size_t)M * N], &V[(size_t)(M + 1) * N]);
+                    AVNORM = b_dnrm2((int)N, &V[(size_t)(M + 1) * N]);
+                }
+                H[(size_t)M * MH + (M + 1)] = 1.0;                        // label 300 (:266)
+            }
+        L401:
+            NEXPH += 1;
+            MX = MBRKDWN + K1;
+            EXPH.resize((size_t)MX * MX);
+            iflag = o_dgpadm(IDEG, MX, SGN * T_STEP, H.data(), MH, EXPH.data(), &NS, &HNORM);
+            if (iflag) return iflag;
+            NSCALE += NS;
+            // label 402: error estimate (:290-305)
+            if (K1 == 0) {
+                ERR_LOC = KRYTOL;
+            } else {
+                P1 = fabs(EXPH[M]) * BETA;
+                P2 = fabs(EXPH[M + 1]) * BETA * AVNORM;
+                if (P1 > 10.0 * P2) {
+                    ERR_LOC = P2;
+                    XM = 1.0 / (double)M;
+                } else if (P1 > P2) {
+                    ERR_LOC = (P1 * P2) / (P1 - P2);
+                    XM = 1.0 / (double)M;
+                } else {
+                    ERR_LOC = P1;
+                    XM = 1.0 / (double)(M - 1);
+                }
+            }
+            if (std::isnan(ERR_LOC)) {                                    // :307-310
+                T_STEP = T_STEP / 5.0;
+                goto L401;
+            }
+            OMEGA_OLD = OMEGA;
+            OMEGA = ERR_LOC / (KRYTOL * T_STEP);
+            if ((M == M_OLD) && (T_STEP != T_OLD) && (IREJECT >= 1)) {    // order estimate (:316-324)
+                ORDER = std::max(1.0, log(OMEGA / OMEGA_OLD) / log(T_STEP / T_OLD));
+                ORDEROLD = false;
+            } else if (ORDEROLD || IREJECT == 0) {
+                ORDER = (double)M / 4.0;
+                ORDEROLD = true;
+            } else {
+                ORDEROLD = true;
+            }
+            if ((M != M_OLD) && (T_STEP == T_OLD) && (IREJECT >= 1)) {    // kappa estimate (:326-334)
+                K_FACTOR = std::max(1.1, pow(OMEGA / OMEGA_OLD, 1.0 / (double)(M_OLD - M)));
+                KESTOLD = false;
+            } else if (KESTOLD || IREJECT == 0) {
+                KESTOLD = true;
+                K_FACTOR = 2.0;
+            } else {
+                KESTOLD = true;
+            }
+            T_OLD = T_STEP;
+            M_OLD = M;
+            if (((M == M_MAX) && (OMEGA > DELTA)) || (IMREJECT > 4)) {    // :339-346
+                T_NEW = std::min(T_OUT - T_NOW,
+                                 std::max(T_STEP / 5.0, std::min(5.0 * T_STEP, GAMMA * T_STEP * pow(OMEGA, -1.0 / ORDER))));
+                P1 = f_powi(10.0, f_nint(log10(T_NEW) - SQR1) - 1);
+                T_NEW = trunc(T_NEW / P1) * P1;
+                M_CHANGED = false;
+            } else {                                                       // :348-373
+                T_OPT = std::min(T_OUT - T_NOW,
+                                 std::max(T_STEP / 5.0, std::min(5.0 * T_STEP, GAMMA * T_STEP * pow(OMEGA, -1.0 / ORDER))));
+                int cl = f_ceiling(log(OMEGA) / log(K_FACTOR));
+                M_OPT = std::min(std::min(std::max(std::max(M_MIN, 3 * M / 4), wrap32((int64_t)M + cl)), M_MAX),
+                                 f_ceiling(4.0 * M / 3.0) + 1);
+                float COST1 = krylov_cost(T_NOW, T_OUT, T_OPT, M, (int)N, HNORM);
+                float COST2 = krylov_cost(T_NOW, T_OUT, T_STEP, M_OPT, (int)N, HNORM);
+                if (COST1 <= COST2) {
+                    T_NEW = T_OPT;
+                    P1 = f_powi(10.0, f_nint(log10(T_NEW) - SQR1) - 1);
+                    T_NEW = trunc(T_NEW / P1) * P1;
+                    M_NEW = M;
+                    M_CHANGED = false;
+                } else {
+                    M_NEW = M_OPT;
+                    T_NEW = T_STEP;
+                    M_CHANGED = true;
+                }
+            }
+            if ((K1 != 0) && (OMEGA > DELTA) && (opt.mxreject == 0 || IREJECT < opt.mxreject)) {   // :375-434
+                if (!M_CHANGED) {
+                    T_STEP = std::min(T_OUT - T_NOW, std::max(T_STEP / 5.0, std::min(5.0 * T_STEP, T_NEW)));
+                    P1 = f_powi(10.0, f_nint(log10(T_STEP) - SQR1) - 1);
+                    T_STEP = trunc(T_STEP / P1 + 0.55) * P1;
+                    IREJECT += 1;
+                    NREJECT += 1;
+                    if ((opt.mxreject != 0) && (IREJECT > opt.mxreject)) { stats.iflag = 2; return 2; }
+                    goto L401;
+                } else {
+                    NREJECT += 1;
+                    IMREJECT += 1;
+                    M = M_NEW;
+                    HTMP = H;
+                    int MH_OLD = MH;
+                    MBRKDWN = M;
+                    K1 = 2;
+                    MH = M + 2;
+                    T_STEP = std::min(T_OUT - T_NOW, T_NEW);
+                    H.assign((size_t)MH * MH, 0.0);
+                    for (int J = 1; J <= M_OLD; ++J)
+                        for (int I = 1; I <= J + 1; ++I)
+                            H[(size_t)(J - 1) * MH + (I - 1)] = HTMP[(size_t)(J - 1) * MH_OLD + (I - 1)];
+                    JOLD = M_OLD;
+                    goto L101;
+                }
+            }
+            IMREJECT = 0;
+            JOLD = 1;
+            if (ERR_LOC < 1.0e-16) T_NEW = std::max(T_NEW, 2.0 * T_STEP);
+            MX = MBRKDWN + std::max(0, K1 - 1);
+            IREJECTFSP = 0;
+            // FSP criterion loop (:442-495)
+            for (;;) {
+                b_dgemv_n((int)N, MX, BETA, V.data(), N, EXPH.data(), W);
+                for (long i = 0; i < fsp.size; ++i) if (W[i] < 0.0) W[i] = 0.0;
+                WSUM = b_dasum((int)fsp.size, W);
+                ERROR_ = WSUM_OLD - WSUM;
+                if (WSUM >= (1.0 - (T_NOW + T_STEP) * fsptol / T_OUT)) break;
+                IEXPAND = 1;
+                IREJECTFSP += 1;
+                if (IREJECTFSP >= opt.fsp_reject_limit) {
+                    for (long i = 0; i < N; ++i) W[i] = BETA * V[i];
+                    NSTEP -= 1;
+                    T_SSA = T_NEW;
+                    to_404 = true;
+                    flags |= 4;
+                    break;
+                } else if (IREJECTFSP == 1) {
+                    FSPORDER = 2;
+                } else {
+                    FSPORDER = log(ERROR_ / ERROROLD) / log(T_STEP / TAU_OLD) - 1.0;
+                }
+                TFSP = GAMMA * T_STEP * pow(fsptol * T_STEP / (ERROR_ * T_OUT), 1.0 / FSPORDER);
+                ERROROLD = ERROR_;
+                TAU_OLD = T_STEP;
+                T_STEP = std::min(T_OUT - T_NOW, std::max(T_STEP / 5.0, std::min(0.9 * T_STEP, TFSP)));
+                P1 = f_powi(10.0, f_nint(log10(T_STEP) - SQR1) - 1);
+                T_STEP = trunc(T_STEP / P1 + 0.55) * P1;
+                NEXPH += 1;
+                EXPH.resize((size_t)MX * MX);
+                iflag = o_dgpadm(IDEG, MX, SGN * T_STEP, H.data(), MH, EXPH.data(), &NS, nullptr);
+                if (iflag) return iflag;
+                NSCALE += NS;
+            }
+            if (!to_404) {
+                T_NOW = T_NOW + T_STEP;
+                WSUM_OLD = WSUM;
+                if (itrace) {
+                    printf(" TIMESTEP %d  FSP SIZE = %ld  STEP_SIZE = %.6g  NEXT_STEP = %.6g  T_NOW = %.8g  M = %d  WSUM = %.12g\n",
+                           NSTEP, fsp.size, T_STEP, T_NEW, T_NOW, M, WSUM);
+                }
+                if (T_NOW >= T_OUT) {
+                    trace.push_back(TraceRow{T_NOW, T_STEP, T_NEW, WSUM, ERR_LOC, BETA, M, (int32_t)N, (int32_t)fsp.size, flags, NMULT, NEXPH});
+                    break;                                                // GO TO 500
+                }
+                if (NSTEP > 1 && IEXPAND != 1 && opt.enable_drop) {       // :509-512
+                    double DSUM = WSUM - (1.0 - T_NOW * fsptol / T_OUT);
+                    if (DSUM > 0.0) {
+                        if (drop_states(fsp, W, DSUM, nullptr, nullptr)) { flags |= 2; n_drop += 1; }
+                    }
+                }
+            }
+            // label 404 (:516-534)
+            if ((IEXPAND == 1) && (T_NOW < T_OUT)) {
+                if (NSTEP == 1) T_NEW = T_STEP;
+                T_SSA = std::min(T_NEW, T_OUT - T_NOW);
+                if (opt.enable_expand) {
+                    ssa_extender(fsp, T_SSA, rng);
+                    rc = onestep_extender(fsp);
+                    if (rc) return rc;
+                    flags |= 1;
+                    n_expand += 1;
+                }
+                IEXPAND = 0;
+            }
+            W = fsp.vec.data();
+            nnz = wrap32((int64_t)(fsp.R + 1) * fsp.size);
+            N_NOW = fsp.size;
+            BETA = b_dnrm2((int)N_NOW, W);
+            HUMP = std::max(HUMP, BETA);
+            ERR_LOC = std::max(ERR_LOC, RNDOFF);
+            STEP_MIN = std::min(STEP_MIN, T_STEP);
+            STEP_MAX = std::max(STEP_MAX, T_STEP);
+            S_ERROR = S_ERROR + ERR_LOC;
+            X_ERROR = std::max(X_ERROR, ERR_LOC);
+            P1 = f_powi(10.0, f_nint(log10(T_NEW) - SQR1) - 1);
+            T_NEW = trunc(T_NEW / P1 + 0.55) * P1;
+            trace.push_back(TraceRow{T_NOW, T_STEP, T_NEW, WSUM, ERR_LOC, BETA, M, (int32_t)N, (int32_t)fsp.size, flags, NMULT, NEXPH});
+            if (!((opt.mxstep == 0) || (NSTEP < opt.mxstep))) { iflag = 1; break; }
+        }
+        stats.nmult = NMULT; stats.nexph = NEXPH; stats.nscale = NSCALE; stats.nstep = NSTEP;
+        stats.nreject = NREJECT; stats.ibrkflag = IBRKFLAG; stats.mbrkdwn = MBRKDWN; stats.iflag = iflag;
+        stats.step_min = STEP_MIN; stats.step_max = STEP_MAX; stats.x_error = X_ERROR; stats.s_error = S_ERROR;
+        stats.tbrkdwn = TBRKDWN; stats.t_now = SGN * T_NOW; stats.hump = HUMP / VNORM; stats.beta_ratio = BETA / VNORM;
+        stats.n_expand = n_expand; stats.n_drop = n_drop;
+        stats.wall_seconds = now_s() - t0;
+        (void)T_SSA; (void)XM; (void)ISTART;
+        return iflag;
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// C API for ctypes
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+void* ko_model_create(int S, int R, int P, const int32_t* stoich /*S x R col-major*/, const double* params) {
+    Model* m = new Model();
+    m->S = S; m->R = R; m->P = P;
+    m->stoich.assign(stoich, stoich + (size_t)S * R);
+    m->params.assign(params, params + P);
+    m->prog.resize(R);
+    return m;
+}
+void ko_model_free(void* mp) { delete (Model*)mp; }
+void ko_model_set_params(void* mp, const double* params) {
+    Model* m = (Model*)mp;
+    m->params.assign(params, params + m->P);
+}
+void ko_model_set_program(void* mp, int reaction0, const int32_t* code, int ncode, const double* immed, int nimmed) {
+    Model* m = (Model*)mp;
+    m->prog[reaction0].code.assign(code, code + ncode);
+    m->prog[reaction0].immed.assign(immed, immed + nimmed);
+}
+void ko_model_set_custom(void* mp, int kind) { ((Model*)mp)->custom = kind; }
+void ko_model_set_callback(void* mp, prop_callback cb, void* ctx) {
+    Model* m = (Model*)mp;
+    m->custom = CUSTOM_CALLBACK; m->cb = cb; m->cb_ctx = ctx;
+}
+double ko_model_propensity(void* mp, const int32_t* state, int reaction1) {
+    return model_propensity(*(Model*)mp, state, reaction1);
+}
+
+void* ko_fsp_create(void* mp, long max_size, int maxmol) {
+    Fsp* f = new Fsp();
+    f->model = (Model*)mp;
+    f->S = f->model->S; f->R = f->model->R;
+    f->max_size = max_size; f->maxmol = maxmol;
+    compute_rkey(*f);
+    return f;
+}
+void ko_fsp_free(void* fp) { delete (Fsp*)fp; }
+// set the caller's states (FSP%SIZE, FSP%STATE) without building anything
+void ko_fsp_set_states(void* fp, const int32_t* states, long n) {
+    Fsp* f = (Fsp*)fp;
+    f->table.clear();
+    f->size = 0;
+    f->reserve(n);
+    memcpy(f->state.data(), states, sizeof(int32_t) * (size_t)n * f->S);
+    f->size = n;
+    for (long i = 0; i < n; ++i) f->vec[i] = 0.0;
+}
+int ko_fsp_matrix_starter(void* fp) { return matrix_starter(*(Fsp*)fp); }
+int ko_fsp_onestep(void* fp) { return onestep_extender(*(Fsp*)fp); }
+long ko_fsp_size(void* fp) { return ((Fsp*)fp)->size; }
+void ko_fsp_get(void* fp, int32_t* states, int32_t* adj, double* offdiag, double* diag, double* vec) {
+    Fsp* f = (Fsp*)fp;
+    size_t n = (size_t)f->size;
+    if (states) memcpy(states, f->state.data(), sizeof(int32_t) * n * f->S);
+    if (adj) memcpy(adj, f->adj.data(), sizeof(int32_t) * n * f->R);
+    if (offdiag) memcpy(offdiag, f->offdiag.data(), sizeof(double) * n * f->R);
+    if (diag) memcpy(diag, f->diag.data(), sizeof(double) * n);
+    if (vec) memcpy(vec, f->vec.data(), sizeof(double) * n);
+}
+void ko_fsp_set_vector(void* fp, const double* v, long n) {
+    Fsp* f = (Fsp*)fp;
+    for (long i = 0; i < f->size; ++i) f->vec[i] = i < n ? v[i] : 0.0;
+}
+int ko_fsp_index(void* fp, const int32_t* state) {          // FSP%INDEX, StateSpace.f90:116-134
+    Fsp* f = (Fsp*)fp;
+    return f->lookup(state2key(state, f->S, f->maxmol));
+}
+void ko_fsp_matvec(void* fp, const double* x, double* y) { fmatvec(*(Fsp*)fp, x, y); }
+
+void* ko_rng_create(int mode, uint64_t seed, const char* libgfortran_path) {
+    Rng* r = new Rng();
+    r->mode = mode; r->seed = seed;
+    if (mode == 0) {
+        void* h = dlopen(libgfortran_path, RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { delete r; return nullptr; }
+        r->gf_random_r8 = (void (*)(double*))dlsym(h, "_gfortran_random_r8");
+        // _gfortran_random_seed_i4(size, put, get): descriptors; seed through PUT with a rank-1 i4 array
+        typedef void (*seed_fn)(int32_t*, void*, void*);
+        seed_fn sf = (seed_fn)dlsym(h, "_gfortran_random_seed_i4");
+        if (!r->gf_random_r8 || !sf) { delete r; return nullptr; }
+        int32_t nseed = 0;
+        sf(&nseed, nullptr, nullptr);
+        if (nseed <= 0 || nseed > 64) { delete r; return nullptr; }
+        static int32_t put[64];
+        for (int i = 0; i < nseed; ++i) put[i] = (int32_t)(seed * 2654435761u + 0x9E3779B9u * (uint32_t)(i + 1));
+        // gfortran >= 8 array descriptor for a rank-1 INTEGER(4) array
+        struct Desc { void* base; size_t offset; size_t elem_len; int32_t version; int8_t rank, type; int16_t attr;
+                      intptr_t span; intptr_t stride, lb, ub; } d;
+        memset(&d, 0, sizeof d);
+        d.base = put; d.offset = (size_t)-1; d.elem_len = 4; d.rank = 1; d.type = 1; d.span = 4;
+        d.stride = 1; d.lb = 1; d.ub = nseed;
+        sf(nullptr, &d, nullptr);
+    }
+    return r;
+}
+void ko_rng_free(void* rp) { delete (Rng*)rp; }
+void ko_rng_draw2(void* rp, uint32_t j0, uint32_t jump, uint32_t call_no, double* r1, double* r2) {
+    Rng* r = (Rng*)rp;
+    uint32_t save = r->call_no;
+    r->call_no = call_no;
+    r->draw2(j0, jump, r1, r2);
+    r->call_no = save;
+}
+void ko_fsp_ssa(void* fp, double timestep, void* rp) { ssa_extender(*(Fsp*)fp, timestep, *(Rng*)rp); }
+// DROP_STATES on a caller-supplied W (length >= size); returns 1 if compacted
+int ko_fsp_drop(void* fp, double* w, double dsum, double* droptol, long* dropcount) {
+    return drop_states(*(Fsp*)fp, w, dsum, droptol, dropcount);
+}
+
+int ko_dgpadm(int ideg, int m, double t, const double* H, int ldh, double* out, int* ns, double* hnorm) {
+    return o_dgpadm(ideg, m, t, H, ldh, out, ns, hnorm);
+}
+
+void* ko_solver_create(void) { return new Solver(); }
+void ko_solver_free(void* sp) { delete (Solver*)sp; }
+void ko_solver_set_options(void* sp, int m_max, int m_min, int n_init_onestep, int enable_drop, int enable_expand) {
+    Solver* s = (Solver*)sp;
+    s->opt.m_max = m_max; s->opt.m_min = m_min; s->opt.n_init_onestep = n_init_onestep;
+    s->opt.enable_drop = enable_drop; s->opt.enable_expand = enable_expand;
+}
+// DGEXPV_FSP: the fsp must hold the caller's initial states (ko_fsp_set_states); v_in is FSP_IN%VECTOR(1:n_in).
+int ko_solve(void* sp, void* fp, double T, const double* v_in, long n_in, double fsptol, double krytol, int itrace, void* rp) {
+    return ((Solver*)sp)->solve(*(Fsp*)fp, T, v_in, n_in, fsptol, krytol, itrace, *(Rng*)rp);
+}
+long ko_trace_len(void* sp) { return (long)((Solver*)sp)->trace.size(); }
+void ko_trace_get(void* sp, double* dbl /*len x 6*/, int32_t* itg /*len x 6*/) {
+    Solver* s = (Solver*)sp;
+    for (size_t i = 0; i < s->trace.size(); ++i) {
+        const TraceRow& r = s->trace[i];
+        dbl[i * 6 + 0] = r.t_now; dbl[i * 6 + 1] = r.t_step; dbl[i * 6 + 2] = r.t_new;
+        dbl[i * 6 + 3] = r.wsum; dbl[i * 6 + 4] = r.err_loc; dbl[i * 6 + 5] = r.beta;
+        itg[i * 6 + 0] = r.m; itg[i * 6 + 1] = r.n_step; itg[i * 6 + 2] = r.n_after;
+        itg[i * 6 + 3] = r.flags; itg[i * 6 + 4] = r.nmult; itg[i * 6 + 5] = r.nexph;
+    }
+}
+void ko_stats_get(void* sp, Stats* out) { *out = ((Solver*)sp)->stats; }
+
+// One Arnoldi/IOP sweep + FMATVEC timing helper for the CPU baseline (KrylovSolver.f90:236-263):
+// runs `m` columns on the fsp's matrix from v (length size), returns seconds; H (m+2)^2 optional.
+double ko_arnoldi_sweep(void* fp, const double* v, int m, double* work /*size*(m+2)*/, double* Hout, int* nmult) {
+    Fsp& f = *(Fsp*)fp;
+    long N = f.size;
+    int MH = m + 2;
+    std::vector<double> H((size_t)MH * MH, 0.0);
+    double beta = b_dnrm2((int)N, v);
+    double t0 = now_s();
+    for (long i = 0; i < N; ++i) work[i] = v[i] / beta;
+    int nm = 0;
+    for (int J = 1; J <= m; ++J) {
+        double* vn = &work[(size_t)J * N];
+        fmatvec(f, &work[(size_t)(J - 1) * N], vn); ++nm;
+        for (int I = std::max(1, J - 1); I <= J; ++I) {
+            double h = b_ddot((int)N, &work[(size_t)(I - 1) * N], vn);
+            b_daxpy((int)N, -h, &work[(size_t)(I - 1) * N], vn);
+            H[(size_t)(J - 1) * MH + (I - 1)] = h;
+        }
+        double hn = b_dnrm2((int)N, vn);
+        H[(size_t)(J - 1) * MH + J] = hn;
+        if (hn <= 1e-7) break;
+        b_dscal((int)N, 1.0 / hn, vn);
+    }
+    fmatvec(f, &work[(size_t)m * N], &work[(size_t)(m + 1) * N]); ++nm;
+    double dt = now_s() - t0;
+    if (Hout) memcpy(Hout, H.data(), sizeof(double) * H.size());
+    if (nmult) *nmult = nm;
+    return dt;
+}
+double ko_time_matvec(void* fp, const double* x, double* y, int reps) {
+    Fsp& f = *(Fsp*)fp;
+    double t0 = now_s();
+    for (int r = 0; r < reps; ++r) fmatvec(f, x, y);
+    return (now_s() - t0) / reps;
+}
+
+}  // extern "C"
