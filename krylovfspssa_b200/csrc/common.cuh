@@ -1,0 +1,90 @@
+// Shared device/host definitions for libkfsp (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/kfsp.h"
+
+namespace kfsp {
+
+constexpr int KFSP_MAX_SPECIES = 8;       // states are held in registers as int32[8]
+constexpr int KFSP_MAX_REACTIONS = 32;
+constexpr int KFSP_MAX_PARAMS = 64;
+constexpr int KFSP_MAX_CODE = 1024;       // total byte-code words over all reactions
+constexpr int KFSP_MAX_IMMED = 256;
+constexpr int KFSP_STACK = 16;            // evaluation stack of the propensity interpreter
+
+// internal index conventions (0-based); the C ABI converts to the Fortran ones
+constexpr int32_t IDX_ABSENT = -1;        // legal neighbour, not in the projection  (ADJ = 0)
+constexpr int32_t IDX_ILLEGAL = -2;       // neighbour has a negative count          (ADJ = -1)
+constexpr int32_t SLOT_EMPTY = -1;
+
+#define KFSP_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            std::fprintf(stderr, "libkfsp: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__), \
+                         __FILE__, __LINE__, cudaGetErrorString(e__));                         \
+            return KFSP_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+#define KFSP_TRY(call)                  \
+    do {                                \
+        int s__ = (call);               \
+        if (s__ != KFSP_OK) return s__; \
+    } while (0)
+
+// Model as the kernels see it (lives in global memory, read through the read-only path).
+struct DeviceModel {
+    int32_t S, R, P;
+    int32_t max_molecules;
+    int32_t stoich[KFSP_MAX_REACTIONS * KFSP_MAX_SPECIES];   // [k*S + s]
+    int32_t code_begin[KFSP_MAX_REACTIONS + 1];
+    int32_t immed_begin[KFSP_MAX_REACTIONS + 1];
+    int32_t code[KFSP_MAX_CODE];
+    double immed[KFSP_MAX_IMMED];
+    double params[KFSP_MAX_PARAMS];
+};
+
+// Philox4x32-10 (Salmon et al., SC'11): one counter-based sub-stream per SSA trajectory.
+// counter = (jump, j0 (1-based start index), call number, 0), key = 64-bit seed.
+__host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__host__ __device__ inline void philox_uniform2(uint64_t seed, uint32_t call_no, uint32_t j0, uint32_t jump,
+                                                double* r1, double* r2) {
+    uint32_t c[4] = {jump, j0, call_no, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t a = ((uint64_t)c[1] << 32) | c[0];
+    const uint64_t b = ((uint64_t)c[3] << 32) | c[2];
+    *r1 = (double)(a >> 11) * (1.0 / 9007199254740992.0);
+    *r2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// Hash of a state vector -> table slot.
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+__host__ __device__ inline uint64_t hash_state(const int32_t* st, int S) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL;
+    for (int s = 0; s < S; ++s) h = mix64(h ^ (uint64_t)(uint32_t)st[s]) + 0x632BE59BD9B4E019ULL * (uint64_t)(s + 1);
+    return h;
+}
+
+}  // namespace kfsp

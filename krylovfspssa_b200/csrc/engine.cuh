@@ -1,0 +1,568 @@
+// Host-side engine: owns the device buffers of one solver handle and sequences the kernels.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "expm.cuh"
+#include "krylov.cuh"
+#include "model_host.h"
+#include "state_space.cuh"
+
+namespace kfsp {
+
+inline double wall_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Engine {
+    kfsp_options opt{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool have_model = false;
+    HostModel hm;
+    DeviceModel* d_model = nullptr;
+    int S = 0, R = 0;
+
+    // state space
+    int64_t ld = 0;                   // capacity in states (multiple of 64)
+    int64_t n = 0;
+    int32_t* d_states = nullptr;
+    int32_t* d_succ = nullptr;
+    double* d_prop = nullptr;
+    double* d_diag = nullptr;
+    int32_t* d_pred = nullptr;
+    double* d_coef = nullptr;
+    double* d_w = nullptr;            // FSP%VECTOR == W
+    int32_t* d_table = nullptr;
+    int64_t table_size = 0;
+    int32_t* d_err = nullptr;         // DevErr bits
+    uint32_t ssa_calls = 0;
+
+    // scratch arena (grows on demand)
+    char* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    // krylov
+    double* d_V = nullptr;            // ld x (m_max+2)
+    int LDH = 0;                      // m_max + 2
+    double* d_H = nullptr;            // LDH x LDH
+    double* d_expm_work = nullptr;
+    double* d_expm_full = nullptr;
+    ExpmResult* d_res = nullptr;
+    ExpmResult* h_res = nullptr;      // pinned
+    SweepCtl* d_ctl = nullptr;
+    SweepCtl* h_ctl = nullptr;        // pinned
+    Reducer rd{};
+    double* d_flush = nullptr;
+    size_t flush_bytes = 0;
+
+    // bookkeeping
+    int64_t launches = 0;
+    std::vector<kfsp_trace_row> trace;
+    bool profile_spmv = false;
+    double spmv_seconds = 0.0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    std::string last_error;
+
+    // ---------------------------------------------------------------- lifetime
+    int init(const kfsp_options* o) {
+        opt = *o;
+        if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
+            opt.max_states > 2000000000LL)
+            return KFSP_ERR_ARG;
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return KFSP_ERR_NO_DEVICE;
+        if (opt.device >= 0) {
+            if (opt.device >= count) return KFSP_ERR_NO_DEVICE;
+            device = opt.device;
+        } else {
+            KFSP_CUDA(cudaGetDevice(&device));
+        }
+        KFSP_CUDA(cudaSetDevice(device));
+        KFSP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        KFSP_CUDA(cudaEventCreate(&ev_a));
+        KFSP_CUDA(cudaEventCreate(&ev_b));
+        KFSP_CUDA(cudaMalloc(&d_model, sizeof(DeviceModel)));
+        KFSP_CUDA(cudaMalloc(&d_err, sizeof(int32_t)));
+        KFSP_CUDA(cudaMemset(d_err, 0, sizeof(int32_t)));
+        LDH = opt.m_max + 2;
+        KFSP_CUDA(cudaMalloc(&d_H, sizeof(double) * LDH * LDH));
+        KFSP_CUDA(cudaMalloc(&d_expm_work, sizeof(double) * 4 * EXPM_MAXN * EXPM_MAXN));
+        KFSP_CUDA(cudaMalloc(&d_expm_full, sizeof(double) * EXPM_MAXN * EXPM_MAXN));
+        KFSP_CUDA(cudaMalloc(&d_res, sizeof(ExpmResult)));
+        KFSP_CUDA(cudaMallocHost(&h_res, sizeof(ExpmResult)));
+        KFSP_CUDA(cudaMalloc(&d_ctl, sizeof(SweepCtl)));
+        KFSP_CUDA(cudaMemset(d_ctl, 0, sizeof(SweepCtl)));
+        KFSP_CUDA(cudaMallocHost(&h_ctl, sizeof(SweepCtl)));
+        KFSP_CUDA(cudaMalloc(&rd.partials, sizeof(double) * 3 * MAX_VEC_BLOCKS));
+        KFSP_CUDA(cudaMalloc(&rd.counter, sizeof(unsigned int)));
+        KFSP_CUDA(cudaMemset(rd.counter, 0, sizeof(unsigned int)));
+        KFSP_CUDA(cudaFuncSetAttribute(k_expm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXPM_SMEM));
+        return KFSP_OK;
+    }
+    void destroy() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        free_state_space();
+        cudaFree(d_model); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
+        cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush);
+        if (h_res) cudaFreeHost(h_res);
+        if (h_ctl) cudaFreeHost(h_ctl);
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    void free_state_space() {
+        cudaFree(d_states); cudaFree(d_succ); cudaFree(d_prop); cudaFree(d_diag); cudaFree(d_pred); cudaFree(d_coef);
+        cudaFree(d_w); cudaFree(d_table); cudaFree(d_V);
+        d_states = d_succ = d_pred = d_table = nullptr;
+        d_prop = d_diag = d_coef = d_w = d_V = nullptr;
+        ld = 0; n = 0;
+    }
+
+    int grid_for(int64_t work, int threads = VEC_THREADS) const {
+        int64_t b = (work + threads - 1) / threads;
+        if (b < 1) b = 1;
+        if (b > MAX_VEC_BLOCKS) b = MAX_VEC_BLOCKS;
+        return (int)b;
+    }
+    int sync() {
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        return KFSP_OK;
+    }
+    int check_launch() {
+        ++launches;
+        KFSP_CUDA(cudaGetLastError());
+        return KFSP_OK;
+    }
+#define KFSP_LAUNCH(kernel, grid, block, smem, ...)            \
+    do {                                                       \
+        kernel<<<(grid), (block), (smem), stream>>>(__VA_ARGS__); \
+        KFSP_TRY(check_launch());                              \
+    } while (0)
+
+    int ensure_scratch(size_t bytes) {
+        if (bytes <= scratch_bytes) return KFSP_OK;
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        if (d_scratch) KFSP_CUDA(cudaFree(d_scratch));
+        size_t want = std::max(bytes, scratch_bytes * 2);
+        want = (want + 255) & ~(size_t)255;
+        KFSP_CUDA(cudaMalloc(&d_scratch, want));
+        scratch_bytes = want;
+        return KFSP_OK;
+    }
+
+    // ---------------------------------------------------------------- model
+    int set_model(const HostModel& m) {
+        if (m.S < 1 || m.S > KFSP_MAX_SPECIES || m.R < 1 || m.R > KFSP_MAX_REACTIONS || m.P > KFSP_MAX_PARAMS || m.P < 0)
+            return KFSP_ERR_UNSUPPORTED;
+        if (m.custom) return KFSP_ERR_UNSUPPORTED;     // host callbacks cannot run on the device ("next")
+        KFSP_CUDA(cudaSetDevice(device));
+        DeviceModel dm;
+        std::memset(&dm, 0, sizeof dm);
+        dm.S = m.S; dm.R = m.R; dm.P = m.P; dm.max_molecules = opt.max_molecules;
+        for (int k = 0; k < m.R; ++k)
+            for (int s = 0; s < m.S; ++s) dm.stoich[k * m.S + s] = m.stoich[(size_t)k * m.S + s];
+        int nc = 0, ni = 0;
+        if ((int)m.programs.size() != m.R) return KFSP_ERR_NO_MODEL;
+        for (int k = 0; k < m.R; ++k) {
+            const Program& p = m.programs[k];
+            if (p.empty()) return KFSP_ERR_NO_MODEL;
+            const int depth = program_stack_depth(p, m.S + m.P);
+            if (depth < 0 || depth > KFSP_STACK) return KFSP_ERR_UNSUPPORTED;
+            if (nc + (int)p.code.size() > KFSP_MAX_CODE || ni + (int)p.immed.size() > KFSP_MAX_IMMED) return KFSP_ERR_UNSUPPORTED;
+            dm.code_begin[k] = nc; dm.immed_begin[k] = ni;
+            for (int32_t c : p.code) dm.code[nc++] = c;
+            for (double v : p.immed) dm.immed[ni++] = v;
+        }
+        dm.code_begin[m.R] = nc; dm.immed_begin[m.R] = ni;
+        for (int i = 0; i < m.P; ++i) dm.params[i] = m.params[i];
+        KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        const bool reshape = !have_model || m.S != S || m.R != R;
+        hm = m;
+        S = m.S; R = m.R;
+        have_model = true;
+        if (reshape) { free_state_space(); }
+        n = 0;
+        return KFSP_OK;
+    }
+
+    int ensure_state_space() {
+        if (!have_model) return KFSP_ERR_NO_MODEL;
+        if (ld > 0) return KFSP_OK;
+        KFSP_CUDA(cudaSetDevice(device));
+        const int64_t cap = ((opt.max_states + 63) / 64) * 64;
+        int64_t ts = 1024;
+        while (ts < 2 * cap) ts <<= 1;
+        KFSP_CUDA(cudaMalloc(&d_states, sizeof(int32_t) * cap * S));
+        KFSP_CUDA(cudaMalloc(&d_succ, sizeof(int32_t) * cap * R));
+        KFSP_CUDA(cudaMalloc(&d_pred, sizeof(int32_t) * cap * R));
+        KFSP_CUDA(cudaMalloc(&d_prop, sizeof(double) * cap * R));
+        KFSP_CUDA(cudaMalloc(&d_coef, sizeof(double) * cap * R));
+        KFSP_CUDA(cudaMalloc(&d_diag, sizeof(double) * cap));
+        KFSP_CUDA(cudaMalloc(&d_w, sizeof(double) * cap));
+        KFSP_CUDA(cudaMalloc(&d_table, sizeof(int32_t) * ts));
+        KFSP_CUDA(cudaMemsetAsync(d_w, 0, sizeof(double) * cap, stream));
+        table_size = ts;
+        ld = cap;
+        n = 0;
+        return KFSP_OK;
+    }
+    int ensure_basis() {
+        if (d_V) return KFSP_OK;
+        KFSP_CUDA(cudaMalloc(&d_V, sizeof(double) * (size_t)ld * (opt.m_max + 2)));
+        return KFSP_OK;
+    }
+    FspView view() const {
+        FspView f;
+        f.S = S; f.R = R; f.ld = ld; f.n = n;
+        f.states = d_states; f.succ = d_succ; f.prop = d_prop; f.diag = d_diag; f.pred = d_pred; f.coef = d_coef;
+        f.table = d_table; f.mask = (uint32_t)(table_size - 1); f.model = d_model;
+        return f;
+    }
+    int read_err(int32_t* e) {
+        KFSP_CUDA(cudaMemcpyAsync(e, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        if (*e) KFSP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
+        return KFSP_OK;
+    }
+    static int err_to_status(int32_t e) {
+        if (e & DEV_BAD_STATE) return KFSP_ERR_BAD_STATE;
+        if (e & DEV_DUPLICATE) return KFSP_ERR_BAD_STATE;
+        if (e & DEV_MOLECULE_LIMIT) return KFSP_ERR_MOLECULE_LIMIT;
+        if (e & DEV_RUNAWAY) return KFSP_ERR_SSA_RUNAWAY;
+        if (e & DEV_TABLE_FULL) return KFSP_ERR_OVERFLOW;
+        return KFSP_OK;
+    }
+
+    // exclusive scan of n int32 values; *total is returned on the host (synchronises)
+    int exclusive_scan(const int32_t* in, int32_t* out, int64_t cnt, int32_t* tile_buf /* >= 2*tiles+2 */, int64_t* total) {
+        const int64_t tiles = (cnt + SCAN_TILE - 1) / SCAN_TILE;
+        if (tiles > SCAN_TILE) return KFSP_ERR_UNSUPPORTED;       // > 16.7M tiles of 4096: not reachable with int32 indices
+        int32_t* sums = tile_buf;
+        int32_t* offs = tile_buf + tiles + 1;
+        KFSP_LAUNCH(k_scan_tiles, (int)tiles, SCAN_THREADS, 0, in, (int32_t*)nullptr, cnt, sums, (const int32_t*)nullptr);
+        if (tiles > 1) {
+            // scan of tile sums: one block handles up to SCAN_TILE tiles
+            KFSP_LAUNCH(k_scan_tiles, 1, SCAN_THREADS, 0, (const int32_t*)sums, offs, tiles, (int32_t*)nullptr, (const int32_t*)nullptr);
+            KFSP_LAUNCH(k_scan_tiles, (int)tiles, SCAN_THREADS, 0, in, out, cnt, (int32_t*)nullptr, (const int32_t*)offs);
+        } else {
+            KFSP_LAUNCH(k_scan_tiles, 1, SCAN_THREADS, 0, in, out, cnt, (int32_t*)nullptr, (const int32_t*)nullptr);
+        }
+        // total = last exclusive value + last input
+        int32_t last_ex = 0, last_in = 0;
+        KFSP_CUDA(cudaMemcpyAsync(&last_ex, out + cnt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        KFSP_CUDA(cudaMemcpyAsync(&last_in, in + cnt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        *total = (int64_t)last_ex + last_in;
+        return KFSP_OK;
+    }
+
+    // ---------------------------------------------------------------- MATRIX_STARTER
+    int fsp_init_device(int64_t count) {
+        // states [0,count) are already in d_states
+        KFSP_CUDA(cudaMemsetAsync(d_table, 0xFF, sizeof(int32_t) * table_size, stream));
+        KFSP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
+        n = count;
+        FspView f = view();
+        KFSP_LAUNCH(k_validate_states, grid_for(count * S), VEC_THREADS, 0, d_states, S, count, opt.max_molecules, d_err);
+        int32_t e = 0;
+        KFSP_TRY(read_err(&e));
+        if (e) { n = 0; return err_to_status(e); }
+        KFSP_LAUNCH(k_insert_states, grid_for(count), VEC_THREADS, 0, f, (int64_t)0, count, d_err);
+        KFSP_LAUNCH(k_propensities, grid_for(count), VEC_THREADS, 0, f, (int64_t)0, count);
+        KFSP_LAUNCH(k_reset_links, grid_for(count * R), VEC_THREADS, 0, f, (int64_t)0, count);
+        KFSP_LAUNCH(k_resolve_links, grid_for(count * R), VEC_THREADS, 0, f);
+        KFSP_TRY(read_err(&e));
+        if (e) { n = 0; return err_to_status(e); }
+        return KFSP_OK;
+    }
+    int fsp_init(int64_t count, const int32_t* states_host) {
+        KFSP_TRY(ensure_state_space());
+        if (count < 1 || count > opt.max_states) return KFSP_ERR_BAD_SIZES;
+        KFSP_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(int32_t) * count * S, cudaMemcpyHostToDevice, stream));
+        KFSP_CUDA(cudaMemsetAsync(d_w, 0, sizeof(double) * count, stream));
+        return fsp_init_device(count);
+    }
+
+    // Insert `ncand` candidate states (in visiting order) that sit in scratch at `cand`;
+    // layout of the scratch after cand: slot[ncand], win[ncand], pos[ncand], tiles.
+    int insert_candidates(int32_t* cand, int64_t ncand, int32_t* slot, int32_t* win, int32_t* pos, int32_t* tile_buf, int64_t* n_new) {
+        FspView f = view();
+        KFSP_LAUNCH(k_insert_candidates, grid_for(ncand), VEC_THREADS, 0, f, (const int32_t*)cand, ncand, slot, d_err);
+        KFSP_LAUNCH(k_mark_winners, grid_for(ncand), VEC_THREADS, 0, (const int32_t*)d_table, (const int32_t*)slot, ncand, (int32_t)n, win);
+        int64_t total = 0;
+        KFSP_TRY(exclusive_scan(win, pos, ncand, tile_buf, &total));
+        int32_t e = 0;
+        KFSP_TRY(read_err(&e));
+        if (e) return err_to_status(e);
+        *n_new = total;
+        return KFSP_OK;
+    }
+    int commit_candidates(int32_t* cand, int64_t ncand, int32_t* slot, int32_t* win, int32_t* pos, int64_t n_new) {
+        FspView f = view();
+        KFSP_LAUNCH(k_commit_winners, grid_for(ncand), VEC_THREADS, 0, f, (const int32_t*)cand, (const int32_t*)slot,
+                    (const int32_t*)win, (const int32_t*)pos, ncand, d_w);
+        const int64_t first = n;
+        n += n_new;
+        f = view();
+        KFSP_LAUNCH(k_propensities, grid_for(n_new), VEC_THREADS, 0, f, first, n_new);
+        KFSP_LAUNCH(k_reset_links, grid_for(n_new * R), VEC_THREADS, 0, f, first, n_new);
+        KFSP_LAUNCH(k_resolve_links, grid_for(n * R), VEC_THREADS, 0, f);
+        return KFSP_OK;
+    }
+    static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+    // ---------------------------------------------------------------- ONESTEP_EXTENDER
+    int fsp_onestep() {
+        if (n < 1) return KFSP_ERR_BAD_SIZES;
+        const int64_t n_old = n;
+        // scratch: cnt[n_old], off[n_old], tiles
+        const int64_t tiles0 = (n_old + SCAN_TILE - 1) / SCAN_TILE;
+        size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * (2 * tiles0 + 4));
+        KFSP_TRY(ensure_scratch(need0));
+        int32_t* cnt = (int32_t*)d_scratch;
+        int32_t* off = (int32_t*)(d_scratch + align_up(sizeof(int32_t) * n_old));
+        int32_t* tb0 = (int32_t*)(d_scratch + 2 * align_up(sizeof(int32_t) * n_old));
+        FspView f = view();
+        KFSP_LAUNCH(k_onestep_count, grid_for(n_old), VEC_THREADS, 0, f, n_old, cnt);
+        int64_t ncand = 0;
+        KFSP_TRY(exclusive_scan(cnt, off, n_old, tb0, &ncand));
+        if (ncand == 0) return KFSP_OK;
+        if (ncand > 2000000000LL - n_old) return KFSP_ERR_OVERFLOW;
+        return expand_with(ncand, n_old, /*ssa=*/false, 0.0);
+    }
+
+    // Shared tail of ONESTEP_EXTENDER and SSA_EXTENDER: off[] (per-start-state offsets) is at
+    // scratch + align(n_old ints); candidates are generated after the offsets.
+    int expand_with(int64_t ncand, int64_t n_old, bool ssa, double timestep) {
+        const size_t a_n = align_up(sizeof(int32_t) * n_old);
+        const int64_t tiles = (ncand + SCAN_TILE - 1) / SCAN_TILE;
+        const size_t a_c = align_up(sizeof(int32_t) * ncand);
+        const size_t need = 2 * a_n + align_up(sizeof(int32_t) * ncand * S) + 3 * a_c + align_up(sizeof(int32_t) * (2 * tiles + 4));
+        // growing the arena would lose off[]: save it first
+        if (need > scratch_bytes) {
+            std::vector<int32_t> keep((size_t)n_old);
+            KFSP_CUDA(cudaMemcpyAsync(keep.data(), d_scratch + a_n, sizeof(int32_t) * n_old, cudaMemcpyDeviceToHost, stream));
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+            KFSP_TRY(ensure_scratch(need));
+            KFSP_CUDA(cudaMemcpyAsync(d_scratch + a_n, keep.data(), sizeof(int32_t) * n_old, cudaMemcpyHostToDevice, stream));
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+        }
+        int32_t* off = (int32_t*)(d_scratch + a_n);
+        char* p = d_scratch + 2 * a_n;
+        int32_t* cand = (int32_t*)p; p += align_up(sizeof(int32_t) * ncand * S);
+        int32_t* slot = (int32_t*)p; p += a_c;
+        int32_t* win = (int32_t*)p; p += a_c;
+        int32_t* pos = (int32_t*)p; p += a_c;
+        int32_t* tb = (int32_t*)p;
+        FspView f = view();
+        if (ssa) {
+            KFSP_LAUNCH(k_ssa_walk<true>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
+                        (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24));
+        } else {
+            KFSP_LAUNCH(k_onestep_fill, grid_for(n_old), VEC_THREADS, 0, f, n_old, (const int32_t*)off, cand, d_err);
+        }
+        int64_t n_new = 0;
+        int st = insert_candidates(cand, ncand, slot, win, pos, tb, &n_new);
+        if (st != KFSP_OK) return st;
+        // ONESTEP: STOP once FSP%SIZE >= KTLEN (StateSpace.f90:388-391); SSA returns silently (:612-616),
+        // and the ONESTEP that always follows it stops -- both are reported as overflow here.
+        if (n + n_new >= opt.max_states) {
+            KFSP_LAUNCH(k_rollback_candidates, grid_for(ncand), VEC_THREADS, 0, d_table, (const int32_t*)slot, ncand, (int32_t)n);
+            KFSP_TRY(sync());
+            return KFSP_ERR_OVERFLOW;
+        }
+        return commit_candidates(cand, ncand, slot, win, pos, n_new);
+    }
+
+    // ---------------------------------------------------------------- SSA_EXTENDER
+    int fsp_ssa(double timestep) {
+        if (n < 1) return KFSP_ERR_BAD_SIZES;
+        const int64_t n_old = n;
+        ssa_calls += 1;
+        const int64_t tiles0 = (n_old + SCAN_TILE - 1) / SCAN_TILE;
+        size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * (2 * tiles0 + 4));
+        KFSP_TRY(ensure_scratch(need0));
+        int32_t* cnt = (int32_t*)d_scratch;
+        int32_t* off = (int32_t*)(d_scratch + align_up(sizeof(int32_t) * n_old));
+        int32_t* tb0 = (int32_t*)(d_scratch + 2 * align_up(sizeof(int32_t) * n_old));
+        FspView f = view();
+        KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
+                    (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24));
+        int64_t ncand = 0;
+        KFSP_TRY(exclusive_scan(cnt, off, n_old, tb0, &ncand));
+        int32_t e = 0;
+        KFSP_TRY(read_err(&e));
+        if (e) return err_to_status(e);
+        if (ncand == 0) return KFSP_OK;
+        if (ncand > 2000000000LL - n_old) return KFSP_ERR_OVERFLOW;
+        return expand_with(ncand, n_old, /*ssa=*/true, timestep);
+    }
+
+    // ---------------------------------------------------------------- FMATVEC
+    template <int MODE>
+    int spmv(const double* x, double* y, const double* first, double* h_out) {
+        const int g = grid_for(n);
+        if (profile_spmv) KFSP_CUDA(cudaEventRecord(ev_a, stream));
+        void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
+                     Reducer, SweepCtl*, double*);
+        switch (R) {
+        case 4: kern = k_spmv<4, MODE>; break;
+        case 6: kern = k_spmv<6, MODE>; break;
+        case 10: kern = k_spmv<10, MODE>; break;
+        default: kern = k_spmv<0, MODE>; break;
+        }
+        kern<<<g, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, first, rd, d_ctl, h_out);
+        KFSP_TRY(check_launch());
+        if (profile_spmv) {
+            KFSP_CUDA(cudaEventRecord(ev_b, stream));
+            KFSP_CUDA(cudaEventSynchronize(ev_b));
+            float ms = 0;
+            KFSP_CUDA(cudaEventElapsedTime(&ms, ev_a, ev_b));
+            spmv_seconds += 1e-3 * ms;
+        }
+        return KFSP_OK;
+    }
+
+    // ---------------------------------------------------------------- DROP_STATES
+    int fsp_drop(double dsum, int32_t* dropped, double* droptol_out, int64_t* count_out) {
+        *dropped = 0;
+        if (n < 1) return KFSP_ERR_BAD_SIZES;
+        const int64_t lsize = n;
+        // FIND_DROPTOL (StateSpace.f90:398-427): thresholds by repeated division, 64 at a time
+        double droptol = opt.drop_tol0;
+        double* d_thr = nullptr;
+        const size_t a_i = align_up(sizeof(int32_t) * lsize);
+        const int64_t tiles = (lsize + SCAN_TILE - 1) / SCAN_TILE;
+        const size_t need = align_up(sizeof(double) * (2 * DROP_BUCKETS + 8)) + 3 * a_i + align_up(sizeof(int32_t) * (2 * tiles + 4)) +
+                            align_up(sizeof(double) * lsize * (size_t)std::max(R, 1)) + 64;
+        KFSP_TRY(ensure_scratch(need));
+        char* p = d_scratch;
+        d_thr = (double*)p;
+        double* d_bsum = d_thr + DROP_BUCKETS;
+        unsigned long long* d_cnt = (unsigned long long*)(d_bsum + DROP_BUCKETS + 2);
+        p += align_up(sizeof(double) * (2 * DROP_BUCKETS + 8));
+        int32_t* drop = (int32_t*)p; p += a_i;
+        int32_t* keep = (int32_t*)p; p += a_i;
+        int32_t* pos = (int32_t*)p; p += a_i;
+        int32_t* tb = (int32_t*)p; p += align_up(sizeof(int32_t) * (2 * tiles + 4));
+        char* tmp = p;
+        bool found = false;
+        for (int round = 0; round < 6 && !found; ++round) {
+            double thr[DROP_BUCKETS], bs[DROP_BUCKETS + 1];
+            thr[0] = droptol;
+            for (int b = 1; b < DROP_BUCKETS; ++b) thr[b] = thr[b - 1] / 10.0;
+            KFSP_CUDA(cudaMemcpyAsync(d_thr, thr, sizeof thr, cudaMemcpyHostToDevice, stream));
+            KFSP_CUDA(cudaMemsetAsync(d_bsum, 0, sizeof(double) * (DROP_BUCKETS + 1), stream));
+            KFSP_LAUNCH(k_drop_histogram, grid_for(lsize), VEC_THREADS, 0, (const double*)d_w, lsize, (const double*)d_thr, DROP_BUCKETS, d_bsum);
+            KFSP_CUDA(cudaMemcpyAsync(bs, d_bsum, sizeof bs, cudaMemcpyDeviceToHost, stream));
+            KFSP_TRY(sync());
+            // sum1(k) = sum of buckets k+1 .. DROP_BUCKETS
+            double tail = 0.0;
+            double sum1[DROP_BUCKETS];
+            for (int k = DROP_BUCKETS - 1; k >= 0; --k) { tail += bs[k + 1]; sum1[k] = tail; }
+            for (int k = 0; k < DROP_BUCKETS; ++k) {
+                if (sum1[k] < dsum) { droptol = thr[k]; found = true; break; }
+            }
+            if (!found) {
+                droptol = thr[DROP_BUCKETS - 1] / 10.0;
+                if (droptol == 0.0) found = true;
+            }
+        }
+        // mark, derivative test, count
+        KFSP_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), stream));
+        KFSP_LAUNCH(k_drop_mark, grid_for(lsize), VEC_THREADS, 0, (const double*)d_w, lsize, droptol, drop, d_cnt);
+        double* aw = (double*)tmp;         // WTMP; the compaction scratch is not in use yet
+        KFSP_TRY(spmv<0>(d_w, aw, nullptr, nullptr));
+        KFSP_LAUNCH(k_drop_unmark, grid_for(lsize), VEC_THREADS, 0, (const double*)aw, lsize, opt.drop_deriv_tol, drop, d_cnt + 1);
+        unsigned long long c[2];
+        KFSP_CUDA(cudaMemcpyAsync(c, d_cnt, sizeof c, cudaMemcpyDeviceToHost, stream));
+        KFSP_TRY(sync());
+        const int64_t drop_count = (int64_t)c[0] - (int64_t)c[1];
+        if (droptol_out) *droptol_out = droptol;
+        if (count_out) *count_out = drop_count;
+        if (!((double)drop_count * 1.0 / ((double)lsize * 1.0) > opt.drop_fraction)) return KFSP_OK;
+        // stable compaction
+        KFSP_LAUNCH(k_invert_flags, grid_for(lsize), VEC_THREADS, 0, (const int32_t*)drop, keep, lsize);
+        int64_t q = 0;
+        KFSP_TRY(exclusive_scan(keep, pos, lsize, tb, &q));
+        if (q < 1) {
+            // every state dropped: the reference would continue with an empty projection and divide by zero
+            return KFSP_ERR_BAD_SIZES;
+        }
+        const int g = grid_for(lsize * std::max(R, S));
+        // states
+        KFSP_LAUNCH(k_compact_states, g, VEC_THREADS, 0, (const int32_t*)d_states, (int32_t*)tmp, (const int32_t*)keep, (const int32_t*)pos, lsize, S);
+        KFSP_CUDA(cudaMemcpyAsync(d_states, tmp, sizeof(int32_t) * q * S, cudaMemcpyDeviceToDevice, stream));
+        // w (zero the tail: W(1:LSIZE) = 0 then copy, StateSpace.f90:528-534)
+        KFSP_LAUNCH(k_compact_rows<double>, g, VEC_THREADS, 0, (const double*)d_w, (double*)tmp, (const int32_t*)keep, (const int32_t*)pos, lsize, lsize, q, 1);
+        KFSP_CUDA(cudaMemsetAsync(d_w, 0, sizeof(double) * lsize, stream));
+        KFSP_CUDA(cudaMemcpyAsync(d_w, tmp, sizeof(double) * q, cudaMemcpyDeviceToDevice, stream));
+        // diag
+        KFSP_LAUNCH(k_compact_rows<double>, g, VEC_THREADS, 0, (const double*)d_diag, (double*)tmp, (const int32_t*)keep, (const int32_t*)pos, lsize, lsize, q, 1);
+        KFSP_CUDA(cudaMemcpyAsync(d_diag, tmp, sizeof(double) * q, cudaMemcpyDeviceToDevice, stream));
+        // prop (R rows)
+        KFSP_LAUNCH(k_compact_rows<double>, g, VEC_THREADS, 0, (const double*)d_prop, (double*)tmp, (const int32_t*)keep, (const int32_t*)pos, lsize, ld, q, R);
+        KFSP_CUDA(cudaMemcpy2DAsync(d_prop, sizeof(double) * ld, tmp, sizeof(double) * q, sizeof(double) * q, R, cudaMemcpyDeviceToDevice, stream));
+        // succ (R rows, re-indexed)
+        KFSP_LAUNCH(k_compact_succ, g, VEC_THREADS, 0, (const int32_t*)d_succ, (int32_t*)tmp, (const int32_t*)keep, (const int32_t*)pos, lsize, ld, q, R);
+        KFSP_CUDA(cudaMemcpy2DAsync(d_succ, sizeof(int32_t) * ld, tmp, sizeof(int32_t) * q, sizeof(int32_t) * q, R, cudaMemcpyDeviceToDevice, stream));
+        // hash table and row form are rebuilt for the survivors
+        n = q;
+        FspView f = view();
+        KFSP_CUDA(cudaMemsetAsync(d_table, 0xFF, sizeof(int32_t) * table_size, stream));
+        KFSP_LAUNCH(k_insert_states, grid_for(q), VEC_THREADS, 0, f, (int64_t)0, q, d_err);
+        KFSP_LAUNCH(k_fill_i32, grid_for(ld * R), VEC_THREADS, 0, d_pred, ld * R, IDX_ABSENT);
+        KFSP_LAUNCH(k_resolve_links, grid_for(q * R), VEC_THREADS, 0, f);
+        int32_t e = 0;
+        KFSP_TRY(read_err(&e));
+        if (e) return err_to_status(e);
+        *dropped = 1;
+        return KFSP_OK;
+    }
+
+    // ---------------------------------------------------------------- Arnoldi / IOP-2 sweep
+    // columns J = jold..m (1-based) then the extra product (KrylovSolver.f90:236-266). No host sync.
+    int arnoldi(int jold, int m) {
+        for (int J = jold; J <= m; ++J) {
+            const double* vj = d_V + (size_t)(J - 1) * ld;
+            double* vn = d_V + (size_t)J * ld;
+            double* hcol = d_H + (size_t)(J - 1) * LDH;
+            if (J >= 2) {
+                const double* vp = d_V + (size_t)(J - 2) * ld;
+                KFSP_TRY(spmv<1>(vj, vn, vp, hcol + (J - 2)));                                   // H(J-1,J)
+                KFSP_LAUNCH(k_axpy_dot, grid_for(n), VEC_THREADS, 0, n, vp, vj, vn, rd, d_ctl, hcol + (J - 1));   // H(J,J)
+                KFSP_LAUNCH(k_axpy_nrm, grid_for(n), VEC_THREADS, 0, n, vj, vn, (int)SC_H2, rd, d_ctl, hcol + J, opt.break_tol, J);
+            } else {
+                KFSP_TRY(spmv<1>(vj, vn, vj, hcol + 0));                                         // H(1,1)
+                KFSP_LAUNCH(k_axpy_nrm, grid_for(n), VEC_THREADS, 0, n, vj, vn, (int)SC_H1, rd, d_ctl, hcol + J, opt.break_tol, J);
+            }
+            KFSP_LAUNCH(k_scale_by_inv, grid_for(n), VEC_THREADS, 0, n, vn, (const SweepCtl*)d_ctl);
+        }
+        KFSP_TRY(spmv<2>(d_V + (size_t)m * ld, d_V + (size_t)(m + 1) * ld, nullptr, nullptr));    // AVNORM
+        return KFSP_OK;
+    }
+    // exp(t*H) on the device; result struct copied to pinned memory (synchronises)
+    int expm_step(int mx_ok, double t_ok, int use_brk, double t_brk, int set_one) {
+        KFSP_LAUNCH(k_expm, 1, EXPM_THREADS, EXPM_SMEM, d_H, LDH, mx_ok, t_ok, use_brk, t_brk, set_one, (const SweepCtl*)d_ctl,
+                    d_expm_work, d_res, (double*)nullptr);
+        KFSP_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(ExpmResult), cudaMemcpyDeviceToHost, stream));
+        KFSP_TRY(sync());
+        return h_res->info;
+    }
+    int read_ctl() {
+        KFSP_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(SweepCtl), cudaMemcpyDeviceToHost, stream));
+        return sync();
+    }
+
+    int solve(double T, double fsptol, double krytol, int itrace, kfsp_stats* stats);
+};
+
+}  // namespace kfsp

@@ -1,0 +1,284 @@
+// exp(t*H) of the small Hessenberg matrix on ONE CTA: DGPADMnorm / DGPADM
+// (src/expokit/dgpadm.f:171-339, :2-169): degree-6 diagonal Pade with scaling and
+// squaring.  The reference spends 6+ns DGEMMs and one DGESV here; with m+2 <= 102 two
+// operands of a product (2 x 104 x 104 doubles = 173 KB) fit in the 227 KB of shared
+// memory of one SM, so every product is staged once into shared memory and each thread
+// accumulates a 4x4 register tile; the linear solve (q-p) X = p is an in-shared-memory
+// Gaussian elimination with partial pivoting, and the ns squarings never leave the SM.
+// The kernel also takes the happy-breakdown decision (which order and which step to
+// exponentiate) from the device-resident sweep flag, so no host round trip separates the
+// Arnoldi sweep from the exponential.
+#pragma once
+#include "common.cuh"
+#include "krylov.cuh"
+
+namespace kfsp {
+
+constexpr int EXPM_MAXN = 104;                 // m_max + 2 = 102, padded to a multiple of 4
+constexpr int EXPM_LDS = EXPM_MAXN;
+constexpr int EXPM_THREADS = 1024;
+constexpr size_t EXPM_SMEM = 2 * (size_t)EXPM_LDS * EXPM_MAXN * sizeof(double) + 64 * sizeof(double);
+
+struct ExpmResult {
+    int32_t ns;
+    int32_t info;               // 0 ok, KFSP_ERR_NULL_H, KFSP_ERR_SINGULAR
+    int32_t mx;                 // order actually exponentiated
+    int32_t brk;                // copy of the sweep's happy-breakdown column
+    double hnorm;               // |t| * ||H||_inf (DGPADMnorm's extra output, dgpadm.f:253)
+    double avnorm;              // copy of the sweep's ||A v_{m+1}||
+    double t_used;
+    double wsum, wssq;          // copies of ctl scalars (filled by the combine readback)
+    double e[EXPM_MAXN];        // first column of exp(t*H)
+};
+
+// load an n x n column-major matrix (ld = lda) into shared memory, scaled by alpha, zero padded to np rows/cols
+__device__ __forceinline__ void expm_load(double* s, const double* __restrict__ g, int lda, int n, int np, double alpha) {
+    for (int t = threadIdx.x; t < np * EXPM_LDS; t += EXPM_THREADS) {
+        const int j = t / EXPM_LDS, i = t % EXPM_LDS;
+        s[t] = (i < n && j < n) ? alpha * g[(size_t)j * lda + i] : 0.0;
+    }
+}
+// C = sA * sB for the n x n leading blocks; each thread owns a 4x4 tile held in acc.
+__device__ __forceinline__ void expm_mma(const double* sA, const double* sB, int n, double (&acc)[4][4]) {
+    const int ti = threadIdx.x & 31, tj = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    if (4 * ti >= n || 4 * tj >= n) return;
+    const double* pa = sA + 4 * ti;
+    const double* pb = sB + (size_t)(4 * tj) * EXPM_LDS;
+    for (int k = 0; k < n; ++k) {
+        const double2 a01 = *reinterpret_cast<const double2*>(pa + (size_t)k * EXPM_LDS);
+        const double2 a23 = *reinterpret_cast<const double2*>(pa + (size_t)k * EXPM_LDS + 2);
+        const double b0 = pb[k], b1 = pb[EXPM_LDS + k], b2 = pb[2 * EXPM_LDS + k], b3 = pb[3 * EXPM_LDS + k];
+        acc[0][0] = fma(a01.x, b0, acc[0][0]); acc[1][0] = fma(a01.y, b0, acc[1][0]);
+        acc[2][0] = fma(a23.x, b0, acc[2][0]); acc[3][0] = fma(a23.y, b0, acc[3][0]);
+        acc[0][1] = fma(a01.x, b1, acc[0][1]); acc[1][1] = fma(a01.y, b1, acc[1][1]);
+        acc[2][1] = fma(a23.x, b1, acc[2][1]); acc[3][1] = fma(a23.y, b1, acc[3][1]);
+        acc[0][2] = fma(a01.x, b2, acc[0][2]); acc[1][2] = fma(a01.y, b2, acc[1][2]);
+        acc[2][2] = fma(a23.x, b2, acc[2][2]); acc[3][2] = fma(a23.y, b2, acc[3][2]);
+        acc[0][3] = fma(a01.x, b3, acc[0][3]); acc[1][3] = fma(a01.y, b3, acc[1][3]);
+        acc[2][3] = fma(a23.x, b3, acc[2][3]); acc[3][3] = fma(a23.y, b3, acc[3][3]);
+    }
+}
+// write the register tiles to a column-major matrix with leading dimension ldc (global or shared)
+__device__ __forceinline__ void expm_store(double* C, int ldc, int n, const double (&acc)[4][4], double diag_add) {
+    const int ti = threadIdx.x & 31, tj = threadIdx.x >> 5;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = 4 * ti + a, j = 4 * tj + b;
+            if (i < n && j < n) C[(size_t)j * ldc + i] = acc[a][b] + (i == j ? diag_add : 0.0);
+        }
+}
+
+// One CTA of 1024 threads.
+//   H, ldh        : the device Hessenberg matrix (column-major)
+//   mx_ok, t_ok   : order and step when the sweep did not break down
+//   use_brk,t_brk : if use_brk and ctl->brk > 0, order = ctl->brk and step = t_brk (KrylovSolver.f90:249-256, 271)
+//   set_one       : if >= 0, first set H(set_one+2, set_one+1) = 1 (label 300, KrylovSolver.f90:266; set_one = M)
+//   work          : 4 * EXPM_MAXN^2 doubles of global scratch
+//   full_out      : optional mx*mx output of the whole exponential (tests)
+__global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, int mx_ok, double t_ok, int use_brk, double t_brk,
+                                                          int set_one, const SweepCtl* ctl, double* work, ExpmResult* res,
+                                                          double* full_out) {
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;
+    double* sB = smem + (size_t)EXPM_LDS * EXPM_MAXN;
+    double* sx = sB + (size_t)EXPM_LDS * EXPM_MAXN;       // 64 doubles of scratch
+    __shared__ int s_piv, s_info, s_ns;
+    __shared__ double s_scale, s_hnorm, s_coef[8];
+    const int tid = threadIdx.x;
+
+    int n = mx_ok;
+    double t = t_ok;
+    const int brk = ctl ? ctl->brk : 0;
+    if (use_brk && brk > 0) { n = brk; t = t_brk; }
+    if (set_one >= 0 && tid == 0) H[(size_t)set_one * ldh + set_one + 1] = 1.0;
+    if (tid == 0) s_info = 0;
+    __syncthreads();
+    const int np = (n + 3) & ~3;
+    const size_t nn = (size_t)EXPM_MAXN * EXPM_MAXN;
+    double* gH2 = work;            // scale2*H*H
+    double* gP = work + nn;
+    double* gQ = work + 2 * nn;
+    double* gF = work + 3 * nn;
+
+    // ---- ||H||_inf by row sums in column order (dgpadm.f:241-253) -------------------------
+    double rs = 0.0;
+    if (tid < n)
+        for (int j = 0; j < n; ++j) rs += fabs(H[(size_t)j * ldh + tid]);
+    {
+        // block max through shared scratch
+        double v = rs;
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) sx[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double mxv = 0.0;
+            for (int w = 0; w < EXPM_THREADS / 32; ++w) mxv = fmax(mxv, sx[w]);
+            const double hnorm = fabs(t * mxv);
+            s_hnorm = hnorm;
+            int ns = 0;
+            if (hnorm == 0.0) {
+                s_info = KFSP_ERR_NULL_H;
+            } else {
+                // ns = max(0, int(log2(hnorm)) + 2), int() truncating toward zero (dgpadm.f:255), computed exactly
+                int ex;
+                const double fr = frexp(hnorm, &ex);               // hnorm = fr * 2^ex, fr in [0.5,1)
+                int il;                                            // trunc(log2(hnorm))
+                if (hnorm >= 1.0) il = ex - 1;
+                else il = (fr == 0.5) ? ex - 1 : ex;               // ceil for negative logarithms
+                ns = il + 2 > 0 ? il + 2 : 0;
+                if (ns > 30) { s_info = KFSP_ERR_BAD_SIZES; ns = 30; }
+            }
+            s_ns = ns;
+            s_scale = ldexp(t, -ns);                               // t / 2**ns
+            // Pade coefficients (dgpadm.f:261-266), ideg = 6
+            s_coef[0] = 1.0;
+            for (int k = 1; k <= 6; ++k) s_coef[k] = (s_coef[k - 1] * (double)(7 - k)) / (double)(k * (13 - k));
+        }
+        __syncthreads();
+    }
+    if (s_info != 0) {
+        if (tid == 0) { res->info = s_info; res->ns = 0; res->mx = n; res->brk = brk; res->hnorm = s_hnorm; res->t_used = t;
+                        res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0; }
+        return;
+    }
+    const double scale = s_scale, scale2 = scale * scale;
+    double acc[4][4];
+
+    // ---- H2 = scale2*H*H (dgpadm.f:270): alpha multiplies the right operand, as DGEMM does ----
+    expm_load(sA, H, ldh, n, np, 1.0);
+    expm_load(sB, H, ldh, n, np, scale2);
+    __syncthreads();
+    expm_mma(sA, sB, n, acc);
+    expm_store(gH2, n, n, acc, 0.0);
+    __syncthreads();
+    // sB <- H2 (stays for the whole Horner recurrence)
+    expm_load(sB, gH2, n, n, np, 1.0);
+    // ---- p = c5*I, q = c6*I ; Horner (dgpadm.f:274-301) -----------------------------------
+    // k = 5: q = q*H2 + c4 I ; k = 4: p = p*H2 + c3 I ; k = 3: q ; k = 2: p ; k = 1: q = q*H2 + c0 I
+    // The first two products have diagonal left operands: (c*I)*H2 = c*H2.
+    double* bufP = gP; double* bufQ = gQ; double* bufF = gF;
+    for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) {
+        const int j = t2 / n, i = t2 % n;
+        const double h2 = gH2[t2];
+        bufF[t2] = s_coef[6] * h2 + (i == j ? s_coef[4] : 0.0);    // new q
+        bufP[t2] = (i == j) ? s_coef[5] : 0.0;                      // p = c5 I
+    }
+    __syncthreads();
+    { double* tmp = bufQ; bufQ = bufF; bufF = tmp; }               // q is now in old F; old Q buffer is free
+    int iodd = 0;
+    for (int k = 4; k >= 1; --k) {
+        double* used = iodd ? bufQ : bufP;
+        expm_load(sA, used, n, n, np, 1.0);
+        __syncthreads();
+        expm_mma(sA, sB, n, acc);
+        expm_store(bufF, n, n, acc, s_coef[k - 1]);
+        __syncthreads();
+        if (iodd) { bufQ = bufF; } else { bufP = bufF; }
+        bufF = used;
+        iodd = 1 - iodd;
+    }
+    // here iodd == 0: p = scale * p * H (dgpadm.f:309-312)
+    expm_load(sA, bufP, n, n, np, 1.0);
+    expm_load(sB, H, ldh, n, np, scale);
+    __syncthreads();
+    expm_mma(sA, sB, n, acc);
+    __syncthreads();
+    // ---- sA <- q - p ; sB <- p ; solve (q-p) X = p (dgpadm.f:314-315) ----------------------
+    expm_store(sB, EXPM_LDS, n, acc, 0.0);
+    expm_load(sA, bufQ, n, n, np, 1.0);
+    __syncthreads();
+    for (int t2 = tid; t2 < n * EXPM_LDS; t2 += EXPM_THREADS) {
+        const int i = t2 % EXPM_LDS;
+        if (i < n) sA[t2] += -1.0 * sB[t2];
+    }
+    __syncthreads();
+    // Gaussian elimination with partial pivoting on [sA | sB]
+    for (int k = 0; k < n; ++k) {
+        if (tid < 32) {
+            double best = -1.0; int bi = k;
+            for (int i = k + tid; i < n; i += 32) {
+                const double v = fabs(sA[(size_t)k * EXPM_LDS + i]);
+                if (v > best) { best = v; bi = i; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_down_sync(0xffffffffu, best, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (tid == 0) { s_piv = bi; if (best == 0.0) s_info = KFSP_ERR_SINGULAR; }
+        }
+        __syncthreads();
+        if (s_info != 0) break;
+        const int p = s_piv;
+        if (p != k) {
+            for (int j = tid; j < 2 * n; j += EXPM_THREADS) {
+                double* col = (j < n ? sA + (size_t)j * EXPM_LDS : sB + (size_t)(j - n) * EXPM_LDS);
+                const double tmp = col[k]; col[k] = col[p]; col[p] = tmp;
+            }
+            __syncthreads();
+        }
+        const double inv = 1.0 / sA[(size_t)k * EXPM_LDS + k];
+        __syncthreads();
+        for (int i = k + 1 + tid; i < n; i += EXPM_THREADS) sA[(size_t)k * EXPM_LDS + i] *= inv;
+        __syncthreads();
+        const int rows = n - k - 1;
+        if (rows > 0) {
+            const int colsA = n - k - 1;
+            const int total = rows * (colsA + n);
+            for (int t2 = tid; t2 < total; t2 += EXPM_THREADS) {
+                const int i = k + 1 + t2 % rows, c = t2 / rows;
+                double* col = c < colsA ? sA + (size_t)(k + 1 + c) * EXPM_LDS : sB + (size_t)(c - colsA) * EXPM_LDS;
+                col[i] = fma(-sA[(size_t)k * EXPM_LDS + i], col[k], col[i]);
+            }
+        }
+        __syncthreads();
+    }
+    if (s_info != 0) {
+        if (tid == 0) { res->info = s_info; res->ns = s_ns; res->mx = n; res->brk = brk; res->hnorm = s_hnorm; res->t_used = t;
+                        res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0; }
+        return;
+    }
+    // back substitution U X = Y, column oriented
+    for (int k = n - 1; k >= 0; --k) {
+        const double ukk = sA[(size_t)k * EXPM_LDS + k];
+        for (int j = tid; j < n; j += EXPM_THREADS) sB[(size_t)j * EXPM_LDS + k] /= ukk;
+        __syncthreads();
+        const int total = k * n;
+        for (int t2 = tid; t2 < total; t2 += EXPM_THREADS) {
+            const int i = t2 % k, j = t2 / k;
+            sB[(size_t)j * EXPM_LDS + i] = fma(-sB[(size_t)j * EXPM_LDS + k], sA[(size_t)k * EXPM_LDS + i], sB[(size_t)j * EXPM_LDS + i]);
+        }
+        __syncthreads();
+    }
+    // ---- E = I + 2 X (dgpadm.f:317-320); iodd == 0 so no sign flip (:322-325) -----------------
+    for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) {
+        const int j = t2 / EXPM_LDS, i = t2 % EXPM_LDS;
+        sB[t2] = (i < n && j < n) ? 2.0 * sB[t2] + (i == j ? 1.0 : 0.0) : 0.0;
+    }
+    __syncthreads();
+    // ---- squarings (dgpadm.f:329-336) ------------------------------------------------------
+    for (int s = 0; s < s_ns; ++s) {
+        for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) sA[t2] = sB[t2];
+        __syncthreads();
+        expm_mma(sA, sB, n, acc);
+        __syncthreads();
+        expm_store(sB, EXPM_LDS, n, acc, 0.0);
+        __syncthreads();
+    }
+    // ---- results -----------------------------------------------------------------------------
+    for (int i = tid; i < EXPM_MAXN; i += EXPM_THREADS) res->e[i] = i < n ? sB[i] : 0.0;
+    if (full_out)
+        for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) full_out[t2] = sB[(size_t)(t2 / n) * EXPM_LDS + t2 % n];
+    if (tid == 0) {
+        res->info = 0; res->ns = s_ns; res->mx = n; res->brk = brk; res->hnorm = s_hnorm; res->t_used = t;
+        res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0;
+    }
+}
+
+}  // namespace kfsp

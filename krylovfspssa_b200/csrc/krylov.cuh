@@ -1,0 +1,224 @@
+// N-sized kernels of the expv loop (src/fsp/KrylovSolver.f90:223-266, 444-450, 577-607).
+// Every one of them is HBM-bound (<= 0.25 flop/byte): the work is to stream the operands
+// exactly once, coalesced, and to keep every scalar (dot products, norms, the happy-
+// breakdown flag) on the device so that a whole Arnoldi sweep needs no host round trip.
+//
+// Reductions are deterministic: fixed grid, fixed per-thread element order, per-block
+// partials written to global memory and summed in block order by the last block to finish.
+#pragma once
+#include "common.cuh"
+
+namespace kfsp {
+
+constexpr int VEC_THREADS = 256;
+constexpr int MAX_VEC_BLOCKS = 148 * 8;       // 148 SMs x 8 resident 256-thread CTAs
+
+// device scalars of the sweep
+enum Scal { SC_H1 = 0, SC_H2, SC_INV_HN, SC_AVNORM, SC_WSUM, SC_WSSQ, SC_HN, SC_COUNT };
+
+struct SweepCtl {
+    double scal[8];
+    int32_t brk;                // happy-breakdown column (1-based), 0 = none
+    int32_t pad;
+};
+
+struct Reducer {
+    double* partials;           // [3 * MAX_VEC_BLOCKS]
+    unsigned int* counter;      // self-resetting ticket
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// Sum over the block; result valid in thread 0.  Fixed tree => deterministic.
+__device__ __forceinline__ double block_sum(double v, double* sh /*>= 32*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+// Grid-wide reduction of NV values.  Returns true in ALL threads of the last block, with the totals in out[].
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(const double (&v)[NV], double (&out)[NV], const Reducer& rd) {
+    __shared__ double sh[32];
+    __shared__ bool last;
+    __shared__ double tot[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const double s = block_sum(v[q], sh);
+        if (threadIdx.x == 0) rd.partials[q * MAX_VEC_BLOCKS + blockIdx.x] = s;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicInc(rd.counter, gridDim.x - 1);
+        last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double s = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(&rd.partials[q * MAX_VEC_BLOCKS + b]);
+        s = block_sum(s, sh);
+        if (threadIdx.x == 0) tot[q] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) out[q] = tot[q];
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// FMATVEC (KrylovSolver.f90:577-607) in gather form: y_i = -DIAG_i x_i + sum_k coef_ki x[pred_ki].
+// Fused epilogue (optional): dot = <first, y> written to H and ctl->scal[SC_H1]  (the first
+// DDOT of the IOP window, :243), or ssq = <y,y> -> AVNORM (:263).
+//   mode 0: plain   mode 1: dot with `first`   mode 2: norm of y
+// Algorithmic traffic per row: R*(4+8) matrix + 8 diag + 8 x_i + 8 y_i  = 12R+24 bytes.
+// ---------------------------------------------------------------------------------------
+template <int RT, int MODE>
+__global__ void __launch_bounds__(VEC_THREADS) k_spmv(int64_t n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
+                                                       const double* __restrict__ coef, const double* __restrict__ diag,
+                                                       const double* __restrict__ x, double* __restrict__ y,
+                                                       const double* __restrict__ first, Reducer rd, SweepCtl* ctl, double* h_out) {
+    const int R = RT > 0 ? RT : R_rt;
+    if (MODE != 0 && ctl->brk != 0) return;
+    double acc0 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double xi = x[i];
+        double s = -__ldcs(diag + i) * xi;
+#pragma unroll
+        for (int k = 0; k < (RT > 0 ? RT : R); ++k) {
+            const int32_t j = __ldcs(pred + (int64_t)k * ld + i);
+            const double a = __ldcs(coef + (int64_t)k * ld + i);
+            if (j >= 0) s = fma(a, x[j], s);
+        }
+        y[i] = s;
+        if (MODE == 1) acc0 = fma(first[i], s, acc0);
+        if (MODE == 2) acc0 = fma(s, s, acc0);
+    }
+    if (MODE == 0) return;
+    double v[1] = {acc0}, tot[1];
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
+        if (MODE == 1) { ctl->scal[SC_H1] = tot[0]; if (h_out) *h_out = tot[0]; }
+        if (MODE == 2) ctl->scal[SC_AVNORM] = sqrt(tot[0]);
+    }
+}
+
+// w -= h1*a ; dot = <b, w>   (DAXPY + the next DDOT, KrylovSolver.f90:243-245)
+__global__ void __launch_bounds__(VEC_THREADS) k_axpy_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                                          double* __restrict__ w, Reducer rd, SweepCtl* ctl, double* h_out) {
+    if (ctl->brk != 0) return;
+    const double h1 = ctl->scal[SC_H1];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double wi = fma(-h1, a[i], w[i]);
+        w[i] = wi;
+        acc = fma(b[i], wi, acc);
+    }
+    double v[1] = {acc}, tot[1];
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
+        ctl->scal[SC_H2] = tot[0];
+        if (h_out) *h_out = tot[0];
+    }
+}
+
+// w -= h*a ; ssq = <w,w>; then HJ1J = sqrt(ssq), happy-breakdown test, H(J+1,J) (KrylovSolver.f90:244-257)
+// which = SC_H1 or SC_H2: the scalar holding h.
+__global__ void __launch_bounds__(VEC_THREADS) k_axpy_nrm(int64_t n, const double* __restrict__ a, double* __restrict__ w, int which,
+                                                          Reducer rd, SweepCtl* ctl, double* h_out, double break_tol, int column) {
+    if (ctl->brk != 0) return;
+    const double h = ctl->scal[which];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double wi = fma(-h, a[i], w[i]);
+        w[i] = wi;
+        acc = fma(wi, wi, acc);
+    }
+    double v[1] = {acc}, tot[1];
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
+        const double hn = sqrt(tot[0]);
+        ctl->scal[SC_HN] = hn;
+        if (hn <= break_tol) {
+            ctl->brk = column;
+        } else {
+            *h_out = hn;
+            ctl->scal[SC_INV_HN] = 1.0 / hn;
+        }
+    }
+}
+
+// DSCAL(N, 1/HJ1J, w) (KrylovSolver.f90:258)
+__global__ void __launch_bounds__(VEC_THREADS) k_scale_by_inv(int64_t n, double* __restrict__ w, const SweepCtl* ctl) {
+    if (ctl->brk != 0) return;
+    const double s = ctl->scal[SC_INV_HN];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = s * w[i];
+}
+
+// V(:,1) = (1/BETA) * W (KrylovSolver.f90:223-226)
+__global__ void __launch_bounds__(VEC_THREADS) k_scale_copy(int64_t n, double s, const double* __restrict__ w, double* __restrict__ v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = s * w[i];
+}
+// W = BETA * V(:,1) (KrylovSolver.f90:467)
+__global__ void __launch_bounds__(VEC_THREADS) k_scale_copy_nrm(int64_t n, double s, const double* __restrict__ v, double* __restrict__ w,
+                                                                Reducer rd, SweepCtl* ctl) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = s * v[i];
+        w[i] = x;
+        a1 += fabs(x);
+        a2 = fma(x, x, a2);
+    }
+    double vv[2] = {a1, a2}, tot[2];
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
+}
+// ||w||_1 and ||w||_2^2 of a vector (BETA = DNRM2(N_NOW, W), KrylovSolver.f90:177,540)
+__global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = w[i];
+        a1 += fabs(x);
+        a2 = fma(x, x, a2);
+    }
+    double vv[2] = {a1, a2}, tot[2];
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
+}
+
+// W = BETA * V(:,1:mx) * e ; W = max(W,0) ; WSUM = ||W||_1 ; also ||W||_2^2 for the next BETA
+// (DGEMV + clamp + DASUM, KrylovSolver.f90:444-450).  Streams 8*N*mx bytes once.
+__global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, int mx, double beta, const double* __restrict__ V,
+                                                         const double* __restrict__ e, double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
+    __shared__ double coef[128];
+    for (int j = threadIdx.x; j < mx; j += blockDim.x) coef[j] = beta * e[j];     // temp = alpha*x(j)
+    __syncthreads();
+    double a1 = 0.0, a2 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        int j = 0;
+        for (; j + 4 <= mx; j += 4) {
+            const double v0 = __ldcs(V + (int64_t)j * ld + i), v1 = __ldcs(V + (int64_t)(j + 1) * ld + i);
+            const double v2 = __ldcs(V + (int64_t)(j + 2) * ld + i), v3 = __ldcs(V + (int64_t)(j + 3) * ld + i);
+            s = fma(coef[j], v0, s); s = fma(coef[j + 1], v1, s); s = fma(coef[j + 2], v2, s); s = fma(coef[j + 3], v3, s);
+        }
+        for (; j < mx; ++j) s = fma(coef[j], __ldcs(V + (int64_t)j * ld + i), s);
+        if (s < 0.0) s = 0.0;
+        w[i] = s;
+        a1 += s;
+        a2 = fma(s, s, a2);
+    }
+    double vv[2] = {a1, a2}, tot[2];
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
+}
+
+__global__ void k_set_entry(double* p, double v) { *p = v; }
+__global__ void k_reset_ctl(SweepCtl* ctl) { ctl->brk = 0; }
+
+}  // namespace kfsp

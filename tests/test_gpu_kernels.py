@@ -1,0 +1,115 @@
+"""GPU parity of the numerical kernels against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy.linalg import expm
+
+import oracle
+from gpu_common import make, rel1
+
+pytestmark = pytest.mark.gpu
+
+
+def grown(name, steps):
+    h, om, x0 = make(name)
+    of = oracle.Fsp(om)
+    h.fsp_init([x0]); of.set_states([x0]); of.matrix_starter()
+    for _ in range(steps):
+        h.onestep(); of.onestep()
+    return h, of
+
+
+@pytest.mark.parametrize("name,steps", [("toggle", 30), ("repressilator", 12), ("goutsias", 8), ("birth_death", 40)])
+def test_fmatvec(name, steps):
+    h, of = grown(name, steps)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(of.size)
+    y, yo = h.matvec(x), of.matvec(x)
+    assert rel1(y, yo) < 1e-14
+    # column sums <= 0: e^T A x for x >= 0 must not be positive
+    assert h.matvec(np.abs(x)).sum() <= 1e-9
+    h.close()
+
+
+@pytest.mark.parametrize("name,steps,m", [("toggle", 40, 10), ("toggle", 40, 30), ("goutsias", 8, 20)])
+def test_arnoldi_hessenberg(name, steps, m):
+    h, of = grown(name, steps)
+    n = of.size
+    v = np.zeros(n); v[0] = 1.0; v[1:5] = 0.3
+    H, av, brk, _ = h.arnoldi(v, m)
+    work = np.zeros(n * (m + 2))
+    Ho = np.zeros((m + 2, m + 2), order="F")
+    nm = C.c_int32()
+    oracle.lib().ko_arnoldi_sweep(of.h, v.ctypes.data_as(C.POINTER(C.c_double)), m, work.ctypes.data_as(C.POINTER(C.c_double)),
+                                  Ho.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nm))
+    Ho[m + 1, m] = 1.0
+    assert brk == 0
+    scale = np.abs(Ho).max()
+    assert np.abs(H - Ho).max() <= 1e-9 * scale
+    avo = np.linalg.norm(work[(m + 1) * n:(m + 2) * n])
+    assert abs(av - avo) <= 1e-9 * avo
+    # IOP-2: H is tridiagonal apart from the unit entry
+    assert np.count_nonzero(np.triu(H[:m, :m], 2)) == 0
+    h.close()
+
+
+def test_happy_breakdown():
+    h, om, _ = make("birth_death")
+    st = [[i] for i in range(6)]
+    h.fsp_init(st)
+    v = np.zeros(6); v[0] = 1.0
+    H, av, brk, _ = h.arnoldi(v, 10)
+    assert 1 <= brk <= 6
+    h.close()
+
+
+@pytest.mark.parametrize("n", [3, 12, 13, 32, 50, 77, 101, 102])
+@pytest.mark.parametrize("t", [1e-3, 0.3, 4.0])
+def test_expm_single_cta(n, t):
+    h, _, _ = make("birth_death", max_states=1000)
+    rng = np.random.default_rng(n)
+    H = np.zeros((n, n))
+    for j in range(max(n - 2, 1)):
+        H[j, j] = -abs(rng.standard_normal()) * 5
+        if j + 1 < n:
+            H[j + 1, j] = abs(rng.standard_normal()) * 5
+        if j > 0:
+            H[j - 1, j] = rng.standard_normal() * 5
+    if n >= 2:
+        H[n - 1, n - 2] = 1.0
+    E, ns, hn = h.expm(H, t)
+    Eo, nso, hno = oracle.dgpadm(H, t)
+    assert ns == nso and abs(hn - hno) <= 1e-15 * hno
+    assert np.abs(E - Eo).max() <= 1e-12 * max(1.0, np.abs(Eo).max())
+    assert np.abs(E - expm(t * H)).max() <= 1e-11 * max(1.0, np.abs(Eo).max())
+    h.close()
+
+
+def test_expm_dense_and_leading_block():
+    h, _, _ = make("birth_death", max_states=1000)
+    rng = np.random.default_rng(2)
+    H = rng.standard_normal((40, 40))
+    E, _, _ = h.expm(H, 0.2)
+    assert np.abs(E - expm(0.2 * H)).max() < 1e-11
+    E2, _, _ = h.expm(H, 0.2, m=39)
+    assert np.abs(E2 - expm(0.2 * H[:39, :39])).max() < 1e-11
+    import krylovfspssa_b200 as k
+    with pytest.raises(k.KfspError) as e:
+        h.expm(np.zeros((5, 5)), 1.0)
+    assert e.value.status == -4
+    h.close()
+
+
+@pytest.mark.parametrize("n,mx", [(1, 3), (1000, 12), (70001, 31), (5000, 102)])
+def test_combine(n, mx):
+    h, _, _ = make("birth_death", max_states=1000)
+    rng = np.random.default_rng(n + mx)
+    V = rng.standard_normal((n, mx))
+    e = rng.standard_normal(mx)
+    w, ws = h.combine(V, e, 0.7)
+    wo = np.maximum(V @ (0.7 * e), 0.0)
+    assert np.abs(w - wo).max() <= 1e-13 * max(1.0, np.abs(wo).max())
+    assert abs(ws - wo.sum()) <= 1e-12 * max(1.0, wo.sum())
+    assert w.min() >= 0.0
+    h.close()
