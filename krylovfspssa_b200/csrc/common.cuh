@@ -46,6 +46,10 @@ struct DeviceModel {
     int32_t code[KFSP_MAX_CODE];
     double immed[KFSP_MAX_IMMED];
     double params[KFSP_MAX_PARAMS];
+    // Propensities with a transcendental operation that depend on ONE species are tabulated on the
+    // host (same libm as the Fortran/C++ host and the oracle) for counts 0..max_molecules.
+    int32_t table_species[KFSP_MAX_REACTIONS];      // species index, or -1 = interpret the byte code
+    const double* table[KFSP_MAX_REACTIONS];         // device pointers, max_molecules+1 entries each
 };
 
 // Philox4x32-10 (Salmon et al., SC'11): one counter-based sub-stream per SSA trajectory.

@@ -26,6 +26,8 @@ struct Engine {
     bool have_model = false;
     HostModel hm;
     DeviceModel* d_model = nullptr;
+    double* d_tables = nullptr;       // host-built propensity tables
+    int n_tabulated = 0, n_inexact_on_device = 0;
     int S = 0, R = 0;
 
     // state space
@@ -99,7 +101,7 @@ struct Engine {
         KFSP_CUDA(cudaMalloc(&d_ctl, sizeof(SweepCtl)));
         KFSP_CUDA(cudaMemset(d_ctl, 0, sizeof(SweepCtl)));
         KFSP_CUDA(cudaMallocHost(&h_ctl, sizeof(SweepCtl)));
-        KFSP_CUDA(cudaMalloc(&rd.partials, sizeof(double) * 3 * MAX_VEC_BLOCKS));
+        KFSP_CUDA(cudaMalloc(&rd.partials, sizeof(double) * 4 * MAX_VEC_BLOCKS));
         KFSP_CUDA(cudaMalloc(&rd.counter, sizeof(unsigned int)));
         KFSP_CUDA(cudaMemset(rd.counter, 0, sizeof(unsigned int)));
         KFSP_CUDA(cudaFuncSetAttribute(k_expm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXPM_SMEM));
@@ -109,7 +111,7 @@ struct Engine {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         free_state_space();
-        cudaFree(d_model); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
+        cudaFree(d_model); cudaFree(d_tables); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
         cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush);
         if (h_res) cudaFreeHost(h_res);
         if (h_ctl) cudaFreeHost(h_ctl);
@@ -182,6 +184,43 @@ struct Engine {
         }
         dm.code_begin[m.R] = nc; dm.immed_begin[m.R] = ni;
         for (int i = 0; i < m.P; ++i) dm.params[i] = m.params[i];
+        // tabulate single-species propensities that contain a transcendental operation
+        n_tabulated = 0; n_inexact_on_device = 0;
+        const int64_t tlen = (int64_t)opt.max_molecules + 1;
+        std::vector<int> tab_k;
+        for (int k = 0; k < m.R; ++k) {
+            uint32_t mask = 0; bool ix = false;
+            program_profile(m.programs[k], m.S, &mask, &ix);
+            dm.table_species[k] = -1;
+            dm.table[k] = nullptr;
+            if (!ix) continue;
+            if ((mask & (mask - 1)) == 0) {                  // zero or one species
+                int sp = 0;
+                while (mask > 1) { mask >>= 1; ++sp; }
+                dm.table_species[k] = sp;
+                tab_k.push_back(k);
+            } else {
+                ++n_inexact_on_device;                        // evaluated with the CUDA math library: may differ by ulps
+            }
+        }
+        if (d_tables) { KFSP_CUDA(cudaFree(d_tables)); d_tables = nullptr; }
+        if (!tab_k.empty()) {
+            std::vector<double> host((size_t)tlen * tab_k.size());
+            std::vector<double> val((size_t)m.S + m.P, 0.0);
+            for (int i = 0; i < m.P; ++i) val[m.S + i] = m.params[i];
+            for (size_t q = 0; q < tab_k.size(); ++q) {
+                const int k = tab_k[q], sp = dm.table_species[k];
+                for (int64_t c = 0; c < tlen; ++c) {
+                    for (int s2 = 0; s2 < m.S; ++s2) val[s2] = 0.0;
+                    val[sp] = (double)c;
+                    host[q * tlen + c] = evaluate_program(m.programs[k], val.data());
+                }
+            }
+            KFSP_CUDA(cudaMalloc(&d_tables, sizeof(double) * host.size()));
+            KFSP_CUDA(cudaMemcpy(d_tables, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
+            for (size_t q = 0; q < tab_k.size(); ++q) dm.table[tab_k[q]] = d_tables + q * tlen;
+            n_tabulated = (int)tab_k.size();
+        }
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
         KFSP_CUDA(cudaStreamSynchronize(stream));
         const bool reshape = !have_model || m.S != S || m.R != R;
@@ -454,27 +493,13 @@ struct Engine {
         int32_t* pos = (int32_t*)p; p += a_i;
         int32_t* tb = (int32_t*)p; p += align_up(sizeof(int32_t) * (2 * tiles + 4));
         char* tmp = p;
-        bool found = false;
-        for (int round = 0; round < 6 && !found; ++round) {
-            double thr[DROP_BUCKETS], bs[DROP_BUCKETS + 1];
-            thr[0] = droptol;
-            for (int b = 1; b < DROP_BUCKETS; ++b) thr[b] = thr[b - 1] / 10.0;
-            KFSP_CUDA(cudaMemcpyAsync(d_thr, thr, sizeof thr, cudaMemcpyHostToDevice, stream));
-            KFSP_CUDA(cudaMemsetAsync(d_bsum, 0, sizeof(double) * (DROP_BUCKETS + 1), stream));
-            KFSP_LAUNCH(k_drop_histogram, grid_for(lsize), VEC_THREADS, 0, (const double*)d_w, lsize, (const double*)d_thr, DROP_BUCKETS, d_bsum);
-            KFSP_CUDA(cudaMemcpyAsync(bs, d_bsum, sizeof bs, cudaMemcpyDeviceToHost, stream));
-            KFSP_TRY(sync());
-            // sum1(k) = sum of buckets k+1 .. DROP_BUCKETS
-            double tail = 0.0;
-            double sum1[DROP_BUCKETS];
-            for (int k = DROP_BUCKETS - 1; k >= 0; --k) { tail += bs[k + 1]; sum1[k] = tail; }
-            for (int k = 0; k < DROP_BUCKETS; ++k) {
-                if (sum1[k] < dsum) { droptol = thr[k]; found = true; break; }
-            }
-            if (!found) {
-                droptol = thr[DROP_BUCKETS - 1] / 10.0;
-                if (droptol == 0.0) found = true;
-            }
+        // one double-double reduction per candidate threshold, exactly the reference's loop
+        for (int it = 0; it < 400; ++it) {
+            KFSP_LAUNCH(k_sum_below, grid_for(lsize), VEC_THREADS, 0, lsize, (const double*)d_w, droptol, rd, d_ctl);
+            KFSP_TRY(read_ctl());
+            if (h_ctl->scal[SC_WSUM] < dsum) break;
+            droptol = droptol / 10.0;
+            if (droptol == 0.0) break;
         }
         // mark, derivative test, count
         KFSP_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), stream));

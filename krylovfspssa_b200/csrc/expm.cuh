@@ -35,7 +35,7 @@ struct ExpmResult {
 __device__ __forceinline__ void expm_load(double* s, const double* __restrict__ g, int lda, int n, int np, double alpha) {
     for (int t = threadIdx.x; t < np * EXPM_LDS; t += EXPM_THREADS) {
         const int j = t / EXPM_LDS, i = t % EXPM_LDS;
-        s[t] = (i < n && j < n) ? alpha * g[(size_t)j * lda + i] : 0.0;
+        s[t] = (i < n && j < n) ? __dmul_rn(alpha, g[(size_t)j * lda + i]) : 0.0;
     }
 }
 // C = sA * sB for the n x n leading blocks; each thread owns a 4x4 tile held in acc.
@@ -70,7 +70,7 @@ __device__ __forceinline__ void expm_store(double* C, int ldc, int n, const doub
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int i = 4 * ti + a, j = 4 * tj + b;
-            if (i < n && j < n) C[(size_t)j * ldc + i] = acc[a][b] + (i == j ? diag_add : 0.0);
+            if (i < n && j < n) C[(size_t)j * ldc + i] = (i == j) ? __dadd_rn(acc[a][b], diag_add) : acc[a][b];
         }
 }
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
                         res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0; }
         return;
     }
-    const double scale = s_scale, scale2 = scale * scale;
+    const double scale = s_scale, scale2 = __dmul_rn(scale, scale);
     double acc[4][4];
 
     // ---- H2 = scale2*H*H (dgpadm.f:270): alpha multiplies the right operand, as DGEMM does ----
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) {
         const int j = t2 / n, i = t2 % n;
         const double h2 = gH2[t2];
-        bufF[t2] = s_coef[6] * h2 + (i == j ? s_coef[4] : 0.0);    // new q
+        bufF[t2] = fma(s_coef[6], h2, (i == j ? s_coef[4] : 0.0));   // new q
         bufP[t2] = (i == j) ? s_coef[5] : 0.0;                      // p = c5 I
     }
     __syncthreads();
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     __syncthreads();
     for (int t2 = tid; t2 < n * EXPM_LDS; t2 += EXPM_THREADS) {
         const int i = t2 % EXPM_LDS;
-        if (i < n) sA[t2] += -1.0 * sB[t2];
+        if (i < n) sA[t2] = __dsub_rn(sA[t2], sB[t2]);
     }
     __syncthreads();
     // Gaussian elimination with partial pivoting on [sA | sB]
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
         }
         const double inv = 1.0 / sA[(size_t)k * EXPM_LDS + k];
         __syncthreads();
-        for (int i = k + 1 + tid; i < n; i += EXPM_THREADS) sA[(size_t)k * EXPM_LDS + i] *= inv;
+        for (int i = k + 1 + tid; i < n; i += EXPM_THREADS) sA[(size_t)k * EXPM_LDS + i] = __dmul_rn(sA[(size_t)k * EXPM_LDS + i], inv);
         __syncthreads();
         const int rows = n - k - 1;
         if (rows > 0) {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     // ---- E = I + 2 X (dgpadm.f:317-320); iodd == 0 so no sign flip (:322-325) -----------------
     for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) {
         const int j = t2 / EXPM_LDS, i = t2 % EXPM_LDS;
-        sB[t2] = (i < n && j < n) ? 2.0 * sB[t2] + (i == j ? 1.0 : 0.0) : 0.0;
+        sB[t2] = (i < n && j < n) ? __dadd_rn(__dmul_rn(2.0, sB[t2]), (i == j ? 1.0 : 0.0)) : 0.0;
     }
     __syncthreads();
     // ---- squarings (dgpadm.f:329-336) ------------------------------------------------------

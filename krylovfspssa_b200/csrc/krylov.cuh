@@ -23,38 +23,73 @@ struct SweepCtl {
 };
 
 struct Reducer {
-    double* partials;           // [3 * MAX_VEC_BLOCKS]
+    double* partials;           // [4 * MAX_VEC_BLOCKS]: (hi, lo) planes for up to two reductions
     unsigned int* counter;      // self-resetting ticket
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
+// Double-double accumulator: every N-element reduction is carried in (hi, lo) and rounded once
+// at the very end, so the rounded value does not depend on the order in which threads, warps and
+// blocks combine their parts (the canonical arithmetic of oracle/kfsp_oracle.cpp).  The kernels
+// stay HBM-bound: ~12 flops per element against 8-24 bytes of traffic.
+struct DD { double hi, lo; };
+__device__ __forceinline__ void dd_add_prod(DD& s, double a, double b) {
+    const double p = __dmul_rn(a, b);
+    const double e = fma(a, b, -p);
+    const double t = __dadd_rn(s.hi, p);
+    const double z = __dsub_rn(t, s.hi);
+    const double err = __dadd_rn(__dsub_rn(s.hi, __dsub_rn(t, z)), __dsub_rn(p, z));
+    s.hi = t;
+    s.lo = __dadd_rn(s.lo, __dadd_rn(err, e));
+}
+__device__ __forceinline__ void dd_add(DD& s, double p) {
+    const double t = __dadd_rn(s.hi, p);
+    const double z = __dsub_rn(t, s.hi);
+    const double err = __dadd_rn(__dsub_rn(s.hi, __dsub_rn(t, z)), __dsub_rn(p, z));
+    s.hi = t;
+    s.lo = __dadd_rn(s.lo, err);
+}
+__device__ __forceinline__ void dd_merge(DD& s, const DD& o) {
+    dd_add(s, o.hi);
+    s.lo = __dadd_rn(s.lo, o.lo);
+}
+__device__ __forceinline__ DD warp_sum(DD v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        DD w;
+        w.hi = __shfl_down_sync(0xffffffffu, v.hi, o);
+        w.lo = __shfl_down_sync(0xffffffffu, v.lo, o);
+        dd_merge(v, w);
+    }
     return v;
 }
-// Sum over the block; result valid in thread 0.  Fixed tree => deterministic.
-__device__ __forceinline__ double block_sum(double v, double* sh /*>= 32*/) {
+// Sum over the block; result valid in thread 0.
+__device__ __forceinline__ DD block_sum(DD v, DD* sh /*>= 32*/) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     v = warp_sum(v);
     __syncthreads();
     if (lane == 0) sh[wid] = v;
     __syncthreads();
     if (wid == 0) {
-        v = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+        DD z; z.hi = 0.0; z.lo = 0.0;
+        v = lane < (blockDim.x >> 5) ? sh[lane] : z;
         v = warp_sum(v);
     }
     return v;
 }
-// Grid-wide reduction of NV values.  Returns true in ALL threads of the last block, with the totals in out[].
+// Grid-wide reduction of NV double-double values.  Returns true in ALL threads of the last block to
+// finish, with the totals rounded once to double in out[].
 template <int NV>
-__device__ __forceinline__ bool grid_reduce(const double (&v)[NV], double (&out)[NV], const Reducer& rd) {
-    __shared__ double sh[32];
+__device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV], const Reducer& rd) {
+    __shared__ DD sh[32];
     __shared__ bool last;
     __shared__ double tot[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        const double s = block_sum(v[q], sh);
-        if (threadIdx.x == 0) rd.partials[q * MAX_VEC_BLOCKS + blockIdx.x] = s;
+        const DD s = block_sum(v[q], sh);
+        if (threadIdx.x == 0) {
+            rd.partials[(2 * q) * MAX_VEC_BLOCKS + blockIdx.x] = s.hi;
+            rd.partials[(2 * q + 1) * MAX_VEC_BLOCKS + blockIdx.x] = s.lo;
+        }
     }
     if (threadIdx.x == 0) {
         __threadfence();
@@ -66,10 +101,15 @@ __device__ __forceinline__ bool grid_reduce(const double (&v)[NV], double (&out)
     __threadfence();
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        double s = 0.0;
-        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(&rd.partials[q * MAX_VEC_BLOCKS + b]);
+        DD s; s.hi = 0.0; s.lo = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            DD o;
+            o.hi = __ldcg(&rd.partials[(2 * q) * MAX_VEC_BLOCKS + b]);
+            o.lo = __ldcg(&rd.partials[(2 * q + 1) * MAX_VEC_BLOCKS + b]);
+            dd_merge(s, o);
+        }
         s = block_sum(s, sh);
-        if (threadIdx.x == 0) tot[q] = s;
+        if (threadIdx.x == 0) tot[q] = __dadd_rn(s.hi, s.lo);
     }
     __syncthreads();
 #pragma unroll
@@ -91,10 +131,10 @@ __global__ void __launch_bounds__(VEC_THREADS) k_spmv(int64_t n, int64_t ld, int
                                                        const double* __restrict__ first, Reducer rd, SweepCtl* ctl, double* h_out) {
     const int R = RT > 0 ? RT : R_rt;
     if (MODE != 0 && ctl->brk != 0) return;
-    double acc0 = 0.0;
+    DD acc0; acc0.hi = 0.0; acc0.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double xi = x[i];
-        double s = -__ldcs(diag + i) * xi;
+        double s = -__dmul_rn(__ldcs(diag + i), xi);
 #pragma unroll
         for (int k = 0; k < (RT > 0 ? RT : R); ++k) {
             const int32_t j = __ldcs(pred + (int64_t)k * ld + i);
@@ -102,11 +142,12 @@ __global__ void __launch_bounds__(VEC_THREADS) k_spmv(int64_t n, int64_t ld, int
             if (j >= 0) s = fma(a, x[j], s);
         }
         y[i] = s;
-        if (MODE == 1) acc0 = fma(first[i], s, acc0);
-        if (MODE == 2) acc0 = fma(s, s, acc0);
+        if (MODE == 1) dd_add_prod(acc0, first[i], s);
+        if (MODE == 2) dd_add_prod(acc0, s, s);
     }
     if (MODE == 0) return;
-    double v[1] = {acc0}, tot[1];
+    DD v[1] = {acc0};
+    double tot[1];
     if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
         if (MODE == 1) { ctl->scal[SC_H1] = tot[0]; if (h_out) *h_out = tot[0]; }
         if (MODE == 2) ctl->scal[SC_AVNORM] = sqrt(tot[0]);
@@ -118,13 +159,14 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy_dot(int64_t n, const doubl
                                                           double* __restrict__ w, Reducer rd, SweepCtl* ctl, double* h_out) {
     if (ctl->brk != 0) return;
     const double h1 = ctl->scal[SC_H1];
-    double acc = 0.0;
+    DD acc; acc.hi = 0.0; acc.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double wi = fma(-h1, a[i], w[i]);
         w[i] = wi;
-        acc = fma(b[i], wi, acc);
+        dd_add_prod(acc, b[i], wi);
     }
-    double v[1] = {acc}, tot[1];
+    DD v[1] = {acc};
+    double tot[1];
     if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
         ctl->scal[SC_H2] = tot[0];
         if (h_out) *h_out = tot[0];
@@ -137,13 +179,14 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy_nrm(int64_t n, const doubl
                                                           Reducer rd, SweepCtl* ctl, double* h_out, double break_tol, int column) {
     if (ctl->brk != 0) return;
     const double h = ctl->scal[which];
-    double acc = 0.0;
+    DD acc; acc.hi = 0.0; acc.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double wi = fma(-h, a[i], w[i]);
         w[i] = wi;
-        acc = fma(wi, wi, acc);
+        dd_add_prod(acc, wi, wi);
     }
-    double v[1] = {acc}, tot[1];
+    DD v[1] = {acc};
+    double tot[1];
     if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
         const double hn = sqrt(tot[0]);
         ctl->scal[SC_HN] = hn;
@@ -160,35 +203,37 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy_nrm(int64_t n, const doubl
 __global__ void __launch_bounds__(VEC_THREADS) k_scale_by_inv(int64_t n, double* __restrict__ w, const SweepCtl* ctl) {
     if (ctl->brk != 0) return;
     const double s = ctl->scal[SC_INV_HN];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = s * w[i];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = __dmul_rn(s, w[i]);
 }
 
 // V(:,1) = (1/BETA) * W (KrylovSolver.f90:223-226)
 __global__ void __launch_bounds__(VEC_THREADS) k_scale_copy(int64_t n, double s, const double* __restrict__ w, double* __restrict__ v) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = s * w[i];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = __dmul_rn(s, w[i]);
 }
 // W = BETA * V(:,1) (KrylovSolver.f90:467)
 __global__ void __launch_bounds__(VEC_THREADS) k_scale_copy_nrm(int64_t n, double s, const double* __restrict__ v, double* __restrict__ w,
                                                                 Reducer rd, SweepCtl* ctl) {
-    double a1 = 0.0, a2 = 0.0;
+    DD a1, a2; a1.hi = a1.lo = a2.hi = a2.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double x = s * v[i];
+        const double x = __dmul_rn(s, v[i]);
         w[i] = x;
-        a1 += fabs(x);
-        a2 = fma(x, x, a2);
+        dd_add(a1, fabs(x));
+        dd_add_prod(a2, x, x);
     }
-    double vv[2] = {a1, a2}, tot[2];
+    DD vv[2] = {a1, a2};
+    double tot[2];
     if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
 }
 // ||w||_1 and ||w||_2^2 of a vector (BETA = DNRM2(N_NOW, W), KrylovSolver.f90:177,540)
 __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
-    double a1 = 0.0, a2 = 0.0;
+    DD a1, a2; a1.hi = a1.lo = a2.hi = a2.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double x = w[i];
-        a1 += fabs(x);
-        a2 = fma(x, x, a2);
+        dd_add(a1, fabs(x));
+        dd_add_prod(a2, x, x);
     }
-    double vv[2] = {a1, a2}, tot[2];
+    DD vv[2] = {a1, a2};
+    double tot[2];
     if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
 }
 
@@ -197,9 +242,9 @@ __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* 
 __global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, int mx, double beta, const double* __restrict__ V,
                                                          const double* __restrict__ e, double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
     __shared__ double coef[128];
-    for (int j = threadIdx.x; j < mx; j += blockDim.x) coef[j] = beta * e[j];     // temp = alpha*x(j)
+    for (int j = threadIdx.x; j < mx; j += blockDim.x) coef[j] = __dmul_rn(beta, e[j]);     // temp = alpha*x(j)
     __syncthreads();
-    double a1 = 0.0, a2 = 0.0;
+    DD a1, a2; a1.hi = a1.lo = a2.hi = a2.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
         int j = 0;
@@ -211,11 +256,24 @@ __global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, 
         for (; j < mx; ++j) s = fma(coef[j], __ldcs(V + (int64_t)j * ld + i), s);
         if (s < 0.0) s = 0.0;
         w[i] = s;
-        a1 += s;
-        a2 = fma(s, s, a2);
+        dd_add(a1, s);
+        dd_add_prod(a2, s, s);
     }
-    double vv[2] = {a1, a2}, tot[2];
+    DD vv[2] = {a1, a2};
+    double tot[2];
     if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
+}
+
+// FIND_DROPTOL's inner sum (StateSpace.f90:418-423): sum of W_i with 0 < W_i < droptol
+__global__ void __launch_bounds__(VEC_THREADS) k_sum_below(int64_t n, const double* __restrict__ w, double droptol, Reducer rd, SweepCtl* ctl) {
+    DD a; a.hi = a.lo = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = w[i];
+        if (x < droptol && x > 0.0) dd_add(a, x);
+    }
+    DD vv[1] = {a};
+    double tot[1];
+    if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) ctl->scal[SC_WSUM] = tot[0];
 }
 
 __global__ void k_set_entry(double* p, double v) { *p = v; }

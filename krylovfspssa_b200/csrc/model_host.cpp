@@ -210,6 +210,17 @@ int program_stack_depth(const Program& p, int nvars) {
     return sp == 1 ? mx : -1;
 }
 
+void program_profile(const Program& p, int S, uint32_t* species_mask, bool* inexact) {
+    uint32_t mask = 0;
+    bool ix = false;
+    for (int32_t op : p.code) {
+        if (op >= VarBegin && op < VarBegin + S) mask |= 1u << (op - VarBegin);
+        else if (op == cPow || op == cExp || op == cLog10 || op == cLog || (op >= cSinh && op <= cAtan)) ix = true;
+    }
+    *species_mask = mask;
+    *inexact = ix;
+}
+
 bool compile_expression(const std::string& expr, const std::vector<std::string>& vars, Program& out, std::string& err) {
     std::string s;
     for (size_t i = 0; i < expr.size(); ++i) {

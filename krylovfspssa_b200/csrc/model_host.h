@@ -41,6 +41,9 @@ bool compile_expression(const std::string& expr, const std::vector<std::string>&
 // Depth of the evaluation stack a program needs, -1 if malformed.
 int program_stack_depth(const Program& p, int nvars);
 double evaluate_program(const Program& p, const double* val);
+// Which species a program reads (bit mask over the first S variables) and whether it contains an
+// operation that is not correctly rounded on every platform (pow, exp, log, trigonometric ...).
+void program_profile(const Program& p, int S, uint32_t* species_mask, bool* inexact);
 bool load_model_file(const std::string& path, HostModel& m, std::string& err);
 bool parse_reaction(const std::string& line, const std::vector<std::string>& species, int32_t* vec, std::string& err);
 

@@ -42,6 +42,12 @@ enum DevErr : int32_t { DEV_OK = 0, DEV_DUPLICATE = 1, DEV_BAD_STATE = 2, DEV_MO
 // propensity interpreter: the stack machine of src/parser/FortranParser.f90:187-302
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double eval_propensity(const DeviceModel* __restrict__ m, int k, const int32_t* st) {
+    const int ts = m->table_species[k];
+    if (ts >= 0) {
+        int c = st[ts];
+        c = c < 0 ? 0 : (c > m->max_molecules ? m->max_molecules : c);
+        return __ldg(m->table[k] + c);
+    }
     double stack[KFSP_STACK];
     int sp = -1;
     int dp = m->immed_begin[k];

@@ -71,6 +71,10 @@ def lib():
         "ko_solver_create": (vp, []),
         "ko_solver_free": (None, [vp]),
         "ko_solver_set_options": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "ko_solver_set_reproducible": (None, [vp, C.c_int]),
+        "ko_fsp_set_reproducible": (None, [vp, C.c_int]),
+        "ko_dgpadm_reproducible": (C.c_int, [C.c_int, C.c_double, dp, C.c_int, dp, i32p, dp]),
+        "ko_dot_reproducible": (C.c_double, [C.c_long, dp, dp]),
         "ko_solve": (C.c_int, [vp, vp, C.c_double, dp, C.c_long, C.c_double, C.c_double, C.c_int, vp]),
         "ko_trace_len": (C.c_long, [vp]),
         "ko_trace_get": (None, [vp, dp, i32p]),
@@ -163,9 +167,11 @@ class Fsp:
     """Oracle-side FINITE_STATE_PROJECTION (StateSpace.f90:19-45)."""
     NMAX = 6291469
 
-    def __init__(self, model, max_size=NMAX, maxmol=10000):
+    def __init__(self, model, max_size=NMAX, maxmol=10000, reproducible=0):
         self.model = model
         self.h = lib().ko_fsp_create(model.h, max_size, maxmol)
+        if reproducible:
+            lib().ko_fsp_set_reproducible(self.h, 1)
 
     def set_states(self, states):
         st = np.ascontiguousarray(np.asarray(states, dtype=np.int32).reshape(-1, self.model.S))
@@ -243,28 +249,40 @@ class Rng:
             pass
 
 
-def dgpadm(H, t, ideg=6, m=None):
-    """exp(t*H[:m,:m]) by the reference's Pade routine; returns (E, ns, hnorm)."""
+def dot_reproducible(x, y):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    return lib().ko_dot_reproducible(len(x), _f64(x), _f64(y))
+
+
+def dgpadm(H, t, ideg=6, m=None, reproducible=0):
+    """exp(t*H[:m,:m]) by the reference's Pade routine; returns (E, ns, hnorm).
+    reproducible=1 selects the canonical operation order the device kernel is held to."""
     H = np.asfortranarray(H, dtype=np.float64)
     ldh = H.shape[0]
     m = ldh if m is None else m
     out = np.zeros((m, m), order="F")
     ns = C.c_int32(0)
     hn = C.c_double(0)
-    rc = lib().ko_dgpadm(ideg, m, t, _f64(H), ldh, _f64(out), C.byref(ns), C.byref(hn))
+    if reproducible:
+        rc = lib().ko_dgpadm_reproducible(m, t, _f64(H), ldh, _f64(out), C.byref(ns), C.byref(hn))
+    else:
+        rc = lib().ko_dgpadm(ideg, m, t, _f64(H), ldh, _f64(out), C.byref(ns), C.byref(hn))
     if rc:
         raise RuntimeError("dgpadm iflag=%d" % rc)
     return out, ns.value, hn.value
 
 
 def solve(model, states0, p0, t, fsptol, krytol, seed=12345, rng_mode=1, max_size=Fsp.NMAX,
-          m_max=100, m_min=10, n_init_onestep=5, enable_drop=1, enable_expand=1, itrace=0):
-    """CME_SOLVE / DGEXPV_FSP (KrylovSolver.f90:7-36, 40-573) on the oracle."""
+          m_max=100, m_min=10, n_init_onestep=5, enable_drop=1, enable_expand=1, itrace=0, reproducible=0):
+    """CME_SOLVE / DGEXPV_FSP (KrylovSolver.f90:7-36, 40-573) on the oracle.
+    reproducible=1: canonical arithmetic (double-double reductions, fixed-order fma chains)."""
     L = lib()
     fsp = Fsp(model, max_size)
     fsp.set_states(states0)
     s = L.ko_solver_create()
     L.ko_solver_set_options(s, m_max, m_min, n_init_onestep, enable_drop, enable_expand)
+    L.ko_solver_set_reproducible(s, 1 if reproducible else 0)
     rng = Rng(rng_mode, seed)
     p0 = np.ascontiguousarray(p0, dtype=np.float64)
     rc = L.ko_solve(s, fsp.h, t, _f64(p0), len(p0), fsptol, krytol, itrace, rng.h)

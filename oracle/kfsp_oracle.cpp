@@ -162,6 +162,145 @@ static int b_dgesv(int m, double* A, double* B) {
 }
 
 // ------------------------------------------------------------------------------------
+// CANONICAL ("reproducible") ARITHMETIC -- the contract the device path is held to bit for bit.
+//
+// The reference links an unpinned BLAS (CMakeLists.txt:8), so the summation order of its
+// DDOT/DNRM2/DASUM/DGEMV/DGEMM is not defined by the reference itself, and the adaptive
+// controller branches on those sums (SURVEY.md hard part 3).  To make "same decisions, same
+// state sets" a testable statement, both the oracle (mode reproducible=1) and the CUDA path
+// evaluate every floating-point quantity by ONE specification:
+//   * element-wise updates and short fixed-length sums are IEEE fma chains in a fixed order
+//     (SpMV row: -(d*x_i) then reactions in order; axpy: fma(-h,a,w); GEMV row: columns in order;
+//     dense products: k ascending from 0);
+//   * every reduction over N elements (dot, sum of squares, 1-norm, FIND_DROPTOL sums) is
+//     accumulated in double-double and rounded once, which makes the rounded value independent
+//     of the summation order (up to a ~2^-47 chance per reduction of a double rounding tie);
+//   * the Pade routine performs the operations of dgpadm.f in the order of the single-CTA
+//     kernel (krylovfspssa_b200/csrc/expm.cuh); ns = max(0, trunc(log2(hnorm)) + 2) is taken
+//     from the exponent of hnorm instead of LOG()/LOG(2).
+// The default mode (reproducible=0) keeps the netlib-order restatement; tests check that the
+// two modes agree to rounding level on every quantity.
+// ------------------------------------------------------------------------------------
+struct dd { double hi, lo; };
+static inline void dd_add_prod(dd& s, double a, double b) {
+    const double p = a * b;
+    const double e = std::fma(a, b, -p);
+    const double t = s.hi + p;
+    const double z = t - s.hi;
+    const double err = (s.hi - (t - z)) + (p - z);
+    s.hi = t;
+    s.lo += err + e;
+}
+static inline void dd_add(dd& s, double p) {
+    const double t = s.hi + p;
+    const double z = t - s.hi;
+    const double err = (s.hi - (t - z)) + (p - z);
+    s.hi = t;
+    s.lo += err;
+}
+static inline double dd_round(const dd& s) { return s.hi + s.lo; }
+static double r_dot(long n, const double* x, const double* y) {
+    dd s{0.0, 0.0};
+    for (long i = 0; i < n; ++i) dd_add_prod(s, x[i], y[i]);
+    return dd_round(s);
+}
+static double r_asum(long n, const double* x) {
+    dd s{0.0, 0.0};
+    for (long i = 0; i < n; ++i) dd_add(s, fabs(x[i]));
+    return dd_round(s);
+}
+static double r_nrm2(long n, const double* x) { return sqrt(r_dot(n, x, x)); }
+// C = A * (alpha*B), n x n, k ascending fma chains; C has leading dimension n
+static void r_gemm(int n, const double* A, int lda, const double* B, int ldb, double alpha, double* C) {
+    std::vector<double> Bs((size_t)n * n);
+    for (int j = 0; j < n; ++j)
+        for (int l = 0; l < n; ++l) Bs[(size_t)j * n + l] = alpha * B[(size_t)j * ldb + l];
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+            double acc = 0.0;
+            for (int l = 0; l < n; ++l) acc = std::fma(A[(size_t)l * lda + i], Bs[(size_t)j * n + l], acc);
+            C[(size_t)j * n + i] = acc;
+        }
+}
+static int r_dgpadm(int n, double t, const double* H, int ldh, double* out, int* ns_out, double* hnorm_out) {
+    const size_t nn = (size_t)n * n;
+    double mx = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double rs = 0.0;
+        for (int j = 0; j < n; ++j) rs += fabs(H[(size_t)j * ldh + i]);
+        mx = std::max(mx, rs);
+    }
+    const double hnorm = fabs(t * mx);
+    if (hnorm_out) *hnorm_out = hnorm;
+    if (hnorm == 0.0) return -4;
+    int ex;
+    const double fr = frexp(hnorm, &ex);
+    int il = hnorm >= 1.0 ? ex - 1 : (fr == 0.5 ? ex - 1 : ex);
+    int ns = il + 2 > 0 ? il + 2 : 0;
+    if (ns > 30) return -3;
+    const double scale = ldexp(t, -ns), scale2 = scale * scale;
+    double c[7];
+    c[0] = 1.0;
+    for (int k = 1; k <= 6; ++k) c[k] = (c[k - 1] * (double)(7 - k)) / (double)(k * (13 - k));
+    std::vector<double> H2(nn), P(nn), Q(nn), F(nn), A(nn), B(nn);
+    r_gemm(n, H, ldh, H, ldh, scale2, H2.data());
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+            Q[(size_t)j * n + i] = std::fma(c[6], H2[(size_t)j * n + i], i == j ? c[4] : 0.0);
+            P[(size_t)j * n + i] = i == j ? c[5] : 0.0;
+        }
+    int iodd = 0;
+    for (int k = 4; k >= 1; --k) {
+        std::vector<double>& used = iodd ? Q : P;
+        r_gemm(n, used.data(), n, H2.data(), n, 1.0, F.data());
+        for (int j = 0; j < n; ++j) F[(size_t)j * n + j] = F[(size_t)j * n + j] + c[k - 1];
+        used.swap(F);
+        iodd = 1 - iodd;
+    }
+    r_gemm(n, P.data(), n, H, ldh, scale, B.data());                 // p = scale*p*H
+    for (size_t x = 0; x < nn; ++x) A[x] = Q[x] + (-1.0 * B[x]);     // q - p
+    // Gaussian elimination with partial pivoting on [A | B]
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        double best = -1.0;
+        for (int i = k; i < n; ++i) {
+            const double v = fabs(A[(size_t)k * n + i]);
+            if (v > best) { best = v; piv = i; }
+        }
+        if (best == 0.0) return -5;
+        if (piv != k)
+            for (int j = 0; j < n; ++j) {
+                std::swap(A[(size_t)j * n + k], A[(size_t)j * n + piv]);
+                std::swap(B[(size_t)j * n + k], B[(size_t)j * n + piv]);
+            }
+        const double inv = 1.0 / A[(size_t)k * n + k];
+        for (int i = k + 1; i < n; ++i) A[(size_t)k * n + i] *= inv;
+        for (int j = k + 1; j < n; ++j)
+            for (int i = k + 1; i < n; ++i)
+                A[(size_t)j * n + i] = std::fma(-A[(size_t)k * n + i], A[(size_t)j * n + k], A[(size_t)j * n + i]);
+        for (int j = 0; j < n; ++j)
+            for (int i = k + 1; i < n; ++i)
+                B[(size_t)j * n + i] = std::fma(-A[(size_t)k * n + i], B[(size_t)j * n + k], B[(size_t)j * n + i]);
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        const double ukk = A[(size_t)k * n + k];
+        for (int j = 0; j < n; ++j) B[(size_t)j * n + k] /= ukk;
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < k; ++i)
+                B[(size_t)j * n + i] = std::fma(-B[(size_t)j * n + k], A[(size_t)k * n + i], B[(size_t)j * n + i]);
+    }
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) B[(size_t)j * n + i] = 2.0 * B[(size_t)j * n + i] + (i == j ? 1.0 : 0.0);
+    for (int s2 = 0; s2 < ns; ++s2) {
+        r_gemm(n, B.data(), n, B.data(), n, 1.0, A.data());
+        A.swap(B);
+    }
+    memcpy(out, B.data(), sizeof(double) * nn);
+    if (ns_out) *ns_out = ns;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
 // DGPADM / DGPADMnorm -- src/expokit/dgpadm.f:2-169 and :171-339
 // out (m x m, ld m) receives exp(t*H).  Returns iflag (0 ok).
 // ------------------------------------------------------------------------------------
@@ -423,6 +562,10 @@ struct Fsp {
     std::vector<u128> rkey;        // REACTIONKEY
     std::vector<int> rsign;        // RKEYSIGN
     int error = 0;
+    bool repro = false;             // canonical arithmetic (see above)
+    bool row_dirty = true;          // row ("gather") form needs rebuilding
+    std::vector<int32_t> pred;      // R x size, 0-based index of x_i - nu_k or -1
+    std::vector<double> coef;       // R x size, a_k(x_i - nu_k)
     // stats
     long n_hash = 0;
 
@@ -495,6 +638,7 @@ static void add_state(Fsp& f, const int32_t* st, u128 key) {
     if (f.table.find(key) != f.table.end()) return;    // FOUND -> nothing happens
     if (f.size >= f.max_size) return;                  // table full: KA = 0
     f.reserve(f.size + 1);
+    f.row_dirty = true;
     long n = f.size;                                   // 0-based slot of the new state
     f.size += 1;
     int32_t idx = (int32_t)f.size;                     // 1-based
@@ -526,6 +670,7 @@ static void add_state(Fsp& f, const int32_t* st, u128 key) {
 // MATRIX_STARTER -- StateSpace.f90:248-345.  f.state[0..size) already holds the caller's states.
 static int matrix_starter(Fsp& f) {
     const Model& m = *f.model;
+    f.row_dirty = true;
     std::vector<int32_t> rs(f.S);
     for (long i = 0; i < f.size; ++i) {
         const int32_t* st = &f.state[(size_t)i * f.S];
@@ -632,9 +777,36 @@ static void ssa_extender(Fsp& f, double timestep, Rng& rng) {
     }
 }
 
+// Row form of the generator for the canonical SpMV: pred(k,i) = index of x_i - nu_k.
+static void build_rows(Fsp& f) {
+    const long n = f.size;
+    f.pred.assign((size_t)n * f.R, -1);
+    f.coef.assign((size_t)n * f.R, 0.0);
+    for (long i = 0; i < n; ++i)
+        for (int k = 0; k < f.R; ++k) {
+            const int j = f.lookup(key2keybw(f, f.key[i], k));
+            if (j > 0) {
+                f.pred[(size_t)i * f.R + k] = j - 1;
+                f.coef[(size_t)i * f.R + k] = f.offdiag[(size_t)(j - 1) * f.R + k];
+            }
+        }
+    f.row_dirty = false;
+}
 // FMATVEC -- src/fsp/KrylovSolver.f90:577-607
-static void fmatvec(const Fsp& f, const double* x, double* y) {
+static void fmatvec(Fsp& f, const double* x, double* y) {
     long n = f.size;
+    if (f.repro) {                  // canonical: gather form, fma chain, reactions in order
+        if (f.row_dirty) build_rows(f);
+        for (long i = 0; i < n; ++i) {
+            double s = -(f.diag[i] * x[i]);
+            for (int k = 0; k < f.R; ++k) {
+                const int32_t j = f.pred[(size_t)i * f.R + k];
+                if (j >= 0) s = std::fma(f.coef[(size_t)i * f.R + k], x[j], s);
+            }
+            y[i] = s;
+        }
+        return;
+    }
     for (long i = 0; i < n; ++i) y[i] = 0.0;
     for (long i = 0; i < n; ++i) {
         for (int j = 0; j < f.R; ++j) {
@@ -646,12 +818,19 @@ static void fmatvec(const Fsp& f, const double* x, double* y) {
 }
 
 // FIND_DROPTOL -- StateSpace.f90:398-427
-static double find_droptol(long n, const double* w, double dsum) {
+static double find_droptol(long n, const double* w, double dsum, bool repro) {
     double droptol = 1.0e-8;
     for (;;) {
         double sum1 = 0.0;
-        for (long i = 0; i < n; ++i)
-            if (w[i] < droptol && w[i] > 0) sum1 = sum1 + w[i];
+        if (repro) {
+            dd acc{0.0, 0.0};
+            for (long i = 0; i < n; ++i)
+                if (w[i] < droptol && w[i] > 0) dd_add(acc, w[i]);
+            sum1 = dd_round(acc);
+        } else {
+            for (long i = 0; i < n; ++i)
+                if (w[i] < droptol && w[i] > 0) sum1 = sum1 + w[i];
+        }
         if (sum1 < dsum) break;
         droptol = droptol / 10.0;
         if (droptol == 0.0) break;                     // guard: cannot loop forever once the threshold underflows
@@ -664,7 +843,7 @@ static int drop_states(Fsp& f, double* w, double dsum, double* droptol_out, long
     long lsize = f.size;
     std::vector<char> drop(lsize);
     std::vector<double> wtmp(lsize);
-    double droptol = find_droptol(lsize, w, dsum);
+    double droptol = find_droptol(lsize, w, dsum, f.repro);
     long drop_count = 0;
     for (long i = 0; i < lsize; ++i) {
         if (w[i] < droptol) { drop[i] = 1; drop_count += 1; } else drop[i] = 0;
@@ -677,6 +856,7 @@ static int drop_states(Fsp& f, double* w, double dsum, double* droptol_out, long
     if (dropcount_out) *dropcount_out = drop_count;
     if (!((double)drop_count * 1.0 / ((double)lsize * 1.0) > 0.1)) return 0;
     std::vector<int32_t> new_index(lsize);
+    f.row_dirty = true;
     long q = 0;
     for (long j = 0; j < lsize; ++j) {
         if (!drop[j]) {
@@ -740,6 +920,27 @@ static double now_s() {
 
 struct Solver {
     Options opt;
+    bool repro = false;
+    double n_dot(long n, const double* x, const double* y) const { return repro ? r_dot(n, x, y) : b_ddot((int)n, x, y); }
+    double n_nrm2(long n, const double* x) const { return repro ? r_nrm2(n, x) : b_dnrm2((int)n, x); }
+    double n_asum(long n, const double* x) const { return repro ? r_asum(n, x) : b_dasum((int)n, x); }
+    void n_axpy(long n, double a, const double* x, double* y) const {
+        if (repro) { for (long i = 0; i < n; ++i) y[i] = std::fma(a, x[i], y[i]); }
+        else b_daxpy((int)n, a, x, y);
+    }
+    void n_gemv(long n, int m, double alpha, const double* A, long lda, const double* x, double* y) const {
+        if (!repro) { b_dgemv_n((int)n, m, alpha, A, lda, x, y); return; }
+        std::vector<double> c(m);
+        for (int j = 0; j < m; ++j) c[j] = alpha * x[j];
+        for (long i = 0; i < n; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < m; ++j) s = std::fma(c[j], A[(size_t)j * lda + i], s);
+            y[i] = s;
+        }
+    }
+    int n_expm(int ideg, int m, double t, const double* H, int ldh, double* out, int* ns, double* hnorm) const {
+        return repro ? r_dgpadm(m, t, H, ldh, out, ns, hnorm) : o_dgpadm(ideg, m, t, H, ldh, out, ns, hnorm);
+    }
     std::vector<TraceRow> trace;
     Stats stats{};
     int nnz = 0;                   // default INTEGER NNZ (:112)
@@ -759,6 +960,7 @@ struct Solver {
         const int M_MAX = opt.m_max, M_MIN = opt.m_min, IDEG = opt.ideg, QIOP = opt.qiop;
         const double DELTA = opt.delta, GAMMA = opt.gamma;
         double t0 = now_s();
+        fsp.repro = repro;
         trace.clear();
         int iflag = 0;
         const double ANORM = 1.0;
@@ -789,7 +991,7 @@ struct Solver {
         // W aliases FSP%VECTOR (CME_SOLVE passes FSP_OUT%VECTOR as W, :33)
         fsp.reserve(fsp.size);
         for (long i = 0; i < fsp.size; ++i) fsp.vec[i] = i < n_in ? v_in[i] : 0.0;     // DCOPY (:176), zero padded
-        double BETA = b_dnrm2((int)fsp.size, fsp.vec.data());
+        double BETA = n_nrm2(fsp.size, fsp.vec.data());
         const double VNORM = BETA;
         double HUMP = BETA;
         const double SQR1 = sqrt(0.1);
@@ -841,11 +1043,11 @@ struct Solver {
                     fmatvec(fsp, vj, vn);
                     if (QIOP > 0) ISTART = std::max(1, J - QIOP + 1);
                     for (int I = ISTART; I <= J; ++I) {
-                        double HIJ = b_ddot((int)N, &V[(size_t)(I - 1) * N], vn);
-                        b_daxpy((int)N, -HIJ, &V[(size_t)(I - 1) * N], vn);
+                        double HIJ = n_dot(N, &V[(size_t)(I - 1) * N], vn);
+                        n_axpy(N, -HIJ, &V[(size_t)(I - 1) * N], vn);
                         H[(size_t)(J - 1) * MH + (I - 1)] = HIJ;
                     }
-                    double HJ1J = b_dnrm2((int)N, vn);
+                    double HJ1J = n_nrm2(N, vn);
                     if (HJ1J <= BREAK_TOL) {                              // happy breakdown (:249-256)
                         K1 = 0;
                         IBRKFLAG = 1;
@@ -862,7 +1064,7 @@ struct Solver {
                 if (!broke) {
                     NMULT += 1;
                     fmatvec(fsp, &V[(size_t)M * N], &V[(size_t)(M + 1) * N]);
-                    AVNORM = b_dnrm2((int)N, &V[(size_t)(M + 1) * N]);
+                    AVNORM = n_nrm2(N, &V[(size_t)(M + 1) * N]);
                 }
                 H[(size_t)M * MH + (M + 1)] = 1.0;                        // label 300 (:266)
             }
@@ -870,7 +1072,7 @@ struct Solver {
             NEXPH += 1;
             MX = MBRKDWN + K1;
             EXPH.resize((size_t)MX * MX);
-            iflag = o_dgpadm(IDEG, MX, SGN * T_STEP, H.data(), MH, EXPH.data(), &NS, &HNORM);
+            iflag = n_expm(IDEG, MX, SGN * T_STEP, H.data(), MH, EXPH.data(), &NS, &HNORM);
             if (iflag) return iflag;
             NSCALE += NS;
             // label 402: error estimate (:290-305)
@@ -976,9 +1178,9 @@ struct Solver {
             IREJECTFSP = 0;
             // FSP criterion loop (:442-495)
             for (;;) {
-                b_dgemv_n((int)N, MX, BETA, V.data(), N, EXPH.data(), W);
+                n_gemv(N, MX, BETA, V.data(), N, EXPH.data(), W);
                 for (long i = 0; i < fsp.size; ++i) if (W[i] < 0.0) W[i] = 0.0;
-                WSUM = b_dasum((int)fsp.size, W);
+                WSUM = n_asum(fsp.size, W);
                 ERROR_ = WSUM_OLD - WSUM;
                 if (WSUM >= (1.0 - (T_NOW + T_STEP) * fsptol / T_OUT)) break;
                 IEXPAND = 1;
@@ -1003,7 +1205,7 @@ struct Solver {
                 T_STEP = trunc(T_STEP / P1 + 0.55) * P1;
                 NEXPH += 1;
                 EXPH.resize((size_t)MX * MX);
-                iflag = o_dgpadm(IDEG, MX, SGN * T_STEP, H.data(), MH, EXPH.data(), &NS, nullptr);
+                iflag = n_expm(IDEG, MX, SGN * T_STEP, H.data(), MH, EXPH.data(), &NS, nullptr);
                 if (iflag) return iflag;
                 NSCALE += NS;
             }
@@ -1041,7 +1243,7 @@ struct Solver {
             W = fsp.vec.data();
             nnz = wrap32((int64_t)(fsp.R + 1) * fsp.size);
             N_NOW = fsp.size;
-            BETA = b_dnrm2((int)N_NOW, W);
+            BETA = n_nrm2(N_NOW, W);
             HUMP = std::max(HUMP, BETA);
             ERR_LOC = std::max(ERR_LOC, RNDOFF);
             STEP_MIN = std::min(STEP_MIN, T_STEP);
@@ -1183,6 +1385,12 @@ int ko_dgpadm(int ideg, int m, double t, const double* H, int ldh, double* out, 
 
 void* ko_solver_create(void) { return new Solver(); }
 void ko_solver_free(void* sp) { delete (Solver*)sp; }
+void ko_solver_set_reproducible(void* sp, int on) { ((Solver*)sp)->repro = on != 0; }
+void ko_fsp_set_reproducible(void* fp, int on) { ((Fsp*)fp)->repro = on != 0; ((Fsp*)fp)->row_dirty = true; }
+int ko_dgpadm_reproducible(int m, double t, const double* H, int ldh, double* out, int* ns, double* hnorm) {
+    return r_dgpadm(m, t, H, ldh, out, ns, hnorm);
+}
+double ko_dot_reproducible(long n, const double* x, const double* y) { return r_dot(n, x, y); }
 void ko_solver_set_options(void* sp, int m_max, int m_min, int n_init_onestep, int enable_drop, int enable_expand) {
     Solver* s = (Solver*)sp;
     s->opt.m_max = m_max; s->opt.m_min = m_min; s->opt.n_init_onestep = n_init_onestep;
@@ -1212,19 +1420,20 @@ double ko_arnoldi_sweep(void* fp, const double* v, int m, double* work /*size*(m
     long N = f.size;
     int MH = m + 2;
     std::vector<double> H((size_t)MH * MH, 0.0);
-    double beta = b_dnrm2((int)N, v);
+    double beta = f.repro ? r_nrm2(N, v) : b_dnrm2((int)N, v);
     double t0 = now_s();
-    for (long i = 0; i < N; ++i) work[i] = v[i] / beta;
+    { const double ib = 1.0 / beta; for (long i = 0; i < N; ++i) work[i] = ib * v[i]; }
     int nm = 0;
     for (int J = 1; J <= m; ++J) {
         double* vn = &work[(size_t)J * N];
         fmatvec(f, &work[(size_t)(J - 1) * N], vn); ++nm;
         for (int I = std::max(1, J - 1); I <= J; ++I) {
-            double h = b_ddot((int)N, &work[(size_t)(I - 1) * N], vn);
-            b_daxpy((int)N, -h, &work[(size_t)(I - 1) * N], vn);
+            double h = f.repro ? r_dot(N, &work[(size_t)(I - 1) * N], vn) : b_ddot((int)N, &work[(size_t)(I - 1) * N], vn);
+            if (f.repro) { for (long i = 0; i < N; ++i) vn[i] = std::fma(-h, work[(size_t)(I - 1) * N + i], vn[i]); }
+            else b_daxpy((int)N, -h, &work[(size_t)(I - 1) * N], vn);
             H[(size_t)(J - 1) * MH + (I - 1)] = h;
         }
-        double hn = b_dnrm2((int)N, vn);
+        double hn = f.repro ? r_nrm2(N, vn) : b_dnrm2((int)N, vn);
         H[(size_t)(J - 1) * MH + J] = hn;
         if (hn <= 1e-7) break;
         b_dscal((int)N, 1.0 / hn, vn);

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 def grown(name, steps):
     h, om, x0 = make(name)
-    of = oracle.Fsp(om)
+    of = oracle.Fsp(om, reproducible=1)          # canonical arithmetic: the device must match bit for bit
     h.fsp_init([x0]); of.set_states([x0]); of.matrix_starter()
     for _ in range(steps):
         h.onestep(); of.onestep()
@@ -26,7 +26,11 @@ def test_fmatvec(name, steps):
     rng = np.random.default_rng(1)
     x = rng.standard_normal(of.size)
     y, yo = h.matvec(x), of.matvec(x)
-    assert rel1(y, yo) < 1e-14
+    assert np.array_equal(y, yo)                                       # canonical order: bit-exact
+    lib = oracle.lib()
+    lib.ko_fsp_set_reproducible(of.h, 0)                               # the reference's scatter order: rounding level
+    assert rel1(y, of.matvec(x)) < 1e-14
+    lib.ko_fsp_set_reproducible(of.h, 1)
     # column sums <= 0: e^T A x for x >= 0 must not be positive
     assert h.matvec(np.abs(x)).sum() <= 1e-9
     h.close()
@@ -45,10 +49,9 @@ def test_arnoldi_hessenberg(name, steps, m):
                                   Ho.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nm))
     Ho[m + 1, m] = 1.0
     assert brk == 0
-    scale = np.abs(Ho).max()
-    assert np.abs(H - Ho).max() <= 1e-9 * scale
-    avo = np.linalg.norm(work[(m + 1) * n:(m + 2) * n])
-    assert abs(av - avo) <= 1e-9 * avo
+    assert np.array_equal(H, Ho)                                       # every Hessenberg entry bit-exact
+    avo = np.sqrt(oracle.dot_reproducible(work[(m + 1) * n:(m + 2) * n], work[(m + 1) * n:(m + 2) * n]))
+    assert av == avo
     # IOP-2: H is tridiagonal apart from the unit entry
     assert np.count_nonzero(np.triu(H[:m, :m], 2)) == 0
     h.close()
@@ -79,7 +82,10 @@ def test_expm_single_cta(n, t):
     if n >= 2:
         H[n - 1, n - 2] = 1.0
     E, ns, hn = h.expm(H, t)
-    Eo, nso, hno = oracle.dgpadm(H, t)
+    Er, nsr, hnr = oracle.dgpadm(H, t, reproducible=1)
+    assert ns == nsr and hn == hnr
+    assert np.array_equal(E, Er)                                       # canonical operation order: bit-exact
+    Eo, nso, hno = oracle.dgpadm(H, t)                                 # netlib-order restatement of dgpadm.f
     assert ns == nso and abs(hn - hno) <= 1e-15 * hno
     assert np.abs(E - Eo).max() <= 1e-12 * max(1.0, np.abs(Eo).max())
     assert np.abs(E - expm(t * H)).max() <= 1e-11 * max(1.0, np.abs(Eo).max())

@@ -83,7 +83,7 @@ def test_drop_states():
         h.onestep(); of.onestep()
     n = of.size
     rng = np.random.default_rng(0)
-    w = np.exp(-0.12 * np.arange(n)) * rng.uniform(0.5, 1.0, n)
+    w = np.exp(-0.6 * np.arange(n)) * rng.uniform(0.5, 1.0, n)
     w /= w.sum()
     h.set_vector(w)
     dropped, tol, cnt = h.drop(1e-7)
