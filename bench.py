@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on its headline configuration.
+
+Metric (BASELINE.json): expv wall time to t_final + generator-SpMV GB/s vs HBM peak.
+Workload (config 5): synthetic toggle switch with copy-number bounds scaled to
+~1e8 FSP states -- rectangle [0,Bx) x [0,By), reactions and propensity strings of
+krylovfspssa_b200/models/toggle_test.input with (kx,ky,dx,dy) = (5000,1600,1,1), p0 = product of
+two discretised Gaussians centred mid-box (sigma = B/16), fixed state set (FSP adaptivity off),
+KRYTOL 1e-8, Krylov dimension adapting in [10, 30].
+
+A "step" is one complete adaptive expv solve exp(t_final*A) p0 over the whole state space.
+`value` = generator state updates per second = N * NMULT / time with the state space and p0
+resident in HBM (kfsp_solve_resident); `e2e` is the same quantity through the reference-facing
+C-ABI call kfsp_solve() with HOST buffers (pinned): H2D of states and p0, MATRIX_STARTER on the
+device, the solve, D2H of states and p -- all inside the timed region.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, netlib-order arithmetic,
+1 thread -- the reference is serial) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PARAMS = [5000.0, 1600.0, 1.0, 1.0]
+METRIC = "expv_generator_state_updates_per_s"
+UNIT = "state-updates/s"
+R_TOGGLE = 4
+BYTES_PER_STATE = 12 * R_TOGGLE + 24          # explicit ELL SpMV, SURVEY.md 8d
+
+
+def synthetic(bx, by):
+    """States in index order i = x + Bx*y (x fastest) and the Gaussian p0."""
+    x = np.tile(np.arange(bx, dtype=np.int32), by)
+    y = np.repeat(np.arange(by, dtype=np.int32), bx)
+    states = np.empty((bx * by, 2), dtype=np.int32)
+    states[:, 0] = x
+    states[:, 1] = y
+
+    def g(n):
+        return np.exp(-0.5 * ((np.arange(n) - n / 2.0) / (n / 16.0)) ** 2)
+    p0 = np.outer(g(by), g(bx)).ravel()
+    p0 /= p0.sum()
+    return states, p0
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [c.strip() for c in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_sample(bx, by, m):
+    """FMATVEC + one IOP-2 Arnoldi sweep of the CPU restatement on a bounded rectangle."""
+    import oracle
+    om = oracle.Model.load(os.path.join(ROOT, "krylovfspssa_b200", "models", "toggle_test.input"), PARAMS)
+    states, p0 = synthetic(bx, by)
+    n = len(p0)
+    f = oracle.Fsp(om, max_size=n + 64)
+    f.set_states(states)
+    f.matrix_starter()
+    work = np.zeros(n * (m + 2))
+    nm = C.c_int32()
+    t_sweep = oracle.lib().ko_arnoldi_sweep(f.h, p0.ctypes.data_as(C.POINTER(C.c_double)), m,
+                                            work.ctypes.data_as(C.POINTER(C.c_double)), None, C.byref(nm))
+    y = np.zeros(n)
+    t_mv = oracle.lib().ko_time_matvec(f.h, p0.ctypes.data_as(C.POINTER(C.c_double)),
+                                       y.ctypes.data_as(C.POINTER(C.c_double)), 5)
+    return n, nm.value, t_sweep, t_mv
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU restatement of the reference's own path, serial like the reference."""
+    if rank != 0:
+        return
+    import oracle
+    bx, by = args.ref_bx, args.ref_by
+    om = oracle.Model.load(os.path.join(ROOT, "krylovfspssa_b200", "models", "toggle_test.input"), PARAMS)
+    states, p0 = synthetic(bx, by)
+    n = len(p0)
+    times, mults = [], []
+    for it in range(args.warmup_ref + args.steps):
+        out = oracle.solve(om, states, p0, args.ref_t_final, 1e-6, 1e-8, max_size=n + 64, m_max=args.m_max, m_min=10,
+                           n_init_onestep=0, enable_drop=0, enable_expand=0)
+        if it >= args.warmup_ref:
+            times.append(out["stats"]["wall_seconds"])
+            mults.append(out["stats"]["nmult"])
+    total = sum(times)
+    value = n * sum(mults) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup_ref, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic toggle rectangle %dx%d (bounded sample of config 5), expv to t=%g, fixed state set"
+                               % (bx, by, args.ref_t_final), "states": n, "m_range": [10, args.m_max]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "full expv solve on a %dx%d rectangle (%d states), %d SpMVs per solve; oracle port of the "
+                                   "serial Fortran reference (no Fortran compiler in this image)" % (bx, by, n, mults[0])},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bx", type=int, default=10000)
+    ap.add_argument("--by", type=int, default=10000)
+    ap.add_argument("--t-final", type=float, default=0.01)
+    ap.add_argument("--m-max", type=int, default=30)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-bx", type=int, default=2000)
+    ap.add_argument("--cpu-by", type=int, default=2000)
+    ap.add_argument("--ref-bx", type=int, default=1500)
+    ap.add_argument("--ref-by", type=int, default=1500)
+    ap.add_argument("--ref-t-final", type=float, default=0.01)
+    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import krylovfspssa_b200 as k
+    from krylovfspssa_b200._lib import Stats, check, lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: krylovfspssa_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = lib()
+    bx, by = args.bx, args.by
+    states_np, p0_np = synthetic(bx, by)
+    n = len(p0_np)
+    # pinned host buffers (inputs and outputs of the C-ABI call)
+    states_h = torch.from_numpy(states_np).pin_memory()
+    p0_h = torch.from_numpy(p0_np).pin_memory()
+    states_out = torch.empty((n, 2), dtype=torch.int32).pin_memory()
+    p_out = torch.empty(n, dtype=torch.float64).pin_memory()
+    del states_np
+
+    model = k.CME_MODEL().load(os.path.join(k.models_dir(), "toggle_test.input"))
+    model.reset_parameters(PARAMS)
+    h = k.KrylovFspHandle(model, max_states=n + 64, m_max=args.m_max, m_min=10, n_init_onestep=0, enable_drop=0,
+                          enable_expand=0, device=local_rank)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    fsp_tol, kry_tol = 1e-6, 1e-8
+
+    # ---- resident setup (not timed for `value`): MATRIX_STARTER on the device, p0 in HBM -------------
+    t_setup = time.time()
+    check(L.kfsp_fsp_init(h._h, n, C.cast(states_h.data_ptr(), i32p)), "MATRIX_STARTER")
+    p0_dev = C.c_void_p()
+    check(L.kfsp_device_alloc(h._h, 8 * n, C.byref(p0_dev)))
+    check(L.kfsp_device_upload(h._h, p0_dev, C.c_void_p(p0_h.data_ptr()), 8 * n))
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+    check(L.kfsp_set_profiling(h._h, 1))
+
+    def resident_step():
+        check(L.kfsp_fsp_set_vector_device(h._h, p0_dev, n))
+        st = Stats()
+        rc = L.kfsp_solve_resident(h._h, args.t_final, fsp_tol, kry_tol, 0, C.byref(st))
+        if rc < 0:
+            raise k.KfspError(rc, "kfsp_solve_resident")
+        return st
+
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.time()
+    dev_s = spmv_s = 0.0
+    nmult = launches = spmv_launches = nstep = 0
+    for _ in range(args.steps):
+        st = resident_step()
+        dev_s += st.device_seconds
+        spmv_s += st.spmv_seconds
+        nmult += st.nmult
+        launches += st.kernel_launches
+        spmv_launches += st.spmv_launches
+        nstep += st.nstep
+    barrier()
+    wall = time.time() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # device-timed, max over ranks
+    tt = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s = float(tt.item())
+    units = float(n) * nmult * world                    # replicas until the row-partitioned path lands
+    value = units / dev_s
+
+    # ---- end to end through kfsp_solve with host buffers --------------------------------------------
+    def e2e_step():
+        n_out = C.c_int64()
+        st = Stats()
+        rc = L.kfsp_solve(h._h, args.t_final, n, C.cast(states_h.data_ptr(), i32p), C.cast(p0_h.data_ptr(), f64p), fsp_tol,
+                          kry_tol, 0, C.byref(n_out), C.cast(states_out.data_ptr(), i32p), C.cast(p_out.data_ptr(), f64p),
+                          n, C.byref(st))
+        if rc < 0:
+            raise k.KfspError(rc, "kfsp_solve")
+        return st
+
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e_step()                                        # warm-up
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e_mult = 0
+        for _ in range(args.e2e_steps):
+            e_mult += e2e_step().nmult
+        barrier()
+        e_wall = time.time() - t0
+        tt = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e_wall = float(tt.item())
+        e2e = {"value": float(n) * e_mult * world / e_wall, "unit": UNIT,
+               "h2d_bytes_per_step": int(states_h.numel() * 4 + p0_h.numel() * 8),
+               "d2h_bytes_per_step": int(states_out.numel() * 4 + p_out.numel() * 8),
+               "ms_per_step": 1e3 * e_wall / args.e2e_steps,
+               "timed": "host wall clock around kfsp_solve (includes H2D, device MATRIX_STARTER, solve, D2H), max over ranks"}
+        total_mass = float(p_out.sum())
+    else:
+        total_mass = None
+
+    peak, peak_kind = measured_peak()
+    spmv_avg = spmv_s / max(spmv_launches, 1)
+    achieved = BYTES_PER_STATE * n / spmv_avg / 1e9 if spmv_avg > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_spmv (generator SpMV, gather ELL)", "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": BYTES_PER_STATE * n, "avg_launch_ms": 1e3 * spmv_avg,
+                "launches_timed": spmv_launches, "share_of_step": spmv_s / dev_s if dev_s > 0 else None,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cn, cm, t_sweep, t_mv = cpu_sample(args.cpu_bx, args.cpu_by, 10)
+        cpu = {"value": cn * cm / t_sweep, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "FMATVEC + one IOP-2 Arnoldi sweep (m=10, %d SpMVs) on a %dx%d rectangle of the same workload "
+                         "(%d states); oracle port of the serial Fortran reference, 1 of %d host cores"
+                         % (cm, args.cpu_bx, args.cpu_by, cn, os.cpu_count()),
+               "spmv_states_per_s": cn / t_mv, "spmv_gbs": BYTES_PER_STATE * cn / t_mv / 1e9}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 5: synthetic toggle, rectangle %dx%d = %d FSP states, expv to t_final=%g, "
+                                   "KRYTOL 1e-8, Krylov dimension in [10,%d], fixed state set" % (bx, by, n, args.t_final, args.m_max),
+                       "states": n, "reactions": R_TOGGLE, "l2": "inputs (7.2 GB matrix, 0.8 GB vectors) exceed the 126 MB L2",
+                       "parallelism": "1 GPU" if world == 1 else "%d replicas" % world},
+            "expv_wall_s_to_t_final": dev_s / args.steps, "krylov_steps_per_solve": nstep / args.steps,
+            "spmv_per_solve": nmult / args.steps, "setup_s": t_setup, "host_wall_s": wall,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(), "probability_mass_out": total_mass,
+        }
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

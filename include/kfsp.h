@@ -92,6 +92,7 @@ typedef struct {
     double device_seconds;     /* CUDA-event time of the solve (device work, after the H2D copy) */
     double spmv_seconds;       /* CUDA-event time inside generator SpMV launches (if profiled)   */
     double wall_seconds;       /* host wall clock of the whole call                              */
+    int64_t spmv_launches;     /* generator SpMV launches timed in spmv_seconds                  */
 } kfsp_stats;
 
 /* One row per pass of the time-step loop (label 100), for decision-trace parity. */
@@ -199,6 +200,11 @@ int kfsp_device_upload(kfsp_handle h, void* dst_device, const void* src_host, in
 int kfsp_device_download(kfsp_handle h, void* dst_host, const void* src_device, int64_t bytes);
 int kfsp_device_vector(kfsp_handle h, double** fsp_vector_device);
 int kfsp_flush_l2(kfsp_handle h);
+/* Bracket every generator-SpMV launch of the next solves with CUDA events on the solver's stream
+ * (no synchronisation inside the solve); the sum is reported in kfsp_stats.spmv_seconds. */
+int kfsp_set_profiling(kfsp_handle h, int32_t on);
+/* FSP%VECTOR(1:n) = src (device pointer), rest zero: device-to-device reset between benchmark steps */
+int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src_device, int64_t n);
 int kfsp_launch_count(kfsp_handle h, int64_t* n);
 
 #ifdef __cplusplus

@@ -24,7 +24,8 @@ class Stats(C.Structure):
                [(n, C.c_double) for n in
                 ("step_min", "step_max", "x_error", "s_error", "tbrkdwn", "t_now", "hump", "beta_ratio")] + \
                [(n, C.c_int64) for n in ("n_expand", "n_drop", "n_final", "n_max", "kernel_launches")] + \
-               [(n, C.c_double) for n in ("device_seconds", "spmv_seconds", "wall_seconds")]
+               [(n, C.c_double) for n in ("device_seconds", "spmv_seconds", "wall_seconds")] + \
+               [("spmv_launches", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -88,6 +89,8 @@ SIGNATURES = {
     "kfsp_device_download": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "kfsp_device_vector": (C.c_int, [_vp, C.POINTER(_vp)]),
     "kfsp_flush_l2": (C.c_int, [_vp]),
+    "kfsp_set_profiling": (C.c_int, [_vp, C.c_int32]),
+    "kfsp_fsp_set_vector_device": (C.c_int, [_vp, _vp, C.c_int64]),
     "kfsp_launch_count": (C.c_int, [_vp, _i64p]),
 }
 

@@ -68,6 +68,9 @@ struct Engine {
     std::vector<kfsp_trace_row> trace;
     bool profile_spmv = false;
     double spmv_seconds = 0.0;
+    int64_t spmv_timed = 0;
+    std::vector<cudaEvent_t> ev_pool;   // pairs of events bracketing SpMV launches (profiling only)
+    size_t ev_used = 0;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     std::string last_error;
 
@@ -115,6 +118,7 @@ struct Engine {
         cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush);
         if (h_res) cudaFreeHost(h_res);
         if (h_ctl) cudaFreeHost(h_ctl);
+        for (auto& e : ev_pool) cudaEventDestroy(e);
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
         if (stream) cudaStreamDestroy(stream);
@@ -449,7 +453,8 @@ struct Engine {
     template <int MODE>
     int spmv(const double* x, double* y, const double* first, double* h_out) {
         const int g = grid_for(n);
-        if (profile_spmv) KFSP_CUDA(cudaEventRecord(ev_a, stream));
+        const bool timed = profile_spmv && ev_used + 2 <= ev_pool.size();
+        if (timed) KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
         void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
                      Reducer, SweepCtl*, double*);
         switch (R) {
@@ -460,13 +465,32 @@ struct Engine {
         }
         kern<<<g, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, first, rd, d_ctl, h_out);
         KFSP_TRY(check_launch());
-        if (profile_spmv) {
-            KFSP_CUDA(cudaEventRecord(ev_b, stream));
-            KFSP_CUDA(cudaEventSynchronize(ev_b));
-            float ms = 0;
-            KFSP_CUDA(cudaEventElapsedTime(&ms, ev_a, ev_b));
-            spmv_seconds += 1e-3 * ms;
+        if (timed) {
+            KFSP_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
+            ev_used += 2;
         }
+        return KFSP_OK;
+    }
+    int set_profiling(bool on) {
+        profile_spmv = on;
+        if (on && ev_pool.empty()) {
+            ev_pool.resize(2 * 4096);
+            for (auto& e : ev_pool) KFSP_CUDA(cudaEventCreate(&e));
+        }
+        ev_used = 0;
+        return KFSP_OK;
+    }
+    // sum the bracketed SpMV times recorded since the last call (synchronises)
+    int collect_profile() {
+        if (!profile_spmv || ev_used == 0) return KFSP_OK;
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        for (size_t i = 0; i + 1 < ev_used; i += 2) {
+            float ms = 0.f;
+            KFSP_CUDA(cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]));
+            spmv_seconds += 1e-3 * ms;
+            spmv_timed += 1;
+        }
+        ev_used = 0;
         return KFSP_OK;
     }
 

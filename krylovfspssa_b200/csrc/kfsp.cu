@@ -91,6 +91,8 @@ int Engine::solve(double T, double fsptol, double krytol, int itrace, kfsp_stats
     const double w0 = wall_now();
     const int64_t l0 = launches;
     spmv_seconds = 0.0;
+    spmv_timed = 0;
+    ev_used = 0;
     cudaEvent_t e0, e1;
     KFSP_CUDA(cudaEventCreate(&e0));
     KFSP_CUDA(cudaEventCreate(&e1));
@@ -109,7 +111,9 @@ int Engine::solve(double T, double fsptol, double krytol, int itrace, kfsp_stats
     local.device_seconds = 1e-3 * ms;
     local.wall_seconds = wall_now() - w0;
     local.kernel_launches = launches - l0;
+    collect_profile();
     local.spmv_seconds = spmv_seconds;
+    local.spmv_launches = spmv_timed;
     local.n_final = n;
     if (stats) *stats = local;
     return st;
@@ -570,6 +574,20 @@ int kfsp_flush_l2(kfsp_handle h) {
     if (!e.d_flush) { KFSP_CUDA(cudaMalloc(&e.d_flush, bytes)); e.flush_bytes = bytes; }
     KFSP_CUDA(cudaMemsetAsync(e.d_flush, 0, e.flush_bytes, e.stream));
     return e.sync();
+}
+int kfsp_set_profiling(kfsp_handle h, int32_t on) {
+    if (!h) return KFSP_ERR_ARG;
+    cudaSetDevice(h->e.device);
+    return h->e.set_profiling(on != 0);
+}
+int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src, int64_t cnt) {
+    if (!h || !src || cnt < 0) return KFSP_ERR_ARG;
+    Engine& e = h->e;
+    if (e.ld == 0 || cnt > e.ld) return KFSP_ERR_BAD_SIZES;
+    cudaSetDevice(e.device);
+    if (cnt < e.n) KFSP_CUDA(cudaMemsetAsync(e.d_w + cnt, 0, sizeof(double) * (e.n - cnt), e.stream));
+    KFSP_CUDA(cudaMemcpyAsync(e.d_w, src, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, e.stream));
+    return KFSP_OK;
 }
 int kfsp_launch_count(kfsp_handle h, int64_t* n) {
     if (!h || !n) return KFSP_ERR_ARG;
