@@ -191,7 +191,14 @@ int kfsp_combine(kfsp_handle h, int64_t n, int32_t mx, double beta, const double
 /* ---- multi-GPU (one process per GPU; rows of the state space are block-partitioned) ---- */
 #define KFSP_NCCL_ID_BYTES 128
 int kfsp_dist_unique_id(uint8_t id[KFSP_NCCL_ID_BYTES]);
+/* Call before kfsp_fsp_init.  Afterwards kfsp_fsp_init takes the GLOBAL state list on every rank and keeps
+ * rows [lo,hi); kfsp_fsp_set_vector takes the global vector; kfsp_fsp_get returns this rank's rows.
+ * Partitioned state sets are fixed: create the handle with enable_expand = enable_drop = n_init_onestep = 0. */
 int kfsp_dist_init(kfsp_handle h, int32_t rank, int32_t nranks, const uint8_t id[KFSP_NCCL_ID_BYTES]);
+/* host-side partition arithmetic (no GPU needed): block partition of n rows */
+int kfsp_dist_partition(int64_t n, int32_t nranks, int32_t rank, int64_t* lo, int64_t* hi);
+int kfsp_dist_owner(int64_t n, int32_t nranks, int64_t row, int32_t* owner);
+int kfsp_dist_info(kfsp_handle h, int64_t* lo, int64_t* hi, int64_t* n_halo, int64_t* n_send, int64_t* halo_bytes, int64_t* reductions);
 
 /* device memory helpers for hosts without their own CUDA runtime (bench, tests) */
 int kfsp_device_alloc(kfsp_handle h, int64_t bytes, void** ptr);

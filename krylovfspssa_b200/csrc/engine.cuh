@@ -3,11 +3,13 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "dist.cuh"
 #include "expm.cuh"
 #include "krylov.cuh"
 #include "model_host.h"
@@ -44,6 +46,9 @@ struct Engine {
     int64_t table_size = 0;
     int32_t* d_err = nullptr;         // DevErr bits
     uint32_t ssa_calls = 0;
+    Dist dist;                        // multi-GPU row partition (nranks == 1: single GPU)
+    int64_t states_cap = 0;           // capacity of d_states / table (global); ld is the capacity of the row arrays
+    int spmv_tune = 0;                // hoisted loads, one row per iteration, grid = one wave of resident CTAs
 
     // scratch arena (grows on demand)
     char* d_scratch = nullptr;
@@ -77,6 +82,7 @@ struct Engine {
     // ---------------------------------------------------------------- lifetime
     int init(const kfsp_options* o) {
         opt = *o;
+        if (const char* ev = std::getenv("KFSP_SPMV_TUNE")) spmv_tune = std::atoi(ev);
         if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
             opt.max_states > 2000000000LL)
             return KFSP_ERR_ARG;
@@ -89,6 +95,7 @@ struct Engine {
             KFSP_CUDA(cudaGetDevice(&device));
         }
         KFSP_CUDA(cudaSetDevice(device));
+        KFSP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         KFSP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         KFSP_CUDA(cudaEventCreate(&ev_a));
         KFSP_CUDA(cudaEventCreate(&ev_b));
@@ -125,12 +132,30 @@ struct Engine {
     }
     void free_state_space() {
         cudaFree(d_states); cudaFree(d_succ); cudaFree(d_prop); cudaFree(d_diag); cudaFree(d_pred); cudaFree(d_coef);
-        cudaFree(d_w); cudaFree(d_table); cudaFree(d_V);
+        cudaFree(d_w); cudaFree(d_table); cudaFree(d_V); cudaFree(dist.send_idx); cudaFree(dist.sendbuf); cudaFree(dist.halo);
+        dist.send_idx = nullptr; dist.sendbuf = nullptr; dist.halo = nullptr;
         d_states = d_succ = d_pred = d_table = nullptr;
         d_prop = d_diag = d_coef = d_w = d_V = nullptr;
         ld = 0; n = 0;
     }
 
+    // Grid for a grid-stride kernel: one full wave of resident CTAs (SMs x CTAs/SM for THIS kernel's
+    // register/shared-memory footprint), so no ragged second wave; capped by MAX_VEC_BLOCKS (reducer arrays).
+    int num_sms = 148;
+    std::vector<std::pair<const void*, int>> occ_cache;
+    int wave_grid(const void* kernel, int64_t work, int threads = VEC_THREADS) {
+        int per_sm = 0;
+        for (auto& pr : occ_cache) if (pr.first == kernel) { per_sm = pr.second; break; }
+        if (per_sm == 0) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            occ_cache.emplace_back(kernel, per_sm);
+        }
+        int64_t b = (work + threads - 1) / threads;
+        const int64_t cap = std::min<int64_t>((int64_t)num_sms * per_sm, MAX_VEC_BLOCKS);
+        if (b > cap) b = cap;
+        if (b < 1) b = 1;
+        return (int)b;
+    }
     int grid_for(int64_t work, int threads = VEC_THREADS) const {
         int64_t b = (work + threads - 1) / threads;
         if (b < 1) b = 1;
@@ -240,10 +265,12 @@ struct Engine {
         if (!have_model) return KFSP_ERR_NO_MODEL;
         if (ld > 0) return KFSP_OK;
         KFSP_CUDA(cudaSetDevice(device));
-        const int64_t cap = ((opt.max_states + 63) / 64) * 64;
+        const int64_t gcap = ((opt.max_states + 63) / 64) * 64;
+        // row arrays (matrix, vectors, basis) hold only this rank's rows when the state space is partitioned
+        const int64_t cap = dist.nranks > 1 ? (((opt.max_states + dist.nranks - 1) / dist.nranks + 1 + 63) / 64) * 64 : gcap;
         int64_t ts = 1024;
-        while (ts < 2 * cap) ts <<= 1;
-        KFSP_CUDA(cudaMalloc(&d_states, sizeof(int32_t) * cap * S));
+        while (ts < 2 * gcap) ts <<= 1;
+        KFSP_CUDA(cudaMalloc(&d_states, sizeof(int32_t) * gcap * S));
         KFSP_CUDA(cudaMalloc(&d_succ, sizeof(int32_t) * cap * R));
         KFSP_CUDA(cudaMalloc(&d_pred, sizeof(int32_t) * cap * R));
         KFSP_CUDA(cudaMalloc(&d_prop, sizeof(double) * cap * R));
@@ -252,6 +279,7 @@ struct Engine {
         KFSP_CUDA(cudaMalloc(&d_w, sizeof(double) * cap));
         KFSP_CUDA(cudaMalloc(&d_table, sizeof(int32_t) * ts));
         KFSP_CUDA(cudaMemsetAsync(d_w, 0, sizeof(double) * cap, stream));
+        states_cap = gcap;
         table_size = ts;
         ld = cap;
         n = 0;
@@ -327,6 +355,7 @@ struct Engine {
         return KFSP_OK;
     }
     int fsp_init(int64_t count, const int32_t* states_host) {
+        if (dist.nranks > 1) return dist_fsp_init(count, states_host);
         KFSP_TRY(ensure_state_space());
         if (count < 1 || count > opt.max_states) return KFSP_ERR_BAD_SIZES;
         KFSP_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(int32_t) * count * S, cudaMemcpyHostToDevice, stream));
@@ -364,6 +393,7 @@ struct Engine {
 
     // ---------------------------------------------------------------- ONESTEP_EXTENDER
     int fsp_onestep() {
+        if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;     // partitioned state sets are fixed (round 1)
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         // scratch: cnt[n_old], off[n_old], tiles
@@ -427,6 +457,7 @@ struct Engine {
 
     // ---------------------------------------------------------------- SSA_EXTENDER
     int fsp_ssa(double timestep) {
+        if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         ssa_calls += 1;
@@ -451,20 +482,30 @@ struct Engine {
 
     // ---------------------------------------------------------------- FMATVEC
     template <int MODE>
-    int spmv(const double* x, double* y, const double* first, double* h_out) {
-        const int g = grid_for(n);
+    int spmv(const double* x, double* y, const double* first, double* h_out, int cx = -1, int cf = -1) {
         const bool timed = profile_spmv && ev_used + 2 <= ev_pool.size();
         if (timed) KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
         void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
-                     Reducer, SweepCtl*, double*);
+                     Reducer, SweepCtl*, double*, int, int, const double*, int64_t);
+        const bool halo = dist.nranks > 1;
+        if (halo) KFSP_TRY(dist_halo_exchange(x));
+        // tuning variant (KFSP_SPMV_TUNE): 0 = 1 row/iter, 1 = 2 rows/iter, 3/4/5 = 1 row/iter capped at 8/6/5 CTAs per SM
+#define KFSP_SPMV_PICK(RR)                                                                                              \
+        kern = halo ? k_spmv<RR, MODE, 1, 1, true>                                                                       \
+             : spmv_tune == 1 ? k_spmv<RR, MODE, 2, 1, false> : spmv_tune == 3 ? k_spmv<RR, MODE, 1, 8, false>           \
+             : spmv_tune == 4 ? k_spmv<RR, MODE, 1, 6, false> : spmv_tune == 5 ? k_spmv<RR, MODE, 1, 5, false>           \
+             : k_spmv<RR, MODE, 1, 1, false>
         switch (R) {
-        case 4: kern = k_spmv<4, MODE>; break;
-        case 6: kern = k_spmv<6, MODE>; break;
-        case 10: kern = k_spmv<10, MODE>; break;
-        default: kern = k_spmv<0, MODE>; break;
+        case 4: KFSP_SPMV_PICK(4); break;
+        case 6: KFSP_SPMV_PICK(6); break;
+        case 10: KFSP_SPMV_PICK(10); break;
+        default: kern = halo ? k_spmv<0, MODE, 1, 1, true> : k_spmv<0, MODE, 1, 1, false>; break;
         }
-        kern<<<g, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, first, rd, d_ctl, h_out);
+#undef KFSP_SPMV_PICK
+        const int g = wave_grid((const void*)kern, n);
+        kern<<<g, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, first, rd, d_ctl, h_out, cx, cf, dist.halo, n);
         KFSP_TRY(check_launch());
+        if (halo && MODE != 0) KFSP_TRY(dist_finalize(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, 1, h_out, 0));
         if (timed) {
             KFSP_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
             ev_used += 2;
@@ -497,6 +538,7 @@ struct Engine {
     // ---------------------------------------------------------------- DROP_STATES
     int fsp_drop(double dsum, int32_t* dropped, double* droptol_out, int64_t* count_out) {
         *dropped = 0;
+        if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t lsize = n;
         // FIND_DROPTOL (StateSpace.f90:398-427): thresholds by repeated division, 64 at a time
@@ -581,21 +623,23 @@ struct Engine {
     // columns J = jold..m (1-based) then the extra product (KrylovSolver.f90:236-266). No host sync.
     int arnoldi(int jold, int m) {
         for (int J = jold; J <= m; ++J) {
-            const double* vj = d_V + (size_t)(J - 1) * ld;
-            double* vn = d_V + (size_t)J * ld;
+            const double* vj = d_V + (size_t)(J - 1) * ld;      // column J-1 (0-based), scale colscale[J-1]
+            double* vn = d_V + (size_t)J * ld;                   // column J receives w, then stays un-normalised
             double* hcol = d_H + (size_t)(J - 1) * LDH;
             if (J >= 2) {
                 const double* vp = d_V + (size_t)(J - 2) * ld;
-                KFSP_TRY(spmv<1>(vj, vn, vp, hcol + (J - 2)));                                   // H(J-1,J)
-                KFSP_LAUNCH(k_axpy_dot, grid_for(n), VEC_THREADS, 0, n, vp, vj, vn, rd, d_ctl, hcol + (J - 1));   // H(J,J)
-                KFSP_LAUNCH(k_axpy_nrm, grid_for(n), VEC_THREADS, 0, n, vj, vn, (int)SC_H2, rd, d_ctl, hcol + J, opt.break_tol, J);
+                KFSP_TRY(spmv<1>(vj, vn, vp, hcol + (J - 2), J - 1, J - 2));                       // H(J-1,J)
+                KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, vj, vn, rd, d_ctl, hcol + (J - 1), J - 2, J - 1);   // H(J,J)
+                KFSP_TRY(dist_finalize(RK_AXPY_DOT, 1, hcol + (J - 1), 0));
+                KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H2, rd, d_ctl, hcol + J, opt.break_tol, J, J - 1);
+                KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, hcol + J, J));
             } else {
-                KFSP_TRY(spmv<1>(vj, vn, vj, hcol + 0));                                         // H(1,1)
-                KFSP_LAUNCH(k_axpy_nrm, grid_for(n), VEC_THREADS, 0, n, vj, vn, (int)SC_H1, rd, d_ctl, hcol + J, opt.break_tol, J);
+                KFSP_TRY(spmv<1>(vj, vn, vj, hcol + 0, 0, 0));                                       // H(1,1)
+                KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H1, rd, d_ctl, hcol + J, opt.break_tol, J, 0);
+                KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, hcol + J, J));
             }
-            KFSP_LAUNCH(k_scale_by_inv, grid_for(n), VEC_THREADS, 0, n, vn, (const SweepCtl*)d_ctl);
         }
-        KFSP_TRY(spmv<2>(d_V + (size_t)m * ld, d_V + (size_t)(m + 1) * ld, nullptr, nullptr));    // AVNORM
+        KFSP_TRY(spmv<2>(d_V + (size_t)m * ld, d_V + (size_t)(m + 1) * ld, nullptr, nullptr, m, -1));    // AVNORM
         return KFSP_OK;
     }
     // exp(t*H) on the device; result struct copied to pinned memory (synchronises)
@@ -609,6 +653,148 @@ struct Engine {
     int read_ctl() {
         KFSP_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(SweepCtl), cudaMemcpyDeviceToHost, stream));
         return sync();
+    }
+
+    // ---------------------------------------------------------------- multi-GPU (dist.cuh)
+    int dist_init(int rank, int nranks, const uint8_t* id) {
+        if (nranks == 1) return KFSP_OK;
+#ifdef KFSP_WITH_NCCL
+        if (ld > 0) return KFSP_ERR_ARG;                     // must come before the state space is created
+        KFSP_CUDA(cudaSetDevice(device));
+        ncclUniqueId u;
+        std::memcpy(&u, id, sizeof u);
+        if (ncclCommInitRank(&dist.comm, nranks, u, rank) != ncclSuccess) return KFSP_ERR_NCCL;
+        dist.rank = rank; dist.nranks = nranks;
+        KFSP_CUDA(cudaMalloc(&dist.red_send, sizeof(double) * 4));
+        KFSP_CUDA(cudaMalloc(&dist.red_recv, sizeof(double) * 4 * nranks));
+        KFSP_CUDA(cudaMemset(dist.red_send, 0, sizeof(double) * 4));
+        rd.dist_send = dist.red_send;
+        return KFSP_OK;
+#else
+        (void)rank; (void)id;
+        return KFSP_ERR_UNSUPPORTED;
+#endif
+    }
+    // all-gather the ranks' double-double partials, merge in rank order, run the reduction's epilogue
+    int dist_finalize(int kind, int nv, double* h_out, int column) {
+        if (dist.nranks == 1) return KFSP_OK;
+#ifdef KFSP_WITH_NCCL
+        if (ncclAllGather(dist.red_send, dist.red_recv, 4, ncclFloat64, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+        KFSP_LAUNCH(k_dist_finalize, 1, 32, 0, kind, nv, (const double*)dist.red_recv, dist.nranks, d_ctl, h_out, opt.break_tol, column);
+        dist.reductions += 1;
+#else
+        (void)kind; (void)nv; (void)h_out; (void)column;
+#endif
+        return KFSP_OK;
+    }
+    // SpMV exchange step: send the x entries other ranks' rows refer to, receive ours into dist.halo
+    int dist_halo_exchange(const double* x) {
+#ifdef KFSP_WITH_NCCL
+        if (dist.n_send > 0)
+            KFSP_LAUNCH(k_dist_pack, grid_for(dist.n_send), VEC_THREADS, 0, x, (const int32_t*)dist.send_idx, dist.n_send, dist.sendbuf);
+        if (ncclGroupStart() != ncclSuccess) return KFSP_ERR_NCCL;
+        for (int p = 0; p < dist.nranks; ++p) {
+            if (p == dist.rank) continue;
+            const int64_t sc = dist.send_off[p + 1] - dist.send_off[p], rc = dist.recv_off[p + 1] - dist.recv_off[p];
+            if (sc > 0 && ncclSend(dist.sendbuf + dist.send_off[p], (size_t)sc, ncclFloat64, p, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+            if (rc > 0 && ncclRecv(dist.halo + dist.recv_off[p], (size_t)rc, ncclFloat64, p, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+        }
+        if (ncclGroupEnd() != ncclSuccess) return KFSP_ERR_NCCL;
+        dist.halo_exchanges += 1;
+        dist.halo_bytes += 8 * dist.n_send;
+        return KFSP_OK;
+#else
+        (void)x;
+        return KFSP_ERR_UNSUPPORTED;
+#endif
+    }
+    // MATRIX_STARTER for a partitioned, fixed state set: all ranks get the full state list, build the
+    // full hash table and their own rows, then agree on the halo plan.
+    int dist_fsp_init(int64_t n_global, const int32_t* states_host) {
+#ifdef KFSP_WITH_NCCL
+        KFSP_TRY(ensure_state_space());
+        if (n_global < dist.nranks || n_global > opt.max_states) return KFSP_ERR_BAD_SIZES;
+        const int P = dist.nranks;
+        dist.n_global = n_global;
+        dist.lo = part_lo(n_global, P, dist.rank);
+        dist.hi = part_lo(n_global, P, dist.rank + 1);
+        const int64_t nloc = dist.hi - dist.lo;
+        if (nloc > ld) return KFSP_ERR_BAD_SIZES;
+        KFSP_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(int32_t) * n_global * S, cudaMemcpyHostToDevice, stream));
+        KFSP_CUDA(cudaMemsetAsync(d_w, 0, sizeof(double) * ld, stream));
+        KFSP_CUDA(cudaMemsetAsync(d_table, 0xFF, sizeof(int32_t) * table_size, stream));
+        KFSP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
+        n = n_global;                                   // view over the global list for validation / table
+        FspView f = view();
+        KFSP_LAUNCH(k_validate_states, grid_for(n_global * S), VEC_THREADS, 0, d_states, S, n_global, opt.max_molecules, d_err);
+        KFSP_LAUNCH(k_insert_states, grid_for(n_global), VEC_THREADS, 0, f, (int64_t)0, n_global, d_err);
+        KFSP_LAUNCH(k_dist_build_rows, grid_for(nloc), VEC_THREADS, 0, f, dist.lo, nloc);
+        int32_t e = 0;
+        KFSP_TRY(read_err(&e));
+        if (e) { n = 0; return err_to_status(e); }
+        // halo plan
+        const size_t a_g = align_up(sizeof(int32_t) * n_global);
+        const int64_t tiles = (n_global + SCAN_TILE - 1) / SCAN_TILE;
+        KFSP_TRY(ensure_scratch(2 * a_g + align_up(sizeof(int32_t) * (2 * tiles + 4)) + align_up(sizeof(int64_t) * 4 * (P + 2))));
+        int32_t* flag = (int32_t*)d_scratch;
+        int32_t* pos = (int32_t*)(d_scratch + a_g);
+        int32_t* tb = (int32_t*)(d_scratch + 2 * a_g);
+        int64_t* d_small = (int64_t*)(d_scratch + 2 * a_g + align_up(sizeof(int32_t) * (2 * tiles + 4)));
+        KFSP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * n_global, stream));
+        KFSP_LAUNCH(k_dist_mark_remote, grid_for(nloc * R), VEC_THREADS, 0, (const int32_t*)d_pred, ld, R, nloc, dist.lo, dist.hi, flag);
+        int64_t nh = 0;
+        KFSP_TRY(exclusive_scan(flag, pos, n_global, tb, &nh));
+        dist.n_halo = nh;
+        int32_t* halo_g = nullptr;
+        KFSP_CUDA(cudaMalloc(&halo_g, sizeof(int32_t) * std::max<int64_t>(nh, 1)));
+        KFSP_LAUNCH(k_dist_halo_list, grid_for(n_global), VEC_THREADS, 0, (const int32_t*)flag, (const int32_t*)pos, n_global, halo_g);
+        KFSP_LAUNCH(k_dist_remap, grid_for(nloc * R), VEC_THREADS, 0, d_pred, ld, R, nloc, dist.lo, dist.hi, (const int32_t*)pos);
+        // segments of the halo list by owner
+        std::vector<int64_t> bound(P + 1), off(P + 1);
+        for (int r = 0; r <= P; ++r) bound[r] = part_lo(n_global, P, r);
+        int64_t* d_bound = d_small;
+        int64_t* d_off = d_small + (P + 2);
+        KFSP_CUDA(cudaMemcpyAsync(d_bound, bound.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, stream));
+        KFSP_LAUNCH(k_dist_bounds, 1, 64, 0, (const int32_t*)halo_g, nh, (const int64_t*)d_bound, P, d_off);
+        KFSP_CUDA(cudaMemcpyAsync(off.data(), d_off, sizeof(int64_t) * (P + 1), cudaMemcpyDeviceToHost, stream));
+        KFSP_TRY(sync());
+        dist.recv_off = off;
+        // tell every owner how many of its rows we want; learn how many each rank wants from us
+        int64_t* d_want = d_small + 2 * (P + 2);
+        int64_t* d_all = nullptr;
+        KFSP_CUDA(cudaMalloc(&d_all, sizeof(int64_t) * P * P));
+        std::vector<int64_t> want(P);
+        for (int o = 0; o < P; ++o) want[o] = off[o + 1] - off[o];
+        KFSP_CUDA(cudaMemcpyAsync(d_want, want.data(), sizeof(int64_t) * P, cudaMemcpyHostToDevice, stream));
+        if (ncclAllGather(d_want, d_all, (size_t)P, ncclInt64, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+        std::vector<int64_t> all((size_t)P * P);
+        KFSP_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(int64_t) * P * P, cudaMemcpyDeviceToHost, stream));
+        KFSP_TRY(sync());
+        dist.send_off.assign(P + 1, 0);
+        for (int r = 0; r < P; ++r) dist.send_off[r + 1] = dist.send_off[r] + all[(size_t)r * P + dist.rank];
+        dist.n_send = dist.send_off[P];
+        cudaFree(dist.send_idx); cudaFree(dist.sendbuf); cudaFree(dist.halo);
+        KFSP_CUDA(cudaMalloc(&dist.send_idx, sizeof(int32_t) * std::max<int64_t>(dist.n_send, 1)));
+        KFSP_CUDA(cudaMalloc(&dist.sendbuf, sizeof(double) * std::max<int64_t>(dist.n_send, 1)));
+        KFSP_CUDA(cudaMalloc(&dist.halo, sizeof(double) * std::max<int64_t>(nh, 1)));
+        if (ncclGroupStart() != ncclSuccess) return KFSP_ERR_NCCL;
+        for (int p = 0; p < P; ++p) {
+            if (p == dist.rank) continue;
+            const int64_t rc = off[p + 1] - off[p], sc = dist.send_off[p + 1] - dist.send_off[p];
+            if (rc > 0 && ncclSend(halo_g + off[p], (size_t)rc, ncclInt32, p, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+            if (sc > 0 && ncclRecv(dist.send_idx + dist.send_off[p], (size_t)sc, ncclInt32, p, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+        }
+        if (ncclGroupEnd() != ncclSuccess) return KFSP_ERR_NCCL;
+        if (dist.n_send > 0) KFSP_LAUNCH(k_dist_to_local, grid_for(dist.n_send), VEC_THREADS, 0, dist.send_idx, dist.n_send, dist.lo);
+        KFSP_TRY(sync());
+        cudaFree(halo_g);
+        cudaFree(d_all);
+        n = nloc;                                       // from here on kernels see this rank's rows only
+        return KFSP_OK;
+#else
+        (void)n_global; (void)states_host;
+        return KFSP_ERR_UNSUPPORTED;
+#endif
     }
 
     int solve(double T, double fsptol, double krytol, int itrace, kfsp_stats* stats);

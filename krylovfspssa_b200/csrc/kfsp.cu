@@ -29,7 +29,7 @@ namespace {
 struct GpuBackend {
     Engine& e;
     explicit GpuBackend(Engine& en) : e(en) {}
-    int64_t size() { return e.n; }
+    int64_t size() { return e.dist.nranks > 1 ? e.dist.n_global : e.n; }
     int onestep() { return e.fsp_onestep(); }
     int ssa(double t) { return e.fsp_ssa(t); }
     int drop(double dsum, int* dropped) {
@@ -39,8 +39,9 @@ struct GpuBackend {
         return st;
     }
     int norms(double* wsum, double* wssq) {
-        k_norms<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.d_w, e.rd, e.d_ctl);
+        k_norms<<<e.wave_grid((const void*)k_norms, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.d_w, e.rd, e.d_ctl);
         KFSP_TRY(e.check_launch());
+        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
         KFSP_TRY(e.read_ctl());
         *wsum = e.h_ctl->scal[SC_WSUM];
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
@@ -48,9 +49,9 @@ struct GpuBackend {
     }
     int begin_step(double inv_beta) {
         KFSP_CUDA(cudaMemsetAsync(e.d_H, 0, sizeof(double) * e.LDH * e.LDH, e.stream));
-        k_reset_ctl<<<1, 1, 0, e.stream>>>(e.d_ctl);
+        k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);
         KFSP_TRY(e.check_launch());
-        k_scale_copy<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, inv_beta, e.d_w, e.d_V);
+        k_scale_copy<<<e.wave_grid((const void*)k_scale_copy, e.n), VEC_THREADS, 0, e.stream>>>(e.n, inv_beta, e.d_w, e.d_V);
         return e.check_launch();
     }
     int arnoldi(int jold, int m) { return e.arnoldi(jold, m); }
@@ -66,8 +67,9 @@ struct GpuBackend {
         return e.check_launch();
     }
     int combine(int mx, double beta, double* wsum, double* wssq) {
-        k_combine<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.rd, e.d_ctl);
+        k_combine<<<e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.rd, e.d_ctl);
         KFSP_TRY(e.check_launch());
+        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
         KFSP_TRY(e.read_ctl());
         *wsum = e.h_ctl->scal[SC_WSUM];
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
@@ -76,6 +78,7 @@ struct GpuBackend {
     int restore_w(double beta, double* wssq) {
         k_scale_copy_nrm<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, beta, e.d_V, e.d_w, e.rd, e.d_ctl);
         KFSP_TRY(e.check_launch());
+        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
         KFSP_TRY(e.read_ctl());
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
         return KFSP_OK;
@@ -331,8 +334,15 @@ int kfsp_fsp_set_vector(kfsp_handle h, const double* v, int64_t cnt) {
     if (!h || (!v && cnt > 0) || cnt < 0) return KFSP_ERR_ARG;
     Engine& e = h->e;
     if (e.ld == 0) return KFSP_ERR_BAD_SIZES;
-    if (cnt > e.ld) return KFSP_ERR_BAD_SIZES;
     cudaSetDevice(e.device);
+    if (e.dist.nranks > 1) {                                       // v is the GLOBAL vector: keep rows [lo, hi)
+        if (cnt > e.dist.n_global) return KFSP_ERR_BAD_SIZES;
+        KFSP_CUDA(cudaMemsetAsync(e.d_w, 0, sizeof(double) * e.ld, e.stream));
+        const int64_t a = std::min<int64_t>(cnt, e.dist.lo), b = std::min<int64_t>(cnt, e.dist.hi);
+        if (b > a) KFSP_CUDA(cudaMemcpyAsync(e.d_w, v + a, sizeof(double) * (b - a), cudaMemcpyHostToDevice, e.stream));
+        return e.sync();
+    }
+    if (cnt > e.ld) return KFSP_ERR_BAD_SIZES;
     KFSP_CUDA(cudaMemsetAsync(e.d_w, 0, sizeof(double) * e.ld, e.stream));
     if (cnt) KFSP_CUDA(cudaMemcpyAsync(e.d_w, v, sizeof(double) * cnt, cudaMemcpyHostToDevice, e.stream));
     return e.sync();
@@ -343,7 +353,9 @@ int kfsp_fsp_get(kfsp_handle h, int32_t* states, int32_t* adj, double* offdiag, 
     if (e.n < 1) return KFSP_ERR_BAD_SIZES;
     cudaSetDevice(e.device);
     const int64_t n = e.n;
-    if (states) KFSP_CUDA(cudaMemcpyAsync(states, e.d_states, sizeof(int32_t) * n * e.S, cudaMemcpyDeviceToHost, e.stream));
+    if (e.dist.nranks > 1 && adj) return KFSP_ERR_UNSUPPORTED;      // the column form is not kept for partitioned sets
+    const int64_t row0 = e.dist.nranks > 1 ? e.dist.lo : 0;          // this rank's rows
+    if (states) KFSP_CUDA(cudaMemcpyAsync(states, e.d_states + row0 * e.S, sizeof(int32_t) * n * e.S, cudaMemcpyDeviceToHost, e.stream));
     if (diag) KFSP_CUDA(cudaMemcpyAsync(diag, e.d_diag, sizeof(double) * n, cudaMemcpyDeviceToHost, e.stream));
     if (vector) KFSP_CUDA(cudaMemcpyAsync(vector, e.d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, e.stream));
     if (adj || offdiag) {
@@ -508,6 +520,8 @@ int kfsp_combine(kfsp_handle h, int64_t n, int32_t mx, double beta, const double
     double* dw = (double*)(e.d_scratch + a + b);
     KFSP_CUDA(cudaMemcpyAsync(dV, V, sizeof(double) * n * mx, cudaMemcpyHostToDevice, e.stream));
     KFSP_CUDA(cudaMemcpyAsync(de, ev, sizeof(double) * mx, cudaMemcpyHostToDevice, e.stream));
+    k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);            // unit column scales: V is given normalised
+    KFSP_TRY(e.check_launch());
     k_combine<<<e.grid_for(n), VEC_THREADS, 0, e.stream>>>(n, n, mx, beta, dV, de, dw, e.rd, e.d_ctl);
     KFSP_TRY(e.check_launch());
     KFSP_CUDA(cudaMemcpyAsync(w, dw, sizeof(double) * n, cudaMemcpyDeviceToHost, e.stream));
@@ -531,9 +545,30 @@ int kfsp_dist_unique_id(uint8_t id[KFSP_NCCL_ID_BYTES]) {
 #endif
 }
 int kfsp_dist_init(kfsp_handle h, int32_t rank, int32_t nranks, const uint8_t id[KFSP_NCCL_ID_BYTES]) {
-    (void)h; (void)rank; (void)id;
-    if (nranks == 1) return KFSP_OK;
-    return KFSP_ERR_UNSUPPORTED;
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id)) return KFSP_ERR_ARG;
+    return h->e.dist_init(rank, nranks, id);
+}
+int kfsp_dist_partition(int64_t n, int32_t nranks, int32_t rank, int64_t* lo, int64_t* hi) {
+    if (n < 0 || nranks < 1 || rank < 0 || rank >= nranks || !lo || !hi) return KFSP_ERR_ARG;
+    *lo = part_lo(n, nranks, rank);
+    *hi = part_lo(n, nranks, rank + 1);
+    return KFSP_OK;
+}
+int kfsp_dist_owner(int64_t n, int32_t nranks, int64_t row, int32_t* owner) {
+    if (n < nranks || nranks < 1 || row < 0 || row >= n || !owner) return KFSP_ERR_ARG;
+    *owner = part_owner(n, nranks, row);
+    return KFSP_OK;
+}
+int kfsp_dist_info(kfsp_handle h, int64_t* lo, int64_t* hi, int64_t* n_halo, int64_t* n_send, int64_t* halo_bytes, int64_t* reductions) {
+    if (!h) return KFSP_ERR_ARG;
+    const Dist& d = h->e.dist;
+    if (lo) *lo = d.nranks > 1 ? d.lo : 0;
+    if (hi) *hi = d.nranks > 1 ? d.hi : h->e.n;
+    if (n_halo) *n_halo = d.n_halo;
+    if (n_send) *n_send = d.n_send;
+    if (halo_bytes) *halo_bytes = d.halo_bytes;
+    if (reductions) *reductions = d.reductions;
+    return KFSP_OK;
 }
 
 // ------------------------------------------------------------------ device helpers

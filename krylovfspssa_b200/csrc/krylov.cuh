@@ -16,15 +16,23 @@ constexpr int MAX_VEC_BLOCKS = 148 * 8;       // 148 SMs x 8 resident 256-thread
 // device scalars of the sweep
 enum Scal { SC_H1 = 0, SC_H2, SC_INV_HN, SC_AVNORM, SC_WSUM, SC_WSSQ, SC_HN, SC_COUNT };
 
+constexpr int MAX_COLS = 104;      // m_max + 2 basis columns
+// DSCAL(N, 1/HJ1J, v) (KrylovSolver.f90:258) is never run as a pass of its own: the basis columns stay
+// un-normalised in HBM and colscale[j] = 1/HJ1J is applied by every consumer on load.  The product
+// __dmul_rn(colscale[j], V(i,j)) is the value DSCAL would have stored, so results are unchanged.
 struct SweepCtl {
     double scal[8];
     int32_t brk;                // happy-breakdown column (1-based), 0 = none
     int32_t pad;
+    double colscale[MAX_COLS];
 };
+__device__ __forceinline__ double col_scale(const SweepCtl* ctl, int c) { return c >= 0 ? ctl->colscale[c] : 1.0; }
 
 struct Reducer {
     double* partials;           // [4 * MAX_VEC_BLOCKS]: (hi, lo) planes for up to two reductions
     unsigned int* counter;      // self-resetting ticket
+    double* dist_send;          // multi-GPU: this rank's double-double totals go here (4 doubles) and the
+                                // epilogue runs in k_dist_finalize after the all-gather; nullptr on one GPU
 };
 
 // Double-double accumulator: every N-element reduction is carried in (hi, lo) and rounded once
@@ -109,12 +117,56 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
             dd_merge(s, o);
         }
         s = block_sum(s, sh);
-        if (threadIdx.x == 0) tot[q] = __dadd_rn(s.hi, s.lo);
+        if (threadIdx.x == 0) {
+            if (rd.dist_send) { rd.dist_send[2 * q] = s.hi; rd.dist_send[2 * q + 1] = s.lo; }
+            else tot[q] = __dadd_rn(s.hi, s.lo);
+        }
     }
+    if (rd.dist_send) return false;          // uniform: totals are combined across ranks first
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < NV; ++q) out[q] = tot[q];
     return true;
+}
+
+// What to do with a finished reduction (same code on one GPU, inside the reducing kernel, and on
+// several GPUs, in k_dist_finalize after the ranks' double-double partials were gathered).
+enum RKind { RK_SPMV_DOT = 0, RK_SPMV_NRM, RK_AXPY_DOT, RK_AXPY_NRM, RK_NORMS, RK_SUM_BELOW };
+__device__ __forceinline__ void reduce_epilogue(int kind, const double* tot, SweepCtl* ctl, double* h_out, double break_tol, int column) {
+    switch (kind) {
+    case RK_SPMV_DOT: ctl->scal[SC_H1] = tot[0]; if (h_out) *h_out = tot[0]; break;
+    case RK_SPMV_NRM: ctl->scal[SC_AVNORM] = sqrt(tot[0]); break;
+    case RK_AXPY_DOT: ctl->scal[SC_H2] = tot[0]; if (h_out) *h_out = tot[0]; break;
+    case RK_AXPY_NRM: {
+        const double hn = sqrt(tot[0]);                     // HJ1J (KrylovSolver.f90:247)
+        ctl->scal[SC_HN] = hn;
+        if (hn <= break_tol) {
+            ctl->brk = column;                              // happy breakdown (:249-256)
+        } else {
+            *h_out = hn;
+            ctl->scal[SC_INV_HN] = 1.0 / hn;
+            ctl->colscale[column] = 1.0 / hn;               // column `column` (0-based) of V holds w un-normalised
+        }
+    } break;
+    case RK_NORMS: ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; break;
+    case RK_SUM_BELOW: ctl->scal[SC_WSUM] = tot[0]; break;
+    }
+}
+// multi-GPU: merge the P gathered (hi,lo) partials in rank order, round once, run the epilogue
+__global__ void k_dist_finalize(int kind, int nv, const double* __restrict__ recv /*[P][4]*/, int nranks, SweepCtl* ctl,
+                                double* h_out, double break_tol, int column) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (kind != RK_NORMS && kind != RK_SUM_BELOW && ctl->brk != 0) return;
+    double tot[2] = {0.0, 0.0};
+    for (int q = 0; q < nv; ++q) {
+        DD s; s.hi = 0.0; s.lo = 0.0;
+        for (int r = 0; r < nranks; ++r) {
+            DD o; o.hi = recv[r * 4 + 2 * q]; o.lo = recv[r * 4 + 2 * q + 1];
+            dd_merge(s, o);
+        }
+        tot[q] = __dadd_rn(s.hi, s.lo);
+    }
+    reduce_epilogue(kind, tot, ctl, h_out, break_tol, column);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -124,86 +176,103 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
 //   mode 0: plain   mode 1: dot with `first`   mode 2: norm of y
 // Algorithmic traffic per row: R*(4+8) matrix + 8 diag + 8 x_i + 8 y_i  = 12R+24 bytes.
 // ---------------------------------------------------------------------------------------
-template <int RT, int MODE>
-__global__ void __launch_bounds__(VEC_THREADS) k_spmv(int64_t n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
-                                                       const double* __restrict__ coef, const double* __restrict__ diag,
-                                                       const double* __restrict__ x, double* __restrict__ y,
-                                                       const double* __restrict__ first, Reducer rd, SweepCtl* ctl, double* h_out) {
+template <int RT, int MODE, int UNROLL, int MINB, bool HALO>
+__global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
+                                                             const double* __restrict__ coef, const double* __restrict__ diag,
+                                                             const double* __restrict__ x, double* __restrict__ y,
+                                                             const double* __restrict__ first, Reducer rd, SweepCtl* ctl, double* h_out,
+                                                             int cx, int cf, const double* __restrict__ xh, int64_t nloc) {
+    // HALO: gathered index j >= nloc addresses the halo buffer xh (rows owned by other GPUs)
     const int R = RT > 0 ? RT : R_rt;
     if (MODE != 0 && ctl->brk != 0) return;
+    const double xs = col_scale(ctl, cx);                  // x = xs * (stored column)
+    const double fs = MODE == 1 ? col_scale(ctl, cf) : 1.0;
     DD acc0; acc0.hi = 0.0; acc0.lo = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double xi = x[i];
-        double s = -__dmul_rn(__ldcs(diag + i), xi);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += stride * UNROLL) {
+        // UNROLL independent rows per iteration: all streaming loads are issued before any gather is consumed
+        double s[UNROLL], f[UNROLL];
+        int32_t j[UNROLL][RT > 0 ? RT : 1];
+        double a[UNROLL][RT > 0 ? RT : 1];
 #pragma unroll
-        for (int k = 0; k < (RT > 0 ? RT : R); ++k) {
-            const int32_t j = __ldcs(pred + (int64_t)k * ld + i);
-            const double a = __ldcs(coef + (int64_t)k * ld + i);
-            if (j >= 0) s = fma(a, x[j], s);
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) {
+                if (MODE == 1) f[u] = __dmul_rn(fs, __ldcs(first + i));
+                s[u] = -__dmul_rn(__ldcs(diag + i), __dmul_rn(xs, x[i]));
+                if (RT > 0) {
+#pragma unroll
+                    for (int k = 0; k < RT; ++k) {
+                        j[u][k] = __ldcs(pred + (int64_t)k * ld + i);
+                        a[u][k] = __ldcs(coef + (int64_t)k * ld + i);
+                    }
+                }
+            }
         }
-        y[i] = s;
-        if (MODE == 1) dd_add_prod(acc0, first[i], s);
-        if (MODE == 2) dd_add_prod(acc0, s, s);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) {
+                double sv = s[u];
+                if (RT > 0) {
+#pragma unroll
+                    for (int k = 0; k < RT; ++k)
+                        if (j[u][k] >= 0) sv = fma(a[u][k], __dmul_rn(xs, (HALO && j[u][k] >= nloc) ? xh[j[u][k] - nloc] : x[j[u][k]]), sv);
+                } else {
+                    for (int k = 0; k < R; ++k) {
+                        const int32_t jj = __ldcs(pred + (int64_t)k * ld + i);
+                        const double aa = __ldcs(coef + (int64_t)k * ld + i);
+                        if (jj >= 0) sv = fma(aa, __dmul_rn(xs, (HALO && jj >= nloc) ? xh[jj - nloc] : x[jj]), sv);
+                    }
+                }
+                __stcs(y + i, sv);
+                if (MODE == 1) dd_add_prod(acc0, f[u], sv);
+                if (MODE == 2) dd_add_prod(acc0, sv, sv);
+            }
+        }
     }
     if (MODE == 0) return;
     DD v[1] = {acc0};
     double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
-        if (MODE == 1) { ctl->scal[SC_H1] = tot[0]; if (h_out) *h_out = tot[0]; }
-        if (MODE == 2) ctl->scal[SC_AVNORM] = sqrt(tot[0]);
-    }
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, 0.0, 0);
 }
 
 // w -= h1*a ; dot = <b, w>   (DAXPY + the next DDOT, KrylovSolver.f90:243-245)
 __global__ void __launch_bounds__(VEC_THREADS) k_axpy_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
-                                                          double* __restrict__ w, Reducer rd, SweepCtl* ctl, double* h_out) {
+                                                          double* __restrict__ w, Reducer rd, SweepCtl* ctl, double* h_out,
+                                                          int ca, int cb) {
     if (ctl->brk != 0) return;
     const double h1 = ctl->scal[SC_H1];
+    const double sa = col_scale(ctl, ca), sb = col_scale(ctl, cb);
     DD acc; acc.hi = 0.0; acc.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double wi = fma(-h1, a[i], w[i]);
+        const double ai = __dmul_rn(sa, __ldcs(a + i)), bi = __dmul_rn(sb, __ldcs(b + i));
+        const double wi = fma(-h1, ai, w[i]);
         w[i] = wi;
-        dd_add_prod(acc, b[i], wi);
+        dd_add_prod(acc, bi, wi);
     }
     DD v[1] = {acc};
     double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
-        ctl->scal[SC_H2] = tot[0];
-        if (h_out) *h_out = tot[0];
-    }
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_AXPY_DOT, tot, ctl, h_out, 0.0, 0);
 }
 
 // w -= h*a ; ssq = <w,w>; then HJ1J = sqrt(ssq), happy-breakdown test, H(J+1,J) (KrylovSolver.f90:244-257)
 // which = SC_H1 or SC_H2: the scalar holding h.
 __global__ void __launch_bounds__(VEC_THREADS) k_axpy_nrm(int64_t n, const double* __restrict__ a, double* __restrict__ w, int which,
-                                                          Reducer rd, SweepCtl* ctl, double* h_out, double break_tol, int column) {
+                                                          Reducer rd, SweepCtl* ctl, double* h_out, double break_tol, int column,
+                                                          int ca) {
     if (ctl->brk != 0) return;
     const double h = ctl->scal[which];
+    const double sa = col_scale(ctl, ca);
     DD acc; acc.hi = 0.0; acc.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double wi = fma(-h, a[i], w[i]);
+        const double wi = fma(-h, __dmul_rn(sa, __ldcs(a + i)), w[i]);
         w[i] = wi;
         dd_add_prod(acc, wi, wi);
     }
     DD v[1] = {acc};
     double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) {
-        const double hn = sqrt(tot[0]);
-        ctl->scal[SC_HN] = hn;
-        if (hn <= break_tol) {
-            ctl->brk = column;
-        } else {
-            *h_out = hn;
-            ctl->scal[SC_INV_HN] = 1.0 / hn;
-        }
-    }
-}
-
-// DSCAL(N, 1/HJ1J, w) (KrylovSolver.f90:258)
-__global__ void __launch_bounds__(VEC_THREADS) k_scale_by_inv(int64_t n, double* __restrict__ w, const SweepCtl* ctl) {
-    if (ctl->brk != 0) return;
-    const double s = ctl->scal[SC_INV_HN];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = __dmul_rn(s, w[i]);
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_AXPY_NRM, tot, ctl, h_out, break_tol, column);
 }
 
 // V(:,1) = (1/BETA) * W (KrylovSolver.f90:223-226)
@@ -222,7 +291,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_scale_copy_nrm(int64_t n, doubl
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, 0.0, 0);
 }
 // ||w||_1 and ||w||_2^2 of a vector (BETA = DNRM2(N_NOW, W), KrylovSolver.f90:177,540)
 __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
@@ -234,7 +303,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* 
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, 0.0, 0);
 }
 
 // W = BETA * V(:,1:mx) * e ; W = max(W,0) ; WSUM = ||W||_1 ; also ||W||_2^2 for the next BETA
@@ -242,7 +311,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* 
 __global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, int mx, double beta, const double* __restrict__ V,
                                                          const double* __restrict__ e, double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
     __shared__ double coef[128];
-    for (int j = threadIdx.x; j < mx; j += blockDim.x) coef[j] = __dmul_rn(beta, e[j]);     // temp = alpha*x(j)
+    __shared__ double cs[128];
+    for (int j = threadIdx.x; j < mx; j += blockDim.x) { coef[j] = __dmul_rn(beta, e[j]); cs[j] = ctl->colscale[j]; }   // temp = alpha*x(j)
     __syncthreads();
     DD a1, a2; a1.hi = a1.lo = a2.hi = a2.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -251,9 +321,10 @@ __global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, 
         for (; j + 4 <= mx; j += 4) {
             const double v0 = __ldcs(V + (int64_t)j * ld + i), v1 = __ldcs(V + (int64_t)(j + 1) * ld + i);
             const double v2 = __ldcs(V + (int64_t)(j + 2) * ld + i), v3 = __ldcs(V + (int64_t)(j + 3) * ld + i);
-            s = fma(coef[j], v0, s); s = fma(coef[j + 1], v1, s); s = fma(coef[j + 2], v2, s); s = fma(coef[j + 3], v3, s);
+            s = fma(coef[j], __dmul_rn(cs[j], v0), s); s = fma(coef[j + 1], __dmul_rn(cs[j + 1], v1), s);
+            s = fma(coef[j + 2], __dmul_rn(cs[j + 2], v2), s); s = fma(coef[j + 3], __dmul_rn(cs[j + 3], v3), s);
         }
-        for (; j < mx; ++j) s = fma(coef[j], __ldcs(V + (int64_t)j * ld + i), s);
+        for (; j < mx; ++j) s = fma(coef[j], __dmul_rn(cs[j], __ldcs(V + (int64_t)j * ld + i)), s);
         if (s < 0.0) s = 0.0;
         w[i] = s;
         dd_add(a1, s);
@@ -261,7 +332,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, 
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) { ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; }
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, 0.0, 0);
 }
 
 // FIND_DROPTOL's inner sum (StateSpace.f90:418-423): sum of W_i with 0 < W_i < droptol
@@ -273,10 +344,13 @@ __global__ void __launch_bounds__(VEC_THREADS) k_sum_below(int64_t n, const doub
     }
     DD vv[1] = {a};
     double tot[1];
-    if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) ctl->scal[SC_WSUM] = tot[0];
+    if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_SUM_BELOW, tot, ctl, nullptr, 0.0, 0);
 }
 
 __global__ void k_set_entry(double* p, double v) { *p = v; }
-__global__ void k_reset_ctl(SweepCtl* ctl) { ctl->brk = 0; }
+__global__ void k_reset_ctl(SweepCtl* ctl) {
+    for (int j = threadIdx.x; j < MAX_COLS; j += blockDim.x) ctl->colscale[j] = 1.0;
+    if (threadIdx.x == 0) ctl->brk = 0;
+}
 
 }  // namespace kfsp

@@ -164,6 +164,22 @@ class KrylovFspHandle:
         except Exception:
             pass
 
+    # ---- multi-GPU (one process per GPU, rows block-partitioned) ---------------------
+    @staticmethod
+    def dist_unique_id():
+        buf = (C.c_uint8 * _lib.NCCL_ID_BYTES)()
+        check(lib().kfsp_dist_unique_id(buf), "kfsp_dist_unique_id")
+        return bytes(buf)
+
+    def dist_init(self, rank, nranks, unique_id):
+        buf = (C.c_uint8 * _lib.NCCL_ID_BYTES).from_buffer_copy(unique_id)
+        check(lib().kfsp_dist_init(self._h, rank, nranks, buf), "kfsp_dist_init")
+
+    def dist_info(self):
+        v = [C.c_int64() for _ in range(6)]
+        check(lib().kfsp_dist_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("lo", "hi", "n_halo", "n_send", "halo_bytes", "reductions"), [x.value for x in v]))
+
     # ---- state space ------------------------------------------------------------------
     def fsp_init(self, states):
         st = np.ascontiguousarray(np.asarray(states, dtype=np.int32).reshape(-1, self.S))

@@ -1,0 +1,22 @@
+"""Row-partitioned multi-GPU solve == single-GPU solve, bit for bit (needs >= 2 GPUs on the box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_partitioned_solve_bit_identical():
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    nproc = 2 if ngpu < 4 else 4
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "dist_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "DIST CHECK OK" in r.stdout
