@@ -37,6 +37,7 @@ METRIC = "expv_generator_state_updates_per_s"
 UNIT = "state-updates/s"
 R_TOGGLE = 4
 BYTES_PER_STATE = 12 * R_TOGGLE + 24          # explicit ELL SpMV, SURVEY.md 8d
+TRAFFIC_PER_STATE = 80.9                      # measured DRAM bytes per state of the dot-fused SpMV (ncu, profiles/)
 
 
 def synthetic(bx, by):
@@ -209,19 +210,32 @@ def main():
                           enable_expand=0, device=local_rank)
     i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
     fsp_tol, kry_tol = 1e-6, 1e-8
+    lo, hi = 0, n
+    if world > 1:
+        # rows of the state space are block-partitioned over the ranks (one process per GPU); the NCCL
+        # communicator of the library is bootstrapped through torch.distributed
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(k.KrylovFspHandle.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        h.dist_init(rank, world, uid.cpu().numpy().tobytes())
+        a, b = C.c_int64(), C.c_int64()
+        check(L.kfsp_dist_partition(n, world, rank, C.byref(a), C.byref(b)))
+        lo, hi = a.value, b.value
+    nloc = hi - lo
 
     # ---- resident setup (not timed for `value`): MATRIX_STARTER on the device, p0 in HBM -------------
     t_setup = time.time()
     check(L.kfsp_fsp_init(h._h, n, C.cast(states_h.data_ptr(), i32p)), "MATRIX_STARTER")
     p0_dev = C.c_void_p()
-    check(L.kfsp_device_alloc(h._h, 8 * n, C.byref(p0_dev)))
-    check(L.kfsp_device_upload(h._h, p0_dev, C.c_void_p(p0_h.data_ptr()), 8 * n))
+    check(L.kfsp_device_alloc(h._h, 8 * nloc, C.byref(p0_dev)))
+    check(L.kfsp_device_upload(h._h, p0_dev, C.c_void_p(p0_h.data_ptr() + 8 * lo), 8 * nloc))
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
     check(L.kfsp_set_profiling(h._h, 1))
 
     def resident_step():
-        check(L.kfsp_fsp_set_vector_device(h._h, p0_dev, n))
+        check(L.kfsp_fsp_set_vector_device(h._h, p0_dev, nloc))
         st = Stats()
         rc = L.kfsp_solve_resident(h._h, args.t_final, fsp_tol, kry_tol, 0, C.byref(st))
         if rc < 0:
@@ -252,17 +266,28 @@ def main():
     tt = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s_rank = dev_s
     dev_s = float(tt.item())
-    units = float(n) * nmult * world                    # replicas until the row-partitioned path lands
+    units = float(n) * nmult                              # the whole job: all ranks together update N states per SpMV
     value = units / dev_s
+    dinfo = h.dist_info() if world > 1 else None
 
-    # ---- end to end through kfsp_solve with host buffers --------------------------------------------
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------
     def e2e_step():
-        n_out = C.c_int64()
         st = Stats()
-        rc = L.kfsp_solve(h._h, args.t_final, n, C.cast(states_h.data_ptr(), i32p), C.cast(p0_h.data_ptr(), f64p), fsp_tol,
-                          kry_tol, 0, C.byref(n_out), C.cast(states_out.data_ptr(), i32p), C.cast(p_out.data_ptr(), f64p),
-                          n, C.byref(st))
+        if world == 1:
+            n_out = C.c_int64()
+            rc = L.kfsp_solve(h._h, args.t_final, n, C.cast(states_h.data_ptr(), i32p), C.cast(p0_h.data_ptr(), f64p), fsp_tol,
+                              kry_tol, 0, C.byref(n_out), C.cast(states_out.data_ptr(), i32p), C.cast(p_out.data_ptr(), f64p),
+                              n, C.byref(st))
+        else:
+            # the same call sequence the single-GPU kfsp_solve performs, spelled out for a partitioned state set:
+            # global states and p0 from the host, this rank's rows of states and p back to the host
+            check(L.kfsp_fsp_init(h._h, n, C.cast(states_h.data_ptr(), i32p)), "MATRIX_STARTER")
+            check(L.kfsp_fsp_set_vector(h._h, C.cast(p0_h.data_ptr(), f64p), n))
+            rc = L.kfsp_solve_resident(h._h, args.t_final, fsp_tol, kry_tol, 0, C.byref(st))
+            if rc >= 0:
+                check(L.kfsp_fsp_get(h._h, C.cast(states_out.data_ptr(), i32p), None, None, None, C.cast(p_out.data_ptr(), f64p)))
         if rc < 0:
             raise k.KfspError(rc, "kfsp_solve")
         return st
@@ -271,7 +296,6 @@ def main():
     if args.e2e_steps > 0:
         e2e_step()                                        # warm-up
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e_mult = 0
         for _ in range(args.e2e_steps):
@@ -282,22 +306,31 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e_wall = float(tt.item())
-        e2e = {"value": float(n) * e_mult * world / e_wall, "unit": UNIT,
-               "h2d_bytes_per_step": int(states_h.numel() * 4 + p0_h.numel() * 8),
-               "d2h_bytes_per_step": int(states_out.numel() * 4 + p_out.numel() * 8),
+        h2d = int(states_h.numel() * 4 + (p0_h.numel() if world == 1 else nloc) * 8)
+        d2h = int(nloc * 2 * 4 + nloc * 8)
+        e2e = {"value": float(n) * e_mult / e_wall, "unit": UNIT,
+               "h2d_bytes_per_step": h2d * world if world > 1 else h2d, "d2h_bytes_per_step": int(n * 2 * 4 + n * 8),
                "ms_per_step": 1e3 * e_wall / args.e2e_steps,
-               "timed": "host wall clock around kfsp_solve (includes H2D, device MATRIX_STARTER, solve, D2H), max over ranks"}
-        total_mass = float(p_out.sum())
+               "timed": "host wall clock around the C-ABI calls with pinned host buffers (H2D of states and p0, device "
+                        "MATRIX_STARTER, solve, D2H of states and p), barrier on both sides, max over ranks"}
+        mass = torch.tensor([float(p_out[:nloc].sum())], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(mass)
+        total_mass = float(mass.item())
     else:
         total_mass = None
 
     peak, peak_kind = measured_peak()
     spmv_avg = spmv_s / max(spmv_launches, 1)
-    achieved = BYTES_PER_STATE * n / spmv_avg / 1e9 if spmv_avg > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_spmv (generator SpMV, gather ELL)", "achieved": achieved, "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "algorithmic_bytes_per_launch": BYTES_PER_STATE * n, "avg_launch_ms": 1e3 * spmv_avg,
-                "launches_timed": spmv_launches, "share_of_step": spmv_s / dev_s if dev_s > 0 else None,
+    achieved = BYTES_PER_STATE * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_spmv (generator SpMV, gather ELL; per GPU, rank 0)", "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_PER_STATE * nloc,
+                "traffic_source": "ncu --set full, profiles/r1_summary.md: 8.09 GB per launch at 1e8 states (dot-fused variant)",
+                "algorithmic_bytes_per_launch": BYTES_PER_STATE * nloc,
+                "algorithmic_bytes_per_launch_incl_fused_dot_operand": (BYTES_PER_STATE + 8) * nloc,
+                "achieved_incl_fused_dot_operand": (BYTES_PER_STATE + 8) * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0,
+                "avg_launch_ms": 1e3 * spmv_avg,
+                "launches_timed": spmv_launches, "share_of_step": spmv_s / dev_s_rank if dev_s_rank > 0 else None,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
     cpu = None
@@ -313,15 +346,17 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
-            "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config 5: synthetic toggle, rectangle %dx%d = %d FSP states, expv to t_final=%g, "
                                    "KRYTOL 1e-8, Krylov dimension in [10,%d], fixed state set" % (bx, by, n, args.t_final, args.m_max),
                        "states": n, "reactions": R_TOGGLE, "l2": "inputs (7.2 GB matrix, 0.8 GB vectors) exceed the 126 MB L2",
-                       "parallelism": "1 GPU" if world == 1 else "%d replicas" % world},
+                       "parallelism": "1 GPU" if world == 1 else
+                       "rows block-partitioned over %d GPUs (NCCL halo exchange per SpMV + double-double all-gather per reduction)" % world},
             "expv_wall_s_to_t_final": dev_s / args.steps, "krylov_steps_per_solve": nstep / args.steps,
             "spmv_per_solve": nmult / args.steps, "setup_s": t_setup, "host_wall_s": wall,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "probability_mass_out": total_mass,
+            "dist": dinfo,
         }
         print(json.dumps(line))
     h.close()

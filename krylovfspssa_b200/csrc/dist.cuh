@@ -10,6 +10,7 @@
 // state list and hash table (0.8 GB + 1 GB at 1e8 states) and builds only its own matrix rows.
 #pragma once
 #include "common.cuh"
+#include "krylov.cuh"
 #include "state_space.cuh"
 
 #ifdef KFSP_WITH_NCCL
@@ -100,8 +101,28 @@ __global__ void k_dist_pack(const double* __restrict__ x, const int32_t* __restr
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < cnt; t += (int64_t)gridDim.x * blockDim.x) sendbuf[t] = x[send_idx[t]];
 }
 
+// halo position -> (owner rank, row on owner), for the peer-load SpMV
+__global__ void k_dist_halo_owner(const int32_t* __restrict__ halo_g, int64_t nh, int64_t nglobal, int p, int32_t* owner, int32_t* lidx) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nh; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = halo_g[t];
+        const int o = part_owner(nglobal, p, g);
+        owner[t] = o;
+        lidx[t] = (int32_t)(g - part_lo(nglobal, p, o));
+    }
+}
+
 struct Dist {
     int rank = 0, nranks = 1;
+    bool p2p = false;                   // peer-memory path active (cudaIpc over NVLink); else NCCL path
+    bool want_p2p = true;
+    bool p2p_red = true, p2p_halo = true;   // which halves use peer memory (KFSP_DIST_P2P: 1 both, 2 reductions only, 3 halo only)
+    void* xchg = nullptr;               // this rank's exchange area + flags (written by peers)
+    DistPeers* d_peers = nullptr;       // device copy of the peer table
+    int32_t* halo_owner = nullptr;
+    int32_t* halo_lidx = nullptr;
+    void* peer_base[8] = {nullptr};     // opened IPC mappings (for closing)
+    void* peer_xbase[8] = {nullptr};
+    unsigned long long seq = 0;
 #ifdef KFSP_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cuda.h>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -288,6 +289,7 @@ struct Engine {
     int ensure_basis() {
         if (d_V) return KFSP_OK;
         KFSP_CUDA(cudaMalloc(&d_V, sizeof(double) * (size_t)ld * (opt.m_max + 2)));
+        if (dist.nranks > 1) KFSP_TRY(dist_setup_p2p());       // collective: every rank allocates its basis here
         return KFSP_OK;
     }
     FspView view() const {
@@ -312,21 +314,33 @@ struct Engine {
         return KFSP_OK;
     }
 
-    // exclusive scan of n int32 values; *total is returned on the host (synchronises)
-    int exclusive_scan(const int32_t* in, int32_t* out, int64_t cnt, int32_t* tile_buf /* >= 2*tiles+2 */, int64_t* total) {
+    // exclusive scan of cnt int32 values (any cnt < 2^31): tile scans, recursive scan of the tile sums.
+    // tile_buf must hold scan_buf_ints(cnt) ints.
+    static int64_t scan_buf_ints(int64_t cnt) {
+        int64_t total = 0;
+        while (cnt > SCAN_TILE) {
+            const int64_t tiles = (cnt + SCAN_TILE - 1) / SCAN_TILE;
+            total += 2 * tiles + 2;
+            cnt = tiles;
+        }
+        return total + 4;
+    }
+    int scan_device(const int32_t* in, int32_t* out, int64_t cnt, int32_t* tile_buf) {
         const int64_t tiles = (cnt + SCAN_TILE - 1) / SCAN_TILE;
-        if (tiles > SCAN_TILE) return KFSP_ERR_UNSUPPORTED;       // > 16.7M tiles of 4096: not reachable with int32 indices
+        if (tiles <= 1) {
+            KFSP_LAUNCH(k_scan_tiles, 1, SCAN_THREADS, 0, in, out, cnt, (int32_t*)nullptr, (const int32_t*)nullptr);
+            return KFSP_OK;
+        }
         int32_t* sums = tile_buf;
         int32_t* offs = tile_buf + tiles + 1;
         KFSP_LAUNCH(k_scan_tiles, (int)tiles, SCAN_THREADS, 0, in, (int32_t*)nullptr, cnt, sums, (const int32_t*)nullptr);
-        if (tiles > 1) {
-            // scan of tile sums: one block handles up to SCAN_TILE tiles
-            KFSP_LAUNCH(k_scan_tiles, 1, SCAN_THREADS, 0, (const int32_t*)sums, offs, tiles, (int32_t*)nullptr, (const int32_t*)nullptr);
-            KFSP_LAUNCH(k_scan_tiles, (int)tiles, SCAN_THREADS, 0, in, out, cnt, (int32_t*)nullptr, (const int32_t*)offs);
-        } else {
-            KFSP_LAUNCH(k_scan_tiles, 1, SCAN_THREADS, 0, in, out, cnt, (int32_t*)nullptr, (const int32_t*)nullptr);
-        }
-        // total = last exclusive value + last input
+        KFSP_TRY(scan_device(sums, offs, tiles, tile_buf + 2 * tiles + 2));
+        KFSP_LAUNCH(k_scan_tiles, (int)tiles, SCAN_THREADS, 0, in, out, cnt, (int32_t*)nullptr, (const int32_t*)offs);
+        return KFSP_OK;
+    }
+    // *total is returned on the host (synchronises)
+    int exclusive_scan(const int32_t* in, int32_t* out, int64_t cnt, int32_t* tile_buf, int64_t* total) {
+        KFSP_TRY(scan_device(in, out, cnt, tile_buf));
         int32_t last_ex = 0, last_in = 0;
         KFSP_CUDA(cudaMemcpyAsync(&last_ex, out + cnt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
         KFSP_CUDA(cudaMemcpyAsync(&last_in, in + cnt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -398,7 +412,7 @@ struct Engine {
         const int64_t n_old = n;
         // scratch: cnt[n_old], off[n_old], tiles
         const int64_t tiles0 = (n_old + SCAN_TILE - 1) / SCAN_TILE;
-        size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * (2 * tiles0 + 4));
+        size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * scan_buf_ints(n_old));
         KFSP_TRY(ensure_scratch(need0));
         int32_t* cnt = (int32_t*)d_scratch;
         int32_t* off = (int32_t*)(d_scratch + align_up(sizeof(int32_t) * n_old));
@@ -418,7 +432,7 @@ struct Engine {
         const size_t a_n = align_up(sizeof(int32_t) * n_old);
         const int64_t tiles = (ncand + SCAN_TILE - 1) / SCAN_TILE;
         const size_t a_c = align_up(sizeof(int32_t) * ncand);
-        const size_t need = 2 * a_n + align_up(sizeof(int32_t) * ncand * S) + 3 * a_c + align_up(sizeof(int32_t) * (2 * tiles + 4));
+        const size_t need = 2 * a_n + align_up(sizeof(int32_t) * ncand * S) + 3 * a_c + align_up(sizeof(int32_t) * scan_buf_ints(ncand));
         // growing the arena would lose off[]: save it first
         if (need > scratch_bytes) {
             std::vector<int32_t> keep((size_t)n_old);
@@ -462,7 +476,7 @@ struct Engine {
         const int64_t n_old = n;
         ssa_calls += 1;
         const int64_t tiles0 = (n_old + SCAN_TILE - 1) / SCAN_TILE;
-        size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * (2 * tiles0 + 4));
+        size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * scan_buf_ints(n_old));
         KFSP_TRY(ensure_scratch(need0));
         int32_t* cnt = (int32_t*)d_scratch;
         int32_t* off = (int32_t*)(d_scratch + align_up(sizeof(int32_t) * n_old));
@@ -486,26 +500,30 @@ struct Engine {
         const bool timed = profile_spmv && ev_used + 2 <= ev_pool.size();
         if (timed) KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
         void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
-                     Reducer, SweepCtl*, double*, int, int, const double*, int64_t);
-        const bool halo = dist.nranks > 1;
-        if (halo) KFSP_TRY(dist_halo_exchange(x));
+                     Reducer, SweepCtl*, double*, int, int, const double*, int64_t, int64_t);
+        const int halo = dist.nranks > 1 ? ((dist.p2p && dist.p2p_halo) ? 2 : 1) : 0;
+        if (halo == 1) KFSP_TRY(dist_halo_exchange(x));
         // tuning variant (KFSP_SPMV_TUNE): 0 = 1 row/iter, 1 = 2 rows/iter, 3/4/5 = 1 row/iter capped at 8/6/5 CTAs per SM
 #define KFSP_SPMV_PICK(RR)                                                                                              \
-        kern = halo ? k_spmv<RR, MODE, 1, 1, true>                                                                       \
-             : spmv_tune == 1 ? k_spmv<RR, MODE, 2, 1, false> : spmv_tune == 3 ? k_spmv<RR, MODE, 1, 8, false>           \
-             : spmv_tune == 4 ? k_spmv<RR, MODE, 1, 6, false> : spmv_tune == 5 ? k_spmv<RR, MODE, 1, 5, false>           \
-             : k_spmv<RR, MODE, 1, 1, false>
+        kern = halo == 2 ? k_spmv<RR, MODE, 1, 4, 2> : halo == 1 ? k_spmv<RR, MODE, 1, 4, 1>                             \
+             : spmv_tune == 1 ? k_spmv<RR, MODE, 2, 1, 0> : spmv_tune == 3 ? k_spmv<RR, MODE, 1, 8, 0>                   \
+             : spmv_tune == 4 ? k_spmv<RR, MODE, 1, 6, 0> : spmv_tune == 5 ? k_spmv<RR, MODE, 1, 5, 0>                   \
+             : k_spmv<RR, MODE, 1, 1, 0>
         switch (R) {
         case 4: KFSP_SPMV_PICK(4); break;
         case 6: KFSP_SPMV_PICK(6); break;
         case 10: KFSP_SPMV_PICK(10); break;
-        default: kern = halo ? k_spmv<0, MODE, 1, 1, true> : k_spmv<0, MODE, 1, 1, false>; break;
+        default: kern = halo == 2 ? k_spmv<0, MODE, 1, 4, 2> : halo == 1 ? k_spmv<0, MODE, 1, 4, 1> : k_spmv<0, MODE, 1, 1, 0>; break;
         }
 #undef KFSP_SPMV_PICK
         const int g = wave_grid((const void*)kern, n);
-        kern<<<g, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, first, rd, d_ctl, h_out, cx, cf, dist.halo, n);
+        const Reducer r = MODE != 0 ? next_rd() : rd;
+        Reducer r2 = r;
+        if (halo == 2 && !r2.peers) r2.peers = dist.d_peers;     // the peer table is also the halo address book
+        kern<<<g, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, first, r2, d_ctl, h_out, cx, cf, dist.halo, n,
+                                           (int64_t)(d_V ? x - d_V : 0));
         KFSP_TRY(check_launch());
-        if (halo && MODE != 0) KFSP_TRY(dist_finalize(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, 1, h_out, 0));
+        if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, 1, h_out, 0));
         if (timed) {
             KFSP_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
             ev_used += 2;
@@ -546,7 +564,7 @@ struct Engine {
         double* d_thr = nullptr;
         const size_t a_i = align_up(sizeof(int32_t) * lsize);
         const int64_t tiles = (lsize + SCAN_TILE - 1) / SCAN_TILE;
-        const size_t need = align_up(sizeof(double) * (2 * DROP_BUCKETS + 8)) + 3 * a_i + align_up(sizeof(int32_t) * (2 * tiles + 4)) +
+        const size_t need = align_up(sizeof(double) * (2 * DROP_BUCKETS + 8)) + 3 * a_i + align_up(sizeof(int32_t) * scan_buf_ints(lsize)) +
                             align_up(sizeof(double) * lsize * (size_t)std::max(R, 1)) + 64;
         KFSP_TRY(ensure_scratch(need));
         char* p = d_scratch;
@@ -557,7 +575,7 @@ struct Engine {
         int32_t* drop = (int32_t*)p; p += a_i;
         int32_t* keep = (int32_t*)p; p += a_i;
         int32_t* pos = (int32_t*)p; p += a_i;
-        int32_t* tb = (int32_t*)p; p += align_up(sizeof(int32_t) * (2 * tiles + 4));
+        int32_t* tb = (int32_t*)p; p += align_up(sizeof(int32_t) * scan_buf_ints(lsize));
         char* tmp = p;
         // one double-double reduction per candidate threshold, exactly the reference's loop
         for (int it = 0; it < 400; ++it) {
@@ -629,13 +647,13 @@ struct Engine {
             if (J >= 2) {
                 const double* vp = d_V + (size_t)(J - 2) * ld;
                 KFSP_TRY(spmv<1>(vj, vn, vp, hcol + (J - 2), J - 1, J - 2));                       // H(J-1,J)
-                KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, vj, vn, rd, d_ctl, hcol + (J - 1), J - 2, J - 1);   // H(J,J)
+                KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, vj, vn, next_rd(), d_ctl, hcol + (J - 1), J - 2, J - 1);   // H(J,J)
                 KFSP_TRY(dist_finalize(RK_AXPY_DOT, 1, hcol + (J - 1), 0));
-                KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H2, rd, d_ctl, hcol + J, opt.break_tol, J, J - 1);
+                KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H2, next_rd(), d_ctl, hcol + J, opt.break_tol, J, J - 1);
                 KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, hcol + J, J));
             } else {
                 KFSP_TRY(spmv<1>(vj, vn, vj, hcol + 0, 0, 0));                                       // H(1,1)
-                KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H1, rd, d_ctl, hcol + J, opt.break_tol, J, 0);
+                KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H1, next_rd(), d_ctl, hcol + J, opt.break_tol, J, 0);
                 KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, hcol + J, J));
             }
         }
@@ -656,6 +674,101 @@ struct Engine {
     }
 
     // ---------------------------------------------------------------- multi-GPU (dist.cuh)
+    // Reducer for the next reducing launch: in the peer-memory path every reduction carries a sequence number
+    // (identical on all ranks: the controller is SPMD) that tags the exchanged partials.
+    Reducer next_rd() {
+        Reducer r = rd;
+        if (dist.p2p && dist.p2p_red) r.seq = ++dist.seq;
+        return r;
+    }
+    // all ranks: everything enqueued so far on every GPU is complete and visible before anything enqueued later starts
+    int dist_barrier() {
+        if (!(dist.p2p && dist.p2p_halo)) return KFSP_OK;       // the NCCL exchange step is ordered by NCCL itself
+        if (!dist.p2p_red) return KFSP_ERR_UNSUPPORTED;         // flags are shared with the reduction exchange
+        KFSP_LAUNCH(k_dist_barrier, 1, 32, 0, (const DistPeers*)dist.d_peers, ++dist.seq);
+        return KFSP_OK;
+    }
+    // Map every peer's basis and exchange area into this process (cudaIpc over NVLink).  Collective.
+    int dist_setup_p2p() {
+#ifdef KFSP_WITH_NCCL
+        if (dist.nranks == 1 || dist.p2p || !dist.want_p2p || dist.nranks > MAX_RANKS) return KFSP_OK;
+        const int P = dist.nranks;
+        struct Info { cudaIpcMemHandle_t hv, hx; unsigned long long offv, offx; long long ok; };
+        Info mine;
+        std::memset(&mine, 0, sizeof mine);
+        mine.ok = 1;
+        const size_t xbytes = 4u << 20;                       // own allocation: 2 slots x P x (4 doubles + flag)
+        if (!dist.xchg) {
+            KFSP_CUDA(cudaMalloc(&dist.xchg, xbytes));
+            KFSP_CUDA(cudaMemset(dist.xchg, 0, xbytes));
+        }
+        // offsets of our pointers inside their allocations (cuMemGetAddressRange through the runtime's driver entry point)
+        typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+        range_fn get_range = nullptr;
+        {
+            void* fp = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &qr) == cudaSuccess && fp) get_range = (range_fn)fp;
+            else cudaGetLastError();
+        }
+        void* base_v = d_V;
+        void* base_x = dist.xchg;
+        if (get_range) {
+            CUdeviceptr b = 0; size_t sz = 0;
+            if (get_range(&b, &sz, (CUdeviceptr)d_V) == CUDA_SUCCESS) { base_v = (void*)b; mine.offv = (unsigned long long)((char*)d_V - (char*)b); }
+            if (get_range(&b, &sz, (CUdeviceptr)dist.xchg) == CUDA_SUCCESS) { base_x = (void*)b; mine.offx = (unsigned long long)((char*)dist.xchg - (char*)b); }
+        }
+        if (cudaIpcGetMemHandle(&mine.hv, base_v) != cudaSuccess || cudaIpcGetMemHandle(&mine.hx, base_x) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+        Info* d_info = nullptr;
+        KFSP_CUDA(cudaMalloc(&d_info, sizeof(Info) * (P + 1)));
+        KFSP_CUDA(cudaMemcpyAsync(d_info + P, &mine, sizeof(Info), cudaMemcpyHostToDevice, stream));
+        if (ncclAllGather(d_info + P, d_info, sizeof(Info), ncclUint8, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+        std::vector<Info> all(P);
+        KFSP_CUDA(cudaMemcpyAsync(all.data(), d_info, sizeof(Info) * P, cudaMemcpyDeviceToHost, stream));
+        KFSP_TRY(sync());
+        DistPeers hp;
+        std::memset(&hp, 0, sizeof hp);
+        hp.rank = dist.rank; hp.nranks = P;
+        long long ok = 1;
+        for (int r = 0; r < P; ++r) ok = ok && all[r].ok;
+        for (int r = 0; r < P && ok; ++r) {
+            char* pv = nullptr; char* px = nullptr;
+            if (r == dist.rank) { pv = (char*)d_V; px = (char*)dist.xchg; }
+            else {
+                void* mv = nullptr; void* mx = nullptr;
+                if (cudaIpcOpenMemHandle(&mv, all[r].hv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                    cudaIpcOpenMemHandle(&mx, all[r].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+                dist.peer_base[r] = mv; dist.peer_xbase[r] = mx;
+                pv = (char*)mv + all[r].offv; px = (char*)mx + all[r].offx;
+            }
+            hp.V[r] = (const double*)pv;
+            hp.part[r] = (double*)px;
+            hp.flag[r] = (unsigned long long*)(px + sizeof(double) * 2 * P * 4);
+        }
+        // every rank must take the same path: agree on success
+        long long* d_ok = (long long*)(d_info);
+        KFSP_CUDA(cudaMemcpyAsync(d_ok + P, &ok, sizeof(long long), cudaMemcpyHostToDevice, stream));
+        if (ncclAllGather(d_ok + P, d_ok, 1, ncclInt64, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+        std::vector<long long> oks(P);
+        KFSP_CUDA(cudaMemcpyAsync(oks.data(), d_ok, sizeof(long long) * P, cudaMemcpyDeviceToHost, stream));
+        KFSP_TRY(sync());
+        cudaFree(d_info);
+        for (int r = 0; r < P; ++r) ok = ok && oks[r];
+        if (!ok) {
+            std::fprintf(stderr, "libkfsp: peer-memory mapping unavailable, using the NCCL exchange path\n");
+            return KFSP_OK;
+        }
+        hp.halo_owner = dist.halo_owner; hp.halo_lidx = dist.halo_lidx; hp.err = d_err;
+        if (!dist.d_peers) KFSP_CUDA(cudaMalloc(&dist.d_peers, sizeof(DistPeers)));
+        KFSP_CUDA(cudaMemcpy(dist.d_peers, &hp, sizeof hp, cudaMemcpyHostToDevice));
+        if (dist.p2p_red) { rd.peers = dist.d_peers; rd.dist_send = nullptr; }
+        dist.p2p = true;
+        dist.seq = 0;
+        return KFSP_OK;
+#else
+        return KFSP_OK;
+#endif
+    }
     int dist_init(int rank, int nranks, const uint8_t* id) {
         if (nranks == 1) return KFSP_OK;
 #ifdef KFSP_WITH_NCCL
@@ -665,6 +778,10 @@ struct Engine {
         std::memcpy(&u, id, sizeof u);
         if (ncclCommInitRank(&dist.comm, nranks, u, rank) != ncclSuccess) return KFSP_ERR_NCCL;
         dist.rank = rank; dist.nranks = nranks;
+        if (const char* ev = std::getenv("KFSP_DIST_P2P")) {
+            const int v = std::atoi(ev);
+            dist.want_p2p = v != 0; dist.p2p_red = v == 1 || v == 2; dist.p2p_halo = v == 1 || v == 3;
+        }
         KFSP_CUDA(cudaMalloc(&dist.red_send, sizeof(double) * 4));
         KFSP_CUDA(cudaMalloc(&dist.red_recv, sizeof(double) * 4 * nranks));
         KFSP_CUDA(cudaMemset(dist.red_send, 0, sizeof(double) * 4));
@@ -677,7 +794,7 @@ struct Engine {
     }
     // all-gather the ranks' double-double partials, merge in rank order, run the reduction's epilogue
     int dist_finalize(int kind, int nv, double* h_out, int column) {
-        if (dist.nranks == 1) return KFSP_OK;
+        if (dist.nranks == 1 || (dist.p2p && dist.p2p_red)) return KFSP_OK;     // peer-memory path: exchanged inside the reducing kernel
 #ifdef KFSP_WITH_NCCL
         if (ncclAllGather(dist.red_send, dist.red_recv, 4, ncclFloat64, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
         KFSP_LAUNCH(k_dist_finalize, 1, 32, 0, kind, nv, (const double*)dist.red_recv, dist.nranks, d_ctl, h_out, opt.break_tol, column);
@@ -735,11 +852,11 @@ struct Engine {
         // halo plan
         const size_t a_g = align_up(sizeof(int32_t) * n_global);
         const int64_t tiles = (n_global + SCAN_TILE - 1) / SCAN_TILE;
-        KFSP_TRY(ensure_scratch(2 * a_g + align_up(sizeof(int32_t) * (2 * tiles + 4)) + align_up(sizeof(int64_t) * 4 * (P + 2))));
+        KFSP_TRY(ensure_scratch(2 * a_g + align_up(sizeof(int32_t) * scan_buf_ints(n_global)) + align_up(sizeof(int64_t) * 4 * (P + 2))));
         int32_t* flag = (int32_t*)d_scratch;
         int32_t* pos = (int32_t*)(d_scratch + a_g);
         int32_t* tb = (int32_t*)(d_scratch + 2 * a_g);
-        int64_t* d_small = (int64_t*)(d_scratch + 2 * a_g + align_up(sizeof(int32_t) * (2 * tiles + 4)));
+        int64_t* d_small = (int64_t*)(d_scratch + 2 * a_g + align_up(sizeof(int32_t) * scan_buf_ints(n_global)));
         KFSP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * n_global, stream));
         KFSP_LAUNCH(k_dist_mark_remote, grid_for(nloc * R), VEC_THREADS, 0, (const int32_t*)d_pred, ld, R, nloc, dist.lo, dist.hi, flag);
         int64_t nh = 0;
@@ -786,6 +903,14 @@ struct Engine {
         }
         if (ncclGroupEnd() != ncclSuccess) return KFSP_ERR_NCCL;
         if (dist.n_send > 0) KFSP_LAUNCH(k_dist_to_local, grid_for(dist.n_send), VEC_THREADS, 0, dist.send_idx, dist.n_send, dist.lo);
+        cudaFree(dist.halo_owner); cudaFree(dist.halo_lidx);
+        KFSP_CUDA(cudaMalloc(&dist.halo_owner, sizeof(int32_t) * std::max<int64_t>(nh, 1)));
+        KFSP_CUDA(cudaMalloc(&dist.halo_lidx, sizeof(int32_t) * std::max<int64_t>(nh, 1)));
+        if (nh > 0) KFSP_LAUNCH(k_dist_halo_owner, grid_for(nh), VEC_THREADS, 0, (const int32_t*)halo_g, nh, n_global, P, dist.halo_owner, dist.halo_lidx);
+        if (dist.d_peers) {                                    // re-initialisation after the peer table was built
+            KFSP_CUDA(cudaMemcpyAsync(&dist.d_peers->halo_owner, &dist.halo_owner, sizeof(void*), cudaMemcpyHostToDevice, stream));
+            KFSP_CUDA(cudaMemcpyAsync(&dist.d_peers->halo_lidx, &dist.halo_lidx, sizeof(void*), cudaMemcpyHostToDevice, stream));
+        }
         KFSP_TRY(sync());
         cudaFree(halo_g);
         cudaFree(d_all);

@@ -39,7 +39,7 @@ struct GpuBackend {
         return st;
     }
     int norms(double* wsum, double* wssq) {
-        k_norms<<<e.wave_grid((const void*)k_norms, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.d_w, e.rd, e.d_ctl);
+        k_norms<<<e.wave_grid((const void*)k_norms, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
         KFSP_TRY(e.read_ctl());
@@ -52,7 +52,8 @@ struct GpuBackend {
         k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);
         KFSP_TRY(e.check_launch());
         k_scale_copy<<<e.wave_grid((const void*)k_scale_copy, e.n), VEC_THREADS, 0, e.stream>>>(e.n, inv_beta, e.d_w, e.d_V);
-        return e.check_launch();
+        KFSP_TRY(e.check_launch());
+        return e.dist_barrier();           // neighbours gather column 0 straight from this GPU's HBM
     }
     int arnoldi(int jold, int m) { return e.arnoldi(jold, m); }
     int expm(int mx_ok, double t_ok, int use_brk, double t_brk, int set_one, StepScalars* out) {
@@ -67,7 +68,7 @@ struct GpuBackend {
         return e.check_launch();
     }
     int combine(int mx, double beta, double* wsum, double* wssq) {
-        k_combine<<<e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.rd, e.d_ctl);
+        k_combine<<<e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
         KFSP_TRY(e.read_ctl());
@@ -76,7 +77,7 @@ struct GpuBackend {
         return KFSP_OK;
     }
     int restore_w(double beta, double* wssq) {
-        k_scale_copy_nrm<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, beta, e.d_V, e.d_w, e.rd, e.d_ctl);
+        k_scale_copy_nrm<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, beta, e.d_V, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
         KFSP_TRY(e.read_ctl());

@@ -28,9 +28,22 @@ struct SweepCtl {
 };
 __device__ __forceinline__ double col_scale(const SweepCtl* ctl, int c) { return c >= 0 ? ctl->colscale[c] : 1.0; }
 
+// Peer memory of the other GPUs of the box (cudaIpc-mapped over NVLink/NVSwitch), multi-GPU runs only.
+constexpr int MAX_RANKS = 8;
+struct DistPeers {
+    int rank, nranks;
+    double* part[MAX_RANKS];                 // rank r's exchange area: part[r][(slot*nranks + src)*4 + v]
+    unsigned long long* flag[MAX_RANKS];     // rank r's arrival flags: flag[r][slot*nranks + src] = sequence number
+    const double* V[MAX_RANKS];              // rank r's Krylov basis (same leading dimension on every rank)
+    const int32_t* halo_owner;               // for halo position h: owning rank ...
+    const int32_t* halo_lidx;                // ... and row index on the owner
+    int32_t* err;
+};
 struct Reducer {
     double* partials;           // [4 * MAX_VEC_BLOCKS]: (hi, lo) planes for up to two reductions
     unsigned int* counter;      // self-resetting ticket
+    const DistPeers* peers;     // multi-GPU, peer-memory path: partials are exchanged INSIDE the reducing kernel
+    unsigned long long seq;     // sequence number of this reduction (same on every rank)
     double* dist_send;          // multi-GPU: this rank's double-double totals go here (4 doubles) and the
                                 // epilogue runs in k_dist_finalize after the all-gather; nullptr on one GPU
 };
@@ -91,6 +104,7 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
     __shared__ DD sh[32];
     __shared__ bool last;
     __shared__ double tot[NV];
+    __shared__ double mine[2 * NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
         const DD s = block_sum(v[q], sh);
@@ -118,11 +132,50 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
         }
         s = block_sum(s, sh);
         if (threadIdx.x == 0) {
-            if (rd.dist_send) { rd.dist_send[2 * q] = s.hi; rd.dist_send[2 * q + 1] = s.lo; }
+            if (rd.peers && rd.seq) { mine[2 * q] = s.hi; mine[2 * q + 1] = s.lo; }
+            else if (rd.dist_send) { rd.dist_send[2 * q] = s.hi; rd.dist_send[2 * q + 1] = s.lo; }
             else tot[q] = __dadd_rn(s.hi, s.lo);
         }
     }
-    if (rd.dist_send) return false;          // uniform: totals are combined across ranks first
+    if (rd.peers && rd.seq) {
+        // Fused all-gather over peer memory: thread r stores this rank's (hi,lo) partials into rank r's exchange
+        // area, fences system-wide and raises the arrival flag; then the block waits for every rank's partial of
+        // THIS sequence number, merges them in rank order and rounds once.  Only this one block is still running
+        // on each GPU, and every GPU runs the same kernel, so the wait cannot deadlock on a healthy box.
+        const DistPeers* __restrict__ dp = rd.peers;
+        const int P = dp->nranks, me = dp->rank;
+        const int slot = (int)(rd.seq & 1ull);
+        __syncthreads();
+        if ((int)threadIdx.x < P) {
+            const int r = threadIdx.x;
+            double* dst = dp->part[r] + ((size_t)slot * P + me) * 4;
+#pragma unroll
+            for (int v2 = 0; v2 < 2 * NV; ++v2) dst[v2] = mine[v2];
+            __threadfence_system();
+            *((volatile unsigned long long*)(dp->flag[r] + (size_t)slot * P + me)) = rd.seq;
+            const volatile unsigned long long* fl = dp->flag[me] + (size_t)slot * P + r;
+            const long long t0 = clock64();
+            while (*fl != rd.seq) {
+                if (clock64() - t0 > 8000000000LL) { atomicOr(dp->err, 32); break; }      // ~4 s: a rank is gone
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                DD s; s.hi = 0.0; s.lo = 0.0;
+                for (int r = 0; r < P; ++r) {
+                    const volatile double* src = dp->part[me] + ((size_t)slot * P + r) * 4;
+                    DD o; o.hi = src[2 * q]; o.lo = src[2 * q + 1];
+                    dd_merge(s, o);
+                }
+                tot[q] = __dadd_rn(s.hi, s.lo);
+            }
+        }
+    } else if (rd.dist_send) {
+        return false;                        // uniform: totals are combined across ranks by NCCL first
+    }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < NV; ++q) out[q] = tot[q];
@@ -176,13 +229,22 @@ __global__ void k_dist_finalize(int kind, int nv, const double* __restrict__ rec
 //   mode 0: plain   mode 1: dot with `first`   mode 2: norm of y
 // Algorithmic traffic per row: R*(4+8) matrix + 8 diag + 8 x_i + 8 y_i  = 12R+24 bytes.
 // ---------------------------------------------------------------------------------------
-template <int RT, int MODE, int UNROLL, int MINB, bool HALO>
+template <int HALO>
+__device__ __forceinline__ double halo_load(const double* __restrict__ x, const double* __restrict__ xh, const DistPeers* __restrict__ dp,
+                                            int32_t j, int64_t nloc, int64_t coloff) {
+    if (HALO == 0 || j < nloc) return x[j];
+    if (HALO == 1) return xh[j - nloc];
+    const int64_t h = j - nloc;
+    return __ldcg(dp->V[dp->halo_owner[h]] + coloff + dp->halo_lidx[h]);
+}
+template <int RT, int MODE, int UNROLL, int MINB, int HALO>
 __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
                                                              const double* __restrict__ coef, const double* __restrict__ diag,
                                                              const double* __restrict__ x, double* __restrict__ y,
                                                              const double* __restrict__ first, Reducer rd, SweepCtl* ctl, double* h_out,
-                                                             int cx, int cf, const double* __restrict__ xh, int64_t nloc) {
-    // HALO: gathered index j >= nloc addresses the halo buffer xh (rows owned by other GPUs)
+                                                             int cx, int cf, const double* __restrict__ xh, int64_t nloc, int64_t coloff) {
+    // HALO 1: gathered index j >= nloc addresses the halo buffer xh filled by the NCCL exchange step;
+    // HALO 2: it is loaded straight from the owning GPU's basis column over NVLink (peer memory).
     const int R = RT > 0 ? RT : R_rt;
     if (MODE != 0 && ctl->brk != 0) return;
     const double xs = col_scale(ctl, cx);                  // x = xs * (stored column)
@@ -217,12 +279,12 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
                 if (RT > 0) {
 #pragma unroll
                     for (int k = 0; k < RT; ++k)
-                        if (j[u][k] >= 0) sv = fma(a[u][k], __dmul_rn(xs, (HALO && j[u][k] >= nloc) ? xh[j[u][k] - nloc] : x[j[u][k]]), sv);
+                        if (j[u][k] >= 0) sv = fma(a[u][k], __dmul_rn(xs, halo_load<HALO>(x, xh, rd.peers, j[u][k], nloc, coloff)), sv);
                 } else {
                     for (int k = 0; k < R; ++k) {
                         const int32_t jj = __ldcs(pred + (int64_t)k * ld + i);
                         const double aa = __ldcs(coef + (int64_t)k * ld + i);
-                        if (jj >= 0) sv = fma(aa, __dmul_rn(xs, (HALO && jj >= nloc) ? xh[jj - nloc] : x[jj]), sv);
+                        if (jj >= 0) sv = fma(aa, __dmul_rn(xs, halo_load<HALO>(x, xh, rd.peers, jj, nloc, coloff)), sv);
                     }
                 }
                 __stcs(y + i, sv);
@@ -345,6 +407,24 @@ __global__ void __launch_bounds__(VEC_THREADS) k_sum_below(int64_t n, const doub
     DD vv[1] = {a};
     double tot[1];
     if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_SUM_BELOW, tot, ctl, nullptr, 0.0, 0);
+}
+
+// Cross-GPU barrier over peer memory (one warp): every rank raises its flag on every peer and waits for all
+// of them.  Needed where a kernel without a reduction (k_scale_copy writing basis column 0) is followed by a
+// SpMV that gathers that column from the neighbours' HBM.
+__global__ void k_dist_barrier(const DistPeers* __restrict__ dp, unsigned long long seq) {
+    const int P = dp->nranks, me = dp->rank, r = threadIdx.x;
+    const int slot = (int)(seq & 1ull);
+    if (r < P) {
+        __threadfence_system();
+        *((volatile unsigned long long*)(dp->flag[r] + (size_t)slot * P + me)) = seq;
+        const volatile unsigned long long* fl = dp->flag[me] + (size_t)slot * P + r;
+        const long long t0 = clock64();
+        while (*fl != seq) {
+            if (clock64() - t0 > 8000000000LL) { atomicOr(dp->err, 32); break; }
+        }
+        __threadfence_system();
+    }
 }
 
 __global__ void k_set_entry(double* p, double v) { *p = v; }

@@ -23,8 +23,19 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    bx, by = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (301, 257)
-    t_final = float(sys.argv[3]) if len(sys.argv) > 3 else 0.05
+    cases = [(int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3]))] if len(sys.argv) > 3 else \
+        [(301, 257, 0.05), (97, 1031, 0.02), (1200, 800, 0.03), (301, 257, 0.05)]
+    all_ok = True
+    for bx, by, t_final in cases:
+        all_ok = run_case(rank, world, local, bx, by, t_final) and all_ok
+    dist.destroy_process_group()
+    if not all_ok:
+        raise SystemExit("DIST CHECK FAILED")
+    if rank == 0:
+        print("DIST CHECK OK")
+
+
+def run_case(rank, world, local, bx, by, t_final):
     states, p0 = bench.synthetic(bx, by)
     n = len(p0)
     model = k.CME_MODEL().load(os.path.join(k.models_dir(), "toggle_test.input"))
@@ -57,16 +68,12 @@ def main():
     ok = ok and len(mine) == info["hi"] - info["lo"] and np.array_equal(mine, ref[info["lo"]:info["hi"]])
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    print("rank %d/%d rows [%d,%d) halo %d send %d steps %d nmult %d bit-identical=%s max|diff|=%.3e" %
-          (rank, world, info["lo"], info["hi"], info["n_halo"], info["n_send"], st2["nstep"], st2["nmult"], ok,
+    print("%dx%d rank %d/%d rows [%d,%d) halo %d send %d steps %d nmult %d bit-identical=%s max|diff|=%.3e" %
+          (bx, by, rank, world, info["lo"], info["hi"], info["n_halo"], info["n_send"], st2["nstep"], st2["nmult"], ok,
            float(np.abs(mine - ref[info["lo"]:info["hi"]]).max()) if len(mine) == info["hi"] - info["lo"] else -1.0), flush=True)
     solo.close()
     part.close()
-    dist.destroy_process_group()
-    if int(flag.item()) != 1:
-        raise SystemExit("DIST CHECK FAILED")
-    if rank == 0:
-        print("DIST CHECK OK")
+    return int(flag.item()) == 1
 
 
 if __name__ == "__main__":
