@@ -213,6 +213,9 @@ int kfsp_set_profiling(kfsp_handle h, int32_t on);
 /* FSP%VECTOR(1:n) = src (device pointer), rest zero: device-to-device reset between benchmark steps */
 int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src_device, int64_t n);
 int kfsp_launch_count(kfsp_handle h, int64_t* n);
+/* Host wall clock of the last solve by phase: [0] Arnoldi sweep + Pade, [1] basis combination + norms,
+ * [2] SSA + one-step expansion, [3] DROP_STATES (each phase ends in a stream synchronisation). */
+int kfsp_phase_seconds(kfsp_handle h, double out[4]);
 
 #ifdef __cplusplus
 }

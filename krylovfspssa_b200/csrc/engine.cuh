@@ -70,6 +70,7 @@ struct Engine {
     size_t flush_bytes = 0;
 
     // bookkeeping
+    double phase_s[8] = {0};          // host wall clock per phase of the last solve: 0 sweep+Pade, 1 combine/norms, 2 expand, 3 drop
     int64_t launches = 0;
     std::vector<kfsp_trace_row> trace;
     bool profile_spmv = false;
@@ -352,6 +353,7 @@ struct Engine {
     // ---------------------------------------------------------------- MATRIX_STARTER
     int fsp_init_device(int64_t count) {
         // states [0,count) are already in d_states
+        ssa_calls = 0;                                  // a fresh state space restarts the per-trajectory SSA streams
         KFSP_CUDA(cudaMemsetAsync(d_table, 0xFF, sizeof(int32_t) * table_size, stream));
         KFSP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
         n = count;

@@ -17,7 +17,10 @@ namespace kfsp {
 constexpr int EXPM_MAXN = 104;                 // m_max + 2 = 102, padded to a multiple of 4
 constexpr int EXPM_LDS = EXPM_MAXN;
 constexpr int EXPM_THREADS = 1024;
-constexpr size_t EXPM_SMEM = 2 * (size_t)EXPM_LDS * EXPM_MAXN * sizeof(double) + 64 * sizeof(double);
+constexpr int EXPM_KL = 6;                     // lower bandwidth of q-p when H is tridiagonal (degree-6 Pade)
+constexpr int EXPM_KU = 12;                    // upper bandwidth of U after partial pivoting (kl + ku)
+constexpr size_t EXPM_SMEM = 2 * (size_t)EXPM_LDS * EXPM_MAXN * sizeof(double) + 64 * sizeof(double) +
+                             (size_t)EXPM_MAXN * (EXPM_KU + 1 + EXPM_KL) * sizeof(double) + (size_t)EXPM_MAXN * sizeof(int);
 
 struct ExpmResult {
     int32_t ns;
@@ -39,7 +42,9 @@ __device__ __forceinline__ void expm_load(double* s, const double* __restrict__ 
     }
 }
 // C = sA * sB for the n x n leading blocks; each thread owns a 4x4 tile held in acc.
-__device__ __forceinline__ void expm_mma(const double* sA, const double* sB, int n, double (&acc)[4][4]) {
+// ba / bb: bandwidths of the left / right operand (>= n: dense).  Terms outside the bands are exact zeros, so
+// leaving them out does not change any accumulated value.
+__device__ __forceinline__ void expm_mma(const double* sA, const double* sB, int n, double (&acc)[4][4], int ba = 1 << 20, int bb = 1 << 20) {
     const int ti = threadIdx.x & 31, tj = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -48,7 +53,12 @@ __device__ __forceinline__ void expm_mma(const double* sA, const double* sB, int
     if (4 * ti >= n || 4 * tj >= n) return;
     const double* pa = sA + 4 * ti;
     const double* pb = sB + (size_t)(4 * tj) * EXPM_LDS;
-    for (int k = 0; k < n; ++k) {
+    int k0 = 0, k1 = n - 1;
+    if (ba < n || bb < n) {
+        k0 = max(0, max(4 * ti - ba, 4 * tj - bb));
+        k1 = min(n - 1, min(4 * ti + 3 + ba, 4 * tj + 3 + bb));
+    }
+    for (int k = k0; k <= k1; ++k) {
         const double2 a01 = *reinterpret_cast<const double2*>(pa + (size_t)k * EXPM_LDS);
         const double2 a23 = *reinterpret_cast<const double2*>(pa + (size_t)k * EXPM_LDS + 2);
         const double b0 = pb[k], b1 = pb[EXPM_LDS + k], b2 = pb[2 * EXPM_LDS + k], b3 = pb[3 * EXPM_LDS + k];
@@ -88,7 +98,10 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     double* sA = smem;
     double* sB = smem + (size_t)EXPM_LDS * EXPM_MAXN;
     double* sx = sB + (size_t)EXPM_LDS * EXPM_MAXN;       // 64 doubles of scratch
-    __shared__ int s_piv, s_info, s_ns;
+    double* sU = sx + 64;                                  // compact U rows of the banded LU: sU[k*(KU+1) + c] = U(k, k+c)
+    double* sL = sU + (size_t)EXPM_MAXN * (EXPM_KU + 1);   // multipliers: sL[k*KL + r-1] = L(k+r, k)
+    int* sPiv = (int*)(sL + (size_t)EXPM_MAXN * EXPM_KL);
+    __shared__ int s_piv, s_info, s_ns, s_kb;
     __shared__ double s_scale, s_hnorm, s_coef[8];
     const int tid = threadIdx.x;
 
@@ -108,8 +121,16 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
 
     // ---- ||H||_inf by row sums in column order (dgpadm.f:241-253) -------------------------
     double rs = 0.0;
+    int kb_row = 0;                                        // widest |i-j| of a non-zero entry in this row
     if (tid < n)
-        for (int j = 0; j < n; ++j) rs += fabs(H[(size_t)j * ldh + tid]);
+        for (int j = 0; j < n; ++j) {
+            const double v = H[(size_t)j * ldh + tid];
+            rs += fabs(v);
+            if (v != 0.0) kb_row = max(kb_row, abs(j - tid));
+        }
+    if (tid == 0) s_kb = 0;
+    __syncthreads();
+    if (kb_row) atomicMax(&s_kb, kb_row);
     {
         // block max through shared scratch
         double v = rs;
@@ -149,12 +170,17 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     }
     const double scale = s_scale, scale2 = __dmul_rn(scale, scale);
     double acc[4][4];
+    // The Krylov H of IOP-2 is tridiagonal (plus the unit sub-diagonal entry): every Pade factor is banded
+    // (H2: 2, q: 2-4-6, p: 0-2-4 then 5, q-p: 6) and only the squarings are dense.
+    const bool tri = s_kb <= 1 && n > 2 * (EXPM_KL + EXPM_KU);
+    const int DENSE = 1 << 20;
+    const int bH = tri ? 1 : DENSE, bH2 = tri ? 2 : DENSE;
 
     // ---- H2 = scale2*H*H (dgpadm.f:270): alpha multiplies the right operand, as DGEMM does ----
     expm_load(sA, H, ldh, n, np, 1.0);
     expm_load(sB, H, ldh, n, np, scale2);
     __syncthreads();
-    expm_mma(sA, sB, n, acc);
+    expm_mma(sA, sB, n, acc, bH, bH);
     expm_store(gH2, n, n, acc, 0.0);
     __syncthreads();
     // sB <- H2 (stays for the whole Horner recurrence)
@@ -172,11 +198,13 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     __syncthreads();
     { double* tmp = bufQ; bufQ = bufF; bufF = tmp; }               // q is now in old F; old Q buffer is free
     int iodd = 0;
+    int bP = tri ? 0 : DENSE, bQ = tri ? 2 : DENSE;         // p = c5 I, q = c6 H2 + c4 I
     for (int k = 4; k >= 1; --k) {
         double* used = iodd ? bufQ : bufP;
         expm_load(sA, used, n, n, np, 1.0);
         __syncthreads();
-        expm_mma(sA, sB, n, acc);
+        expm_mma(sA, sB, n, acc, iodd ? bQ : bP, bH2);
+        if (tri) { if (iodd) bQ += 2; else bP += 2; }
         expm_store(bufF, n, n, acc, s_coef[k - 1]);
         __syncthreads();
         if (iodd) { bufQ = bufF; } else { bufP = bufF; }
@@ -187,7 +215,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     expm_load(sA, bufP, n, n, np, 1.0);
     expm_load(sB, H, ldh, n, np, scale);
     __syncthreads();
-    expm_mma(sA, sB, n, acc);
+    expm_mma(sA, sB, n, acc, bP, bH);
     __syncthreads();
     // ---- sA <- q - p ; sB <- p ; solve (q-p) X = p (dgpadm.f:314-315) ----------------------
     expm_store(sB, EXPM_LDS, n, acc, 0.0);
@@ -198,6 +226,91 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
         if (i < n) sA[t2] = __dsub_rn(sA[t2], sB[t2]);
     }
     __syncthreads();
+    if (tri) {
+        // ---- banded path: q-p has lower bandwidth 6; with partial pivoting U has upper bandwidth 12 ---------
+        // Phase A: ONE warp factors the band in place (no block-wide barriers), keeping compact U rows,
+        // multipliers and pivots.  Every element sees the same operations, in the same order, as in the dense
+        // elimination below (terms with an exactly-zero multiplier or pivot-row entry leave a value unchanged).
+        if (tid < 32) {
+            const int lane = tid;
+            for (int k = 0; k < n; ++k) {
+                double best = -1.0; int bi = k;
+                if (lane <= EXPM_KL && k + lane < n) { best = fabs(sA[(size_t)k * EXPM_LDS + k + lane]); bi = k + lane; }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_down_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                best = __shfl_sync(0xffffffffu, best, 0);
+                const int p = __shfl_sync(0xffffffffu, bi, 0);
+                if (best == 0.0) { if (lane == 0) s_info = KFSP_ERR_SINGULAR; break; }
+                if (p != k && lane <= EXPM_KU && k + lane < n) {
+                    double* col = sA + (size_t)(k + lane) * EXPM_LDS;
+                    const double tmp = col[k]; col[k] = col[p]; col[p] = tmp;
+                }
+                __syncwarp();
+                const double inv = 1.0 / sA[(size_t)k * EXPM_LDS + k];
+                __syncwarp();
+                if (lane >= 1 && lane <= EXPM_KL) {
+                    double m = 0.0;
+                    if (k + lane < n) {
+                        m = __dmul_rn(sA[(size_t)k * EXPM_LDS + k + lane], inv);
+                        sA[(size_t)k * EXPM_LDS + k + lane] = m;
+                    }
+                    sL[k * EXPM_KL + lane - 1] = m;
+                }
+                if (lane <= EXPM_KU) sU[k * (EXPM_KU + 1) + lane] = k + lane < n ? sA[(size_t)(k + lane) * EXPM_LDS + k] : 0.0;
+                if (lane == 0) sPiv[k] = p;
+                __syncwarp();
+                for (int e = lane; e < EXPM_KL * EXPM_KU; e += 32) {
+                    const int i = k + 1 + e % EXPM_KL, j = k + 1 + e / EXPM_KL;
+                    if (i < n && j < n) {
+                        double* col = sA + (size_t)j * EXPM_LDS;
+                        col[i] = fma(-sA[(size_t)k * EXPM_LDS + i], col[k], col[i]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (s_info != 0) {
+            if (tid == 0) { res->info = s_info; res->ns = s_ns; res->mx = n; res->brk = brk; res->hnorm = s_hnorm; res->t_used = t;
+                            res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0; }
+            return;
+        }
+        // Phase B: the n right-hand sides are independent -> transpose B so that thread j owns column j with
+        // conflict-free shared-memory accesses, then forward and backward substitution without any barrier.
+        for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) {
+            const int i = t2 / n, j = t2 % n;
+            sA[(size_t)i * EXPM_LDS + j] = sB[(size_t)j * EXPM_LDS + i];
+        }
+        __syncthreads();
+        if (tid < n) {
+            double* b = sA + tid;                                  // element i of this column: b[i * EXPM_LDS]
+            for (int k = 0; k < n; ++k) {
+                const int p = sPiv[k];
+                if (p != k) { const double tmp = b[(size_t)k * EXPM_LDS]; b[(size_t)k * EXPM_LDS] = b[(size_t)p * EXPM_LDS]; b[(size_t)p * EXPM_LDS] = tmp; }
+                const double bk = b[(size_t)k * EXPM_LDS];
+#pragma unroll
+                for (int r = 1; r <= EXPM_KL; ++r)
+                    if (k + r < n) b[(size_t)(k + r) * EXPM_LDS] = fma(-sL[k * EXPM_KL + r - 1], bk, b[(size_t)(k + r) * EXPM_LDS]);
+            }
+            for (int k = n - 1; k >= 0; --k) {
+                const double xk = b[(size_t)k * EXPM_LDS] / sU[k * (EXPM_KU + 1)];
+                b[(size_t)k * EXPM_LDS] = xk;
+#pragma unroll
+                for (int c = 1; c <= EXPM_KU; ++c)
+                    if (k - c >= 0) b[(size_t)(k - c) * EXPM_LDS] = fma(-xk, sU[(k - c) * (EXPM_KU + 1) + c], b[(size_t)(k - c) * EXPM_LDS]);
+            }
+        }
+        __syncthreads();
+        // back to the column-major operand layout, fused with E = I + 2 X
+        for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) {
+            const int j = t2 / EXPM_LDS, i = t2 % EXPM_LDS;
+            sB[t2] = (i < n && j < n) ? __dadd_rn(__dmul_rn(2.0, sA[(size_t)i * EXPM_LDS + j]), (i == j ? 1.0 : 0.0)) : 0.0;
+        }
+        __syncthreads();
+    } else {
     // Gaussian elimination with partial pivoting on [sA | sB]
     for (int k = 0; k < n; ++k) {
         if (tid < 32) {
@@ -262,6 +375,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
         sB[t2] = (i < n && j < n) ? __dadd_rn(__dmul_rn(2.0, sB[t2]), (i == j ? 1.0 : 0.0)) : 0.0;
     }
     __syncthreads();
+    }   // dense path
     // ---- squarings (dgpadm.f:329-336) ------------------------------------------------------
     for (int s = 0; s < s_ns; ++s) {
         for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) sA[t2] = sB[t2];

@@ -30,15 +30,19 @@ struct GpuBackend {
     Engine& e;
     explicit GpuBackend(Engine& en) : e(en) {}
     int64_t size() { return e.dist.nranks > 1 ? e.dist.n_global : e.n; }
-    int onestep() { return e.fsp_onestep(); }
-    int ssa(double t) { return e.fsp_ssa(t); }
+    // phase timers: every timed call ends in a stream synchronisation, so host wall clock is device time + latency
+    struct Tick { double& acc; double t0; explicit Tick(double& a) : acc(a), t0(wall_now()) {} ~Tick() { acc += wall_now() - t0; } };
+    int onestep() { Tick t(e.phase_s[2]); int st = e.fsp_onestep(); if (st == KFSP_OK) st = e.sync(); return st; }
+    int ssa(double ts) { Tick t(e.phase_s[2]); return e.fsp_ssa(ts); }
     int drop(double dsum, int* dropped) {
+        Tick t(e.phase_s[3]);
         int32_t d = 0;
         int st = e.fsp_drop(dsum, &d, nullptr, nullptr);
         *dropped = d;
         return st;
     }
     int norms(double* wsum, double* wssq) {
+        Tick t(e.phase_s[1]);
         k_norms<<<e.wave_grid((const void*)k_norms, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
@@ -55,8 +59,9 @@ struct GpuBackend {
         KFSP_TRY(e.check_launch());
         return e.dist_barrier();           // neighbours gather column 0 straight from this GPU's HBM
     }
-    int arnoldi(int jold, int m) { return e.arnoldi(jold, m); }
+    int arnoldi(int jold, int m) { Tick t(e.phase_s[0]); return e.arnoldi(jold, m); }
     int expm(int mx_ok, double t_ok, int use_brk, double t_brk, int set_one, StepScalars* out) {
+        Tick t(e.phase_s[0]);
         int st = e.expm_step(mx_ok, t_ok, use_brk, t_brk, set_one);
         if (st != KFSP_OK) return st;
         out->ns = e.h_res->ns; out->brk = use_brk ? e.h_res->brk : 0; out->mx = e.h_res->mx;
@@ -68,6 +73,7 @@ struct GpuBackend {
         return e.check_launch();
     }
     int combine(int mx, double beta, double* wsum, double* wssq) {
+        Tick t(e.phase_s[1]);
         k_combine<<<e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
@@ -94,6 +100,7 @@ int Engine::solve(double T, double fsptol, double krytol, int itrace, kfsp_stats
     KFSP_TRY(ensure_basis());
     const double w0 = wall_now();
     const int64_t l0 = launches;
+    for (double& v : phase_s) v = 0.0;
     spmv_seconds = 0.0;
     spmv_timed = 0;
     ev_used = 0;
@@ -623,6 +630,11 @@ int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src, int64_t cnt) {
     cudaSetDevice(e.device);
     if (cnt < e.n) KFSP_CUDA(cudaMemsetAsync(e.d_w + cnt, 0, sizeof(double) * (e.n - cnt), e.stream));
     KFSP_CUDA(cudaMemcpyAsync(e.d_w, src, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, e.stream));
+    return KFSP_OK;
+}
+int kfsp_phase_seconds(kfsp_handle h, double out[4]) {
+    if (!h || !out) return KFSP_ERR_ARG;
+    for (int i = 0; i < 4; ++i) out[i] = h->e.phase_s[i];
     return KFSP_OK;
 }
 int kfsp_launch_count(kfsp_handle h, int64_t* n) {

@@ -298,6 +298,11 @@ class KrylovFspHandle:
         i = np.array([[r.m, r.n_step, r.n_after, r.flags, r.nmult, r.nexph] for r in rows[:n.value]], dtype=np.int32).reshape(-1, 6)
         return dict(d=d, i=i)
 
+    def phase_seconds(self):
+        buf = (C.c_double * 4)()
+        check(lib().kfsp_phase_seconds(self._h, buf))
+        return dict(zip(("sweep_pade", "combine_norms", "expand", "drop"), list(buf)))
+
     @property
     def launches(self):
         n = C.c_int64()

@@ -74,3 +74,50 @@ def test_cme_solve_host_api():
     assert j == 4 and fsp.probability(fsp.state[:, 3]) == fsp.vector[3]
     assert fsp.index([9000, 9000]) == 0 and fsp.probability([9000, 9000]) == 0.0
     fsp.clear()
+
+
+def test_repeated_solves_are_reproducible():
+    h, om, x0 = make("toggle")
+    a = h.solve(3.0, [x0], [1.0], 1e-4, 1e-10)
+    b = h.solve(3.0, [x0], [1.0], 1e-4, 1e-10)          # same handle: SSA streams restart with the state space
+    assert np.array_equal(a["states"], b["states"]) and np.array_equal(a["vector"], b["vector"])
+    assert np.array_equal(a["trace"]["i"], b["trace"]["i"])
+    ph = h.phase_seconds()
+    assert set(ph) == {"sweep_pade", "combine_norms", "expand", "drop"} and ph["sweep_pade"] > 0
+    h.close()
+
+
+def test_chained_solves_equal_oracle_chain():
+    """CME_SOLVE output fed back as input (FSP_OUT -> next call).  The FSP criterion WSUM >= 1 - FSPTOL*t/T
+    (KrylovSolver.f90:458) assumes unit initial mass, so the caller renormalises between calls; an
+    un-normalised restart can never satisfy it and ends in KFSP_ERR_MOLECULE_LIMIT / overflow instead of
+    looping forever like the reference would."""
+    h, om, x0 = make("birth_death")
+    a = h.solve(1.0, [x0], [1.0], 1e-6, 1e-10)
+    p1 = a["vector"] / a["vector"].sum()
+    b = h.solve(1.0, a["states"], p1, 1e-6, 1e-10)
+    ra = oracle.solve(om, [x0], [1.0], 1.0, 1e-6, 1e-10, reproducible=1)
+    assert np.array_equal(a["vector"], ra["vector"])
+    rb = oracle.solve(om, ra["states"], ra["vector"] / ra["vector"].sum(), 1.0, 1e-6, 1e-10, reproducible=1)
+    assert np.array_equal(b["states"], rb["states"]) and np.array_equal(b["vector"], rb["vector"])
+    h.close()
+
+
+def test_customprop_is_rejected_loudly():
+    model = k.CME_MODEL().create(1, 2, 2)
+    model.stoichiometry = [[1, -1]]
+    model.reset_parameters([5.0, 1.0])
+    model.set_customprop(lambda st, r, p: p[0] if r == 1 else p[1] * st[0])
+    assert model.propensity([3], 2) == 3.0               # host-side CUSTOMPROP works (ModelModule.f90:188-189)
+    with pytest.raises(k.KfspError) as e:
+        k.KrylovFspHandle(model, max_states=1000)
+    assert e.value.status == -26                         # ... but cannot be shipped to the device yet
+
+
+def test_small_krylov_range_option():
+    h, om, x0 = make("toggle", m_max=20, m_min=5)
+    out = h.solve(1.0, [x0], [1.0], 1e-4, 1e-8)
+    ref = oracle.solve(om, [x0], [1.0], 1.0, 1e-4, 1e-8, m_max=20, m_min=5, reproducible=1)
+    assert np.array_equal(out["states"], ref["states"]) and np.array_equal(out["vector"], ref["vector"])
+    assert out["trace"]["i"][:, 0].max() <= 20
+    h.close()
