@@ -454,7 +454,7 @@ struct Engine {
         FspView f = view();
         if (ssa) {
             KFSP_LAUNCH(k_ssa_walk<true>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
-                        (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24));
+                        (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand);
         } else {
             KFSP_LAUNCH(k_onestep_fill, grid_for(n_old), VEC_THREADS, 0, f, n_old, (const int32_t*)off, cand, d_err);
         }
@@ -485,7 +485,7 @@ struct Engine {
         int32_t* tb0 = (int32_t*)(d_scratch + 2 * align_up(sizeof(int32_t) * n_old));
         FspView f = view();
         KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
-                    (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24));
+                    (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0);
         int64_t ncand = 0;
         KFSP_TRY(exclusive_scan(cnt, off, n_old, tb0, &ncand));
         int32_t e = 0;

@@ -32,8 +32,8 @@ struct GpuBackend {
     int64_t size() { return e.dist.nranks > 1 ? e.dist.n_global : e.n; }
     // phase timers: every timed call ends in a stream synchronisation, so host wall clock is device time + latency
     struct Tick { double& acc; double t0; explicit Tick(double& a) : acc(a), t0(wall_now()) {} ~Tick() { acc += wall_now() - t0; } };
-    int onestep() { Tick t(e.phase_s[2]); int st = e.fsp_onestep(); if (st == KFSP_OK) st = e.sync(); return st; }
-    int ssa(double ts) { Tick t(e.phase_s[2]); return e.fsp_ssa(ts); }
+    int onestep() { Tick t(e.phase_s[4]); int st = e.fsp_onestep(); if (st == KFSP_OK) st = e.sync(); return st; }
+    int ssa(double ts) { Tick t(e.phase_s[2]); int st = e.fsp_ssa(ts); if (st == KFSP_OK) st = e.sync(); return st; }
     int drop(double dsum, int* dropped) {
         Tick t(e.phase_s[3]);
         int32_t d = 0;
@@ -632,9 +632,9 @@ int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src, int64_t cnt) {
     KFSP_CUDA(cudaMemcpyAsync(e.d_w, src, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, e.stream));
     return KFSP_OK;
 }
-int kfsp_phase_seconds(kfsp_handle h, double out[4]) {
+int kfsp_phase_seconds(kfsp_handle h, double out[8]) {
     if (!h || !out) return KFSP_ERR_ARG;
-    for (int i = 0; i < 4; ++i) out[i] = h->e.phase_s[i];
+    for (int i = 0; i < 8; ++i) out[i] = h->e.phase_s[i];
     return KFSP_OK;
 }
 int kfsp_launch_count(kfsp_handle h, int64_t* n) {

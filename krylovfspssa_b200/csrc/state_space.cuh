@@ -227,13 +227,21 @@ __global__ void k_onestep_fill(FspView f, int64_t n_old, const int32_t* __restri
 // ---------------------------------------------------------------------------------------
 // candidate generation: SSA_EXTENDER (StateSpace.f90:571-629).  One thread per start state;
 // the walk is replayed twice (count, then fill) from its own Philox sub-stream.
+// (Measured: persistent lanes with dynamic work fetch were 2x SLOWER on the Goutsias model -- walks are
+// short and the cost is dependent memory latency per walk, not divergence -- so the grid-stride form stays.)
 // ---------------------------------------------------------------------------------------
 template <bool FILL>
 __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t seed, uint32_t call_no,
-                           int32_t* cnt, const int32_t* __restrict__ off, int32_t* cand, int32_t* err, int32_t max_jumps) {
+                           int32_t* cnt, const int32_t* __restrict__ off, int32_t* cand, int32_t* err, int32_t max_jumps,
+                           int64_t ncand) {
     const DeviceModel* __restrict__ m = f.model;
     const int S = f.S, R = f.R;
     for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j0 < n_old; j0 += (int64_t)gridDim.x * blockDim.x) {
+        if (FILL) {
+            // replay only the walks that left the projection in the counting pass (a small boundary fraction)
+            const int64_t end = j0 + 1 < n_old ? (int64_t)off[j0 + 1] : ncand;
+            if (end == (int64_t)off[j0]) continue;
+        }
         int32_t st[KFSP_MAX_SPECIES], nb[KFSP_MAX_SPECIES];
         for (int s = 0; s < S; ++s) st[s] = f.states[j0 * S + s];
         int64_t j = j0;                 // index of the current state, or -1 if it is not (yet) in the projection
@@ -244,21 +252,25 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
             if ((int32_t)jump >= max_jumps) { atomicOr(err, DEV_RUNAWAY); break; }
             double r1, r2;
             philox_uniform2(seed, call_no, (uint32_t)(j0 + 1), jump, &r1, &r2);
+            // all R propensities of the current state at once: independent loads (one memory latency instead of
+            // a dependent chain through the cumulative sum), and a single byte-code evaluation for unknown states
+            double pr[KFSP_MAX_REACTIONS];
             double dg;
             if (j >= 0) {
                 dg = f.diag[j];
+                for (int k = 0; k < R; ++k) pr[k] = f.prop[(int64_t)k * f.ld + j];
             } else {
                 dg = 0.0;
-                for (int k = 0; k < R; ++k) dg = __dadd_rn(dg, eval_propensity(m, k, st));
+                for (int k = 0; k < R; ++k) { pr[k] = eval_propensity(m, k, st); dg = __dadd_rn(dg, pr[k]); }
             }
             t = fmin(timestep, __dadd_rn(t, __ddiv_rn(-log(r1), dg)));
             if (!(t <= timestep)) break;
             const double r2a = fmin(__dmul_rn(r2, dg), dg);
             int k = 0;
-            double tmp = j >= 0 ? f.prop[j] : eval_propensity(m, 0, st);
+            double tmp = pr[0];
             while (tmp < r2a && k < R - 1) {
                 ++k;
-                tmp = __dadd_rn(tmp, j >= 0 ? f.prop[(int64_t)k * f.ld + j] : eval_propensity(m, k, st));
+                tmp = __dadd_rn(tmp, pr[k]);
             }
             bool neg = false, over = false;
             for (int s = 0; s < S; ++s) {

@@ -299,9 +299,9 @@ class KrylovFspHandle:
         return dict(d=d, i=i)
 
     def phase_seconds(self):
-        buf = (C.c_double * 4)()
+        buf = (C.c_double * 8)()
         check(lib().kfsp_phase_seconds(self._h, buf))
-        return dict(zip(("sweep_pade", "combine_norms", "expand", "drop"), list(buf)))
+        return dict(zip(("sweep_pade", "combine_norms", "ssa", "drop", "onestep"), list(buf)[:5]))
 
     @property
     def launches(self):

@@ -83,7 +83,7 @@ def test_repeated_solves_are_reproducible():
     assert np.array_equal(a["states"], b["states"]) and np.array_equal(a["vector"], b["vector"])
     assert np.array_equal(a["trace"]["i"], b["trace"]["i"])
     ph = h.phase_seconds()
-    assert set(ph) == {"sweep_pade", "combine_norms", "expand", "drop"} and ph["sweep_pade"] > 0
+    assert set(ph) == {"sweep_pade", "combine_norms", "ssa", "drop", "onestep"} and ph["sweep_pade"] > 0
     h.close()
 
 

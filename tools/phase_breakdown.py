@@ -15,8 +15,8 @@ RUNS = {"toggle": (1000.0, 1e-4, 1e-10, 400000), "repressilator": (10.0, 1e-4, 1
 for name in sys.argv[1:] or list(RUNS):
     t, ftol, ktol, cap = RUNS[name]
     h, _, x0 = make(name, max_states=cap, seed=12345)
-    for rep in range(2):
-        out = h.solve(t, [x0], [1.0], ftol, ktol)
+    out = h.solve(t, [x0], [1.0], ftol, ktol)
+    out = h.solve(t, [x0], [1.0], ftol, ktol)
     st = out["stats"]
     ph = h.phase_seconds()
     print("%s: N=%d steps=%d nmult=%d nexph=%d expand=%d drop=%d launches=%d device %.3f s wall %.3f s | %s" %
