@@ -27,7 +27,6 @@ struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool have_model = false;
-    HostModel hm;
     DeviceModel* d_model = nullptr;
     double* d_tables = nullptr;       // host-built propensity tables
     int n_tabulated = 0, n_inexact_on_device = 0;
@@ -49,6 +48,7 @@ struct Engine {
     uint32_t ssa_calls = 0;
     Dist dist;                        // multi-GPU row partition (nranks == 1: single GPU)
     int64_t states_cap = 0;           // capacity of d_states / table (global); ld is the capacity of the row arrays
+    bool small_sweep = true;          // KFSP_SMALL_SWEEP=0 disables the single-CTA sweep (A/B)
     int spmv_tune = 0;                // hoisted loads, one row per iteration, grid = one wave of resident CTAs
 
     // scratch arena (grows on demand)
@@ -79,12 +79,12 @@ struct Engine {
     std::vector<cudaEvent_t> ev_pool;   // pairs of events bracketing SpMV launches (profiling only)
     size_t ev_used = 0;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-    std::string last_error;
 
     // ---------------------------------------------------------------- lifetime
     int init(const kfsp_options* o) {
         opt = *o;
         if (const char* ev = std::getenv("KFSP_SPMV_TUNE")) spmv_tune = std::atoi(ev);
+        if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
         if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
             opt.max_states > 2000000000LL)
             return KFSP_ERR_ARG;
@@ -255,7 +255,6 @@ struct Engine {
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
         KFSP_CUDA(cudaStreamSynchronize(stream));
         const bool reshape = !have_model || m.S != S || m.R != R;
-        hm = m;
         S = m.S; R = m.R;
         have_model = true;
         if (reshape) { free_state_space(); }
@@ -561,19 +560,14 @@ struct Engine {
         if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t lsize = n;
-        // FIND_DROPTOL (StateSpace.f90:398-427): thresholds by repeated division, 64 at a time
+        // FIND_DROPTOL (StateSpace.f90:398-427): thresholds by repeated division
         double droptol = opt.drop_tol0;
-        double* d_thr = nullptr;
         const size_t a_i = align_up(sizeof(int32_t) * lsize);
-        const int64_t tiles = (lsize + SCAN_TILE - 1) / SCAN_TILE;
-        const size_t need = align_up(sizeof(double) * (2 * DROP_BUCKETS + 8)) + 3 * a_i + align_up(sizeof(int32_t) * scan_buf_ints(lsize)) +
+        const size_t need = 256 + 3 * a_i + align_up(sizeof(int32_t) * scan_buf_ints(lsize)) +
                             align_up(sizeof(double) * lsize * (size_t)std::max(R, 1)) + 64;
         KFSP_TRY(ensure_scratch(need));
         char* p = d_scratch;
-        d_thr = (double*)p;
-        double* d_bsum = d_thr + DROP_BUCKETS;
-        unsigned long long* d_cnt = (unsigned long long*)(d_bsum + DROP_BUCKETS + 2);
-        p += align_up(sizeof(double) * (2 * DROP_BUCKETS + 8));
+        unsigned long long* d_cnt = (unsigned long long*)p; p += 256;
         int32_t* drop = (int32_t*)p; p += a_i;
         int32_t* keep = (int32_t*)p; p += a_i;
         int32_t* pos = (int32_t*)p; p += a_i;
@@ -642,6 +636,18 @@ struct Engine {
     // ---------------------------------------------------------------- Arnoldi / IOP-2 sweep
     // columns J = jold..m (1-based) then the extra product (KrylovSolver.f90:236-266). No host sync.
     int arnoldi(int jold, int m) {
+        // small state spaces: the whole sweep in one single-CTA launch (bit-identical, see k_sweep_small)
+        if (dist.nranks == 1 && !profile_spmv && small_sweep && n * (int64_t)(12 * R + 88) <= (1 << 20)) {
+            void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, double*, double*, int, int, int, SweepCtl*, double);
+            switch (R) {
+            case 4: kern = k_sweep_small<4>; break;
+            case 6: kern = k_sweep_small<6>; break;
+            case 10: kern = k_sweep_small<10>; break;
+            default: kern = k_sweep_small<0>; break;
+            }
+            kern<<<1, SWEEP_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, d_V, d_H, LDH, jold, m, d_ctl, opt.break_tol);
+            return check_launch();
+        }
         for (int J = jold; J <= m; ++J) {
             const double* vj = d_V + (size_t)(J - 1) * ld;      // column J-1 (0-based), scale colscale[J-1]
             double* vn = d_V + (size_t)J * ld;                   // column J receives w, then stays un-normalised
@@ -667,12 +673,20 @@ struct Engine {
         KFSP_LAUNCH(k_expm, 1, EXPM_THREADS, EXPM_SMEM, d_H, LDH, mx_ok, t_ok, use_brk, t_brk, set_one, (const SweepCtl*)d_ctl,
                     d_expm_work, d_res, (double*)nullptr);
         KFSP_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(ExpmResult), cudaMemcpyDeviceToHost, stream));
-        KFSP_TRY(sync());
+        KFSP_TRY(dist.nranks > 1 ? sync_check_peers() : sync());
         return h_res->info;
     }
     int read_ctl() {
         KFSP_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(SweepCtl), cudaMemcpyDeviceToHost, stream));
-        return sync();
+        return dist.nranks > 1 ? sync_check_peers() : sync();
+    }
+    // multi-GPU: a peer that never delivered its partial (crashed rank) sets bit 32 after a 4 s spin; abort the
+    // solve on the surviving ranks instead of spinning through every remaining reduction
+    int sync_check_peers() {
+        int32_t e = 0;
+        KFSP_CUDA(cudaMemcpyAsync(&e, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        KFSP_TRY(sync());
+        return (e & 32) ? KFSP_ERR_NCCL : KFSP_OK;
     }
 
     // ---------------------------------------------------------------- multi-GPU (dist.cuh)

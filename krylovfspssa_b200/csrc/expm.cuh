@@ -30,7 +30,6 @@ struct ExpmResult {
     double hnorm;               // |t| * ||H||_inf (DGPADMnorm's extra output, dgpadm.f:253)
     double avnorm;              // copy of the sweep's ||A v_{m+1}||
     double t_used;
-    double wsum, wssq;          // copies of ctl scalars (filled by the combine readback)
     double e[EXPM_MAXN];        // first column of exp(t*H)
 };
 

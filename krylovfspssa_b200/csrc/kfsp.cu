@@ -153,7 +153,7 @@ const char* kfsp_status_string(int s) {
     case KFSP_ERR_IO: return "cannot open file";
     case KFSP_ERR_UNSUPPORTED: return "not supported by the device path";
     case KFSP_ERR_OUT_TOO_SMALL: return "output buffers too small";
-    case KFSP_ERR_NCCL: return "NCCL error";
+    case KFSP_ERR_NCCL: return "multi-GPU exchange failed (NCCL error or a peer stopped responding)";
     case KFSP_ERR_SSA_RUNAWAY: return "SSA trajectory exceeded the jump limit";
     }
     return "unknown status";

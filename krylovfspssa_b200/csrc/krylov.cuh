@@ -409,6 +409,115 @@ __global__ void __launch_bounds__(VEC_THREADS) k_sum_below(int64_t n, const doub
     if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_SUM_BELOW, tot, ctl, nullptr, 0.0, 0);
 }
 
+// ---------------------------------------------------------------------------------------
+// Whole Arnoldi/IOP-2 sweep in ONE launch for small state spaces (N of a few thousand: BASELINE configs 1-2).
+// At that size a column is ~10 KB of traffic and three kernel launches of pure latency; here one CTA walks
+// through columns jold..m and the extra product, with __syncthreads between the phases instead of kernel
+// boundaries.  Every element sees exactly the operations of k_spmv / k_axpy_dot / k_axpy_nrm, and the
+// reductions are the same double-double sums, so H, the basis and the breakdown flag are bit-identical.
+// ---------------------------------------------------------------------------------------
+constexpr int SWEEP_THREADS = 1024;
+__device__ __forceinline__ double cta_dd_total(DD v, DD* sh, double* bc) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        DD z; z.hi = 0.0; z.lo = 0.0;
+        v = lane < (SWEEP_THREADS >> 5) ? sh[lane] : z;
+        v = warp_sum(v);
+        if (lane == 0) *bc = __dadd_rn(v.hi, v.lo);
+    }
+    __syncthreads();
+    return *bc;
+}
+template <int RT>
+__device__ __forceinline__ double spmv_row(int64_t i, int64_t ld, int R, const int32_t* __restrict__ pred, const double* __restrict__ coef,
+                                           const double* __restrict__ diag, const double* x, double xs) {
+    double sv = -__dmul_rn(diag[i], __dmul_rn(xs, x[i]));
+#pragma unroll
+    for (int k = 0; k < (RT > 0 ? RT : R); ++k) {
+        const int32_t j = pred[(int64_t)k * ld + i];
+        const double a = coef[(int64_t)k * ld + i];
+        if (j >= 0) sv = fma(a, __dmul_rn(xs, x[j]), sv);
+    }
+    return sv;
+}
+template <int RT>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
+                                                                   const double* __restrict__ coef, const double* __restrict__ diag,
+                                                                   double* V, double* H, int ldh, int jold, int m, SweepCtl* ctl,
+                                                                   double break_tol) {
+    __shared__ DD sh[32];
+    __shared__ double bc;
+    __shared__ double cs[MAX_COLS];
+    __shared__ int s_brk;
+    const int R = RT > 0 ? RT : R_rt;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < MAX_COLS; j += SWEEP_THREADS) cs[j] = ctl->colscale[j];
+    if (tid == 0) s_brk = ctl->brk;
+    __syncthreads();
+    if (s_brk != 0) return;
+    for (int J = jold; J <= m; ++J) {
+        const double* x = V + (size_t)(J - 1) * ld;
+        double* y = V + (size_t)J * ld;
+        const double xs = cs[J - 1];
+        const double* first = J >= 2 ? V + (size_t)(J - 2) * ld : x;
+        const double fs = J >= 2 ? cs[J - 2] : xs;
+        double* hcol = H + (size_t)(J - 1) * ldh;
+        // FMATVEC + first DDOT of the IOP window
+        DD acc; acc.hi = 0.0; acc.lo = 0.0;
+        for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
+            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x, xs);
+            y[i] = sv;
+            dd_add_prod(acc, __dmul_rn(fs, first[i]), sv);
+        }
+        const double h1 = cta_dd_total(acc, sh, &bc);
+        double h = h1;
+        if (J >= 2) {
+            if (tid == 0) hcol[J - 2] = h1;                                  // H(J-1,J)
+            acc.hi = 0.0; acc.lo = 0.0;
+            for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
+                const double ai = __dmul_rn(fs, first[i]), bi = __dmul_rn(xs, x[i]);
+                const double wi = fma(-h1, ai, y[i]);
+                y[i] = wi;
+                dd_add_prod(acc, bi, wi);
+            }
+            h = cta_dd_total(acc, sh, &bc);
+        }
+        if (tid == 0) hcol[J - 1] = h;                                       // H(J,J)
+        acc.hi = 0.0; acc.lo = 0.0;
+        for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
+            const double wi = fma(-h, __dmul_rn(xs, x[i]), y[i]);
+            y[i] = wi;
+            dd_add_prod(acc, wi, wi);
+        }
+        const double hn = sqrt(cta_dd_total(acc, sh, &bc));
+        if (hn <= break_tol) {                                               // happy breakdown: uniform over the CTA
+            if (tid == 0) { ctl->scal[SC_HN] = hn; ctl->brk = J; }
+            s_brk = J;
+            break;
+        }
+        if (tid == 0) { hcol[J] = hn; cs[J] = 1.0 / hn; }                    // H(J+1,J), DSCAL factor
+        __syncthreads();
+    }
+    if (s_brk == 0) {
+        const double* x = V + (size_t)m * ld;
+        double* y = V + (size_t)(m + 1) * ld;
+        const double xs = cs[m];
+        DD acc; acc.hi = 0.0; acc.lo = 0.0;
+        for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
+            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x, xs);
+            y[i] = sv;
+            dd_add_prod(acc, sv, sv);
+        }
+        const double av = sqrt(cta_dd_total(acc, sh, &bc));
+        if (tid == 0) ctl->scal[SC_AVNORM] = av;
+    }
+    __syncthreads();
+    for (int j = tid; j < MAX_COLS; j += SWEEP_THREADS) ctl->colscale[j] = cs[j];
+}
+
 // Cross-GPU barrier over peer memory (one warp): every rank raises its flag on every peer and waits for all
 // of them.  Needed where a kernel without a reduction (k_scale_copy writing basis column 0) is followed by a
 // SpMV that gathers that column from the neighbours' HBM.

@@ -414,25 +414,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int32_t* __re
 // ---------------------------------------------------------------------------------------
 // DROP_STATES pieces (StateSpace.f90:398-548)
 // ---------------------------------------------------------------------------------------
-constexpr int DROP_BUCKETS = 64;
-// bucket b collects W_i with exactly b thresholds above it (thr[0] > thr[1] > ...): sum1 for
-// threshold k is the sum of buckets > k.  FIND_DROPTOL sums W_i with 0 < W_i < DROPTOL.
-__global__ void k_drop_histogram(const double* __restrict__ w, int64_t n, const double* __restrict__ thr, int nthr, double* bucket_sums) {
-    __shared__ double sh[DROP_BUCKETS + 1];
-    for (int b = threadIdx.x; b <= DROP_BUCKETS; b += blockDim.x) sh[b] = 0.0;
-    __syncthreads();
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double x = w[i];
-        if (x > 0.0 && x < thr[0]) {
-            int b = 1;
-            while (b < nthr && x < thr[b]) ++b;
-            atomicAdd(&sh[b], x);
-        }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b <= DROP_BUCKETS; b += blockDim.x)
-        if (sh[b] != 0.0) atomicAdd(&bucket_sums[b], sh[b]);
-}
 // DROP(I) = W(I) < DROPTOL; count (StateSpace.f90:475-484)
 __global__ void k_drop_mark(const double* __restrict__ w, int64_t n, double droptol, int32_t* drop, unsigned long long* count) {
     unsigned long long c = 0;
