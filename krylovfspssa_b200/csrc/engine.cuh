@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -31,6 +32,13 @@ struct Engine {
     double* d_tables = nullptr;       // host-built propensity tables
     int n_tabulated = 0, n_inexact_on_device = 0;
     int S = 0, R = 0;
+    // host-evaluated propensities: CUSTOMPROP callbacks (ModelModule.f90:6-12,188-190), or byte code evaluated
+    // by the host libm when a multi-species program holds a transcendental operation (KFSP_HOST_PROP=1)
+    bool host_prop = false;
+    HostModel hm;                     // copy of the host model (callback, parameters, programs)
+    PropCache pc;                     // device side cache used by SSA walks in host_prop mode
+    int64_t pc_n = 0;                 // cached states
+    int64_t host_prop_evals = 0, host_prop_rounds = 0;
 
     // state space
     int64_t ld = 0;                   // capacity in states (multiple of 64)
@@ -123,6 +131,7 @@ struct Engine {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         free_state_space();
+        free_prop_cache();
         cudaFree(d_model); cudaFree(d_tables); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
         cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush);
         if (h_res) cudaFreeHost(h_res);
@@ -194,8 +203,8 @@ struct Engine {
     int set_model(const HostModel& m) {
         if (m.S < 1 || m.S > KFSP_MAX_SPECIES || m.R < 1 || m.R > KFSP_MAX_REACTIONS || m.P > KFSP_MAX_PARAMS || m.P < 0)
             return KFSP_ERR_UNSUPPORTED;
-        if (m.custom) return KFSP_ERR_UNSUPPORTED;     // host callbacks cannot run on the device ("next")
         KFSP_CUDA(cudaSetDevice(device));
+        if (m.custom) return set_model_hostprop(m);
         DeviceModel dm;
         std::memset(&dm, 0, sizeof dm);
         dm.S = m.S; dm.R = m.R; dm.P = m.P; dm.max_molecules = opt.max_molecules;
@@ -257,8 +266,143 @@ struct Engine {
         const bool reshape = !have_model || m.S != S || m.R != R;
         S = m.S; R = m.R;
         have_model = true;
+        host_prop = false;
+        free_prop_cache();
         if (reshape) { free_state_space(); }
         n = 0;
+        return KFSP_OK;
+    }
+
+    // CUSTOMPROP: the propensity is an opaque host function.  Sizes, stoichiometry and parameters go to the
+    // device; a_k(x) is evaluated on the host in batches (propensities_host) and, inside SSA walks, served
+    // from the device side cache (fsp_ssa_hostprop).
+    int set_model_hostprop(const HostModel& m) {
+        if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;       // partitioned rows are built from device byte code
+        DeviceModel dm;
+        std::memset(&dm, 0, sizeof dm);
+        dm.S = m.S; dm.R = m.R; dm.P = m.P; dm.max_molecules = opt.max_molecules;
+        for (int k = 0; k < m.R; ++k)
+            for (int s = 0; s < m.S; ++s) dm.stoich[k * m.S + s] = m.stoich[(size_t)k * m.S + s];
+        for (int i = 0; i < m.P; ++i) dm.params[i] = m.params[i];
+        for (int k = 0; k < m.R; ++k) { dm.table_species[k] = -1; dm.table[k] = nullptr; }
+        n_tabulated = 0; n_inexact_on_device = 0;
+        KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        const bool reshape = !have_model || m.S != S || m.R != R;
+        S = m.S; R = m.R;
+        have_model = true;
+        host_prop = true;
+        hm = m;
+        free_prop_cache();
+        if (reshape) { free_state_space(); }
+        n = 0;
+        return KFSP_OK;
+    }
+
+    // ---------------------------------------------------------------- host-evaluated propensities
+    void free_prop_cache() {
+        cudaFree(pc.states); cudaFree(pc.table); cudaFree(pc.prop); cudaFree(pc.diag); cudaFree(pc.req); cudaFree(pc.nreq);
+        pc = PropCache();
+        pc_n = 0;
+    }
+    // capacity for `want` cached states (contents are preserved) and a request list of req_cap states
+    int ensure_prop_cache(int64_t want) {
+        if (pc.table && want <= pc.ld) return KFSP_OK;
+        int64_t cap = std::max<int64_t>(1 << 14, pc.ld);
+        while (cap < want) cap <<= 1;
+        PropCache q;
+        q.ld = cap;
+        int64_t ts = 1024;
+        while (ts < 2 * cap) ts <<= 1;
+        q.mask = (uint32_t)(ts - 1);
+        q.req_cap = 1 << 16;
+        KFSP_CUDA(cudaMalloc(&q.states, sizeof(int32_t) * cap * S));
+        KFSP_CUDA(cudaMalloc(&q.table, sizeof(int32_t) * ts));
+        KFSP_CUDA(cudaMalloc(&q.prop, sizeof(double) * cap * R));
+        KFSP_CUDA(cudaMalloc(&q.diag, sizeof(double) * cap));
+        KFSP_CUDA(cudaMalloc(&q.req, sizeof(int32_t) * (size_t)q.req_cap * S));
+        KFSP_CUDA(cudaMalloc(&q.nreq, sizeof(int32_t)));
+        KFSP_CUDA(cudaMemsetAsync(q.table, 0xFF, sizeof(int32_t) * ts, stream));
+        KFSP_CUDA(cudaMemsetAsync(q.nreq, 0, sizeof(int32_t), stream));
+        if (pc_n > 0) {
+            KFSP_CUDA(cudaMemcpyAsync(q.states, pc.states, sizeof(int32_t) * pc_n * S, cudaMemcpyDeviceToDevice, stream));
+            KFSP_CUDA(cudaMemcpyAsync(q.diag, pc.diag, sizeof(double) * pc_n, cudaMemcpyDeviceToDevice, stream));
+            for (int k = 0; k < R; ++k)
+                KFSP_CUDA(cudaMemcpyAsync(q.prop + (int64_t)k * cap, pc.prop + (int64_t)k * pc.ld, sizeof(double) * pc_n,
+                                          cudaMemcpyDeviceToDevice, stream));
+            KFSP_LAUNCH(k_cache_insert, grid_for(pc_n), VEC_THREADS, 0, q, S, (int64_t)0, pc_n, d_err);
+        }
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        const int64_t keep = pc_n;
+        free_prop_cache();
+        pc = q;
+        pc_n = keep;
+        return KFSP_OK;
+    }
+    int clear_prop_cache() {
+        if (!pc.table) return KFSP_OK;
+        KFSP_CUDA(cudaMemsetAsync(pc.table, 0xFF, sizeof(int32_t) * ((size_t)pc.mask + 1), stream));
+        pc_n = 0;
+        return KFSP_OK;
+    }
+    // R propensities + their sum (reaction order, StateSpace.f90:207-212) of `cnt` states: out[t*(R+1) + k]
+    void eval_host(const int32_t* st, int64_t cnt, double* out) {
+        const double t0 = wall_now();
+        for (int64_t t = 0; t < cnt; ++t) {
+            double d = 0.0;
+            for (int k = 0; k < R; ++k) {
+                const double a = hm.propensity(st + t * S, k + 1);
+                out[t * (R + 1) + k] = a;
+                d = d + a;
+            }
+            out[t * (R + 1) + R] = d;
+        }
+        host_prop_evals += cnt * R;
+        phase_s[5] += wall_now() - t0;
+    }
+    // OFFDIAG/DIAG of states [first, first+count): from the side cache where the SSA walks already paid for
+    // them, by the host function for the rest.
+    int propensities_host(int64_t first, int64_t count) {
+        if (count < 1) return KFSP_OK;
+        const size_t a_q = align_up(sizeof(int32_t) * count);
+        std::vector<int32_t> q((size_t)count, -1);
+        FspView f = view();
+        int32_t* d_q = nullptr;
+        KFSP_CUDA(cudaMalloc(&d_q, a_q));
+        if (pc.table && pc_n > 0) {
+            KFSP_LAUNCH(k_props_from_cache, grid_for(count), VEC_THREADS, 0, f, first, count, pc, d_q);
+            KFSP_CUDA(cudaMemcpyAsync(q.data(), d_q, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, stream));
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+        }
+        std::vector<int32_t> idx;
+        for (int64_t t = 0; t < count; ++t) if (q[t] < 0) idx.push_back((int32_t)(first + t));
+        if (!idx.empty()) {
+            std::vector<int32_t> st((size_t)count * S);
+            KFSP_CUDA(cudaMemcpyAsync(st.data(), d_states + first * S, sizeof(int32_t) * count * S, cudaMemcpyDeviceToHost, stream));
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+            std::vector<int32_t> pick(idx.size() * (size_t)S);
+            for (size_t t = 0; t < idx.size(); ++t)
+                std::memcpy(&pick[t * S], &st[(size_t)(idx[t] - first) * S], sizeof(int32_t) * S);
+            std::vector<double> vals(idx.size() * (size_t)(R + 1));
+            eval_host(pick.data(), (int64_t)idx.size(), vals.data());
+            int32_t* d_idx = nullptr;
+            double* d_vals = nullptr;
+            KFSP_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * idx.size()));
+            KFSP_CUDA(cudaMalloc(&d_vals, sizeof(double) * vals.size()));
+            KFSP_CUDA(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice, stream));
+            KFSP_CUDA(cudaMemcpyAsync(d_vals, vals.data(), sizeof(double) * vals.size(), cudaMemcpyHostToDevice, stream));
+            KFSP_LAUNCH(k_scatter_props, grid_for((int64_t)vals.size()), VEC_THREADS, 0, f, (const int32_t*)d_idx, (const double*)d_vals,
+                        (int64_t)idx.size());
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(d_idx); cudaFree(d_vals);
+        }
+        cudaFree(d_q);
+        return KFSP_OK;
+    }
+    int propensities(int64_t first, int64_t count) {
+        if (host_prop) return propensities_host(first, count);
+        FspView f = view();
+        KFSP_LAUNCH(k_propensities, grid_for(count), VEC_THREADS, 0, f, first, count);
         return KFSP_OK;
     }
 
@@ -362,7 +506,7 @@ struct Engine {
         KFSP_TRY(read_err(&e));
         if (e) { n = 0; return err_to_status(e); }
         KFSP_LAUNCH(k_insert_states, grid_for(count), VEC_THREADS, 0, f, (int64_t)0, count, d_err);
-        KFSP_LAUNCH(k_propensities, grid_for(count), VEC_THREADS, 0, f, (int64_t)0, count);
+        KFSP_TRY(propensities(0, count));
         KFSP_LAUNCH(k_reset_links, grid_for(count * R), VEC_THREADS, 0, f, (int64_t)0, count);
         KFSP_LAUNCH(k_resolve_links, grid_for(count * R), VEC_THREADS, 0, f);
         KFSP_TRY(read_err(&e));
@@ -399,7 +543,7 @@ struct Engine {
         const int64_t first = n;
         n += n_new;
         f = view();
-        KFSP_LAUNCH(k_propensities, grid_for(n_new), VEC_THREADS, 0, f, first, n_new);
+        KFSP_TRY(propensities(first, n_new));
         KFSP_LAUNCH(k_reset_links, grid_for(n_new * R), VEC_THREADS, 0, f, first, n_new);
         KFSP_LAUNCH(k_resolve_links, grid_for(n * R), VEC_THREADS, 0, f);
         return KFSP_OK;
@@ -412,7 +556,6 @@ struct Engine {
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         // scratch: cnt[n_old], off[n_old], tiles
-        const int64_t tiles0 = (n_old + SCAN_TILE - 1) / SCAN_TILE;
         size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * scan_buf_ints(n_old));
         KFSP_TRY(ensure_scratch(need0));
         int32_t* cnt = (int32_t*)d_scratch;
@@ -431,7 +574,6 @@ struct Engine {
     // scratch + align(n_old ints); candidates are generated after the offsets.
     int expand_with(int64_t ncand, int64_t n_old, bool ssa, double timestep) {
         const size_t a_n = align_up(sizeof(int32_t) * n_old);
-        const int64_t tiles = (ncand + SCAN_TILE - 1) / SCAN_TILE;
         const size_t a_c = align_up(sizeof(int32_t) * ncand);
         const size_t need = 2 * a_n + align_up(sizeof(int32_t) * ncand * S) + 3 * a_c + align_up(sizeof(int32_t) * scan_buf_ints(ncand));
         // growing the arena would lose off[]: save it first
@@ -453,7 +595,7 @@ struct Engine {
         FspView f = view();
         if (ssa) {
             KFSP_LAUNCH(k_ssa_walk<true>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
-                        (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand);
+                        (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand, host_prop ? pc : PropCache());
         } else {
             KFSP_LAUNCH(k_onestep_fill, grid_for(n_old), VEC_THREADS, 0, f, n_old, (const int32_t*)off, cand, d_err);
         }
@@ -476,15 +618,61 @@ struct Engine {
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         ssa_calls += 1;
-        const int64_t tiles0 = (n_old + SCAN_TILE - 1) / SCAN_TILE;
         size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * scan_buf_ints(n_old));
         KFSP_TRY(ensure_scratch(need0));
         int32_t* cnt = (int32_t*)d_scratch;
         int32_t* off = (int32_t*)(d_scratch + align_up(sizeof(int32_t) * n_old));
         int32_t* tb0 = (int32_t*)(d_scratch + 2 * align_up(sizeof(int32_t) * n_old));
         FspView f = view();
-        KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
-                    (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0);
+        if (host_prop) {
+            // Rounds: walks that step onto a state the host has not evaluated yet are suspended (cnt = -1) and
+            // replayed once the host has put a_k of the requested states into the side cache.
+            KFSP_TRY(ensure_prop_cache(1));
+            KFSP_TRY(clear_prop_cache());
+            KFSP_LAUNCH(k_fill_i32, grid_for(n_old), VEC_THREADS, 0, cnt, n_old, (int32_t)-1);
+            std::vector<int32_t> req;
+            std::vector<double> vals;
+            for (int64_t round = 0;; ++round) {
+                if (round > (1 << 24)) return KFSP_ERR_SSA_RUNAWAY;
+                KFSP_CUDA(cudaMemsetAsync(pc.nreq, 0, sizeof(int32_t), stream));
+                KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
+                            (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, pc);
+                int32_t nreq = 0;
+                KFSP_CUDA(cudaMemcpyAsync(&nreq, pc.nreq, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+                KFSP_CUDA(cudaStreamSynchronize(stream));
+                if (nreq == 0) break;
+                ++host_prop_rounds;
+                const int64_t got = std::min<int64_t>(nreq, pc.req_cap);
+                req.resize((size_t)got * S);
+                KFSP_CUDA(cudaMemcpyAsync(req.data(), pc.req, sizeof(int32_t) * got * S, cudaMemcpyDeviceToHost, stream));
+                KFSP_CUDA(cudaStreamSynchronize(stream));
+                // several walks may ask for the same state in one round
+                std::unordered_set<std::string> seen;
+                std::vector<int32_t> uniq;
+                for (int64_t t = 0; t < got; ++t) {
+                    std::string key((const char*)&req[(size_t)t * S], sizeof(int32_t) * S);
+                    if (seen.insert(std::move(key)).second) uniq.insert(uniq.end(), &req[(size_t)t * S], &req[(size_t)t * S] + S);
+                }
+                const int64_t nu = (int64_t)uniq.size() / S;
+                vals.resize((size_t)nu * (R + 1));
+                eval_host(uniq.data(), nu, vals.data());
+                KFSP_TRY(ensure_prop_cache(pc_n + nu));
+                // cache layout is reaction-major: transpose on the host
+                std::vector<double> col((size_t)nu);
+                KFSP_CUDA(cudaMemcpyAsync(pc.states + pc_n * S, uniq.data(), sizeof(int32_t) * nu * S, cudaMemcpyHostToDevice, stream));
+                for (int k = 0; k <= R; ++k) {
+                    for (int64_t t = 0; t < nu; ++t) col[t] = vals[(size_t)t * (R + 1) + k];
+                    double* dst = k < R ? pc.prop + (int64_t)k * pc.ld + pc_n : pc.diag + pc_n;
+                    KFSP_CUDA(cudaMemcpyAsync(dst, col.data(), sizeof(double) * nu, cudaMemcpyHostToDevice, stream));
+                    KFSP_CUDA(cudaStreamSynchronize(stream));
+                }
+                KFSP_LAUNCH(k_cache_insert, grid_for(nu), VEC_THREADS, 0, pc, S, pc_n, nu, d_err);
+                pc_n += nu;
+            }
+        } else {
+            KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
+                        (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, PropCache());
+        }
         int64_t ncand = 0;
         KFSP_TRY(exclusive_scan(cnt, off, n_old, tb0, &ncand));
         int32_t e = 0;
@@ -492,7 +680,9 @@ struct Engine {
         if (e) return err_to_status(e);
         if (ncand == 0) return KFSP_OK;
         if (ncand > 2000000000LL - n_old) return KFSP_ERR_OVERFLOW;
-        return expand_with(ncand, n_old, /*ssa=*/true, timestep);
+        const int st = expand_with(ncand, n_old, /*ssa=*/true, timestep);
+        if (host_prop) KFSP_TRY(clear_prop_cache());
+        return st;
     }
 
     // ---------------------------------------------------------------- FMATVEC
@@ -867,7 +1057,6 @@ struct Engine {
         if (e) { n = 0; return err_to_status(e); }
         // halo plan
         const size_t a_g = align_up(sizeof(int32_t) * n_global);
-        const int64_t tiles = (n_global + SCAN_TILE - 1) / SCAN_TILE;
         KFSP_TRY(ensure_scratch(2 * a_g + align_up(sizeof(int32_t) * scan_buf_ints(n_global)) + align_up(sizeof(int64_t) * 4 * (P + 2))));
         int32_t* flag = (int32_t*)d_scratch;
         int32_t* pos = (int32_t*)(d_scratch + a_g);

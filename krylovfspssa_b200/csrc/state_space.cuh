@@ -38,6 +38,24 @@ struct FspView {
 enum DevErr : int32_t { DEV_OK = 0, DEV_DUPLICATE = 1, DEV_BAD_STATE = 2, DEV_MOLECULE_LIMIT = 4, DEV_RUNAWAY = 8,
                         DEV_TABLE_FULL = 16 };
 
+// Host-evaluated propensities (CUSTOMPROP, src/model/ModelModule.f90:6-12,31,188-190): a host callback
+// cannot run inside a device SSA walk, so the walk reads a_k of states that are not yet in the projection
+// from this side cache (state -> R propensities + their sum).  A state missing from the cache is appended to
+// the request list and the walk is suspended; the host evaluates the requests, inserts them, and the
+// suspended walks are replayed from their own Philox sub-stream (Engine::fsp_ssa_hostprop).
+// table == nullptr: propensities are evaluated on the device (byte code / tables).
+struct PropCache {
+    int32_t* states = nullptr;  // [q*S + s]
+    int32_t* table = nullptr;   // open addressing, value = q or SLOT_EMPTY
+    uint32_t mask = 0;
+    int64_t ld = 0;             // capacity in cached states
+    double* prop = nullptr;     // [k*ld + q]
+    double* diag = nullptr;     // [q]
+    int32_t* req = nullptr;     // request list [r*S + s]
+    int32_t* nreq = nullptr;    // number of requests made (may exceed req_cap; the excess is re-requested)
+    int32_t req_cap = 0;
+};
+
 // ---------------------------------------------------------------------------------------
 // propensity interpreter: the stack machine of src/parser/FortranParser.f90:187-302
 // ---------------------------------------------------------------------------------------
@@ -105,6 +123,17 @@ __device__ __forceinline__ int32_t table_lookup(const FspView& f, const int32_t*
         if (v == SLOT_EMPTY) return IDX_ABSENT;
         if (same_state(f.states + (int64_t)v * f.S, st, f.S)) return v;
         slot = (slot + 1) & f.mask;
+    }
+    return IDX_ABSENT;
+}
+
+__device__ __forceinline__ int32_t cache_lookup(const PropCache& pc, const int32_t* st, int S) {
+    uint32_t slot = (uint32_t)hash_state(st, S) & pc.mask;
+    for (uint32_t probes = 0; probes <= pc.mask; ++probes) {
+        const int32_t v = pc.table[slot];
+        if (v == SLOT_EMPTY) return IDX_ABSENT;
+        if (same_state(pc.states + (int64_t)v * S, st, S)) return v;
+        slot = (slot + 1) & pc.mask;
     }
     return IDX_ABSENT;
 }
@@ -233,10 +262,12 @@ __global__ void k_onestep_fill(FspView f, int64_t n_old, const int32_t* __restri
 template <bool FILL>
 __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t seed, uint32_t call_no,
                            int32_t* cnt, const int32_t* __restrict__ off, int32_t* cand, int32_t* err, int32_t max_jumps,
-                           int64_t ncand) {
+                           int64_t ncand, PropCache pc) {
     const DeviceModel* __restrict__ m = f.model;
     const int S = f.S, R = f.R;
     for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j0 < n_old; j0 += (int64_t)gridDim.x * blockDim.x) {
+        if (!FILL && pc.table && cnt[j0] >= 0) continue;     // host-propensity rounds: this walk already completed
+        bool suspended = false;
         if (FILL) {
             // replay only the walks that left the projection in the counting pass (a small boundary fraction)
             const int64_t end = j0 + 1 < n_old ? (int64_t)off[j0 + 1] : ncand;
@@ -259,6 +290,18 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
             if (j >= 0) {
                 dg = f.diag[j];
                 for (int k = 0; k < R; ++k) pr[k] = f.prop[(int64_t)k * f.ld + j];
+            } else if (pc.table) {
+                const int32_t q = cache_lookup(pc, st, S);
+                if (q < 0) {
+                    // unknown to the host cache: request it and suspend (the FILL pass never gets here)
+                    const int32_t r = atomicAdd(pc.nreq, 1);
+                    if (r < pc.req_cap)
+                        for (int s = 0; s < S; ++s) pc.req[(int64_t)r * S + s] = st[s];
+                    suspended = true;
+                    break;
+                }
+                dg = pc.diag[q];
+                for (int k = 0; k < R; ++k) pr[k] = pc.prop[(int64_t)k * pc.ld + q];
             } else {
                 dg = 0.0;
                 for (int k = 0; k < R; ++k) { pr[k] = eval_propensity(m, k, st); dg = __dadd_rn(dg, pr[k]); }
@@ -296,7 +339,46 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
                 if (!(t < timestep)) break;
             }
         }
-        if (!FILL) cnt[j0] = emitted;
+        if (!FILL) cnt[j0] = suspended ? -1 : emitted;
+    }
+}
+
+// Host-propensity mode: OFFDIAG/DIAG of the new states [first, first+count) from the side cache;
+// cache_q[t] = cache entry used, or -1 (the host evaluates those and scatters them with k_scatter_props).
+__global__ void k_props_from_cache(FspView f, int64_t first, int64_t count, PropCache pc, int32_t* cache_q) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = first + t;
+        int32_t st[KFSP_MAX_SPECIES];
+        for (int s = 0; s < f.S; ++s) st[s] = f.states[i * f.S + s];
+        const int32_t q = pc.table ? cache_lookup(pc, st, f.S) : IDX_ABSENT;
+        cache_q[t] = q;
+        if (q < 0) continue;
+        for (int k = 0; k < f.R; ++k) f.prop[(int64_t)k * f.ld + i] = pc.prop[(int64_t)k * pc.ld + q];
+        f.diag[i] = pc.diag[q];
+    }
+}
+// vals[t*(R+1) + k] = a_k of state idx[t] (k < R), vals[t*(R+1) + R] = their sum in reaction order
+__global__ void k_scatter_props(FspView f, const int32_t* __restrict__ idx, const double* __restrict__ vals, int64_t count) {
+    const int64_t total = count * (f.R + 1);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = t / (f.R + 1);
+        const int k = (int)(t % (f.R + 1));
+        const int64_t i = idx[c];
+        if (k < f.R) f.prop[(int64_t)k * f.ld + i] = vals[t];
+        else f.diag[i] = vals[t];
+    }
+}
+// cache entries [first, first+count): states already stored in pc.states; no duplicates (the host dedupes)
+__global__ void k_cache_insert(PropCache pc, int S, int64_t first, int64_t count, int32_t* err) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = first + t;
+        uint32_t slot = (uint32_t)hash_state(pc.states + q * S, S) & pc.mask;
+        uint32_t probes = 0;
+        for (;;) {
+            if (atomicCAS(&pc.table[slot], SLOT_EMPTY, (int32_t)q) == SLOT_EMPTY) break;
+            slot = (slot + 1) & pc.mask;
+            if (++probes > pc.mask) { atomicOr(err, DEV_TABLE_FULL); break; }
+        }
     }
 }
 

@@ -112,7 +112,13 @@ class CME_MODEL:
         return code[:nc.value].tolist(), imm[:ni.value].tolist()
 
     def set_customprop(self, fn):
-        """MODEL%CUSTOMPROP => fn(state, reaction, parameters)  (ModelModule.f90:6-12, 31)."""
+        """MODEL%CUSTOMPROP => fn(state, reaction, parameters)  (ModelModule.f90:6-12, 31).
+        `fn` is a Python callable, or a compiled host function given as a ctypes function pointer."""
+        if isinstance(fn, C._CFuncPtr):
+            self._cb = C.cast(fn, _lib.PROPENSITY_FN)
+            self.customprop = fn
+            check(lib().kfsp_model_set_custom_propensity(self._h, self._cb, None))
+            return
         s = self._dims()[0]
         p = max(self._dims()[2], 1)
 

@@ -1,4 +1,4 @@
-"""Full-horizon runs of BASELINE configs 1-3 on the CPU oracle (canonical arithmetic): too large to
+"""Full-horizon runs of BASELINE configs 1-4 (and the other two example drivers) on the CPU oracle (canonical arithmetic): too large to
 commit as arrays, so tests/golden/full_digests.json keeps sizes, counters and SHA-256 digests of the
 state list, the decision trace and the probability vector.  The GPU test (tests/test_gpu_full_configs.py)
 must reproduce the digests, i.e. be bit-identical at full scale.
@@ -25,6 +25,8 @@ FULL_RUNS = {
     "repressilator_full": ("repressilator", 10.0, 1e-4, 1e-10),
     "goutsias_full": ("goutsias", 300.0, 1e-6, 1e-8),
 }
+# the reference's example programs with their hard-coded CUSTOMPROP (config 4 = transcr6d): tag -> driver name
+DRIVER_RUNS = {"driver_toggle_full": "toggle", "driver_repressilator_full": "repressilator", "transcr6d_full": "transcr6d"}
 STAT_KEYS = ("nmult", "nexph", "nscale", "nstep", "nreject", "ibrkflag", "mbrkdwn", "n_expand", "n_drop")
 
 
@@ -39,11 +41,18 @@ def digest(out_states, out_vector, trace_i, trace_d, stats):
 def main():
     path = os.path.join(HERE, "full_digests.json")
     db = json.load(open(path)) if os.path.exists(path) else {}
-    tags = sys.argv[1:] or list(FULL_RUNS)
+    tags = sys.argv[1:] or list(FULL_RUNS) + list(DRIVER_RUNS)
     for tag in tags:
-        name, t, ftol, ktol = FULL_RUNS[tag]
-        fname, params, x0 = CASES[name]
-        m = oracle.Model.load(os.path.join(ROOT, "krylovfspssa_b200", "models", fname), params)
+        if tag in DRIVER_RUNS:
+            from krylovfspssa_b200.examples import DRIVERS
+            dr = DRIVERS[DRIVER_RUNS[tag]]
+            m = oracle.Model(dr["S"], dr["R"], dr["P"], dr["stoich"], dr["params"])
+            m.set_custom(dr["oracle_kind"])
+            x0, t, ftol, ktol = dr["x0"], dr["t"], dr["fsp_tol"], dr["exp_tol"]
+        else:
+            name, t, ftol, ktol = FULL_RUNS[tag]
+            fname, params, x0 = CASES[name]
+            m = oracle.Model.load(os.path.join(ROOT, "krylovfspssa_b200", "models", fname), params)
         t0 = time.time()
         out = oracle.solve(m, [x0], [1.0], t, ftol, ktol, seed=12345, reproducible=1)
         assert out["iflag"] == 0

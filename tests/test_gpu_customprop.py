@@ -1,0 +1,85 @@
+"""CUSTOMPROP on the device path (BASELINE config 4: examples/transcr6d.f90, and the other two example
+drivers): the propensity is an opaque HOST function, evaluated in batches for MATRIX_STARTER /
+ONESTEP_EXTENDER and served to the device SSA walks from a side cache filled in rounds.  Decision
+trace, state list and probability vector must be bit-identical to the CPU oracle, which uses its own
+restatement of the same Fortran functions."""
+import numpy as np
+import pytest
+
+import krylovfspssa_b200 as k
+import oracle
+from krylovfspssa_b200 import examples
+
+pytestmark = pytest.mark.gpu
+
+# shortened horizons (the oracle must finish in seconds); full horizons: test_gpu_full_configs.py
+SHORT_T = {"toggle": 10.0, "repressilator": 2.0, "transcr6d": 100.0}
+
+
+def oracle_model(name):
+    d = examples.DRIVERS[name]
+    om = oracle.Model(d["S"], d["R"], d["P"], d["stoich"], d["params"])
+    om.set_custom(d["oracle_kind"])
+    return om
+
+
+@pytest.mark.parametrize("name", sorted(examples.DRIVERS))
+def test_fsp_routines_with_host_callback(name):
+    d = examples.DRIVERS[name]
+    h = k.KrylovFspHandle(examples.driver_model(name), max_states=400000, seed=777)
+    f = oracle.Fsp(oracle_model(name), max_size=400000, reproducible=1)
+    h.fsp_init([d["x0"]])
+    f.set_states([d["x0"]])
+    f.matrix_starter()
+    rng = oracle.Rng(1, 777)
+    for it in range(4):
+        h.onestep()
+        f.onestep()
+    for it in range(3):
+        ts = 0.05 * (it + 1) if name != "transcr6d" else 2.0 * (it + 1)
+        h.ssa(ts)
+        f.ssa(ts, rng)
+        h.onestep()
+        f.onestep()
+        a, b = h.get(), f.get()
+        assert h.size == f.size and h.size > 50
+        for key in ("states", "adj", "offdiag", "diag"):
+            assert np.array_equal(a[key], b[key]), (name, it, key)
+    h.close()
+
+
+@pytest.mark.parametrize("name", sorted(examples.DRIVERS))
+def test_solve_with_host_callback_bit_identical(name):
+    d = examples.DRIVERS[name]
+    t = SHORT_T[name]
+    h = k.KrylovFspHandle(examples.driver_model(name), max_states=2000000, seed=12345)
+    out = h.solve(t, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
+    ref = oracle.solve(oracle_model(name), [d["x0"]], [1.0], t, d["fsp_tol"], d["exp_tol"], seed=12345,
+                       max_size=2000000, reproducible=1)
+    assert out["iflag"] == 0 and ref["iflag"] == 0
+    assert np.array_equal(out["trace"]["i"], ref["trace_i"])                 # decision trace
+    assert np.array_equal(out["trace"]["d"][:, 1], ref["trace_d"][:, 1])     # step sizes
+    assert np.array_equal(out["states"], ref["states"])                      # state set and indices bit-exact
+    err = np.abs(out["vector"] - ref["vector"]).sum() / np.abs(ref["vector"]).sum()
+    assert err <= 1e-10, err                                                 # north-star tolerance
+    assert np.array_equal(out["vector"], ref["vector"])                      # in fact bit-identical
+    assert out["stats"]["n_expand"] == ref["stats"]["n_expand"]
+    h.close()
+
+
+def test_cme_solve_driver_program():
+    """examples/toggle.f90 as a program: CREATE, CUSTOMPROP =>, FSP%CREATE, CME_SOLVE."""
+    d = examples.DRIVERS["toggle"]
+    model = examples.driver_model("toggle")
+    fsp_in, fsp = k.FINITE_STATE_PROJECTION(), k.FINITE_STATE_PROJECTION()
+    fsp_in.create(model, 400000)
+    fsp.create(model, 400000)
+    fsp_in.set([d["x0"]], [1.0])
+    fsp.set([d["x0"]], [1.0])
+    k.CME_SOLVE(model, 5.0, fsp_in, fsp, d["fsp_tol"], d["exp_tol"], verbosity=0)
+    w = fsp.vector[:fsp.size]
+    assert (w >= 0).all() and 1.0 - d["fsp_tol"] <= w.sum() <= 1.0 + 1e-12
+    top = int(np.argmax(w))
+    assert fsp.index(fsp.state[:, top]) == top + 1                           # FSP%INDEX is 1-based
+    assert fsp.probability(fsp.state[:, top]) == w[top]
+    assert fsp.index([9999, 9999]) == 0

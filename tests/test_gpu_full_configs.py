@@ -1,4 +1,4 @@
-"""BASELINE configs 1-3 at their full horizons on the GPU, against SHA-256 digests of the CPU oracle's
+"""BASELINE configs 1-4 (and the other example drivers, CUSTOMPROP host callbacks) at their full horizons on the GPU, against SHA-256 digests of the CPU oracle's
 canonical-arithmetic outputs (tests/golden/full_digests.json, made by tests/golden/make_full_digests.py):
 state list, decision trace and probability vector must be bit-identical at full scale."""
 import hashlib
@@ -17,6 +17,9 @@ FULL_RUNS = {
     "repressilator_full": ("repressilator", 10.0, 1e-4, 1e-10, 2000000),
     "goutsias_full": ("goutsias", 300.0, 1e-6, 1e-8, 6291469),
 }
+# the reference's example programs (hard-coded CUSTOMPROP): tag -> (driver, max_states); config 4 = transcr6d
+DRIVER_RUNS = {"driver_toggle_full": ("toggle", 400000), "driver_repressilator_full": ("repressilator", 2000000),
+               "transcr6d_full": ("transcr6d", 6291469)}
 STAT_KEYS = ("nmult", "nexph", "nscale", "nstep", "nreject", "ibrkflag", "mbrkdwn", "n_expand", "n_drop")
 
 
@@ -24,15 +27,23 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("tag", sorted(FULL_RUNS))
+@pytest.mark.parametrize("tag", sorted(FULL_RUNS) + sorted(DRIVER_RUNS))
 def test_full_config_bit_identical(tag):
     path = os.path.join(HERE, "golden", "full_digests.json")
     db = json.load(open(path)) if os.path.exists(path) else {}
     if tag not in db:
         pytest.skip("no digest committed for " + tag)
     g = db[tag]
-    name, t, ftol, ktol, cap = FULL_RUNS[tag]
-    h, _, x0 = make(name, max_states=cap, seed=12345)
+    if tag in DRIVER_RUNS:
+        import krylovfspssa_b200 as k
+        from krylovfspssa_b200 import examples
+        name, cap = DRIVER_RUNS[tag]
+        d = examples.DRIVERS[name]
+        x0, t, ftol, ktol = d["x0"], d["t"], d["fsp_tol"], d["exp_tol"]
+        h = k.KrylovFspHandle(examples.driver_model(name), max_states=cap, seed=12345)
+    else:
+        name, t, ftol, ktol, cap = FULL_RUNS[tag]
+        h, _, x0 = make(name, max_states=cap, seed=12345)
     out = h.solve(t, [x0], [1.0], ftol, ktol)
     st = out["stats"]
     print("%s: N=%d steps=%d nmult=%d device %.2f s (oracle %.1f s on one CPU core)" %
