@@ -36,8 +36,12 @@ PARAMS = [5000.0, 1600.0, 1.0, 1.0]
 METRIC = "expv_generator_state_updates_per_s"
 UNIT = "state-updates/s"
 R_TOGGLE = 4
-BYTES_PER_STATE = 12 * R_TOGGLE + 24          # explicit ELL SpMV, SURVEY.md 8d
-TRAFFIC_PER_STATE = 80.9                      # measured DRAM bytes per state of the dot-fused SpMV (ncu, profiles/)
+# algorithmic bytes per state of one generator SpMV and measured DRAM traffic per state of the
+# dot-fused launch (ncu --set full, profiles/), per SpMV variant: 0 explicit gather-ELL, 1 matrix-free lattice
+BYTES_PER_STATE = {0: 12 * R_TOGGLE + 24, 1: 16}
+TRAFFIC_PER_STATE = {0: 80.9, 1: None}
+KERNEL_NAME = {0: "k_spmv (generator SpMV, explicit gather ELL; per GPU, rank 0)",
+               1: "k_spmv_box (generator SpMV, matrix-free on the lattice; per GPU, rank 0)"}
 
 
 def synthetic(bx, by):
@@ -166,6 +170,9 @@ def main():
     ap.add_argument("--ref-t-final", type=float, default=0.05)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spmv-variant", type=int, default=1, choices=[0, 1],
+                    help="0: explicit gather-ELL matrix (the reference's data model); 1: matrix-free lattice SpMV "
+                         "(bit-identical results, 16 instead of 72 bytes per state)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,7 +214,8 @@ def main():
     model = k.CME_MODEL().load(os.path.join(k.models_dir(), "toggle_test.input"))
     model.reset_parameters(PARAMS)
     h = k.KrylovFspHandle(model, max_states=n + 64, m_max=args.m_max, m_min=10, n_init_onestep=0, enable_drop=0,
-                          enable_expand=0, device=local_rank)
+                          enable_expand=0, device=local_rank, spmv_variant=args.spmv_variant)
+    variant = args.spmv_variant
     i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
     fsp_tol, kry_tol = 1e-6, 1e-8
     lo, hi = 0, n
@@ -219,14 +227,14 @@ def main():
             uid.copy_(torch.frombuffer(bytearray(k.KrylovFspHandle.dist_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         h.dist_init(rank, world, uid.cpu().numpy().tobytes())
-        a, b = C.c_int64(), C.c_int64()
-        check(L.kfsp_dist_partition(n, world, rank, C.byref(a), C.byref(b)))
-        lo, hi = a.value, b.value
-    nloc = hi - lo
 
     # ---- resident setup (not timed for `value`): MATRIX_STARTER on the device, p0 in HBM -------------
     t_setup = time.time()
     check(L.kfsp_fsp_init(h._h, n, C.cast(states_h.data_ptr(), i32p)), "MATRIX_STARTER")
+    if world > 1:
+        info = h.dist_info()                              # this rank's rows (blocks of rows / slabs of the slowest species)
+        lo, hi = info["lo"], info["hi"]
+    nloc = hi - lo
     p0_dev = C.c_void_p()
     check(L.kfsp_device_alloc(h._h, 8 * nloc, C.byref(p0_dev)))
     check(L.kfsp_device_upload(h._h, p0_dev, C.c_void_p(p0_h.data_ptr() + 8 * lo), 8 * nloc))
@@ -306,7 +314,8 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e_wall = float(tt.item())
-        h2d = int(states_h.numel() * 4 + (p0_h.numel() if world == 1 else nloc) * 8)
+        # the lattice variant ships only this rank's slab of the state list; the explicit one needs the global list for its hash table
+        h2d = int((states_h.numel() if (world == 1 or variant == 0) else nloc * 2) * 4 + (p0_h.numel() if world == 1 else nloc) * 8)
         d2h = int(nloc * 2 * 4 + nloc * 8)
         e2e = {"value": float(n) * e_mult / e_wall, "unit": UNIT,
                "h2d_bytes_per_step": h2d * world if world > 1 else h2d, "d2h_bytes_per_step": int(n * 2 * 4 + n * 8),
@@ -322,13 +331,17 @@ def main():
 
     peak, peak_kind = measured_peak()
     spmv_avg = spmv_s / max(spmv_launches, 1)
-    achieved = BYTES_PER_STATE * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_spmv (generator SpMV, gather ELL; per GPU, rank 0)", "achieved": achieved, "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_PER_STATE * nloc,
-                "traffic_source": "ncu --set full, profiles/r1_summary.md: 8.09 GB per launch at 1e8 states (dot-fused variant)",
-                "algorithmic_bytes_per_launch": BYTES_PER_STATE * nloc,
-                "algorithmic_bytes_per_launch_incl_fused_dot_operand": (BYTES_PER_STATE + 8) * nloc,
-                "achieved_incl_fused_dot_operand": (BYTES_PER_STATE + 8) * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0,
+    bps = BYTES_PER_STATE[variant]
+    achieved = bps * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": KERNEL_NAME[variant], "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": TRAFFIC_PER_STATE[variant] * nloc if TRAFFIC_PER_STATE[variant] else None,
+                "traffic_source": "ncu --set full of the dot-fused launch at 1e8 states, profiles/r1_summary.md",
+                "algorithmic_bytes_per_state": bps,
+                "algorithmic_bytes_per_launch": bps * nloc,
+                "algorithmic_bytes_per_launch_incl_fused_dot_operand": (bps + 8) * nloc,
+                "achieved_incl_fused_dot_operand": (bps + 8) * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0,
+                "states_per_s_per_launch": nloc / spmv_avg if spmv_avg > 0 else 0.0,
                 "avg_launch_ms": 1e3 * spmv_avg,
                 "launches_timed": spmv_launches, "share_of_step": spmv_s / dev_s_rank if dev_s_rank > 0 else None,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
@@ -340,7 +353,7 @@ def main():
                "sample": "FMATVEC + one IOP-2 Arnoldi sweep (m=10, %d SpMVs) on a %dx%d rectangle of the same workload "
                          "(%d states); oracle port of the serial Fortran reference, 1 of %d host cores"
                          % (cm, args.cpu_bx, args.cpu_by, cn, os.cpu_count()),
-               "spmv_states_per_s": cn / t_mv, "spmv_gbs": BYTES_PER_STATE * cn / t_mv / 1e9}
+               "spmv_states_per_s": cn / t_mv, "spmv_gbs": BYTES_PER_STATE[0] * cn / t_mv / 1e9}
 
     if rank == 0:
         line = {
@@ -349,7 +362,10 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config 5: synthetic toggle, rectangle %dx%d = %d FSP states, expv to t_final=%g, "
                                    "KRYTOL 1e-8, Krylov dimension in [10,%d], fixed state set" % (bx, by, n, args.t_final, args.m_max),
-                       "states": n, "reactions": R_TOGGLE, "l2": "inputs (7.2 GB matrix, 0.8 GB vectors) exceed the 126 MB L2",
+                       "states": n, "reactions": R_TOGGLE,
+                       "spmv_variant": "matrix-free lattice (FMATVEC recomputed from the integer state, bit-identical to the explicit "
+                                       "matrix)" if variant == 1 else "explicit gather-ELL matrix (ADJ/OFFDIAG/DIAG in HBM)",
+                       "l2": "inputs (0.8 GB per vector%s) exceed the 126 MB L2" % (", 7.2 GB matrix" if variant == 0 else ""),
                        "parallelism": "1 GPU" if world == 1 else
                        "rows block-partitioned over %d GPUs; per SpMV the halo is gathered straight from the neighbours' HBM and per "
                        "reduction the double-double partials are exchanged inside the reducing kernel (cudaIpc peer memory over "

@@ -70,7 +70,9 @@ typedef struct {
     int32_t enable_expand;     /* 1        SSA_EXTENDER + ONESTEP_EXTENDER on                    */
     int32_t max_molecules;     /* 10000    StateSpace.f90:11                                     */
     int32_t device;            /* CUDA device ordinal; -1 = current device                       */
-    int32_t spmv_variant;      /* 0 explicit gather-ELL (reference data model)                   */
+    int32_t spmv_variant;      /* 0 explicit gather-ELL (reference data model); 1 matrix-free on a lattice:
+                                  the state set must be a full box in natural order (first species fastest),
+                                  every propensity must read at most one species, the state set is fixed   */
     int64_t max_states;        /* 6291469  NMAX, StateSpace.f90:10                               */
     double delta;              /* 1.2      KrylovSolver.f90:85                                   */
     double gamma;              /* 0.9      KrylovSolver.f90:87                                   */
@@ -157,6 +159,11 @@ int kfsp_trace_get(kfsp_handle h, kfsp_trace_row* rows, int64_t cap);
 /* ---- the state-space routines DGEXPV_FSP calls, one entry point each ------------------ */
 /* MATRIX_STARTER   src/state_space/StateSpace.f90:248-345 on FSP%STATE(:,1:n) */
 int kfsp_fsp_init(kfsp_handle h, int64_t n, const int32_t* states);
+/* spmv_variant = 1 only: the projection is the lattice [0,bounds[0]) x ... x [0,bounds[S-1]) in natural order
+ * (index = sum_s x_s * prod_{r<s} bounds[r]); no state list is shipped, ADJ/OFFDIAG/DIAG are never materialised
+ * (FMATVEC recomputes them from the integer state, KrylovSolver.f90:577-607 + StateSpace.f90:303-327).
+ * kfsp_fsp_init / kfsp_solve accept such a set as an explicit state list too and verify it on the device. */
+int kfsp_fsp_init_box(kfsp_handle h, const int32_t* bounds /* S */);
 /* ONESTEP_EXTENDER src/state_space/StateSpace.f90:347-396 */
 int kfsp_fsp_onestep(kfsp_handle h);
 /* SSA_EXTENDER     src/state_space/StateSpace.f90:550-630 (one Philox sub-stream per trajectory) */

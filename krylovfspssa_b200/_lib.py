@@ -68,6 +68,7 @@ SIGNATURES = {
     "kfsp_trace_length": (C.c_int, [_vp, _i64p]),
     "kfsp_trace_get": (C.c_int, [_vp, C.POINTER(TraceRow), C.c_int64]),
     "kfsp_fsp_init": (C.c_int, [_vp, C.c_int64, _i32p]),
+    "kfsp_fsp_init_box": (C.c_int, [_vp, _i32p]),
     "kfsp_fsp_onestep": (C.c_int, [_vp]),
     "kfsp_fsp_ssa": (C.c_int, [_vp, C.c_double]),
     "kfsp_fsp_drop": (C.c_int, [_vp, C.c_double, _i32p, _dp, _i64p]),

@@ -14,6 +14,7 @@
 #include "dist.cuh"
 #include "expm.cuh"
 #include "krylov.cuh"
+#include "lattice.cuh"
 #include "model_host.h"
 #include "state_space.cuh"
 
@@ -39,6 +40,11 @@ struct Engine {
     PropCache pc;                     // device side cache used by SSA walks in host_prop mode
     int64_t pc_n = 0;                 // cached states
     int64_t host_prop_evals = 0, host_prop_rounds = 0;
+    // matrix-free lattice (opt.spmv_variant == 1, lattice.cuh): the projection is a full box in natural order
+    bool box = false;
+    Lattice lat{};
+    DeviceModel h_dm{};               // host mirror of *d_model (table pointers, stoichiometry)
+    int box_tune = 0;                 // KFSP_BOX_TUNE: rows per batch / CTAs per SM of the lattice SpMV (A/B)
 
     // state space
     int64_t ld = 0;                   // capacity in states (multiple of 64)
@@ -92,6 +98,7 @@ struct Engine {
     int init(const kfsp_options* o) {
         opt = *o;
         if (const char* ev = std::getenv("KFSP_SPMV_TUNE")) spmv_tune = std::atoi(ev);
+        if (const char* ev = std::getenv("KFSP_BOX_TUNE")) box_tune = std::atoi(ev);
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
         if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
             opt.max_states > 2000000000LL)
@@ -148,17 +155,18 @@ struct Engine {
         d_states = d_succ = d_pred = d_table = nullptr;
         d_prop = d_diag = d_coef = d_w = d_V = nullptr;
         ld = 0; n = 0;
+        box = false;
     }
 
     // Grid for a grid-stride kernel: one full wave of resident CTAs (SMs x CTAs/SM for THIS kernel's
     // register/shared-memory footprint), so no ragged second wave; capped by MAX_VEC_BLOCKS (reducer arrays).
     int num_sms = 148;
     std::vector<std::pair<const void*, int>> occ_cache;
-    int wave_grid(const void* kernel, int64_t work, int threads = VEC_THREADS) {
+    int wave_grid(const void* kernel, int64_t work, int threads = VEC_THREADS, size_t dyn_smem = 0) {
         int per_sm = 0;
         for (auto& pr : occ_cache) if (pr.first == kernel) { per_sm = pr.second; break; }
         if (per_sm == 0) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
             occ_cache.emplace_back(kernel, per_sm);
         }
         int64_t b = (work + threads - 1) / threads;
@@ -233,13 +241,13 @@ struct Engine {
             program_profile(m.programs[k], m.S, &mask, &ix);
             dm.table_species[k] = -1;
             dm.table[k] = nullptr;
-            if (!ix) continue;
+            if (!ix && opt.spmv_variant != 1) continue;       // the lattice SpMV reads every propensity from a table
             if ((mask & (mask - 1)) == 0) {                  // zero or one species
                 int sp = 0;
                 while (mask > 1) { mask >>= 1; ++sp; }
                 dm.table_species[k] = sp;
                 tab_k.push_back(k);
-            } else {
+            } else if (ix) {
                 ++n_inexact_on_device;                        // evaluated with the CUDA math library: may differ by ulps
             }
         }
@@ -263,7 +271,8 @@ struct Engine {
         }
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
         KFSP_CUDA(cudaStreamSynchronize(stream));
-        const bool reshape = !have_model || m.S != S || m.R != R;
+        h_dm = dm;
+        const bool reshape = !have_model || m.S != S || m.R != R || box;
         S = m.S; R = m.R;
         have_model = true;
         host_prop = false;
@@ -277,7 +286,7 @@ struct Engine {
     // device; a_k(x) is evaluated on the host in batches (propensities_host) and, inside SSA walks, served
     // from the device side cache (fsp_ssa_hostprop).
     int set_model_hostprop(const HostModel& m) {
-        if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;       // partitioned rows are built from device byte code
+        if (dist.nranks > 1 || opt.spmv_variant == 1) return KFSP_ERR_UNSUPPORTED;   // those rows are built from device byte code / tables
         DeviceModel dm;
         std::memset(&dm, 0, sizeof dm);
         dm.S = m.S; dm.R = m.R; dm.P = m.P; dm.max_molecules = opt.max_molecules;
@@ -514,6 +523,7 @@ struct Engine {
         return KFSP_OK;
     }
     int fsp_init(int64_t count, const int32_t* states_host) {
+        if (opt.spmv_variant == 1) return box_init_from_states(count, states_host);
         if (dist.nranks > 1) return dist_fsp_init(count, states_host);
         KFSP_TRY(ensure_state_space());
         if (count < 1 || count > opt.max_states) return KFSP_ERR_BAD_SIZES;
@@ -552,7 +562,7 @@ struct Engine {
 
     // ---------------------------------------------------------------- ONESTEP_EXTENDER
     int fsp_onestep() {
-        if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;     // partitioned state sets are fixed (round 1)
+        if (dist.nranks > 1 || box) return KFSP_ERR_UNSUPPORTED;     // partitioned / lattice state sets are fixed
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         // scratch: cnt[n_old], off[n_old], tiles
@@ -614,7 +624,7 @@ struct Engine {
 
     // ---------------------------------------------------------------- SSA_EXTENDER
     int fsp_ssa(double timestep) {
-        if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;
+        if (dist.nranks > 1 || box) return KFSP_ERR_UNSUPPORTED;
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         ssa_calls += 1;
@@ -690,6 +700,14 @@ struct Engine {
     int spmv(const double* x, double* y, const double* first, double* h_out, int cx = -1, int cf = -1) {
         const bool timed = profile_spmv && ev_used + 2 <= ev_pool.size();
         if (timed) KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
+        if (box) {
+            KFSP_TRY(spmv_box<MODE>(x, y, first, h_out, cx, cf));
+            if (timed) {
+                KFSP_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
+                ev_used += 2;
+            }
+            return KFSP_OK;
+        }
         void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
                      Reducer, SweepCtl*, double*, int, int, const double*, int64_t, int64_t);
         const int halo = dist.nranks > 1 ? ((dist.p2p && dist.p2p_halo) ? 2 : 1) : 0;
@@ -747,7 +765,7 @@ struct Engine {
     // ---------------------------------------------------------------- DROP_STATES
     int fsp_drop(double dsum, int32_t* dropped, double* droptol_out, int64_t* count_out) {
         *dropped = 0;
-        if (dist.nranks > 1) return KFSP_ERR_UNSUPPORTED;
+        if (dist.nranks > 1 || box) return KFSP_ERR_UNSUPPORTED;
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t lsize = n;
         // FIND_DROPTOL (StateSpace.f90:398-427): thresholds by repeated division
@@ -827,7 +845,7 @@ struct Engine {
     // columns J = jold..m (1-based) then the extra product (KrylovSolver.f90:236-266). No host sync.
     int arnoldi(int jold, int m) {
         // small state spaces: the whole sweep in one single-CTA launch (bit-identical, see k_sweep_small)
-        if (dist.nranks == 1 && !profile_spmv && small_sweep && n * (int64_t)(12 * R + 88) <= (1 << 20)) {
+        if (dist.nranks == 1 && !box && !profile_spmv && small_sweep && n * (int64_t)(12 * R + 88) <= (1 << 20)) {
             void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, double*, double*, int, int, int, SweepCtl*, double);
             switch (R) {
             case 4: kern = k_sweep_small<4>; break;
@@ -1125,6 +1143,133 @@ struct Engine {
         (void)n_global; (void)states_host;
         return KFSP_ERR_UNSUPPORTED;
 #endif
+    }
+
+    // ---------------------------------------------------------------- matrix-free lattice (lattice.cuh)
+    template <int MODE>
+    int spmv_box(const double* x, double* y, const double* first, double* h_out, int cx, int cf) {
+        const bool halo = dist.nranks > 1;
+        // column blocks: the plane split evenly into the fewest blocks of at most 256 columns
+        const int64_t ncb0 = (lat.plane + VEC_THREADS - 1) / VEC_THREADS;
+        const int cbw = (int)((lat.plane + ncb0 - 1) / ncb0);
+        const int64_t ncb = (lat.plane + cbw - 1) / cbw;
+        const int nzl = lat.zhi - lat.zlo;
+        const Reducer r = MODE != 0 ? next_rd() : rd;
+        Reducer r2 = r;
+        if (halo && !r2.peers) r2.peers = dist.d_peers;
+        // z-chunks: at most (and as close as possible to) 4 work items per resident CTA so that no CTA runs a
+        // fifth one while the rest idle, at least 16 planes each (2 halo rows per chunk are re-read)
+        auto chunking = [&](int wave, int* zc, int* g) {
+            int64_t nzc = std::max<int64_t>(1, (4 * (int64_t)wave) / ncb);
+            nzc = std::min<int64_t>(nzc, std::max(1, nzl / 16));
+            int z = (int)((nzl + nzc - 1) / nzc);
+            while (z < nzl && ncb * ((nzl + z - 1) / z) > 4 * (int64_t)wave) ++z;      // rounding must not push it past 4 waves
+            *zc = z;
+            const int64_t items = ncb * ((nzl + z - 1) / z);
+            *g = (int)std::min<int64_t>(items, wave);
+        };
+        void (*kern)(const Lattice, int, int, const double*, double*, const double*, Reducer, SweepCtl*, double*, int, int, int64_t) = nullptr;
+        const int tune = box_tune;
+#define KFSP_BOX_PICK(RR)                                                                                                   \
+        kern = halo ? (S == 2 ? k_spmv_box<RR, 2, MODE, 2, 1, 6, 3> : k_spmv_box<RR, 0, MODE, 2, 1, 6, 3>)                      \
+             : S != 2 ? k_spmv_box<RR, 0, MODE, 0, 1, 6, 4>                                                                     \
+             : tune == 1 ? k_spmv_box<RR, 2, MODE, 0, 0, 1, 4> : k_spmv_box<RR, 2, MODE, 0, 1, 6, 4>
+        switch (R) {
+        case 2: KFSP_BOX_PICK(2); break;
+        case 4: KFSP_BOX_PICK(4); break;
+        case 6: KFSP_BOX_PICK(6); break;
+        case 8: KFSP_BOX_PICK(8); break;
+        default: return KFSP_ERR_UNSUPPORTED;
+        }
+#undef KFSP_BOX_PICK
+        const int wave = wave_grid((const void*)kern, (int64_t)1 << 40);
+        int zc, g;
+        chunking(wave, &zc, &g);
+        kern<<<g, VEC_THREADS, 0, stream>>>(lat, zc, cbw, x, y, first, r2, d_ctl, h_out, cx, cf, (int64_t)(d_V ? x - d_V : 0));
+        return check_launch();
+    }
+    // kfsp_fsp_init_box: the projection is the lattice [0,B_1) x ... x [0,B_S) in natural order.
+    int fsp_init_box(const int32_t* bounds) {
+        if (!have_model) return KFSP_ERR_NO_MODEL;
+        if (opt.spmv_variant != 1) return KFSP_ERR_ARG;
+        if (opt.enable_expand || opt.enable_drop || opt.n_init_onestep) return KFSP_ERR_ARG;      // fixed state set
+        if (S < 2 || R > BOX_MAX_R || host_prop) return KFSP_ERR_UNSUPPORTED;
+        KFSP_CUDA(cudaSetDevice(device));
+        Lattice L;
+        std::memset(&L, 0, sizeof L);
+        L.S = S; L.R = R;
+        int64_t total = 1;
+        for (int s = 0; s < S; ++s) {
+            if (bounds[s] < 1 || bounds[s] > opt.max_molecules + 1) return KFSP_ERR_BAD_STATE;
+            L.B[s] = bounds[s];
+            L.stride[s] = total;
+            total *= bounds[s];
+            if (total > opt.max_states || total > 2000000000LL) return KFSP_ERR_BAD_SIZES;
+        }
+        L.plane = L.stride[S - 1];
+        L.nz = L.B[S - 1];
+        for (int k = 0; k < R; ++k) {
+            if (h_dm.table_species[k] < 0 || !h_dm.table[k]) return KFSP_ERR_UNSUPPORTED;   // a propensity reads several species
+            L.sp[k] = h_dm.table_species[k];
+            L.tab[k] = h_dm.table[k];
+            for (int s = 0; s < S; ++s) L.nu[k][s] = h_dm.stoich[k * S + s];
+        }
+        const int P = dist.nranks;
+        if (P > 1 && !dist.want_p2p) return KFSP_ERR_UNSUPPORTED;       // halo rows are read straight from the neighbours' HBM
+        if (L.nz < P) return KFSP_ERR_BAD_SIZES;
+        int64_t thick = 0;
+        for (int r = 0; r <= P; ++r) L.zb[r] = (int32_t)((int64_t)L.nz * r / P);
+        for (int r = 0; r < P; ++r) thick = std::max<int64_t>(thick, L.zb[r + 1] - L.zb[r]);
+        L.zlo = L.zb[dist.rank]; L.zhi = L.zb[dist.rank + 1];
+        const int64_t nloc = L.plane * (L.zhi - L.zlo);
+        const int64_t cap = ((L.plane * thick + 63) / 64) * 64;          // same leading dimension on every rank
+        if (cap != ld || !box || nloc != n) {
+            if (dist.nranks > 1 && d_V) return KFSP_ERR_UNSUPPORTED;     // peers hold mappings of this rank's basis
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+            free_state_space();
+            KFSP_CUDA(cudaMalloc(&d_w, sizeof(double) * cap));
+            ld = cap;
+        }
+        KFSP_CUDA(cudaMemsetAsync(d_w, 0, sizeof(double) * ld, stream));
+        KFSP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
+        lat = L;
+        box = true;
+        n = nloc;
+        states_cap = 0;
+        dist.n_global = total; dist.lo = L.plane * L.zlo; dist.hi = L.plane * L.zhi;
+        dist.n_halo = P > 1 ? L.plane * ((dist.rank > 0) + (dist.rank < P - 1)) : 0;
+        return KFSP_OK;
+    }
+    // d_states of this rank's rows (generated on demand: the lattice itself needs no state list)
+    int box_states() {
+        if (d_states) return KFSP_OK;
+        KFSP_CUDA(cudaMalloc(&d_states, sizeof(int32_t) * std::max<int64_t>(n, 1) * S));
+        KFSP_LAUNCH(k_box_gen_states, grid_for(n), VEC_THREADS, 0, lat, dist.lo, n, d_states);
+        return KFSP_OK;
+    }
+    // kfsp_fsp_init / kfsp_solve with spmv_variant = 1: the caller's state list must be a lattice in natural
+    // order.  Bounds come from the last state; this rank's rows are verified on the device.
+    int box_init_from_states(int64_t count, const int32_t* states_host) {
+        if (!have_model) return KFSP_ERR_NO_MODEL;
+        if (count < 1) return KFSP_ERR_BAD_SIZES;
+        int32_t bounds[KFSP_MAX_SPECIES];
+        int64_t total = 1;
+        for (int s = 0; s < S; ++s) {
+            const int32_t top = states_host[(count - 1) * S + s];
+            if (top < 0 || top > opt.max_molecules) return KFSP_ERR_BAD_STATE;
+            bounds[s] = top + 1;
+            total *= bounds[s];
+            if (total > count) return KFSP_ERR_UNSUPPORTED;
+        }
+        if (total != count) return KFSP_ERR_UNSUPPORTED;          // not a full box: use spmv_variant = 0
+        KFSP_TRY(fsp_init_box(bounds));
+        if (!d_states) KFSP_CUDA(cudaMalloc(&d_states, sizeof(int32_t) * n * S));     // n is fixed while ld is (fsp_init_box)
+        KFSP_CUDA(cudaMemcpyAsync(d_states, states_host + dist.lo * S, sizeof(int32_t) * n * S, cudaMemcpyHostToDevice, stream));
+        KFSP_LAUNCH(k_box_check_states, grid_for(n), VEC_THREADS, 0, lat, dist.lo, n, (const int32_t*)d_states, d_err);
+        int32_t e = 0;
+        KFSP_TRY(read_err(&e));
+        if (e) { n = 0; box = false; return KFSP_ERR_UNSUPPORTED; }
+        return KFSP_OK;
     }
 
     int solve(double T, double fsptol, double krytol, int itrace, kfsp_stats* stats);

@@ -312,6 +312,11 @@ int kfsp_fsp_init(kfsp_handle h, int64_t n, const int32_t* states) {
     cudaSetDevice(h->e.device);
     return h->e.fsp_init(n, states);
 }
+int kfsp_fsp_init_box(kfsp_handle h, const int32_t* bounds) {
+    if (!h || !bounds) return KFSP_ERR_ARG;
+    cudaSetDevice(h->e.device);
+    return h->e.fsp_init_box(bounds);
+}
 int kfsp_fsp_onestep(kfsp_handle h) {
     if (!h) return KFSP_ERR_ARG;
     cudaSetDevice(h->e.device);
@@ -361,6 +366,27 @@ int kfsp_fsp_get(kfsp_handle h, int32_t* states, int32_t* adj, double* offdiag, 
     if (e.n < 1) return KFSP_ERR_BAD_SIZES;
     cudaSetDevice(e.device);
     const int64_t n = e.n;
+    if (e.box) {                                                     // lattice: the column form is computed, not stored
+        if (states) {
+            KFSP_TRY(e.box_states());
+            KFSP_CUDA(cudaMemcpyAsync(states, e.d_states, sizeof(int32_t) * n * e.S, cudaMemcpyDeviceToHost, e.stream));
+        }
+        if (vector) KFSP_CUDA(cudaMemcpyAsync(vector, e.d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, e.stream));
+        if (adj || offdiag || diag) {
+            const size_t a = Engine::align_up(sizeof(int32_t) * n * e.R), b = Engine::align_up(sizeof(double) * n * e.R);
+            KFSP_TRY(e.ensure_scratch(a + b + Engine::align_up(sizeof(double) * n)));
+            int32_t* dadj = (int32_t*)e.d_scratch;
+            double* doff = (double*)(e.d_scratch + a);
+            double* ddiag = (double*)(e.d_scratch + a + b);
+            k_box_export<<<e.grid_for(n), VEC_THREADS, 0, e.stream>>>(e.lat, e.dist.lo, n, adj ? dadj : nullptr, offdiag ? doff : nullptr,
+                                                                     diag ? ddiag : nullptr);
+            KFSP_TRY(e.check_launch());
+            if (adj) KFSP_CUDA(cudaMemcpyAsync(adj, dadj, sizeof(int32_t) * n * e.R, cudaMemcpyDeviceToHost, e.stream));
+            if (offdiag) KFSP_CUDA(cudaMemcpyAsync(offdiag, doff, sizeof(double) * n * e.R, cudaMemcpyDeviceToHost, e.stream));
+            if (diag) KFSP_CUDA(cudaMemcpyAsync(diag, ddiag, sizeof(double) * n, cudaMemcpyDeviceToHost, e.stream));
+        }
+        return e.sync();
+    }
     if (e.dist.nranks > 1 && adj) return KFSP_ERR_UNSUPPORTED;      // the column form is not kept for partitioned sets
     const int64_t row0 = e.dist.nranks > 1 ? e.dist.lo : 0;          // this rank's rows
     if (states) KFSP_CUDA(cudaMemcpyAsync(states, e.d_states + row0 * e.S, sizeof(int32_t) * n * e.S, cudaMemcpyDeviceToHost, e.stream));
@@ -389,7 +415,10 @@ static int lookup_common(kfsp_handle h, int64_t nq, const int32_t* states, int32
     int32_t* di = (int32_t*)(e.d_scratch + a);
     double* dp = (double*)(e.d_scratch + a + b);
     KFSP_CUDA(cudaMemcpyAsync(dq, states, sizeof(int32_t) * nq * e.S, cudaMemcpyHostToDevice, e.stream));
-    k_lookup_states<<<e.grid_for(nq), VEC_THREADS, 0, e.stream>>>(e.view(), dq, nq, idx ? di : nullptr, e.d_w, p ? dp : nullptr);
+    if (e.box)
+        k_box_lookup<<<e.grid_for(nq), VEC_THREADS, 0, e.stream>>>(e.lat, dq, nq, idx ? di : nullptr, e.d_w, e.dist.lo, e.n, p ? dp : nullptr);
+    else
+        k_lookup_states<<<e.grid_for(nq), VEC_THREADS, 0, e.stream>>>(e.view(), dq, nq, idx ? di : nullptr, e.d_w, p ? dp : nullptr);
     KFSP_TRY(e.check_launch());
     if (idx) KFSP_CUDA(cudaMemcpyAsync(idx, di, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, e.stream));
     if (p) KFSP_CUDA(cudaMemcpyAsync(p, dp, sizeof(double) * nq, cudaMemcpyDeviceToHost, e.stream));
@@ -422,6 +451,7 @@ int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, 
     *n_out = e.n;
     if (st == KFSP_OK || st == KFSP_IFLAG_MXSTEP) {
         if (e.n > max_out) return KFSP_ERR_OUT_TOO_SMALL;
+        if (e.box && states_out) KFSP_TRY(e.box_states());
         if (states_out) KFSP_CUDA(cudaMemcpyAsync(states_out, e.d_states, sizeof(int32_t) * e.n * e.S, cudaMemcpyDeviceToHost, e.stream));
         if (p_out) KFSP_CUDA(cudaMemcpyAsync(p_out, e.d_w, sizeof(double) * e.n, cudaMemcpyDeviceToHost, e.stream));
         KFSP_TRY(e.sync());

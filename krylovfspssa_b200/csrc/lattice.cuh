@@ -1,0 +1,231 @@
+// Matrix-free generator SpMV on a lattice (spmv_variant = 1).
+//
+// FMATVEC (src/fsp/KrylovSolver.f90:577-607) streams ADJ/OFFDIAG/DIAG, 12R+24 bytes per state.  When the
+// projection is a full box [0,B_1) x ... x [0,B_S) held in the reference's natural order (first species
+// fastest, index = sum_s x_s * stride_s) and every propensity reads at most ONE species, none of the three
+// arrays carries information: the predecessor index is i - sum_s nu_ks*stride_s, legality is a bounds check
+// on x - nu_k, and a_k(x - nu_k) is one entry of a per-reaction table over that species' count (the same
+// host-built tables the explicit path evaluates its OFFDIAG from, so the values are the same doubles).
+// The row is then evaluated with the explicit kernel's operation order
+//     y_i = -(d_i * x_i);  y_i = fma(a_k(x_i - nu_k), x[pred_k], y_i)  for k = 1..R,   d_i = ((a_1+a_2)+...)
+// and the result is bit-identical to k_spmv on the explicit matrix (tests/test_gpu_lattice.py), for
+// 16 bytes of HBM traffic per state (x read once, y written once) instead of 12R+24.
+//
+// Work decomposition: a CTA owns up to 256 consecutive "columns" c (all species but the slowest one, flattened)
+// and walks a chunk of the slowest species z.  Everything that depends on the column only -- the decoded
+// counts, bounds checks, predecessor offsets, table entries of the column species -- is hoisted out of the
+// walk; rows z-1, z, z+1 of x are re-read through L1 and row z+PF is prefetched, so every x element comes
+// from HBM once per chunk.
+#pragma once
+#include "common.cuh"
+#include "krylov.cuh"
+
+namespace kfsp {
+
+constexpr int BOX_MAX_R = 16;
+
+struct Lattice {
+    int32_t S, R;
+    int32_t B[KFSP_MAX_SPECIES];          // bounds: 0 <= x_s < B[s]
+    int64_t stride[KFSP_MAX_SPECIES];     // stride[0] = 1, stride[s] = stride[s-1]*B[s-1]
+    int64_t plane;                        // stride[S-1]: rows per unit of the slowest species z = x_{S-1}
+    int32_t nz;                           // B[S-1]
+    int32_t zlo, zhi;                     // this rank's slab of z (one GPU: 0, nz)
+    int32_t nu[BOX_MAX_R][KFSP_MAX_SPECIES];
+    int32_t sp[BOX_MAX_R];                // the species reaction k's propensity reads
+    const double* tab[BOX_MAX_R];         // a_k as a function of that species' count, 0..max_molecules
+    int32_t zb[MAX_RANKS + 1];            // slab boundaries of every rank
+};
+
+__device__ __forceinline__ void lattice_decode(const Lattice& L, int64_t g, int32_t* st) {
+    for (int s = 0; s < L.S; ++s) {
+        st[s] = (int32_t)(g % L.B[s]);
+        g /= L.B[s];
+    }
+}
+
+// states[t*S + s] for global rows [g0, g0+count)
+__global__ void k_box_gen_states(const __grid_constant__ Lattice L, int64_t g0, int64_t count, int32_t* states) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        int32_t st[KFSP_MAX_SPECIES];
+        lattice_decode(L, g0 + t, st);
+        for (int s = 0; s < L.S; ++s) states[t * L.S + s] = st[s];
+    }
+}
+// the caller's state list must BE the lattice in natural order: *bad is raised otherwise
+__global__ void k_box_check_states(const __grid_constant__ Lattice L, int64_t g0, int64_t count, const int32_t* __restrict__ states, int32_t* bad) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        int32_t st[KFSP_MAX_SPECIES];
+        lattice_decode(L, g0 + t, st);
+        bool ok = true;
+        for (int s = 0; s < L.S; ++s) ok = ok && states[t * L.S + s] == st[s];
+        if (!ok) atomicOr(bad, 1);
+    }
+}
+
+// x at column c of global plane zz (any rank's slab when HALO)
+template <int HALO>
+__device__ __forceinline__ double lattice_load(const Lattice& L, const double* __restrict__ x, const DistPeers* __restrict__ dp,
+                                               int64_t c, int32_t zz, int64_t coloff) {
+    if (HALO == 0 || (zz >= L.zlo && zz < L.zhi)) return x[c + L.plane * (zz - L.zlo)];
+    int r = 0;
+    while (zz >= L.zb[r + 1]) ++r;
+    return __ldcg(dp->V[r] + coloff + c + L.plane * (zz - L.zb[r]));
+}
+
+template <int LEVEL>
+__device__ __forceinline__ void lattice_prefetch(const void* p) {
+    if (LEVEL == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    if (LEVEL == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// mode 0: y = A x   mode 1: + dot = <first, y>   mode 2: + ssq = <y, y>     (same contract as k_spmv)
+// Every reaction runs the same few instructions with per-thread data hoisted out of the walk over z: the
+// element offset of its predecessor, the bounds check of the column species, and the table entries that do
+// not depend on z.  The rows z-1, z, z+1 of x are re-read through L1 (the CTA touched them one and two
+// iterations earlier); the first touch of row z+PF is a prefetch, so the depth of the memory pipeline does
+// not cost registers.
+// ST > 0: number of species fixed at compile time (stoichiometry entries become constant-bank operands).
+template <int RT, int ST, int MODE, int HALO, int PFL, int PF, int MINB>
+__global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_constant__ Lattice L, int zc, int cbw, const double* __restrict__ x,
+                                                                double* __restrict__ y, const double* __restrict__ first, Reducer rd,
+                                                                SweepCtl* ctl, double* h_out, int cx, int cf, int64_t coloff) {
+    constexpr int R = RT;
+    if (MODE != 0 && ctl->brk != 0) return;
+    const double xs = col_scale(ctl, cx);
+    const double fs = MODE == 1 ? col_scale(ctl, cf) : 1.0;
+    const int S = ST > 0 ? ST : L.S;
+    const int64_t plane = L.plane;
+    const int nzl = L.zhi - L.zlo;
+    const int64_t ncb = (plane + cbw - 1) / cbw;                 // column blocks of cbw <= 256 columns (even split of the plane)
+    const int64_t nzc = (nzl + zc - 1) / zc;
+    const DistPeers* __restrict__ dp = rd.peers;
+    DD acc; acc.hi = 0.0; acc.lo = 0.0;
+    for (int64_t item = blockIdx.x; item < ncb * nzc; item += gridDim.x) {
+        const int64_t c = (item % ncb) * cbw + threadIdx.x;
+        if ((int)threadIdx.x >= cbw || c >= plane) continue;
+        const int32_t z0 = L.zlo + (int32_t)(item / ncb) * zc;
+        const int32_t z1 = min(z0 + zc, L.zhi);
+        // column invariants (local element indices fit 32 bits: n <= 2e9)
+        bool lowok[R];
+        double ad[R], ac[R];
+        int32_t off[R];
+        const int32_t plane32 = (int32_t)plane;
+#pragma unroll
+        for (int k = 0; k < R; ++k) { lowok[k] = true; ad[k] = 0.0; ac[k] = 0.0; off[k] = -L.nu[k][S - 1] * plane32; }
+        {
+            int64_t rem = c;
+#pragma unroll
+            for (int s = 0; s < (ST > 0 ? ST : KFSP_MAX_SPECIES) - 1; ++s) {
+                if (s >= S - 1) break;
+                const int32_t xv = (int32_t)(rem % L.B[s]);
+                rem /= L.B[s];
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int32_t v = xv - L.nu[k][s];
+                    const bool in = v >= 0 && v < L.B[s];
+                    lowok[k] = lowok[k] && in;
+                    off[k] -= L.nu[k][s] * (int32_t)L.stride[s];
+                    if (L.sp[k] == s) {
+                        ad[k] = __ldg(L.tab[k] + xv);
+                        ac[k] = in ? __ldg(L.tab[k] + v) : 0.0;
+                    }
+                }
+            }
+        }
+        uint32_t i = (uint32_t)(c + plane * (z0 - L.zlo));
+        const uint32_t pfo = (uint32_t)(plane32 * PF);
+        if (PFL > 0) {
+#pragma unroll
+            for (int q = 1; q < PF; ++q)
+                if (z0 + q < L.zhi) { lattice_prefetch<PFL>(x + (i + plane32 * q)); if (MODE == 1) lattice_prefetch<PFL>(first + (i + plane32 * q)); }
+        }
+        for (int32_t z = z0; z < z1; ++z) {
+            if (PFL > 0 && z + PF < L.zhi) { lattice_prefetch<PFL>(x + (i + pfo)); if (MODE == 1) lattice_prefetch<PFL>(first + (i + pfo)); }
+            const double x0 = x[i];
+            double f = 0.0;
+            if (MODE == 1) f = __dmul_rn(fs, __ldcs(first + i));
+            double d = 0.0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                if (L.sp[k] == S - 1) {                             // uniform: this reaction's table runs over z
+                    const int32_t zz = z - L.nu[k][S - 1];
+                    ad[k] = __ldg(L.tab[k] + z);
+                    ac[k] = (zz >= 0 && zz < L.nz) ? __ldg(L.tab[k] + zz) : 0.0;
+                }
+                d = __dadd_rn(d, ad[k]);
+            }
+            double sv = -__dmul_rn(d, __dmul_rn(xs, x0));
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int32_t zz = z - L.nu[k][S - 1];
+                if (lowok[k] && zz >= 0 && zz < L.nz) {
+                    double xv;
+                    if (HALO != 0 && (zz < L.zlo || zz >= L.zhi)) {
+                        int r = 0;
+                        while (zz >= L.zb[r + 1]) ++r;
+                        const int64_t cc = c + (int64_t)off[k] + (int64_t)L.nu[k][S - 1] * plane;      // column of the predecessor
+                        xv = __ldcg(dp->V[r] + coloff + cc + plane * (zz - L.zb[r]));
+                    } else {
+                        xv = x[(uint32_t)(i + off[k])];
+                    }
+                    sv = fma(ac[k], __dmul_rn(xs, xv), sv);
+                }
+            }
+            __stcs(y + i, sv);
+            if (MODE == 1) dd_add_prod(acc, f, sv);
+            if (MODE == 2) dd_add_prod(acc, sv, sv);
+            i += (uint32_t)plane32;
+        }
+    }
+    if (MODE == 0) return;
+    DD v[1] = {acc};
+    double tot[1];
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, 0.0, 0);
+}
+
+// The reference's column form ADJ/OFFDIAG/DIAG (StateSpace.f90:13-17) of local rows [0, count), computed from
+// the lattice (for kfsp_fsp_get and the parity tests); adj/offdiag are [i*R + k], Fortran conventions.
+__global__ void k_box_export(const __grid_constant__ Lattice L, int64_t g0, int64_t count, int32_t* adj, double* offdiag, double* diag) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        int32_t st[KFSP_MAX_SPECIES];
+        lattice_decode(L, g0 + t, st);
+        double d = 0.0;
+        for (int k = 0; k < L.R; ++k) {
+            const double a = __ldg(L.tab[k] + st[L.sp[k]]);
+            d = __dadd_rn(d, a);
+            if (offdiag) offdiag[t * L.R + k] = a;
+            if (adj) {
+                bool neg = false, out = false;
+                int64_t o = 0;
+                for (int s = 0; s < L.S; ++s) {
+                    const int32_t v = st[s] + L.nu[k][s];
+                    neg = neg || v < 0;
+                    out = out || v >= L.B[s];
+                    o += (int64_t)L.nu[k][s] * L.stride[s];
+                }
+                adj[t * L.R + k] = neg ? -1 : out ? 0 : (int32_t)(g0 + t + o + 1);
+            }
+        }
+        if (diag) diag[t] = d;
+    }
+}
+
+// FSP%INDEX / FSP%PROBABILITY on the lattice (1-based global index, 0 = not in the projection); w holds the
+// local rows starting at global row g0
+__global__ void k_box_lookup(const __grid_constant__ Lattice L, const int32_t* __restrict__ q, int64_t nq, int32_t* idx1,
+                             const double* __restrict__ w, int64_t g0, int64_t nloc, double* p) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nq; t += (int64_t)gridDim.x * blockDim.x) {
+        bool in = true;
+        int64_t g = 0;
+        for (int s = 0; s < L.S; ++s) {
+            const int32_t v = q[t * L.S + s];
+            in = in && v >= 0 && v < L.B[s];
+            g += (int64_t)v * L.stride[s];
+        }
+        if (idx1) idx1[t] = in ? (int32_t)(g + 1) : 0;
+        if (p) p[t] = (in && g >= g0 && g < g0 + nloc) ? w[g - g0] : 0.0;
+    }
+}
+
+}  // namespace kfsp

@@ -191,6 +191,11 @@ class KrylovFspHandle:
         st = np.ascontiguousarray(np.asarray(states, dtype=np.int32).reshape(-1, self.S))
         check(lib().kfsp_fsp_init(self._h, st.shape[0], _i32(st)), "MATRIX_STARTER")
 
+    def fsp_init_box(self, bounds):
+        """spmv_variant = 1: the projection is the lattice [0,bounds[0]) x ... in natural order (no state list)."""
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        check(lib().kfsp_fsp_init_box(self._h, _i32(b)), "kfsp_fsp_init_box")
+
     def onestep(self):
         check(lib().kfsp_fsp_onestep(self._h), "ONESTEP_EXTENDER")
 
