@@ -8,6 +8,10 @@ krylovfspssa_b200/models/toggle_test.input with (kx,ky,dx,dy) = (5000,1600,1,1),
 two discretised Gaussians centred mid-box (sigma = B/16), fixed state set (FSP adaptivity off),
 KRYTOL 1e-8, Krylov dimension adapting in [10, 30].
 
+The generator SpMV runs matrix-free on the lattice by default (--spmv-variant 1, csrc/lattice.cuh: FMATVEC recomputed
+from the integer state, 16 B/state, bit-identical to the explicit matrix); the same line carries a companion measurement
+of the identical solves on the explicit gather-ELL matrix (--spmv-variant 0 makes that one the main measurement).
+
 A "step" is one complete adaptive expv solve exp(t_final*A) p0 over the whole state space.
 `value` = generator state updates per second = N * NMULT / time with the state space and p0
 resident in HBM (kfsp_solve_resident); `e2e` is the same quantity through the reference-facing
@@ -39,7 +43,7 @@ R_TOGGLE = 4
 # algorithmic bytes per state of one generator SpMV and measured DRAM traffic per state of the
 # dot-fused launch (ncu --set full, profiles/), per SpMV variant: 0 explicit gather-ELL, 1 matrix-free lattice
 BYTES_PER_STATE = {0: 12 * R_TOGGLE + 24, 1: 16}
-TRAFFIC_PER_STATE = {0: 80.9, 1: None}
+TRAFFIC_PER_STATE = {0: 80.9, 1: 27.0}
 KERNEL_NAME = {0: "k_spmv (generator SpMV, explicit gather ELL; per GPU, rank 0)",
                1: "k_spmv_box (generator SpMV, matrix-free on the lattice; per GPU, rank 0)"}
 
@@ -170,6 +174,8 @@ def main():
     ap.add_argument("--ref-t-final", type=float, default=0.05)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-companion", action="store_true",
+                    help="skip the explicit-matrix companion measurement that a --spmv-variant 1 run adds to its line")
     ap.add_argument("--spmv-variant", type=int, default=1, choices=[0, 1],
                     help="0: explicit gather-ELL matrix (the reference's data model); 1: matrix-free lattice SpMV "
                          "(bit-identical results, 16 instead of 72 bytes per state)")
@@ -346,6 +352,58 @@ def main():
                 "launches_timed": spmv_launches, "share_of_step": spmv_s / dev_s_rank if dev_s_rank > 0 else None,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
+    # ---- companion: the same resident solves on the EXPLICIT gather-ELL matrix (the reference's data model), so that one
+    # line shows both generator-SpMV kernels against the HBM roofline; results of the two variants are bit-identical
+    companion = None
+    if variant == 1 and not args.no_companion:
+        h0 = k.KrylovFspHandle(model, max_states=n + 64, m_max=args.m_max, m_min=10, n_init_onestep=0, enable_drop=0,
+                               enable_expand=0, device=local_rank, spmv_variant=0)
+        if world > 1:
+            uid0 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid0.copy_(torch.frombuffer(bytearray(k.KrylovFspHandle.dist_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid0, 0)
+            h0.dist_init(rank, world, uid0.cpu().numpy().tobytes())
+        check(L.kfsp_fsp_init(h0._h, n, C.cast(states_h.data_ptr(), i32p)), "MATRIX_STARTER")
+        lo0, hi0 = 0, n
+        if world > 1:
+            info0 = h0.dist_info()
+            lo0, hi0 = info0["lo"], info0["hi"]
+        p0_dev0 = C.c_void_p()
+        check(L.kfsp_device_alloc(h0._h, 8 * (hi0 - lo0), C.byref(p0_dev0)))
+        check(L.kfsp_device_upload(h0._h, p0_dev0, C.c_void_p(p0_h.data_ptr() + 8 * lo0), 8 * (hi0 - lo0)))
+        check(L.kfsp_set_profiling(h0._h, 1))
+        c_dev = c_spmv = 0.0
+        c_mult = c_launch = 0
+        for it in range(args.warmup + args.steps):
+            if it == args.warmup:
+                barrier()
+            check(L.kfsp_fsp_set_vector_device(h0._h, p0_dev0, hi0 - lo0))
+            st = Stats()
+            rc = L.kfsp_solve_resident(h0._h, args.t_final, fsp_tol, kry_tol, 0, C.byref(st))
+            if rc < 0:
+                raise k.KfspError(rc, "kfsp_solve_resident (explicit companion)")
+            if it >= args.warmup:
+                c_dev += st.device_seconds
+                c_spmv += st.spmv_seconds
+                c_mult += st.nmult
+                c_launch += st.spmv_launches
+        barrier()
+        same = bool(c_mult == nmult)
+        tt = torch.tensor([c_dev], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        c_avg = c_spmv / max(c_launch, 1)
+        c_ach = BYTES_PER_STATE[0] * (hi0 - lo0) / c_avg / 1e9 if c_avg > 0 else 0.0
+        companion = {"spmv_variant": "explicit gather-ELL matrix", "value": float(n) * c_mult / float(tt.item()), "unit": UNIT,
+                     "ms_per_step": 1e3 * float(tt.item()) / args.steps, "same_spmv_count_as_main": same,
+                     "roofline": {"bound": "hbm", "kernel": KERNEL_NAME[0], "achieved": c_ach, "peak": peak, "unit": "GB/s",
+                                  "frac": c_ach / peak, "algorithmic_bytes_per_state": BYTES_PER_STATE[0],
+                                  "avg_launch_ms": 1e3 * c_avg, "launches_timed": c_launch,
+                                  "share_of_step": c_spmv / c_dev if c_dev > 0 else None,
+                                  "traffic": TRAFFIC_PER_STATE[0] * (hi0 - lo0)}}
+        h0.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cn, cm, t_sweep, t_mv = cpu_sample(args.cpu_bx, args.cpu_by, 10)
@@ -372,7 +430,7 @@ def main():
                        "NVLink/NVSwitch; NCCL only bootstraps, KFSP_DIST_P2P=0 selects the NCCL send/recv + all-gather path)" % world},
             "expv_wall_s_to_t_final": dev_s / args.steps, "krylov_steps_per_solve": nstep / args.steps,
             "spmv_per_solve": nmult / args.steps, "setup_s": t_setup, "host_wall_s": wall,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "explicit_matrix_companion": companion, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "probability_mass_out": total_mass,
             "dist": dinfo,
         }

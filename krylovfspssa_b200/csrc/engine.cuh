@@ -1157,13 +1157,17 @@ struct Engine {
         const Reducer r = MODE != 0 ? next_rd() : rd;
         Reducer r2 = r;
         if (halo && !r2.peers) r2.peers = dist.d_peers;
-        // z-chunks: at most (and as close as possible to) 4 work items per resident CTA so that no CTA runs a
-        // fifth one while the rest idle, at least 16 planes each (2 halo rows per chunk are re-read)
+        // z-chunks: k work items per resident CTA, never k+1 for some while the rest idle; k = 4 when that leaves
+        // chunks of >= 96 planes (2 halo rows are re-read and PF rows start un-prefetched per chunk), else fewer
         auto chunking = [&](int wave, int* zc, int* g) {
-            int64_t nzc = std::max<int64_t>(1, (4 * (int64_t)wave) / ncb);
-            nzc = std::min<int64_t>(nzc, std::max(1, nzl / 16));
-            int z = (int)((nzl + nzc - 1) / nzc);
-            while (z < nzl && ncb * ((nzl + z - 1) / z) > 4 * (int64_t)wave) ++z;      // rounding must not push it past 4 waves
+            int z = nzl;
+            for (int k = 4; k >= 1; --k) {
+                int64_t nzc = std::max<int64_t>(1, (k * (int64_t)wave) / ncb);
+                nzc = std::min<int64_t>(nzc, nzl);
+                z = (int)((nzl + nzc - 1) / nzc);
+                while (z < nzl && ncb * ((nzl + z - 1) / z) > k * (int64_t)wave) ++z;      // rounding must not push it past k waves
+                if (z >= 96 || k == 1) break;
+            }
             *zc = z;
             const int64_t items = ncb * ((nzl + z - 1) / z);
             *g = (int)std::min<int64_t>(items, wave);

@@ -103,15 +103,22 @@ def test_chained_solves_equal_oracle_chain():
     h.close()
 
 
-def test_customprop_is_rejected_loudly():
+def test_python_callable_customprop_solves_like_the_file_model():
+    """MODEL%CUSTOMPROP => a Python callable (ModelModule.f90:6-12,188-189): host callbacks in batches and through
+    the SSA side cache give the same bits as the byte-code model with the same arithmetic (birth-death)."""
     model = k.CME_MODEL().create(1, 2, 2)
     model.stoichiometry = [[1, -1]]
-    model.reset_parameters([5.0, 1.0])
+    model.reset_parameters([20.0, 1.0])
     model.set_customprop(lambda st, r, p: p[0] if r == 1 else p[1] * st[0])
-    assert model.propensity([3], 2) == 3.0               # host-side CUSTOMPROP works (ModelModule.f90:188-189)
-    with pytest.raises(k.KfspError) as e:
-        k.KrylovFspHandle(model, max_states=1000)
-    assert e.value.status == -26                         # ... but cannot be shipped to the device yet
+    assert model.propensity([3], 2) == 3.0
+    h = k.KrylovFspHandle(model, max_states=5000)
+    out = h.solve(2.0, [[0]], [1.0], 1e-6, 1e-10)
+    hf, om, x0 = make("birth_death", max_states=5000)
+    ref = hf.solve(2.0, [x0], [1.0], 1e-6, 1e-10)
+    assert out["iflag"] == ref["iflag"] == 0
+    assert np.array_equal(out["states"], ref["states"]) and np.array_equal(out["vector"], ref["vector"])
+    assert np.array_equal(out["trace"]["i"], ref["trace"]["i"])
+    h.close(); hf.close()
 
 
 def test_small_krylov_range_option():
