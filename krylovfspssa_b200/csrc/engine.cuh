@@ -39,6 +39,9 @@ struct Engine {
     HostModel hm;                     // copy of the host model (callback, parameters, programs)
     PropCache pc;                     // device side cache used by SSA walks in host_prop mode
     int64_t pc_n = 0;                 // cached states
+    char* hp_dev = nullptr;           // device staging of the host-propensity path (grows on demand)
+    char* hp_host = nullptr;          // pinned host staging
+    size_t hp_dev_bytes = 0, hp_host_bytes = 0;
     int64_t host_prop_evals = 0, host_prop_rounds = 0;
     // matrix-free lattice (opt.spmv_variant == 1, lattice.cuh): the projection is a full box in natural order
     bool box = false;
@@ -140,7 +143,8 @@ struct Engine {
         free_state_space();
         free_prop_cache();
         cudaFree(d_model); cudaFree(d_tables); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
-        cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush);
+        cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush); cudaFree(hp_dev);
+        if (hp_host) cudaFreeHost(hp_host);
         if (h_res) cudaFreeHost(h_res);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (auto& e : ev_pool) cudaEventDestroy(e);
@@ -310,14 +314,31 @@ struct Engine {
 
     // ---------------------------------------------------------------- host-evaluated propensities
     void free_prop_cache() {
-        cudaFree(pc.states); cudaFree(pc.table); cudaFree(pc.prop); cudaFree(pc.diag); cudaFree(pc.req); cudaFree(pc.nreq);
+        cudaFree(pc.states); cudaFree(pc.table); cudaFree(pc.prop); cudaFree(pc.req); cudaFree(pc.nreq);
         pc = PropCache();
         pc_n = 0;
+    }
+    // staging buffers of the host-propensity path: allocated once and grown geometrically (a cudaMalloc/cudaFree
+    // pair per expansion cost more than the callbacks themselves)
+    int ensure_hp(size_t dev_bytes, size_t host_bytes) {
+        if (dev_bytes > hp_dev_bytes) {
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+            if (hp_dev) KFSP_CUDA(cudaFree(hp_dev));
+            hp_dev_bytes = align_up(std::max(dev_bytes, 2 * hp_dev_bytes));
+            KFSP_CUDA(cudaMalloc(&hp_dev, hp_dev_bytes));
+        }
+        if (host_bytes > hp_host_bytes) {
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+            if (hp_host) KFSP_CUDA(cudaFreeHost(hp_host));
+            hp_host_bytes = align_up(std::max(host_bytes, 2 * hp_host_bytes));
+            KFSP_CUDA(cudaMallocHost(&hp_host, hp_host_bytes));
+        }
+        return KFSP_OK;
     }
     // capacity for `want` cached states (contents are preserved) and a request list of req_cap states
     int ensure_prop_cache(int64_t want) {
         if (pc.table && want <= pc.ld) return KFSP_OK;
-        int64_t cap = std::max<int64_t>(1 << 14, pc.ld);
+        int64_t cap = std::max<int64_t>(1 << 16, pc.ld);
         while (cap < want) cap <<= 1;
         PropCache q;
         q.ld = cap;
@@ -327,18 +348,14 @@ struct Engine {
         q.req_cap = 1 << 16;
         KFSP_CUDA(cudaMalloc(&q.states, sizeof(int32_t) * cap * S));
         KFSP_CUDA(cudaMalloc(&q.table, sizeof(int32_t) * ts));
-        KFSP_CUDA(cudaMalloc(&q.prop, sizeof(double) * cap * R));
-        KFSP_CUDA(cudaMalloc(&q.diag, sizeof(double) * cap));
+        KFSP_CUDA(cudaMalloc(&q.prop, sizeof(double) * cap * (R + 1)));
         KFSP_CUDA(cudaMalloc(&q.req, sizeof(int32_t) * (size_t)q.req_cap * S));
         KFSP_CUDA(cudaMalloc(&q.nreq, sizeof(int32_t)));
         KFSP_CUDA(cudaMemsetAsync(q.table, 0xFF, sizeof(int32_t) * ts, stream));
         KFSP_CUDA(cudaMemsetAsync(q.nreq, 0, sizeof(int32_t), stream));
         if (pc_n > 0) {
             KFSP_CUDA(cudaMemcpyAsync(q.states, pc.states, sizeof(int32_t) * pc_n * S, cudaMemcpyDeviceToDevice, stream));
-            KFSP_CUDA(cudaMemcpyAsync(q.diag, pc.diag, sizeof(double) * pc_n, cudaMemcpyDeviceToDevice, stream));
-            for (int k = 0; k < R; ++k)
-                KFSP_CUDA(cudaMemcpyAsync(q.prop + (int64_t)k * cap, pc.prop + (int64_t)k * pc.ld, sizeof(double) * pc_n,
-                                          cudaMemcpyDeviceToDevice, stream));
+            KFSP_CUDA(cudaMemcpyAsync(q.prop, pc.prop, sizeof(double) * pc_n * (R + 1), cudaMemcpyDeviceToDevice, stream));
             KFSP_LAUNCH(k_cache_insert, grid_for(pc_n), VEC_THREADS, 0, q, S, (int64_t)0, pc_n, d_err);
         }
         KFSP_CUDA(cudaStreamSynchronize(stream));
@@ -350,7 +367,7 @@ struct Engine {
     }
     int clear_prop_cache() {
         if (!pc.table) return KFSP_OK;
-        KFSP_CUDA(cudaMemsetAsync(pc.table, 0xFF, sizeof(int32_t) * ((size_t)pc.mask + 1), stream));
+        if (pc_n > 0) KFSP_CUDA(cudaMemsetAsync(pc.table, 0xFF, sizeof(int32_t) * ((size_t)pc.mask + 1), stream));
         pc_n = 0;
         return KFSP_OK;
     }
@@ -373,39 +390,35 @@ struct Engine {
     // them, by the host function for the rest.
     int propensities_host(int64_t first, int64_t count) {
         if (count < 1) return KFSP_OK;
-        const size_t a_q = align_up(sizeof(int32_t) * count);
-        std::vector<int32_t> q((size_t)count, -1);
+        const size_t a_i = align_up(sizeof(int32_t) * count), a_s = align_up(sizeof(int32_t) * count * S),
+                     a_v = align_up(sizeof(double) * count * (R + 1));
+        KFSP_TRY(ensure_hp(a_i + a_v, a_i + a_s + a_v));
+        int32_t* d_q = (int32_t*)hp_dev;                 // cache entry per new state, later reused as the index list
+        double* d_vals = (double*)(hp_dev + a_i);
+        int32_t* h_q = (int32_t*)hp_host;
+        int32_t* h_st = (int32_t*)(hp_host + a_i);
+        double* h_vals = (double*)(hp_host + a_i + a_s);
         FspView f = view();
-        int32_t* d_q = nullptr;
-        KFSP_CUDA(cudaMalloc(&d_q, a_q));
-        if (pc.table && pc_n > 0) {
+        const bool cached = pc.table && pc_n > 0;
+        if (cached) {
             KFSP_LAUNCH(k_props_from_cache, grid_for(count), VEC_THREADS, 0, f, first, count, pc, d_q);
-            KFSP_CUDA(cudaMemcpyAsync(q.data(), d_q, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, stream));
-            KFSP_CUDA(cudaStreamSynchronize(stream));
+            KFSP_CUDA(cudaMemcpyAsync(h_q, d_q, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, stream));
         }
-        std::vector<int32_t> idx;
-        for (int64_t t = 0; t < count; ++t) if (q[t] < 0) idx.push_back((int32_t)(first + t));
-        if (!idx.empty()) {
-            std::vector<int32_t> st((size_t)count * S);
-            KFSP_CUDA(cudaMemcpyAsync(st.data(), d_states + first * S, sizeof(int32_t) * count * S, cudaMemcpyDeviceToHost, stream));
-            KFSP_CUDA(cudaStreamSynchronize(stream));
-            std::vector<int32_t> pick(idx.size() * (size_t)S);
-            for (size_t t = 0; t < idx.size(); ++t)
-                std::memcpy(&pick[t * S], &st[(size_t)(idx[t] - first) * S], sizeof(int32_t) * S);
-            std::vector<double> vals(idx.size() * (size_t)(R + 1));
-            eval_host(pick.data(), (int64_t)idx.size(), vals.data());
-            int32_t* d_idx = nullptr;
-            double* d_vals = nullptr;
-            KFSP_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * idx.size()));
-            KFSP_CUDA(cudaMalloc(&d_vals, sizeof(double) * vals.size()));
-            KFSP_CUDA(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice, stream));
-            KFSP_CUDA(cudaMemcpyAsync(d_vals, vals.data(), sizeof(double) * vals.size(), cudaMemcpyHostToDevice, stream));
-            KFSP_LAUNCH(k_scatter_props, grid_for((int64_t)vals.size()), VEC_THREADS, 0, f, (const int32_t*)d_idx, (const double*)d_vals,
-                        (int64_t)idx.size());
-            KFSP_CUDA(cudaStreamSynchronize(stream));
-            cudaFree(d_idx); cudaFree(d_vals);
+        KFSP_CUDA(cudaMemcpyAsync(h_st, d_states + first * S, sizeof(int32_t) * count * S, cudaMemcpyDeviceToHost, stream));
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        // compact the states the cache did not serve to the front of h_st; h_q becomes their row indices
+        int64_t nm = 0;
+        for (int64_t t = 0; t < count; ++t) {
+            if (cached && h_q[t] >= 0) continue;
+            if (nm != t) std::memcpy(h_st + nm * S, h_st + t * S, sizeof(int32_t) * S);
+            h_q[nm++] = (int32_t)(first + t);
         }
-        cudaFree(d_q);
+        if (nm == 0) return KFSP_OK;
+        eval_host(h_st, nm, h_vals);
+        KFSP_CUDA(cudaMemcpyAsync(d_q, h_q, sizeof(int32_t) * nm, cudaMemcpyHostToDevice, stream));
+        KFSP_CUDA(cudaMemcpyAsync(d_vals, h_vals, sizeof(double) * nm * (R + 1), cudaMemcpyHostToDevice, stream));
+        KFSP_LAUNCH(k_scatter_props, grid_for(nm * (R + 1)), VEC_THREADS, 0, f, (const int32_t*)d_q, (const double*)d_vals, nm);
+        KFSP_CUDA(cudaStreamSynchronize(stream));         // the staging buffers are reused by the next call
         return KFSP_OK;
     }
     int propensities(int64_t first, int64_t count) {
@@ -605,7 +618,8 @@ struct Engine {
         FspView f = view();
         if (ssa) {
             KFSP_LAUNCH(k_ssa_walk<true>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
-                        (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand, host_prop ? pc : PropCache());
+                        (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand, host_prop ? pc : PropCache(),
+                        (int32_t*)nullptr);
         } else {
             KFSP_LAUNCH(k_onestep_fill, grid_for(n_old), VEC_THREADS, 0, f, n_old, (const int32_t*)off, cand, d_err);
         }
@@ -629,10 +643,13 @@ struct Engine {
         const int64_t n_old = n;
         ssa_calls += 1;
         size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * scan_buf_ints(n_old));
+        const size_t wsave_at = need0;                  // suspended walks of the host-propensity rounds (dead before the scan)
+        if (host_prop) need0 += align_up(sizeof(int32_t) * n_old * (size_t)(S + 4));
         KFSP_TRY(ensure_scratch(need0));
         int32_t* cnt = (int32_t*)d_scratch;
         int32_t* off = (int32_t*)(d_scratch + align_up(sizeof(int32_t) * n_old));
         int32_t* tb0 = (int32_t*)(d_scratch + 2 * align_up(sizeof(int32_t) * n_old));
+        int32_t* wsave = (int32_t*)(d_scratch + wsave_at);
         FspView f = view();
         if (host_prop) {
             // Rounds: walks that step onto a state the host has not evaluated yet are suspended (cnt = -1) and
@@ -640,48 +657,52 @@ struct Engine {
             KFSP_TRY(ensure_prop_cache(1));
             KFSP_TRY(clear_prop_cache());
             KFSP_LAUNCH(k_fill_i32, grid_for(n_old), VEC_THREADS, 0, cnt, n_old, (int32_t)-1);
-            std::vector<int32_t> req;
-            std::vector<double> vals;
+            const size_t a_r = align_up(sizeof(int32_t) * (size_t)pc.req_cap * S), a_v = align_up(sizeof(double) * (size_t)pc.req_cap * (R + 1));
+            KFSP_TRY(ensure_hp(256, 256 + 2 * a_r + a_v));
+            int32_t* h_nreq = (int32_t*)hp_host;
+            int32_t* h_req = (int32_t*)(hp_host + 256);
+            int32_t* h_uniq = (int32_t*)(hp_host + 256 + a_r);
+            double* h_vals = (double*)(hp_host + 256 + 2 * a_r);
+            struct Key { int32_t v[KFSP_MAX_SPECIES]; bool operator==(const Key& o) const { return std::memcmp(v, o.v, sizeof v) == 0; } };
+            struct KeyHash { size_t operator()(const Key& k) const { return (size_t)hash_state(k.v, KFSP_MAX_SPECIES); } };
+            std::unordered_set<Key, KeyHash> seen;
             for (int64_t round = 0;; ++round) {
                 if (round > (1 << 24)) return KFSP_ERR_SSA_RUNAWAY;
                 KFSP_CUDA(cudaMemsetAsync(pc.nreq, 0, sizeof(int32_t), stream));
                 KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
-                            (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, pc);
-                int32_t nreq = 0;
-                KFSP_CUDA(cudaMemcpyAsync(&nreq, pc.nreq, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+                            (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, pc, wsave);
+                KFSP_CUDA(cudaMemcpyAsync(h_nreq, pc.nreq, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+                // the request list is small: fetch it with the counter instead of paying a second round trip
+                KFSP_CUDA(cudaMemcpyAsync(h_req, pc.req, sizeof(int32_t) * (size_t)std::min<int64_t>(pc.req_cap, 4096) * S, cudaMemcpyDeviceToHost, stream));
                 KFSP_CUDA(cudaStreamSynchronize(stream));
+                const int32_t nreq = *h_nreq;
                 if (nreq == 0) break;
                 ++host_prop_rounds;
                 const int64_t got = std::min<int64_t>(nreq, pc.req_cap);
-                req.resize((size_t)got * S);
-                KFSP_CUDA(cudaMemcpyAsync(req.data(), pc.req, sizeof(int32_t) * got * S, cudaMemcpyDeviceToHost, stream));
-                KFSP_CUDA(cudaStreamSynchronize(stream));
-                // several walks may ask for the same state in one round
-                std::unordered_set<std::string> seen;
-                std::vector<int32_t> uniq;
-                for (int64_t t = 0; t < got; ++t) {
-                    std::string key((const char*)&req[(size_t)t * S], sizeof(int32_t) * S);
-                    if (seen.insert(std::move(key)).second) uniq.insert(uniq.end(), &req[(size_t)t * S], &req[(size_t)t * S] + S);
-                }
-                const int64_t nu = (int64_t)uniq.size() / S;
-                vals.resize((size_t)nu * (R + 1));
-                eval_host(uniq.data(), nu, vals.data());
-                KFSP_TRY(ensure_prop_cache(pc_n + nu));
-                // cache layout is reaction-major: transpose on the host
-                std::vector<double> col((size_t)nu);
-                KFSP_CUDA(cudaMemcpyAsync(pc.states + pc_n * S, uniq.data(), sizeof(int32_t) * nu * S, cudaMemcpyHostToDevice, stream));
-                for (int k = 0; k <= R; ++k) {
-                    for (int64_t t = 0; t < nu; ++t) col[t] = vals[(size_t)t * (R + 1) + k];
-                    double* dst = k < R ? pc.prop + (int64_t)k * pc.ld + pc_n : pc.diag + pc_n;
-                    KFSP_CUDA(cudaMemcpyAsync(dst, col.data(), sizeof(double) * nu, cudaMemcpyHostToDevice, stream));
+                if (got > 4096) {
+                    KFSP_CUDA(cudaMemcpyAsync(h_req + 4096 * S, pc.req + 4096 * S, sizeof(int32_t) * (got - 4096) * S, cudaMemcpyDeviceToHost, stream));
                     KFSP_CUDA(cudaStreamSynchronize(stream));
                 }
+                // several walks may ask for the same state in one round
+                seen.clear();
+                int64_t nu = 0;
+                for (int64_t t = 0; t < got; ++t) {
+                    Key key;
+                    std::memset(key.v, 0, sizeof key.v);
+                    std::memcpy(key.v, h_req + t * S, sizeof(int32_t) * S);
+                    if (seen.insert(key).second) { std::memcpy(h_uniq + nu * S, h_req + t * S, sizeof(int32_t) * S); ++nu; }
+                }
+                eval_host(h_uniq, nu, h_vals);
+                KFSP_TRY(ensure_prop_cache(pc_n + nu));
+                KFSP_CUDA(cudaMemcpyAsync(pc.states + pc_n * S, h_uniq, sizeof(int32_t) * nu * S, cudaMemcpyHostToDevice, stream));
+                KFSP_CUDA(cudaMemcpyAsync(pc.prop + pc_n * (R + 1), h_vals, sizeof(double) * nu * (R + 1), cudaMemcpyHostToDevice, stream));
                 KFSP_LAUNCH(k_cache_insert, grid_for(nu), VEC_THREADS, 0, pc, S, pc_n, nu, d_err);
+                KFSP_CUDA(cudaStreamSynchronize(stream));        // h_uniq / h_vals are rewritten by the next round
                 pc_n += nu;
             }
         } else {
             KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
-                        (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, PropCache());
+                        (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, PropCache(), (int32_t*)nullptr);
         }
         int64_t ncand = 0;
         KFSP_TRY(exclusive_scan(cnt, off, n_old, tb0, &ncand));

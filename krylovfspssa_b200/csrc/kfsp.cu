@@ -101,6 +101,7 @@ int Engine::solve(double T, double fsptol, double krytol, int itrace, kfsp_stats
     const double w0 = wall_now();
     const int64_t l0 = launches;
     for (double& v : phase_s) v = 0.0;
+    host_prop_rounds = host_prop_evals = 0;
     spmv_seconds = 0.0;
     spmv_timed = 0;
     ev_used = 0;
@@ -665,6 +666,8 @@ int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src, int64_t cnt) {
 int kfsp_phase_seconds(kfsp_handle h, double out[8]) {
     if (!h || !out) return KFSP_ERR_ARG;
     for (int i = 0; i < 8; ++i) out[i] = h->e.phase_s[i];
+    out[6] = (double)h->e.host_prop_rounds;
+    out[7] = (double)h->e.host_prop_evals;
     return KFSP_OK;
 }
 int kfsp_launch_count(kfsp_handle h, int64_t* n) {

@@ -49,8 +49,7 @@ struct PropCache {
     int32_t* table = nullptr;   // open addressing, value = q or SLOT_EMPTY
     uint32_t mask = 0;
     int64_t ld = 0;             // capacity in cached states
-    double* prop = nullptr;     // [k*ld + q]
-    double* diag = nullptr;     // [q]
+    double* prop = nullptr;     // [q*(R+1) + k]: a_k of cached state q for k < R, their sum (DIAG) at k = R
     int32_t* req = nullptr;     // request list [r*S + s]
     int32_t* nreq = nullptr;    // number of requests made (may exceed req_cap; the excess is re-requested)
     int32_t req_cap = 0;
@@ -262,11 +261,13 @@ __global__ void k_onestep_fill(FspView f, int64_t n_old, const int32_t* __restri
 template <bool FILL>
 __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t seed, uint32_t call_no,
                            int32_t* cnt, const int32_t* __restrict__ off, int32_t* cand, int32_t* err, int32_t max_jumps,
-                           int64_t ncand, PropCache pc) {
+                           int64_t ncand, PropCache pc, int32_t* wsave) {
     const DeviceModel* __restrict__ m = f.model;
     const int S = f.S, R = f.R;
     for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j0 < n_old; j0 += (int64_t)gridDim.x * blockDim.x) {
-        if (!FILL && pc.table && cnt[j0] >= 0) continue;     // host-propensity rounds: this walk already completed
+        // host-propensity rounds: cnt >= 0 walk completed, -1 not started, -2 suspended (state saved in wsave)
+        const int32_t status = (!FILL && pc.table) ? cnt[j0] : -1;
+        if (status >= 0) continue;
         bool suspended = false;
         if (FILL) {
             // replay only the walks that left the projection in the counting pass (a small boundary fraction)
@@ -279,7 +280,16 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
         double t = 0.0;
         int32_t emitted = 0;
         int64_t o = FILL ? (int64_t)off[j0] : 0;
-        for (uint32_t jump = 0;; ++jump) {
+        uint32_t jump0 = 0;
+        if (status == -2) {             // resume where the walk stopped: counter-based RNG, so the draws repeat exactly
+            const int32_t* __restrict__ sv = wsave + j0 * (int64_t)(S + 4);
+            for (int s = 0; s < S; ++s) st[s] = sv[s];
+            t = __hiloint2double(sv[S + 1], sv[S]);
+            jump0 = (uint32_t)sv[S + 2];
+            emitted = sv[S + 3];
+            j = -1;
+        }
+        for (uint32_t jump = jump0;; ++jump) {
             if ((int32_t)jump >= max_jumps) { atomicOr(err, DEV_RUNAWAY); break; }
             double r1, r2;
             philox_uniform2(seed, call_no, (uint32_t)(j0 + 1), jump, &r1, &r2);
@@ -297,11 +307,16 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
                     const int32_t r = atomicAdd(pc.nreq, 1);
                     if (r < pc.req_cap)
                         for (int s = 0; s < S; ++s) pc.req[(int64_t)r * S + s] = st[s];
+                    int32_t* sv = wsave + j0 * (int64_t)(S + 4);
+                    for (int s = 0; s < S; ++s) sv[s] = st[s];
+                    sv[S] = __double2loint(t); sv[S + 1] = __double2hiint(t);
+                    sv[S + 2] = (int32_t)jump; sv[S + 3] = emitted;
                     suspended = true;
                     break;
                 }
-                dg = pc.diag[q];
-                for (int k = 0; k < R; ++k) pr[k] = pc.prop[(int64_t)k * pc.ld + q];
+                const double* __restrict__ row = pc.prop + (int64_t)q * (R + 1);
+                dg = row[R];
+                for (int k = 0; k < R; ++k) pr[k] = row[k];
             } else {
                 dg = 0.0;
                 for (int k = 0; k < R; ++k) { pr[k] = eval_propensity(m, k, st); dg = __dadd_rn(dg, pr[k]); }
@@ -339,7 +354,7 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
                 if (!(t < timestep)) break;
             }
         }
-        if (!FILL) cnt[j0] = suspended ? -1 : emitted;
+        if (!FILL) cnt[j0] = suspended ? -2 : emitted;
     }
 }
 
@@ -353,8 +368,9 @@ __global__ void k_props_from_cache(FspView f, int64_t first, int64_t count, Prop
         const int32_t q = pc.table ? cache_lookup(pc, st, f.S) : IDX_ABSENT;
         cache_q[t] = q;
         if (q < 0) continue;
-        for (int k = 0; k < f.R; ++k) f.prop[(int64_t)k * f.ld + i] = pc.prop[(int64_t)k * pc.ld + q];
-        f.diag[i] = pc.diag[q];
+        const double* __restrict__ row = pc.prop + (int64_t)q * (f.R + 1);
+        for (int k = 0; k < f.R; ++k) f.prop[(int64_t)k * f.ld + i] = row[k];
+        f.diag[i] = row[f.R];
     }
 }
 // vals[t*(R+1) + k] = a_k of state idx[t] (k < R), vals[t*(R+1) + R] = their sum in reaction order

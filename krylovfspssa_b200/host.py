@@ -312,7 +312,8 @@ class KrylovFspHandle:
     def phase_seconds(self):
         buf = (C.c_double * 8)()
         check(lib().kfsp_phase_seconds(self._h, buf))
-        return dict(zip(("sweep_pade", "combine_norms", "ssa", "drop", "onestep"), list(buf)[:5]))
+        return dict(zip(("sweep_pade", "combine_norms", "ssa", "drop", "onestep", "host_callbacks", "ssa_cache_rounds",
+                         "host_propensity_evals"), list(buf)))
 
     @property
     def launches(self):

@@ -11,10 +11,18 @@ sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import krylovfspssa_b200 as k
 from gpu_common import make
 
+from krylovfspssa_b200 import examples
+
+DRIVERS = {"driver_toggle": ("toggle", 400000), "driver_repressilator": ("repressilator", 2000000), "transcr6d": ("transcr6d", 6291469)}
 RUNS = {"toggle": (1000.0, 1e-4, 1e-10, 400000), "repressilator": (10.0, 1e-4, 1e-10, 2000000), "goutsias": (300.0, 1e-6, 1e-8, 6291469)}
 for name in sys.argv[1:] or list(RUNS):
-    t, ftol, ktol, cap = RUNS[name]
-    h, _, x0 = make(name, max_states=cap, seed=12345)
+    if name in DRIVERS:                       # the reference's example programs: CUSTOMPROP host callbacks
+        d = examples.DRIVERS[DRIVERS[name][0]]
+        t, ftol, ktol, cap, x0 = d["t"], d["fsp_tol"], d["exp_tol"], DRIVERS[name][1], d["x0"]
+        h = k.KrylovFspHandle(examples.driver_model(DRIVERS[name][0]), max_states=cap, seed=12345)
+    else:
+        t, ftol, ktol, cap = RUNS[name]
+        h, _, x0 = make(name, max_states=cap, seed=12345)
     out = h.solve(t, [x0], [1.0], ftol, ktol)
     out = h.solve(t, [x0], [1.0], ftol, ktol)
     st = out["stats"]
