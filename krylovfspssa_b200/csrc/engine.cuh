@@ -1180,7 +1180,7 @@ struct Engine {
         if (halo && !r2.peers) r2.peers = dist.d_peers;
         // z-chunks: k work items per resident CTA, never k+1 for some while the rest idle; k = 4 when that leaves
         // chunks of >= 96 planes (2 halo rows are re-read and PF rows start un-prefetched per chunk), else fewer
-        auto chunking = [&](int wave, int* zc, int* g) {
+        auto chunking = [&](int wave, int64_t ncb, int* zc, int* g) {
             int z = nzl;
             for (int k = 4; k >= 1; --k) {
                 int64_t nzc = std::max<int64_t>(1, (k * (int64_t)wave) / ncb);
@@ -1193,8 +1193,27 @@ struct Engine {
             const int64_t items = ncb * ((nzl + z - 1) / z);
             *g = (int)std::min<int64_t>(items, wave);
         };
+        // 2-species one-molecule-step networks in the reference's reaction orders (config 5, the toggle models): stencil kernel
+        const int bd_ord = box_tune < 10 ? lattice_bd2_order(lat) : -1;
+        if (bd_ord >= 0) {
+            void (*kb)(const Lattice, int, int, const double*, double*, const double*, Reducer, SweepCtl*, double*, int, int, int64_t) = nullptr;
+            int ts = 0;
+            for (int k = 0; k < 4; ++k) ts |= (lat.sp[k] == 1 ? 1 : 0) << k;
+#define KFSP_BD2(T) case T: kb = bd_ord == 0 ? k_spmv_bd2<0, T, MODE, 4, 3> : k_spmv_bd2<1, T, MODE, 4, 3>; break
+            switch (ts) {
+                KFSP_BD2(0); KFSP_BD2(1); KFSP_BD2(2); KFSP_BD2(3); KFSP_BD2(4); KFSP_BD2(5); KFSP_BD2(6); KFSP_BD2(7);
+                KFSP_BD2(8); KFSP_BD2(9); KFSP_BD2(10); KFSP_BD2(11); KFSP_BD2(12); KFSP_BD2(13); KFSP_BD2(14); KFSP_BD2(15);
+            }
+#undef KFSP_BD2
+            const int64_t ncb_bd = (lat.plane + BD2_CBW - 1) / BD2_CBW;
+            const int wave = wave_grid((const void*)kb, (int64_t)1 << 40);
+            int zc, g;
+            chunking(wave, ncb_bd, &zc, &g);
+            kb<<<g, VEC_THREADS, 0, stream>>>(lat, zc, halo ? 1 : 0, x, y, first, r2, d_ctl, h_out, cx, cf, (int64_t)(d_V ? x - d_V : 0));
+            return check_launch();
+        }
         void (*kern)(const Lattice, int, int, const double*, double*, const double*, Reducer, SweepCtl*, double*, int, int, int64_t) = nullptr;
-        const int tune = box_tune;
+        const int tune = box_tune >= 10 ? box_tune - 10 : box_tune;
 #define KFSP_BOX_PICK(RR)                                                                                                   \
         kern = halo ? (S == 2 ? k_spmv_box<RR, 2, MODE, 2, 1, 6, 3> : k_spmv_box<RR, 0, MODE, 2, 1, 6, 3>)                      \
              : S != 2 ? k_spmv_box<RR, 0, MODE, 0, 1, 6, 4>                                                                     \
@@ -1209,7 +1228,7 @@ struct Engine {
 #undef KFSP_BOX_PICK
         const int wave = wave_grid((const void*)kern, (int64_t)1 << 40);
         int zc, g;
-        chunking(wave, &zc, &g);
+        chunking(wave, ncb, &zc, &g);
         kern<<<g, VEC_THREADS, 0, stream>>>(lat, zc, cbw, x, y, first, r2, d_ctl, h_out, cx, cf, (int64_t)(d_V ? x - d_V : 0));
         return check_launch();
     }

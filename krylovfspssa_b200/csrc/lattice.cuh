@@ -184,6 +184,160 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
     if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, 0.0, 0);
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast path for the network shape of the synthetic large-copy-number workload (BASELINE config 5) and of the
+// reference's 2-species models: two species, four reactions, each adding or removing ONE molecule of one
+// species, in one of the two orders the reference's model files use
+//     ORD 0:  0->X, X->0, 0->Y, Y->0   (toggle_model.input, bursting_gene_model.input)
+//     ORD 1:  0->X, 0->Y, X->0, Y->0   (toggle_test_model.input = config 5)
+// each propensity a table over x or over y (bit k of TS set: reaction k's table runs over y = z).
+// With the stencil known at compile time nothing is re-read from memory: rows z-1, z, z+1 of a column live in a
+// rolling register window fed by ONE first-touch load per row (issued PF rows before its use through a register
+// ring), the +-1 neighbours in x are the adjacent lanes' registers (warp shuffle: a warp covers 30 columns plus
+// one halo lane on each side, which loads but does not store), the y-tables roll like x.  ncu on the generic kernel
+// showed 43 % of all stall samples on the re-read of x(c-1, z) through L1 (hit rate 51 %).
+// Same operation order as k_spmv_box / k_spmv (reactions in model order): bit-identical results
+// (tests/test_gpu_lattice.py runs all three).
+// ---------------------------------------------------------------------------------------
+enum Bd2Dir : int { BD_XP = 0, BD_XM = 1, BD_YP = 2, BD_YM = 3 };      // the species and sign of the reaction's step
+__host__ __device__ constexpr int bd2_dir(int ord, int k) {
+    return ord == 0 ? k : (k == 0 ? BD_XP : k == 1 ? BD_YP : k == 2 ? BD_XM : BD_YM);
+}
+// -1 if the lattice is not of this family, else the ORD id
+inline int lattice_bd2_order(const Lattice& L) {
+    if (L.S != 2 || L.R != 4) return -1;
+    const int step[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+    for (int ord = 0; ord < 2; ++ord) {
+        bool ok = true;
+        for (int k = 0; k < 4; ++k) {
+            const int d = bd2_dir(ord, k);
+            ok = ok && L.nu[k][0] == step[d][0] && L.nu[k][1] == step[d][1];
+        }
+        if (ok) return ord;
+    }
+    return -1;
+}
+constexpr int BD2_WCOLS = 30;                                  // live columns per warp (lanes 1..30; lanes 0 and 31 are halo)
+constexpr int BD2_CBW = BD2_WCOLS * (VEC_THREADS / 32);        // live columns per CTA
+template <int ORD, int TS, int MODE, int PF, int MINB>
+__global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_constant__ Lattice L, int zc, int halo,
+                                                                const double* __restrict__ x, double* __restrict__ y,
+                                                                const double* __restrict__ first, Reducer rd, SweepCtl* ctl, double* h_out,
+                                                                int cx, int cf, int64_t coloff) {
+    if (MODE != 0 && ctl->brk != 0) return;
+    const double xs = col_scale(ctl, cx);
+    const double fs = MODE == 1 ? col_scale(ctl, cf) : 1.0;
+    const int32_t Bx = L.B[0], nz = L.nz;
+    const int nzl = L.zhi - L.zlo;
+    const int64_t ncb = (Bx + BD2_CBW - 1) / BD2_CBW;
+    const int64_t nzc = (nzl + zc - 1) / zc;
+    const DistPeers* __restrict__ dp = rd.peers;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // x(c, zz) for any plane zz of the box: this rank's slab, or (several GPUs) the owner's basis column over NVLink
+    auto row = [&](int32_t c, int32_t zz) -> double {
+        if (!halo || (zz >= L.zlo && zz < L.zhi)) return x[(uint32_t)(c + Bx * (zz - L.zlo))];
+        int r = 0;
+        while (zz >= L.zb[r + 1]) ++r;
+        return __ldcg(dp->V[r] + coloff + c + (int64_t)Bx * (zz - L.zb[r]));
+    };
+    DD acc; acc.hi = 0.0; acc.lo = 0.0;
+    for (int64_t item = blockIdx.x; item < ncb * nzc; item += gridDim.x) {
+        // lanes 1..30 own a column, lanes 0 / 31 shadow the column to the left / right (clamped into the box): every
+        // lane walks z and keeps x(c, z) in a register, so x(c-1, z) and x(c+1, z) are one shuffle away
+        const int32_t c_raw = (int32_t)((item % ncb) * BD2_CBW) + warp * BD2_WCOLS + lane - 1;
+        const bool live = lane >= 1 && lane <= BD2_WCOLS && c_raw < Bx;
+        const int32_t c = c_raw < 0 ? 0 : (c_raw >= Bx ? Bx - 1 : c_raw);
+        const int32_t z0 = L.zlo + (int32_t)(item / ncb) * zc;
+        const int32_t z1 = min(z0 + zc, L.zhi);
+        const bool okl = c >= 1, okr = c + 1 < Bx;
+        // per reaction: a_k(x) for the diagonal and a_k(x - nu_k) for the off-diagonal term.  Tables over x are constant
+        // along the walk; tables over y roll: tcur = T[z], tprev = T[z-1], and T[z+1] is fetched per row.
+        double adc[4], acn[4], tprev[4], tcur[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int dir = bd2_dir(ORD, k);
+            const bool tz = (TS >> k) & 1;
+            adc[k] = 0.0; acn[k] = 0.0; tprev[k] = 0.0; tcur[k] = 0.0;
+            if (!tz) {
+                adc[k] = __ldg(L.tab[k] + c);
+                acn[k] = dir == BD_XP ? (okl ? __ldg(L.tab[k] + c - 1) : 0.0) : dir == BD_XM ? (okr ? __ldg(L.tab[k] + c + 1) : 0.0) : adc[k];
+            } else {
+                tcur[k] = __ldg(L.tab[k] + z0);
+                if (dir == BD_YP && z0 >= 1) tprev[k] = __ldg(L.tab[k] + z0 - 1);
+            }
+        }
+        uint32_t i = (uint32_t)(c + Bx * (z0 - L.zlo));
+        double xm = z0 >= 1 ? row(c, z0 - 1) : 0.0;
+        double x0 = x[i];
+        // software pipeline in registers: slot u holds x(c, z+1) and first(c, z) of the row that will be evaluated
+        // PF rows after the slot was filled, so a row never waits for its own first-touch loads
+        double xq[PF], fq[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int32_t z = z0 + u;
+            xq[u] = (z < z1 && z + 1 < nz) ? row(c, z + 1) : 0.0;
+            fq[u] = (MODE == 1 && live && z < z1) ? __ldcs(first + (i + (uint32_t)(Bx * u))) : 0.0;
+        }
+        for (int32_t zb = z0; zb < z1; zb += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int32_t z = zb + u;
+                if (z < z1) {                                   // uniform over the CTA: the shuffles below are convergent
+                    const bool up = z + 1 < nz;
+                    const double xp = xq[u];
+                    const double f = __dmul_rn(fs, fq[u]);
+                    {   // refill the slot for row z + PF
+                        const int32_t zn = z + PF;
+                        xq[u] = (zn < z1 && zn + 1 < nz) ? row(c, zn + 1) : 0.0;
+                        if (MODE == 1) fq[u] = (live && zn < z1) ? __ldcs(first + (i + (uint32_t)(Bx * PF))) : 0.0;
+                    }
+                    const double xl = __shfl_up_sync(0xffffffffu, x0, 1);
+                    const double xr = __shfl_down_sync(0xffffffffu, x0, 1);
+                    double ad[4], ac[4], tnext[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int dir = bd2_dir(ORD, k);
+                        const bool tz = (TS >> k) & 1;
+                        tnext[k] = 0.0;
+                        if (tz) {
+                            if (up) tnext[k] = __ldg(L.tab[k] + z + 1);
+                            ad[k] = tcur[k];
+                            ac[k] = dir == BD_YP ? tprev[k] : dir == BD_YM ? tnext[k] : tcur[k];
+                        } else {
+                            ad[k] = adc[k];
+                            ac[k] = acn[k];
+                        }
+                    }
+                    double d = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) d = __dadd_rn(d, ad[k]);
+                    double sv = -__dmul_rn(d, __dmul_rn(xs, x0));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int dir = bd2_dir(ORD, k);
+                        const bool ok = dir == BD_XP ? okl : dir == BD_XM ? okr : dir == BD_YP ? z >= 1 : up;
+                        const double xv = dir == BD_XP ? xl : dir == BD_XM ? xr : dir == BD_YP ? xm : xp;
+                        if (ok) sv = fma(ac[k], __dmul_rn(xs, xv), sv);
+                    }
+                    if (live) {
+                        __stcs(y + i, sv);
+                        if (MODE == 1) dd_add_prod(acc, f, sv);
+                        if (MODE == 2) dd_add_prod(acc, sv, sv);
+                    }
+                    xm = x0; x0 = xp;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { tprev[k] = tcur[k]; tcur[k] = tnext[k]; }
+                    i += (uint32_t)Bx;
+                }
+            }
+        }
+    }
+    if (MODE == 0) return;
+    DD v[1] = {acc};
+    double tot[1];
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, 0.0, 0);
+}
+
 // The reference's column form ADJ/OFFDIAG/DIAG (StateSpace.f90:13-17) of local rows [0, count), computed from
 // the lattice (for kfsp_fsp_get and the parity tests); adj/offdiag are [i*R + k], Fortran conventions.
 __global__ void k_box_export(const __grid_constant__ Lattice L, int64_t g0, int64_t count, int32_t* adj, double* offdiag, double* diag) {

@@ -48,6 +48,6 @@ if __name__ == "__main__":
         one(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     else:
         bx, by = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (10000, 10000)
-        for variant, tune in [(0, "0"), (1, "0"), (1, "1")]:
+        for variant, tune in [(1, "0"), (1, "10")]:
             env = dict(os.environ, KFSP_BOX_TUNE=tune)
             subprocess.run([sys.executable, os.path.abspath(__file__), "one", str(variant), str(bx), str(by)], env=env)
