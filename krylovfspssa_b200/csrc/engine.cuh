@@ -1199,7 +1199,7 @@ struct Engine {
             void (*kb)(const Lattice, int, int, const double*, double*, const double*, Reducer, SweepCtl*, double*, int, int, int64_t) = nullptr;
             int ts = 0;
             for (int k = 0; k < 4; ++k) ts |= (lat.sp[k] == 1 ? 1 : 0) << k;
-#define KFSP_BD2(T) case T: kb = bd_ord == 0 ? k_spmv_bd2<0, T, MODE, 4, 3> : k_spmv_bd2<1, T, MODE, 4, 3>; break
+#define KFSP_BD2(T) case T: kb = bd_ord == 0 ? k_spmv_bd2<0, T, MODE, 3, 4> : k_spmv_bd2<1, T, MODE, 3, 4>; break
             switch (ts) {
                 KFSP_BD2(0); KFSP_BD2(1); KFSP_BD2(2); KFSP_BD2(3); KFSP_BD2(4); KFSP_BD2(5); KFSP_BD2(6); KFSP_BD2(7);
                 KFSP_BD2(8); KFSP_BD2(9); KFSP_BD2(10); KFSP_BD2(11); KFSP_BD2(12); KFSP_BD2(13); KFSP_BD2(14); KFSP_BD2(15);
@@ -1209,6 +1209,10 @@ struct Engine {
             const int wave = wave_grid((const void*)kb, (int64_t)1 << 40);
             int zc, g;
             chunking(wave, ncb_bd, &zc, &g);
+            if (zc > BD2_ZT) {                              // the staged y-tables bound the chunk length
+                zc = BD2_ZT;
+                g = (int)std::min<int64_t>(ncb_bd * ((nzl + zc - 1) / zc), wave);
+            }
             kb<<<g, VEC_THREADS, 0, stream>>>(lat, zc, halo ? 1 : 0, x, y, first, r2, d_ctl, h_out, cx, cf, (int64_t)(d_V ? x - d_V : 0));
             return check_launch();
         }

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
 // With the stencil known at compile time nothing is re-read from memory: rows z-1, z, z+1 of a column live in a
 // rolling register window fed by ONE first-touch load per row (issued PF rows before its use through a register
 // ring), the +-1 neighbours in x are the adjacent lanes' registers (warp shuffle: a warp covers 30 columns plus
-// one halo lane on each side, which loads but does not store), the y-tables roll like x.  ncu on the generic kernel
+// one halo lane on each side, which loads but does not store), the y-tables of a chunk sit in shared memory.  ncu on the generic kernel
 // showed 43 % of all stall samples on the re-read of x(c-1, z) through L1 (hit rate 51 %).
 // Same operation order as k_spmv_box / k_spmv (reactions in model order): bit-identical results
 // (tests/test_gpu_lattice.py runs all three).
@@ -219,6 +219,7 @@ inline int lattice_bd2_order(const Lattice& L) {
 }
 constexpr int BD2_WCOLS = 30;                                  // live columns per warp (lanes 1..30; lanes 0 and 31 are halo)
 constexpr int BD2_CBW = BD2_WCOLS * (VEC_THREADS / 32);        // live columns per CTA
+constexpr int BD2_ZT = 256;                                    // longest z-chunk (rows of the y-tables staged in shared memory)
 template <int ORD, int TS, int MODE, int PF, int MINB>
 __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_constant__ Lattice L, int zc, int halo,
                                                                 const double* __restrict__ x, double* __restrict__ y,
@@ -240,8 +241,22 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
         while (zz >= L.zb[r + 1]) ++r;
         return __ldcg(dp->V[r] + coloff + c + (int64_t)Bx * (zz - L.zb[r]));
     };
+    // y-tables of the chunk, staged once per work item: ztab[k][j] = T_k[z0 - 1 + j].  (Read per row straight from global
+    // memory they missed the streaming-thrashed L1 half of the time: 62 % of all stall samples sat on the fma waiting for
+    // T[z+1], profiles/r1_summary.md.)
+    __shared__ double ztab[4][BD2_ZT + 2];
     DD acc; acc.hi = 0.0; acc.lo = 0.0;
     for (int64_t item = blockIdx.x; item < ncb * nzc; item += gridDim.x) {
+        {
+            const int32_t zs = L.zlo + (int32_t)(item / ncb) * zc - 1, cnt = min(zc, L.zhi - (zs + 1)) + 2;
+            __syncthreads();
+            for (int q = threadIdx.x; q < 4 * cnt; q += VEC_THREADS) {
+                const int k = q / cnt, j = q - k * cnt;
+                const int32_t zz = zs + j;
+                ztab[k][j] = (((TS >> k) & 1) && zz >= 0 && zz < nz) ? __ldg(L.tab[k] + zz) : 0.0;
+            }
+            __syncthreads();
+        }
         // lanes 1..30 own a column, lanes 0 / 31 shadow the column to the left / right (clamped into the box): every
         // lane walks z and keeps x(c, z) in a register, so x(c-1, z) and x(c+1, z) are one shuffle away
         const int32_t c_raw = (int32_t)((item % ncb) * BD2_CBW) + warp * BD2_WCOLS + lane - 1;
@@ -251,24 +266,23 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
         const int32_t z1 = min(z0 + zc, L.zhi);
         const bool okl = c >= 1, okr = c + 1 < Bx;
         // per reaction: a_k(x) for the diagonal and a_k(x - nu_k) for the off-diagonal term.  Tables over x are constant
-        // along the walk; tables over y roll: tcur = T[z], tprev = T[z-1], and T[z+1] is fetched per row.
-        double adc[4], acn[4], tprev[4], tcur[4];
+        // along the walk; tables over y come from the staged chunk (ztab).
+        double adc[4], acn[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int dir = bd2_dir(ORD, k);
             const bool tz = (TS >> k) & 1;
-            adc[k] = 0.0; acn[k] = 0.0; tprev[k] = 0.0; tcur[k] = 0.0;
+            adc[k] = 0.0; acn[k] = 0.0;
             if (!tz) {
                 adc[k] = __ldg(L.tab[k] + c);
                 acn[k] = dir == BD_XP ? (okl ? __ldg(L.tab[k] + c - 1) : 0.0) : dir == BD_XM ? (okr ? __ldg(L.tab[k] + c + 1) : 0.0) : adc[k];
-            } else {
-                tcur[k] = __ldg(L.tab[k] + z0);
-                if (dir == BD_YP && z0 >= 1) tprev[k] = __ldg(L.tab[k] + z0 - 1);
             }
         }
         uint32_t i = (uint32_t)(c + Bx * (z0 - L.zlo));
-        double xm = z0 >= 1 ? row(c, z0 - 1) : 0.0;
-        double x0 = x[i];
+        // the window holds xs * x (the column scale DSCAL would have applied, krylov.cuh): one multiplication per element
+        // instead of one per use -- FP64 issue, not HBM, is what bounds this kernel on B200 (profiles/r1_summary.md)
+        double xm = z0 >= 1 ? __dmul_rn(xs, row(c, z0 - 1)) : 0.0;
+        double x0 = __dmul_rn(xs, x[i]);
         // software pipeline in registers: slot u holds x(c, z+1) and first(c, z) of the row that will be evaluated
         // PF rows after the slot was filled, so a row never waits for its own first-touch loads
         double xq[PF], fq[PF];
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                 const int32_t z = zb + u;
                 if (z < z1) {                                   // uniform over the CTA: the shuffles below are convergent
                     const bool up = z + 1 < nz;
-                    const double xp = xq[u];
+                    const double xp = __dmul_rn(xs, xq[u]);
                     const double f = __dmul_rn(fs, fq[u]);
                     {   // refill the slot for row z + PF
                         const int32_t zn = z + PF;
@@ -293,16 +307,15 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                     }
                     const double xl = __shfl_up_sync(0xffffffffu, x0, 1);
                     const double xr = __shfl_down_sync(0xffffffffu, x0, 1);
-                    double ad[4], ac[4], tnext[4];
+                    double ad[4], ac[4];
+                    const int jz = z - z0 + 1;                  // row z in the staged y-tables
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int dir = bd2_dir(ORD, k);
                         const bool tz = (TS >> k) & 1;
-                        tnext[k] = 0.0;
                         if (tz) {
-                            if (up) tnext[k] = __ldg(L.tab[k] + z + 1);
-                            ad[k] = tcur[k];
-                            ac[k] = dir == BD_YP ? tprev[k] : dir == BD_YM ? tnext[k] : tcur[k];
+                            ad[k] = ztab[k][jz];
+                            ac[k] = dir == BD_YP ? ztab[k][jz - 1] : dir == BD_YM ? ztab[k][jz + 1] : ad[k];
                         } else {
                             ad[k] = adc[k];
                             ac[k] = acn[k];
@@ -311,13 +324,13 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                     double d = 0.0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) d = __dadd_rn(d, ad[k]);
-                    double sv = -__dmul_rn(d, __dmul_rn(xs, x0));
+                    double sv = -__dmul_rn(d, x0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int dir = bd2_dir(ORD, k);
                         const bool ok = dir == BD_XP ? okl : dir == BD_XM ? okr : dir == BD_YP ? z >= 1 : up;
                         const double xv = dir == BD_XP ? xl : dir == BD_XM ? xr : dir == BD_YP ? xm : xp;
-                        if (ok) sv = fma(ac[k], __dmul_rn(xs, xv), sv);
+                        if (ok) sv = fma(ac[k], xv, sv);
                     }
                     if (live) {
                         __stcs(y + i, sv);
@@ -325,8 +338,6 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                         if (MODE == 2) dd_add_prod(acc, sv, sv);
                     }
                     xm = x0; x0 = xp;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { tprev[k] = tcur[k]; tcur[k] = tnext[k]; }
                     i += (uint32_t)Bx;
                 }
             }
