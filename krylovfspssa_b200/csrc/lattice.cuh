@@ -219,6 +219,7 @@ inline int lattice_bd2_order(const Lattice& L) {
 }
 constexpr int BD2_WCOLS = 30;                                  // live columns per warp (lanes 1..30; lanes 0 and 31 are halo)
 constexpr int BD2_CBW = BD2_WCOLS * (VEC_THREADS / 32);        // live columns per CTA
+constexpr int BD2_L2AHEAD = 10;                                // rows ahead of the walk that are prefetched into L2
 constexpr int BD2_ZT = 256;                                    // longest z-chunk (rows of the y-tables staged in shared memory)
 template <int ORD, int TS, int MODE, int PF, int MINB>
 __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_constant__ Lattice L, int zc, int halo,
@@ -300,10 +301,14 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                     const bool up = z + 1 < nz;
                     const double xp = __dmul_rn(xs, xq[u]);
                     const double f = __dmul_rn(fs, fq[u]);
-                    {   // refill the slot for row z + PF
+                    {   // refill the slot for row z + PF; rows further ahead are pulled into L2 (costs no registers)
                         const int32_t zn = z + PF;
                         xq[u] = (zn < z1 && zn + 1 < nz) ? row(c, zn + 1) : 0.0;
                         if (MODE == 1) fq[u] = (live && zn < z1) ? __ldcs(first + (i + (uint32_t)(Bx * PF))) : 0.0;
+                        if (MODE == 1 && z + BD2_L2AHEAD + 1 < L.zhi) {      // measured: helps the two-stream (dot-fused) variant only
+                            lattice_prefetch<1>(x + (i + (uint32_t)(Bx * (BD2_L2AHEAD + 1))));
+                            lattice_prefetch<1>(first + (i + (uint32_t)(Bx * BD2_L2AHEAD)));
+                        }
                     }
                     const double xl = __shfl_up_sync(0xffffffffu, x0, 1);
                     const double xr = __shfl_down_sync(0xffffffffu, x0, 1);
