@@ -43,9 +43,9 @@ R_TOGGLE = 4
 # algorithmic bytes per state of one generator SpMV and measured DRAM traffic per state of the
 # dot-fused launch (ncu --set full, profiles/), per SpMV variant: 0 explicit gather-ELL, 1 matrix-free lattice
 BYTES_PER_STATE = {0: 12 * R_TOGGLE + 24, 1: 16}
-TRAFFIC_PER_STATE = {0: 80.9, 1: 27.0}
+TRAFFIC_PER_STATE = {0: 80.9, 1: 27.2}
 KERNEL_NAME = {0: "k_spmv (generator SpMV, explicit gather ELL; per GPU, rank 0)",
-               1: "k_spmv_box (generator SpMV, matrix-free on the lattice; per GPU, rank 0)"}
+               1: "k_spmv_bd2 (generator SpMV, matrix-free stencil kernel on the lattice; per GPU, rank 0)"}
 
 
 def synthetic(bx, by):
