@@ -205,6 +205,13 @@ int kfsp_dist_init(kfsp_handle h, int32_t rank, int32_t nranks, const uint8_t id
 /* host-side partition arithmetic (no GPU needed): block partition of n rows */
 int kfsp_dist_partition(int64_t n, int32_t nranks, int32_t rank, int64_t* lo, int64_t* hi);
 int kfsp_dist_owner(int64_t n, int32_t nranks, int64_t row, int32_t* owner);
+/* host-side arithmetic of the lattice variant (spmv_variant = 1; no GPU needed): rank's slab [zlo,zhi) of the slowest
+ * species, and which SpMV kernel a lattice model gets (*kind: 0 generic, 1 / 2 two-species stencil kernel with the
+ * reaction order of toggle_model.input / toggle_test_model.input; *table_mask bit k: reaction k's table runs over
+ * the slowest species). */
+int kfsp_lattice_partition(int32_t nz, int32_t nranks, int32_t rank, int32_t* zlo, int32_t* zhi);
+int kfsp_lattice_kernel(int32_t S, int32_t R, const int32_t* stoich /* S*R */, const int32_t* table_species /* R */,
+                        int32_t* kind, int32_t* table_mask);
 int kfsp_dist_info(kfsp_handle h, int64_t* lo, int64_t* hi, int64_t* n_halo, int64_t* n_send, int64_t* halo_bytes, int64_t* reductions);
 
 /* device memory helpers for hosts without their own CUDA runtime (bench, tests) */

@@ -86,6 +86,8 @@ SIGNATURES = {
     "kfsp_dist_init": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
     "kfsp_dist_partition": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _i64p, _i64p]),
     "kfsp_dist_owner": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _i32p]),
+    "kfsp_lattice_partition": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p]),
+    "kfsp_lattice_kernel": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p]),
     "kfsp_dist_info": (C.c_int, [_vp, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p]),
     "kfsp_device_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "kfsp_device_free": (C.c_int, [_vp, _vp]),

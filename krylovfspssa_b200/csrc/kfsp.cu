@@ -598,6 +598,32 @@ int kfsp_dist_owner(int64_t n, int32_t nranks, int64_t row, int32_t* owner) {
     *owner = part_owner(n, nranks, row);
     return KFSP_OK;
 }
+// host-side arithmetic of the lattice variant (no GPU needed): slab of the slowest species owned by `rank`
+int kfsp_lattice_partition(int32_t nz, int32_t nranks, int32_t rank, int32_t* zlo, int32_t* zhi) {
+    if (nz < 1 || nranks < 1 || nz < nranks || rank < 0 || rank >= nranks || !zlo || !zhi) return KFSP_ERR_ARG;
+    *zlo = (int32_t)((int64_t)nz * rank / nranks);
+    *zhi = (int32_t)((int64_t)nz * (rank + 1) / nranks);
+    return KFSP_OK;
+}
+// which SpMV kernel a lattice model gets: *kind = 0 generic k_spmv_box, 1 / 2 = k_spmv_bd2 with reaction order 0 / 1;
+// *table_mask bit k = reaction k's propensity table runs over the slowest species.  stoich is species-fastest (S*R),
+// table_species[k] is the one species reaction k's propensity reads.
+int kfsp_lattice_kernel(int32_t S, int32_t R, const int32_t* stoich, const int32_t* table_species, int32_t* kind, int32_t* table_mask) {
+    if (S < 2 || S > KFSP_MAX_SPECIES || R < 1 || R > BOX_MAX_R || !stoich || !table_species || !kind) return KFSP_ERR_ARG;
+    Lattice L;
+    std::memset(&L, 0, sizeof L);
+    L.S = S; L.R = R;
+    int32_t mask = 0;
+    for (int k = 0; k < R; ++k) {
+        if (table_species[k] < 0 || table_species[k] >= S) return KFSP_ERR_UNSUPPORTED;
+        for (int s = 0; s < S; ++s) L.nu[k][s] = stoich[k * S + s];
+        L.sp[k] = table_species[k];
+        if (table_species[k] == S - 1) mask |= 1 << k;
+    }
+    *kind = lattice_bd2_order(L) + 1;
+    if (table_mask) *table_mask = mask;
+    return KFSP_OK;
+}
 int kfsp_dist_info(kfsp_handle h, int64_t* lo, int64_t* hi, int64_t* n_halo, int64_t* n_send, int64_t* halo_bytes, int64_t* reductions) {
     if (!h) return KFSP_ERR_ARG;
     const Dist& d = h->e.dist;
