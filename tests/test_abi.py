@@ -31,6 +31,28 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert set(_lib.SIGNATURES) <= set(names)
 
 
+def test_fortran_shim_binds_only_exported_symbols():
+    """Every BIND(C, NAME='...') of the reference-side binding names a symbol the header declares and the library exports,
+    and its derived types list the fields of the C structs in order (the shim cannot be compiled here: no Fortran compiler)."""
+    src = open(os.path.join(ROOT, "krylovfspssa_b200", "fortran", "kfsp_c_binding.f90")).read()
+    bound = sorted(set(re.findall(r"NAME\s*=\s*'(kfsp_[a-z0-9_]+)'", src)))
+    assert len(bound) >= 8 and "kfsp_solve" in bound and "kfsp_model_set_custom_propensity" in bound
+    L = C.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    for n in bound:
+        assert n in names and hasattr(L, n), n
+
+    def fortran_fields(type_name):
+        body = re.search(r"TYPE, BIND\(C\) :: %s(.*?)END TYPE" % type_name, src, flags=re.S).group(1)
+        out = []
+        for line in body.splitlines():
+            if "::" in line:
+                out += [f.strip().lower() for f in line.split("::")[1].split(",")]
+        return out
+    assert fortran_fields("KFSP_OPTIONS") == [n for n, _ in _lib.Options._fields_]
+    assert fortran_fields("KFSP_STATS") == [n for n, _ in _lib.Stats._fields_]
+
+
 def test_struct_layouts_match_the_header():
     # sizes the Fortran shim (krylovfspssa_b200/fortran/kfsp_c_binding.f90) relies on
     assert C.sizeof(_lib.Options) == 12 * 4 + 8 + 6 * 8 + 8
