@@ -139,3 +139,34 @@ def test_lattice_rejects_what_it_cannot_do():
     with pytest.raises(k.KfspError):                      # adaptivity must be off
         h3 = k.KrylovFspHandle(model, max_states=10000, spmv_variant=1)
         h3.fsp_init_box((20, 10))
+
+
+def role_model(order, mask):
+    """2-species model of four one-molecule reactions in reaction order `order` (0: X+,X-,Y+,Y-; 1: X+,Y+,X-,Y-) whose
+    k-th propensity reads Y if bit k of `mask` is set, else X: every instantiation of the stencil kernel k_spmv_bd2."""
+    steps = {0: [(1, 0), (-1, 0), (0, 1), (0, -1)], 1: [(1, 0), (0, 1), (-1, 0), (0, -1)]}[order]
+    m = k.CME_MODEL().create(2, 4, 4)
+    m.stoichiometry = np.array(steps, dtype=np.int32).T
+    m.reset_parameters([3.0, 0.7, 2.5, 1.1])
+    for r in range(4):
+        v = "X2" if (mask >> r) & 1 else "X1"
+        # production terms are Hill-like (transcendental: host-tabulated), degradation terms linear
+        expr = "p%d/(1.0+%s^1.5)" % (r + 1, v) if steps[r][0] + steps[r][1] > 0 else "p%d*%s" % (r + 1, v)
+        m.set_propensity(r + 1, expr)
+    m.loaded = True
+    return m
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_stencil_kernel_every_table_role(order):
+    bounds = (67, 35)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(bounds[0] * bounds[1])
+    v = np.abs(rng.standard_normal(bounds[0] * bounds[1]))
+    for mask in range(16):
+        a, b, st = pair(role_model(order, mask), bounds)
+        assert np.array_equal(a.matvec(x), b.matvec(x)), (order, mask)           # plain SpMV
+        Ha, ava, _, _ = a.arnoldi(v, 10)
+        Hb, avb, _, _ = b.arnoldi(v, 10)
+        assert np.array_equal(Ha, Hb) and ava == avb, (order, mask)              # dot-fused and norm-fused variants
+        a.close(); b.close()
