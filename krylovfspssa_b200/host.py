@@ -159,6 +159,14 @@ class KrylovFspHandle:
         check(lib().kfsp_set_model(self._h, model._h), "kfsp_set_model")
         self.S, self.R, _ = model._dims()
 
+    def set_model(self, model=None):
+        """Ship MODEL to the device again, e.g. after RESET_PARAMETERS (ModelModule.f90:201-217): the device state space
+        and workspaces of the handle are kept when the model's shape is unchanged."""
+        if model is not None:
+            self.model = model
+        check(lib().kfsp_set_model(self._h, self.model._h), "kfsp_set_model")
+        self.S, self.R, _ = self.model._dims()
+
     def close(self):
         if self._h:
             lib().kfsp_destroy(self._h)

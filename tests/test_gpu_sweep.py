@@ -1,0 +1,26 @@
+"""Parameter sweep on one GPU: one handle, RESET_PARAMETERS + kfsp_set_model between solves, every set bit-identical to
+the oracle solved with that set."""
+import os
+
+import numpy as np
+import pytest
+
+import krylovfspssa_b200 as k
+import oracle
+from krylovfspssa_b200 import sweep
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sweep_matches_oracle_per_set():
+    path = os.path.join(k.models_dir(), "toggle.input")
+    sets = [[1.0, 100.0, 1.0, 1.0, 100.0, 1.0], [2.0, 60.0, 1.0, 1.0, 80.0, 1.5], [1.0, 100.0, 1.0, 1.0, 100.0, 1.0]]
+    model = k.CME_MODEL().load(path)
+    res = sweep.run_share(model, sets, [0, 0], 2.0, 1e-4, 1e-10, max_states=400000, seed=12345, device=0)
+    assert sorted(res) == [0, 1, 2]
+    for i, ps in enumerate(sets):
+        ref = oracle.solve(oracle.Model.load(path, ps), [[0, 0]], [1.0], 2.0, 1e-4, 1e-10, seed=12345, reproducible=1)
+        assert np.array_equal(res[i]["states"], ref["states"]) and np.array_equal(res[i]["vector"], ref["vector"]), i
+    assert np.array_equal(res[0]["vector"], res[2]["vector"])            # the handle carries nothing over between sets
+    summ = sweep.gather_summaries(res, 3)
+    assert [s["n"] for s in summ] == [len(res[i]["vector"]) for i in range(3)]
