@@ -347,6 +347,9 @@ def main():
                 "algorithmic_bytes_per_launch": bps * nloc,
                 "algorithmic_bytes_per_launch_incl_fused_dot_operand": (bps + 8) * nloc,
                 "achieved_incl_fused_dot_operand": (bps + 8) * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0,
+                "frac_incl_fused_dot_operand": (bps + 8) * nloc / spmv_avg / 1e9 / peak if spmv_avg > 0 else 0.0,
+                "note": "achieved/frac count the SpMV's own algorithmic bytes (SURVEY 8d); 10 of every 11 timed launches also "
+                        "compute the first IOP dot product in the same pass, which reads 8 B/state more (the *_incl_fused_dot_operand fields)",
                 "states_per_s_per_launch": nloc / spmv_avg if spmv_avg > 0 else 0.0,
                 "avg_launch_ms": 1e3 * spmv_avg,
                 "launches_timed": spmv_launches, "share_of_step": spmv_s / dev_s_rank if dev_s_rank > 0 else None,

@@ -227,6 +227,9 @@ int kfsp_set_profiling(kfsp_handle h, int32_t on);
 /* FSP%VECTOR(1:n) = src (device pointer), rest zero: device-to-device reset between benchmark steps */
 int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src_device, int64_t n);
 int kfsp_launch_count(kfsp_handle h, int64_t* n);
+/* Generator-SpMV launches of the last solve by kind: [0] plain FMATVEC, [1] fused with the first IOP DDOT
+ * (KrylovSolver.f90:240-243), [2] fused with the norm of the extra product (AVNORM, :261-263). */
+int kfsp_spmv_launch_counts(kfsp_handle h, int64_t out[3]);
 /* Host wall clock of the last solve by phase: [0] Arnoldi sweep + Pade, [1] basis combination + norms,
  * [2] SSA_EXTENDER, [3] DROP_STATES, [4] ONESTEP_EXTENDER, [5] host propensity callbacks (CUSTOMPROP; included in 2 and 4), [6] SSA side-cache rounds and [7] host propensity evaluations (counts) (each phase ends in a stream synchronisation). */
 int kfsp_phase_seconds(kfsp_handle h, double out[8]);

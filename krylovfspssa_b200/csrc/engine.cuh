@@ -93,6 +93,7 @@ struct Engine {
     bool profile_spmv = false;
     double spmv_seconds = 0.0;
     int64_t spmv_timed = 0;
+    int64_t spmv_by_mode[3] = {0, 0, 0};    // generator SpMV launches of the last solve: plain, dot-fused, norm-fused
     std::vector<cudaEvent_t> ev_pool;   // pairs of events bracketing SpMV launches (profiling only)
     size_t ev_used = 0;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -721,6 +722,7 @@ struct Engine {
     int spmv(const double* x, double* y, const double* first, double* h_out, int cx = -1, int cf = -1) {
         const bool timed = profile_spmv && ev_used + 2 <= ev_pool.size();
         if (timed) KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
+        spmv_by_mode[MODE] += 1;
         if (box) {
             KFSP_TRY(spmv_box<MODE>(x, y, first, h_out, cx, cf));
             if (timed) {

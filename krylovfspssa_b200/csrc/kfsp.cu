@@ -102,6 +102,7 @@ int Engine::solve(double T, double fsptol, double krytol, int itrace, kfsp_stats
     const int64_t l0 = launches;
     for (double& v : phase_s) v = 0.0;
     host_prop_rounds = host_prop_evals = 0;
+    spmv_by_mode[0] = spmv_by_mode[1] = spmv_by_mode[2] = 0;
     spmv_seconds = 0.0;
     spmv_timed = 0;
     ev_used = 0;
@@ -694,6 +695,11 @@ int kfsp_phase_seconds(kfsp_handle h, double out[8]) {
     for (int i = 0; i < 8; ++i) out[i] = h->e.phase_s[i];
     out[6] = (double)h->e.host_prop_rounds;
     out[7] = (double)h->e.host_prop_evals;
+    return KFSP_OK;
+}
+int kfsp_spmv_launch_counts(kfsp_handle h, int64_t out[3]) {
+    if (!h || !out) return KFSP_ERR_ARG;
+    for (int i = 0; i < 3; ++i) out[i] = h->e.spmv_by_mode[i];
     return KFSP_OK;
 }
 int kfsp_launch_count(kfsp_handle h, int64_t* n) {
