@@ -134,3 +134,62 @@ def test_drop_states_semantics(models_dir):
     assert np.array_equal(d["states"][:, 0], np.arange(f.size))     # stable compaction keeps order
     assert d["adj"][f.size - 1, 0] == 0                             # dropped target becomes explorable
     assert np.array_equal(w2, w[: f.size])
+
+
+def cme_on_a_big_box(model, bounds, x0, t):
+    """Independent solution of dp/dt = A p: the CME generator on a box far larger than the support, assembled from
+    MODEL%PROPENSITY, integrated by scipy.sparse.linalg.expm_multiply (no Krylov-FSP code involved)."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import expm_multiply
+    S, R = model.S, model.R
+    grids = np.meshgrid(*[np.arange(b) for b in bounds], indexing="ij")
+    states = np.stack([g.ravel() for g in grids], axis=1).astype(np.int32)
+    strides = np.array([int(np.prod(bounds[s + 1:])) for s in range(S)])
+    n = len(states)
+    rows, cols, vals = [], [], []
+    diag = np.zeros(n)
+    for k in range(R):
+        a = np.array([model.propensity(s, k + 1) for s in states])
+        nxt = states + model.stoich[k]
+        inside = np.all((nxt >= 0) & (nxt < np.array(bounds)), axis=1)
+        diag -= a
+        rows.append((nxt[inside] * strides).sum(axis=1)); cols.append(np.nonzero(inside)[0]); vals.append(a[inside])
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)) + sp.diags(diag)
+    p0 = np.zeros(n)
+    p0[int((np.asarray(x0) * strides).sum())] = 1.0
+    return states, strides, expm_multiply(A * t, p0)
+
+
+@pytest.mark.parametrize("repro", [0, 1])
+def test_toggle_against_an_independent_cme_solver(models_dir, repro):
+    """The whole adaptive algorithm (Krylov steps + SSA/one-step expansion + pruning) against scipy on a big box: the
+    FSP solution must be within FSPTOL (plus Krylov tolerance) of the CME solution in 1-norm -- the error bound the
+    algorithm promises (KrylovSolver.f90:458), checked without any of its own code."""
+    params, t, ftol = [1, 100, 1, 1, 100, 1], 2.0, 1e-4
+    m = oracle.Model.load(os.path.join(models_dir, "toggle.input"), params)
+    out = oracle.solve(m, [[0, 0]], [1.0], t, ftol, 1e-10, reproducible=repro)
+    assert out["iflag"] == 0
+    bounds = (int(out["states"][:, 0].max()) + 40, int(out["states"][:, 1].max()) + 40)
+    states, strides, ptrue = cme_on_a_big_box(m, bounds, [0, 0], t)
+    assert ptrue.sum() > 1 - 1e-9                                   # the box itself loses nothing
+    idx = (out["states"] * strides).sum(axis=1)
+    inside = np.zeros(len(ptrue), dtype=bool)
+    inside[idx] = True
+    err = np.abs(out["vector"] - ptrue[idx]).sum() + ptrue[~inside].sum()
+    assert err <= 1.05 * ftol, err
+    assert err > 1e-9                                               # and it IS a truncation, not the same computation
+
+
+def test_repressilator_against_an_independent_cme_solver(models_dir):
+    params, x0, t, ftol = [100.0, 100.0, 100.0, 1.0, 1.0, 1.0], [22, 0, 0], 0.3, 1e-4
+    m = oracle.Model.load(os.path.join(models_dir, "repressilator.input"), params)
+    out = oracle.solve(m, [x0], [1.0], t, ftol, 1e-10, reproducible=1)
+    assert out["iflag"] == 0
+    bounds = tuple(int(out["states"][:, s].max()) + 12 for s in range(3))
+    states, strides, ptrue = cme_on_a_big_box(m, bounds, x0, t)
+    assert ptrue.sum() > 1 - 1e-8
+    idx = (out["states"] * strides).sum(axis=1)
+    inside = np.zeros(len(ptrue), dtype=bool)
+    inside[idx] = True
+    err = np.abs(out["vector"] - ptrue[idx]).sum() + ptrue[~inside].sum()
+    assert 1e-9 < err <= 1.05 * ftol, err
