@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--ref-t-final", type=float, default=0.05)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scattered", action="store_true",
+                    help="SURVEY 8d scattered-order variant: the same state set with its indices permuted by a fixed Philox permutation "
+                         "(seed 12345) -- the irregular gather a real FSP ordering produces; explicit matrix only")
     ap.add_argument("--no-companion", action="store_true",
                     help="skip the explicit-matrix companion measurement that a --spmv-variant 1 run adds to its line")
     ap.add_argument("--spmv-variant", type=int, default=1, choices=[0, 1],
@@ -210,6 +213,13 @@ def main():
     bx, by = args.bx, args.by
     states_np, p0_np = synthetic(bx, by)
     n = len(p0_np)
+    if args.scattered:
+        if args.spmv_variant != 0:
+            raise SystemExit("--scattered needs --spmv-variant 0: the lattice variant requires the natural order")
+        perm = np.random.Generator(np.random.Philox(12345)).permutation(n)
+        states_np = np.ascontiguousarray(states_np[perm])
+        p0_np = np.ascontiguousarray(p0_np[perm])
+        del perm
     # pinned host buffers (inputs and outputs of the C-ABI call)
     states_h = torch.from_numpy(states_np).pin_memory()
     p0_h = torch.from_numpy(p0_np).pin_memory()
@@ -422,7 +432,8 @@ def main():
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config 5: synthetic toggle, rectangle %dx%d = %d FSP states, expv to t_final=%g, "
-                                   "KRYTOL 1e-8, Krylov dimension in [10,%d], fixed state set" % (bx, by, n, args.t_final, args.m_max),
+                                   "KRYTOL 1e-8, Krylov dimension in [10,%d], fixed state set%s"
+                                   % (bx, by, n, args.t_final, args.m_max, ", indices in scattered (Philox-permuted) order" if args.scattered else ""),
                        "states": n, "reactions": R_TOGGLE,
                        "spmv_variant": "matrix-free lattice (FMATVEC recomputed from the integer state, bit-identical to the explicit "
                                        "matrix)" if variant == 1 else "explicit gather-ELL matrix (ADJ/OFFDIAG/DIAG in HBM)",
