@@ -437,7 +437,8 @@ def main():
                        "states": n, "reactions": R_TOGGLE,
                        "spmv_variant": "matrix-free lattice (FMATVEC recomputed from the integer state, bit-identical to the explicit "
                                        "matrix)" if variant == 1 else "explicit gather-ELL matrix (ADJ/OFFDIAG/DIAG in HBM)",
-                       "l2": "inputs (0.8 GB per vector%s) exceed the 126 MB L2" % (", 7.2 GB matrix" if variant == 0 else ""),
+                       "l2": "inputs (%.2f GB per vector%s) %s the 126 MB L2" % (8e-9 * n, ", %.1f GB matrix" % (56e-9 * n) if variant == 0 else "",
+                                                                               "exceed" if 8 * n > 126e6 else "DO NOT exceed"),
                        "parallelism": "1 GPU" if world == 1 else
                        "rows block-partitioned over %d GPUs; per SpMV the halo is gathered straight from the neighbours' HBM and per "
                        "reduction the double-double partials are exchanged inside the reducing kernel (cudaIpc peer memory over "
