@@ -192,8 +192,11 @@ int kfsp_arnoldi(kfsp_handle h, const double* v, int32_t m, double* H_out, doubl
                  double* seconds);
 /* DGPADMnorm  src/expokit/dgpadm.f:171-339 on one CTA: out = exp(t*H(1:m,1:m)), ld(out)=m */
 int kfsp_expm(kfsp_handle h, int32_t m, double t, const double* H, int32_t ldh, double* out, int32_t* ns, double* hnorm);
-/* W = beta*V(:,1:mx)*e, clamp, 1-norm (KrylovSolver.f90:444-450) exposed for tests: V is n x mx column-major */
-int kfsp_combine(kfsp_handle h, int64_t n, int32_t mx, double beta, const double* V, const double* e, double* w, double* wsum);
+/* W = beta*V(:,1:mx)*e, clamp, 1-norm (KrylovSolver.f90:444-450) exposed for tests: V is n x mx column-major.
+ * colscale (mx entries, NULL = all 1): the device keeps the basis un-normalised, column j of V is multiplied by
+ * colscale[j] = 1/HJ1J on load (the DSCAL of KrylovSolver.f90:258, never run as a pass).  wssq (optional): sum w^2. */
+int kfsp_combine(kfsp_handle h, int64_t n, int32_t mx, double beta, const double* V, const double* e, const double* colscale,
+                 double* w, double* wsum, double* wssq);
 
 /* ---- multi-GPU (one process per GPU; rows of the state space are block-partitioned) ---- */
 #define KFSP_NCCL_ID_BYTES 128

@@ -81,7 +81,7 @@ SIGNATURES = {
     "kfsp_matvec_device": (C.c_int, [_vp, _vp, _vp, C.c_int32, _dp]),
     "kfsp_arnoldi": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp, _i32p, _dp]),
     "kfsp_expm": (C.c_int, [_vp, C.c_int32, C.c_double, _dp, C.c_int32, _dp, _i32p, _dp]),
-    "kfsp_combine": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_double, _dp, _dp, _dp, _dp]),
+    "kfsp_combine": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp]),
     "kfsp_dist_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "kfsp_dist_init": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
     "kfsp_dist_partition": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _i64p, _i64p]),

@@ -31,10 +31,12 @@ struct Engine {
     bool have_model = false;
     DeviceModel* d_model = nullptr;
     double* d_tables = nullptr;       // host-built propensity tables
-    int n_tabulated = 0, n_inexact_on_device = 0;
+    int n_tabulated = 0, n_inexact_on_device = 0, n_host_evaluated = 0;
     int S = 0, R = 0;
-    // host-evaluated propensities: CUSTOMPROP callbacks (ModelModule.f90:6-12,188-190), or byte code evaluated
-    // by the host libm when a multi-species program holds a transcendental operation (KFSP_HOST_PROP=1)
+    // host-evaluated propensities: CUSTOMPROP callbacks (ModelModule.f90:6-12,188-190), and byte code that holds a
+    // transcendental operation on SEVERAL species (not tabulable): the CUDA math library may differ from the host libm by
+    // ulps there, which could flip an SSA reaction pick or a DROP decision, so such programs are evaluated by the host
+    // interpreter through the CUSTOMPROP machinery (KFSP_DEVICE_MATH=1 keeps them on the device; kfsp_model_info reports it)
     bool host_prop = false;
     HostModel hm;                     // copy of the host model (callback, parameters, programs)
     PropCache pc;                     // device side cache used by SSA walks in host_prop mode
@@ -48,6 +50,7 @@ struct Engine {
     Lattice lat{};
     DeviceModel h_dm{};               // host mirror of *d_model (table pointers, stoichiometry)
     int box_tune = 0;                 // KFSP_BOX_TUNE: rows per batch / CTAs per SM of the lattice SpMV (A/B)
+    int bd2_zc = 0;                   // KFSP_BD2_ZC: forced rows per z-chunk of the stencil kernel (0 = automatic)
 
     // state space
     int64_t ld = 0;                   // capacity in states (multiple of 64)
@@ -103,6 +106,7 @@ struct Engine {
         opt = *o;
         if (const char* ev = std::getenv("KFSP_SPMV_TUNE")) spmv_tune = std::atoi(ev);
         if (const char* ev = std::getenv("KFSP_BOX_TUNE")) box_tune = std::atoi(ev);
+        if (const char* ev = std::getenv("KFSP_BD2_ZC")) bd2_zc = std::atoi(ev);
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
         if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
             opt.max_states > 2000000000LL)
@@ -225,6 +229,22 @@ struct Engine {
             for (int s = 0; s < m.S; ++s) dm.stoich[k * m.S + s] = m.stoich[(size_t)k * m.S + s];
         int nc = 0, ni = 0;
         if ((int)m.programs.size() != m.R) return KFSP_ERR_NO_MODEL;
+        {   // multi-species transcendental programs: host evaluation keeps the results bit-identical to the host's
+            int inexact_multi = 0;
+            for (int k = 0; k < m.R; ++k) {
+                if (m.programs[k].empty()) return KFSP_ERR_NO_MODEL;
+                uint32_t mask = 0; bool ix = false;
+                program_profile(m.programs[k], m.S, &mask, &ix);
+                if (ix && (mask & (mask - 1)) != 0) ++inexact_multi;
+            }
+            const char* ev = std::getenv("KFSP_DEVICE_MATH");
+            if (inexact_multi > 0 && !(ev && std::atoi(ev) != 0)) {
+                const int st = set_model_hostprop(m);
+                n_inexact_on_device = 0;
+                n_host_evaluated = inexact_multi;
+                return st;
+            }
+        }
         for (int k = 0; k < m.R; ++k) {
             const Program& p = m.programs[k];
             if (p.empty()) return KFSP_ERR_NO_MODEL;
@@ -238,7 +258,7 @@ struct Engine {
         dm.code_begin[m.R] = nc; dm.immed_begin[m.R] = ni;
         for (int i = 0; i < m.P; ++i) dm.params[i] = m.params[i];
         // tabulate single-species propensities that contain a transcendental operation
-        n_tabulated = 0; n_inexact_on_device = 0;
+        n_tabulated = 0; n_inexact_on_device = 0; n_host_evaluated = 0;
         const int64_t tlen = (int64_t)opt.max_molecules + 1;
         std::vector<int> tab_k;
         for (int k = 0; k < m.R; ++k) {
@@ -299,7 +319,7 @@ struct Engine {
             for (int s = 0; s < m.S; ++s) dm.stoich[k * m.S + s] = m.stoich[(size_t)k * m.S + s];
         for (int i = 0; i < m.P; ++i) dm.params[i] = m.params[i];
         for (int k = 0; k < m.R; ++k) { dm.table_species[k] = -1; dm.table[k] = nullptr; }
-        n_tabulated = 0; n_inexact_on_device = 0;
+        n_tabulated = 0; n_inexact_on_device = 0; n_host_evaluated = m.custom ? m.R : 0;
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
         KFSP_CUDA(cudaStreamSynchronize(stream));
         const bool reshape = !have_model || m.S != S || m.R != R;
@@ -455,7 +475,9 @@ struct Engine {
     }
     int ensure_basis() {
         if (d_V) return KFSP_OK;
-        KFSP_CUDA(cudaMalloc(&d_V, sizeof(double) * (size_t)ld * (opt.m_max + 2)));
+        // m_max+2 basis columns, the scratch column T of the fused lattice sweep (lattice.cuh), and slack for its L2 prefetches
+        const size_t slack = box ? (size_t)(BD2_L2AHEAD + 8) * (size_t)lat.B[0] : 0;
+        KFSP_CUDA(cudaMalloc(&d_V, sizeof(double) * ((size_t)ld * (opt.m_max + 3) + slack)));
         if (dist.nranks > 1) KFSP_TRY(dist_setup_p2p());       // collective: every rank allocates its basis here
         return KFSP_OK;
     }
@@ -556,7 +578,11 @@ struct Engine {
         KFSP_TRY(exclusive_scan(win, pos, ncand, tile_buf, &total));
         int32_t e = 0;
         KFSP_TRY(read_err(&e));
-        if (e) return err_to_status(e);
+        if (e) {                                            // the table holds provisional slots >= n: release them
+            KFSP_LAUNCH(k_rollback_candidates, grid_for(ncand), VEC_THREADS, 0, d_table, (const int32_t*)slot, ncand, (int32_t)n);
+            KFSP_TRY(sync());
+            return err_to_status(e);
+        }
         *n_new = total;
         return KFSP_OK;
     }
@@ -720,6 +746,19 @@ struct Engine {
     // ---------------------------------------------------------------- FMATVEC
     template <int MODE>
     int spmv(const double* x, double* y, const double* first, double* h_out, int cx = -1, int cf = -1) {
+        // several GPUs, peer-memory halo: remote rows are addressed as (peer's basis) + (x - d_V), which only means
+        // something for a column of the basis.  Any other operand (kfsp_matvec, kfsp_matvec_device) is staged in the
+        // scratch column first; the barrier makes every rank's copy visible before any rank gathers from it.
+        if (dist.nranks > 1 && dist.p2p && dist.p2p_halo) {
+            KFSP_TRY(ensure_basis());
+            const double* vend = d_V + (size_t)ld * (opt.m_max + 3);
+            if (x < d_V || x >= vend) {
+                double* stage = d_V + (size_t)ld * (opt.m_max + 2);
+                KFSP_CUDA(cudaMemcpyAsync(stage, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+                KFSP_TRY(dist_barrier());
+                x = stage;
+            }
+        }
         const bool timed = profile_spmv && ev_used + 2 <= ev_pool.size();
         if (timed) KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
         spmv_by_mode[MODE] += 1;
@@ -755,7 +794,7 @@ struct Engine {
         kern<<<g, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, first, r2, d_ctl, h_out, cx, cf, dist.halo, n,
                                            (int64_t)(d_V ? x - d_V : 0));
         KFSP_TRY(check_launch());
-        if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, 1, h_out, 0));
+        if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, 1, h_out, nullptr, cx));
         if (timed) {
             KFSP_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
             ev_used += 2;
@@ -795,7 +834,7 @@ struct Engine {
         double droptol = opt.drop_tol0;
         const size_t a_i = align_up(sizeof(int32_t) * lsize);
         const size_t need = 256 + 3 * a_i + align_up(sizeof(int32_t) * scan_buf_ints(lsize)) +
-                            align_up(sizeof(double) * lsize * (size_t)std::max(R, 1)) + 64;
+                            align_up((size_t)lsize * (size_t)std::max(std::max(8 * R, 4 * S), 8)) + 64;     // compaction scratch: R doubles or S ints per state
         KFSP_TRY(ensure_scratch(need));
         char* p = d_scratch;
         unsigned long long* d_cnt = (unsigned long long*)p; p += 256;
@@ -879,24 +918,61 @@ struct Engine {
             kern<<<1, SWEEP_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, d_V, d_H, LDH, jold, m, d_ctl, opt.break_tol);
             return check_launch();
         }
+        if (box && box_tune < 10 && lattice_bd2_order(lat) >= 0) return arnoldi_fused(jold, m);
         for (int J = jold; J <= m; ++J) {
             const double* vj = d_V + (size_t)(J - 1) * ld;      // column J-1 (0-based), scale colscale[J-1]
-            double* vn = d_V + (size_t)J * ld;                   // column J receives w, then stays un-normalised
+            double* vn = d_V + (size_t)J * ld;                   // column J receives A U_{J-1}, then w, and stays un-normalised
             double* hcol = d_H + (size_t)(J - 1) * LDH;
             if (J >= 2) {
                 const double* vp = d_V + (size_t)(J - 2) * ld;
                 KFSP_TRY(spmv<1>(vj, vn, vp, hcol + (J - 2), J - 1, J - 2));                       // H(J-1,J)
-                KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, vj, vn, next_rd(), d_ctl, hcol + (J - 1), J - 2, J - 1);   // H(J,J)
-                KFSP_TRY(dist_finalize(RK_AXPY_DOT, 1, hcol + (J - 1), 0));
+                KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, vj, (const double*)vn, vn, next_rd(), d_ctl,
+                            hcol + (J - 1), J - 2, J - 1);                                        // H(J,J)
+                KFSP_TRY(dist_finalize(RK_AXPY_DOT, 1, hcol + (J - 1), nullptr, 0));
                 KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H2, next_rd(), d_ctl, hcol + J, opt.break_tol, J, J - 1);
-                KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, hcol + J, J));
+                KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, nullptr, hcol + J, J));
             } else {
                 KFSP_TRY(spmv<1>(vj, vn, vj, hcol + 0, 0, 0));                                       // H(1,1)
                 KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H1, next_rd(), d_ctl, hcol + J, opt.break_tol, J, 0);
-                KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, hcol + J, J));
+                KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, nullptr, hcol + J, J));
             }
         }
         KFSP_TRY(spmv<2>(d_V + (size_t)m * ld, d_V + (size_t)(m + 1) * ld, nullptr, nullptr, m, -1));    // AVNORM
+        return KFSP_OK;
+    }
+    // The same sweep on the stencil lattice kernel with the tail of every column fused into the next SpMV launch
+    // (lattice.cuh, FIN = 1): per column one k_spmv_bd2 launch (finalise U_{J-1} = T - h v_{J-2}, its norm, A U_{J-1},
+    // <v_{J-2}, A U_{J-1}>) and one k_axpy_dot (w -> the scratch column T, <v_{J-1}, w>): 64 bytes per state and column
+    // instead of 80, two reductions instead of three.  The first column of a sweep has nothing to finalise (column 0 comes
+    // from k_scale_copy; on a resumed sweep, KrylovSolver.f90:400-433, column jold-1 is complete).
+    int arnoldi_fused(int jold, int m) {
+        double* T = d_V + (size_t)(opt.m_max + 2) * ld;
+        for (int J = jold; J <= m + 1; ++J) {                    // J = m+1: the extra product for AVNORM (:261-263)
+            const int c = J - 1;
+            double* vj = d_V + (size_t)c * ld;
+            double* vn = d_V + (size_t)J * ld;
+            const bool fin = J > jold;
+            const bool extra = J == m + 1;
+            Bd2Args a;
+            std::memset(&a, 0, sizeof a);
+            a.src = fin ? T : vj;
+            a.xout = vj;
+            a.y = (J == 1) ? T : vn;                            // column 1 has no k_axpy_dot: A U_0 is finalised by the next launch
+            a.first = J >= 2 ? d_V + (size_t)(c - 1) * ld : vj;
+            a.cf = J >= 2 ? c - 1 : c;
+            a.cx = c;
+            a.hsel = c == 1 ? SC_H1 : SC_H2;                    // H(c,c): column 1's only coefficient is H(1,1)
+            a.h_out = extra ? nullptr : d_H + (size_t)c * LDH + (J >= 2 ? c - 1 : 0);        // H(J-1,J); H(1,1)
+            a.hn_out = fin ? d_H + (size_t)(c - 1) * LDH + c : nullptr;                      // H(c+1,c) = ||U_c||
+            a.break_tol = opt.break_tol;
+            if (extra) KFSP_TRY(spmv_bd2<2>(a, true));
+            else KFSP_TRY(spmv_bd2<1>(a, fin));
+            if (J >= 2 && !extra) {
+                const double* vp = d_V + (size_t)(c - 1) * ld;
+                KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, (const double*)vj, (const double*)vn, T, next_rd(), d_ctl,
+                            d_H + (size_t)c * LDH + c, c - 1, c);                             // H(J,J)
+            }
+        }
         return KFSP_OK;
     }
     // exp(t*H) on the device; result struct copied to pinned memory (synchronises)
@@ -1040,14 +1116,14 @@ struct Engine {
 #endif
     }
     // all-gather the ranks' double-double partials, merge in rank order, run the reduction's epilogue
-    int dist_finalize(int kind, int nv, double* h_out, int column) {
+    int dist_finalize(int kind, int nv, double* h_out, double* hn_out, int column) {
         if (dist.nranks == 1 || (dist.p2p && dist.p2p_red)) return KFSP_OK;     // peer-memory path: exchanged inside the reducing kernel
 #ifdef KFSP_WITH_NCCL
         if (ncclAllGather(dist.red_send, dist.red_recv, 4, ncclFloat64, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
-        KFSP_LAUNCH(k_dist_finalize, 1, 32, 0, kind, nv, (const double*)dist.red_recv, dist.nranks, d_ctl, h_out, opt.break_tol, column);
+        KFSP_LAUNCH(k_dist_finalize, 1, 32, 0, kind, nv, (const double*)dist.red_recv, dist.nranks, d_ctl, h_out, hn_out, opt.break_tol, column);
         dist.reductions += 1;
 #else
-        (void)kind; (void)nv; (void)h_out; (void)column;
+        (void)kind; (void)nv; (void)h_out; (void)hn_out; (void)column;
 #endif
         return KFSP_OK;
     }
@@ -1169,6 +1245,65 @@ struct Engine {
     }
 
     // ---------------------------------------------------------------- matrix-free lattice (lattice.cuh)
+    // z-chunks: k work items per resident CTA, never k+1 for some while the rest idle; k = 4 when that leaves
+    // chunks of >= 96 planes (2 halo rows are re-read and PF rows start un-prefetched per chunk), else fewer
+    void lattice_chunking(int wave, int64_t ncb, int* zc, int* g) const {
+        const int nzl = lat.zhi - lat.zlo;
+        int z = nzl;
+        for (int k = 4; k >= 1; --k) {
+            int64_t nzc = std::max<int64_t>(1, (k * (int64_t)wave) / ncb);
+            nzc = std::min<int64_t>(nzc, nzl);
+            z = (int)((nzl + nzc - 1) / nzc);
+            while (z < nzl && ncb * ((nzl + z - 1) / z) > k * (int64_t)wave) ++z;      // rounding must not push it past k waves
+            if (z >= 96 || k == 1) break;
+        }
+        *zc = z;
+        const int64_t items = ncb * ((nzl + z - 1) / z);
+        *g = (int)std::min<int64_t>(items, wave);
+    }
+    // the stencil kernel k_spmv_bd2; fin: finalise the operand on the fly (a.src = scratch column, a.xout = the column)
+    template <int MODE>
+    int spmv_bd2(Bd2Args a, bool fin) {
+        const int bd_ord = lattice_bd2_order(lat);
+        if (bd_ord < 0) return KFSP_ERR_UNSUPPORTED;
+        const bool halo = dist.nranks > 1;
+        Reducer r = (MODE != 0 || fin) ? next_rd() : rd;
+        if (halo && !r.peers) r.peers = dist.d_peers;
+        void (*kb)(const Lattice, const Bd2Args, Reducer, SweepCtl*) = nullptr;
+        int ts = 0;
+        for (int k = 0; k < 4; ++k) ts |= (lat.sp[k] == 1 ? 1 : 0) << k;
+        constexpr int FINOK = MODE != 0;                        // the plain product never finalises
+#define KFSP_BD2(T) case T:                                                                                              \
+            kb = fin ? (bd_ord == 0 ? k_spmv_bd2<0, T, MODE, FINOK, BD2_PF, BD2_MINB> : k_spmv_bd2<1, T, MODE, FINOK, BD2_PF, BD2_MINB>)   \
+                     : (bd_ord == 0 ? k_spmv_bd2<0, T, MODE, 0, BD2_PF, BD2_MINB> : k_spmv_bd2<1, T, MODE, 0, BD2_PF, BD2_MINB>);            \
+            break
+        switch (ts) {
+            KFSP_BD2(0); KFSP_BD2(1); KFSP_BD2(2); KFSP_BD2(3); KFSP_BD2(4); KFSP_BD2(5); KFSP_BD2(6); KFSP_BD2(7);
+            KFSP_BD2(8); KFSP_BD2(9); KFSP_BD2(10); KFSP_BD2(11); KFSP_BD2(12); KFSP_BD2(13); KFSP_BD2(14); KFSP_BD2(15);
+        }
+#undef KFSP_BD2
+        if (fin && MODE == 0) return KFSP_ERR_ARG;
+        const int64_t ncb_bd = (lat.plane + BD2_CBW - 1) / BD2_CBW;
+        const int wave = wave_grid((const void*)kb, (int64_t)1 << 40);
+        int zc, g;
+        lattice_chunking(wave, ncb_bd, &zc, &g);
+        const int nzl = lat.zhi - lat.zlo;
+        if (bd2_zc > 0) {                                       // KFSP_BD2_ZC: forced chunk length (tests / tuning)
+            zc = std::min(bd2_zc, nzl);
+            g = (int)std::min<int64_t>(ncb_bd * ((nzl + zc - 1) / zc), wave);
+        }
+        if (zc > BD2_ZT) {                                      // the staged y-tables bound the chunk length
+            zc = BD2_ZT;
+            g = (int)std::min<int64_t>(ncb_bd * ((nzl + zc - 1) / zc), wave);
+        }
+        a.zc = zc;
+        a.halo = halo ? 1 : 0;
+        a.off_src = d_V ? (int64_t)(a.src - d_V) : 0;
+        a.off_first = (d_V && a.first) ? (int64_t)(a.first - d_V) : 0;
+        if (!a.first) a.first = a.src;
+        kb<<<g, VEC_THREADS, 0, stream>>>(lat, a, r, d_ctl);
+        return check_launch();
+    }
     template <int MODE>
     int spmv_box(const double* x, double* y, const double* first, double* h_out, int cx, int cf) {
         const bool halo = dist.nranks > 1;
@@ -1177,47 +1312,16 @@ struct Engine {
         const int cbw = (int)((lat.plane + ncb0 - 1) / ncb0);
         const int64_t ncb = (lat.plane + cbw - 1) / cbw;
         const int nzl = lat.zhi - lat.zlo;
+        // 2-species one-molecule-step networks in the reference's reaction orders (config 5, the toggle models): stencil kernel
+        if (box_tune < 10 && lattice_bd2_order(lat) >= 0) {
+            Bd2Args a;
+            std::memset(&a, 0, sizeof a);
+            a.src = x; a.y = y; a.first = first; a.h_out = h_out; a.cx = cx; a.cf = cf;
+            return spmv_bd2<MODE>(a, false);
+        }
         const Reducer r = MODE != 0 ? next_rd() : rd;
         Reducer r2 = r;
         if (halo && !r2.peers) r2.peers = dist.d_peers;
-        // z-chunks: k work items per resident CTA, never k+1 for some while the rest idle; k = 4 when that leaves
-        // chunks of >= 96 planes (2 halo rows are re-read and PF rows start un-prefetched per chunk), else fewer
-        auto chunking = [&](int wave, int64_t ncb, int* zc, int* g) {
-            int z = nzl;
-            for (int k = 4; k >= 1; --k) {
-                int64_t nzc = std::max<int64_t>(1, (k * (int64_t)wave) / ncb);
-                nzc = std::min<int64_t>(nzc, nzl);
-                z = (int)((nzl + nzc - 1) / nzc);
-                while (z < nzl && ncb * ((nzl + z - 1) / z) > k * (int64_t)wave) ++z;      // rounding must not push it past k waves
-                if (z >= 96 || k == 1) break;
-            }
-            *zc = z;
-            const int64_t items = ncb * ((nzl + z - 1) / z);
-            *g = (int)std::min<int64_t>(items, wave);
-        };
-        // 2-species one-molecule-step networks in the reference's reaction orders (config 5, the toggle models): stencil kernel
-        const int bd_ord = box_tune < 10 ? lattice_bd2_order(lat) : -1;
-        if (bd_ord >= 0) {
-            void (*kb)(const Lattice, int, int, const double*, double*, const double*, Reducer, SweepCtl*, double*, int, int, int64_t) = nullptr;
-            int ts = 0;
-            for (int k = 0; k < 4; ++k) ts |= (lat.sp[k] == 1 ? 1 : 0) << k;
-#define KFSP_BD2(T) case T: kb = bd_ord == 0 ? k_spmv_bd2<0, T, MODE, 3, 4> : k_spmv_bd2<1, T, MODE, 3, 4>; break
-            switch (ts) {
-                KFSP_BD2(0); KFSP_BD2(1); KFSP_BD2(2); KFSP_BD2(3); KFSP_BD2(4); KFSP_BD2(5); KFSP_BD2(6); KFSP_BD2(7);
-                KFSP_BD2(8); KFSP_BD2(9); KFSP_BD2(10); KFSP_BD2(11); KFSP_BD2(12); KFSP_BD2(13); KFSP_BD2(14); KFSP_BD2(15);
-            }
-#undef KFSP_BD2
-            const int64_t ncb_bd = (lat.plane + BD2_CBW - 1) / BD2_CBW;
-            const int wave = wave_grid((const void*)kb, (int64_t)1 << 40);
-            int zc, g;
-            chunking(wave, ncb_bd, &zc, &g);
-            if (zc > BD2_ZT) {                              // the staged y-tables bound the chunk length
-                zc = BD2_ZT;
-                g = (int)std::min<int64_t>(ncb_bd * ((nzl + zc - 1) / zc), wave);
-            }
-            kb<<<g, VEC_THREADS, 0, stream>>>(lat, zc, halo ? 1 : 0, x, y, first, r2, d_ctl, h_out, cx, cf, (int64_t)(d_V ? x - d_V : 0));
-            return check_launch();
-        }
         void (*kern)(const Lattice, int, int, const double*, double*, const double*, Reducer, SweepCtl*, double*, int, int, int64_t) = nullptr;
         const int tune = box_tune >= 10 ? box_tune - 10 : box_tune;
 #define KFSP_BOX_PICK(RR)                                                                                                   \
@@ -1234,7 +1338,7 @@ struct Engine {
 #undef KFSP_BOX_PICK
         const int wave = wave_grid((const void*)kern, (int64_t)1 << 40);
         int zc, g;
-        chunking(wave, ncb, &zc, &g);
+        lattice_chunking(wave, ncb, &zc, &g);
         kern<<<g, VEC_THREADS, 0, stream>>>(lat, zc, cbw, x, y, first, r2, d_ctl, h_out, cx, cf, (int64_t)(d_V ? x - d_V : 0));
         return check_launch();
     }

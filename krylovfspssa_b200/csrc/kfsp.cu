@@ -45,7 +45,7 @@ struct GpuBackend {
         Tick t(e.phase_s[1]);
         k_norms<<<e.wave_grid((const void*)k_norms, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
-        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
+        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, nullptr, 0));
         KFSP_TRY(e.read_ctl());
         *wsum = e.h_ctl->scal[SC_WSUM];
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
@@ -76,7 +76,7 @@ struct GpuBackend {
         Tick t(e.phase_s[1]);
         k_combine<<<e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
-        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
+        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, nullptr, 0));
         KFSP_TRY(e.read_ctl());
         *wsum = e.h_ctl->scal[SC_WSUM];
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
@@ -85,7 +85,7 @@ struct GpuBackend {
     int restore_w(double beta, double* wssq) {
         k_scale_copy_nrm<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, beta, e.d_V, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
-        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, 0));
+        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, nullptr, 0));
         KFSP_TRY(e.read_ctl());
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
         return KFSP_OK;
@@ -549,8 +549,9 @@ int kfsp_expm(kfsp_handle h, int32_t m, double t, const double* H, int32_t ldh, 
     if (hnorm) *hnorm = e.h_res->hnorm;
     return e.h_res->info;
 }
-int kfsp_combine(kfsp_handle h, int64_t n, int32_t mx, double beta, const double* V, const double* ev, double* w, double* wsum) {
-    if (!h || !V || !ev || !w || n < 1 || mx < 1 || mx > EXPM_MAXN) return KFSP_ERR_ARG;
+int kfsp_combine(kfsp_handle h, int64_t n, int32_t mx, double beta, const double* V, const double* ev, const double* colscale,
+                 double* w, double* wsum, double* wssq) {
+    if (!h || !V || !ev || !w || n < 1 || mx < 1 || mx > MAX_COLS) return KFSP_ERR_ARG;
     Engine& e = h->e;
     cudaSetDevice(e.device);
     const size_t a = Engine::align_up(sizeof(double) * n * mx), b = Engine::align_up(sizeof(double) * EXPM_MAXN), c = Engine::align_up(sizeof(double) * n);
@@ -560,14 +561,17 @@ int kfsp_combine(kfsp_handle h, int64_t n, int32_t mx, double beta, const double
     double* dw = (double*)(e.d_scratch + a + b);
     KFSP_CUDA(cudaMemcpyAsync(dV, V, sizeof(double) * n * mx, cudaMemcpyHostToDevice, e.stream));
     KFSP_CUDA(cudaMemcpyAsync(de, ev, sizeof(double) * mx, cudaMemcpyHostToDevice, e.stream));
-    k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);            // unit column scales: V is given normalised
+    k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);            // unit column scales unless the caller gives them
     KFSP_TRY(e.check_launch());
+    if (colscale) KFSP_CUDA(cudaMemcpyAsync(e.d_ctl->colscale, colscale, sizeof(double) * mx, cudaMemcpyHostToDevice, e.stream));
     k_combine<<<e.grid_for(n), VEC_THREADS, 0, e.stream>>>(n, n, mx, beta, dV, de, dw, e.rd, e.d_ctl);
     KFSP_TRY(e.check_launch());
     KFSP_CUDA(cudaMemcpyAsync(w, dw, sizeof(double) * n, cudaMemcpyDeviceToHost, e.stream));
     KFSP_TRY(e.read_ctl());
     if (wsum) *wsum = e.h_ctl->scal[SC_WSUM];
-    return KFSP_OK;
+    if (wssq) *wssq = e.h_ctl->scal[SC_WSSQ];
+    k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);
+    return e.check_launch();
 }
 
 // ------------------------------------------------------------------ multi-GPU plumbing

@@ -18,8 +18,13 @@ enum Scal { SC_H1 = 0, SC_H2, SC_INV_HN, SC_AVNORM, SC_WSUM, SC_WSSQ, SC_HN, SC_
 
 constexpr int MAX_COLS = 104;      // m_max + 2 basis columns
 // DSCAL(N, 1/HJ1J, v) (KrylovSolver.f90:258) is never run as a pass of its own: the basis columns stay
-// un-normalised in HBM and colscale[j] = 1/HJ1J is applied by every consumer on load.  The product
-// __dmul_rn(colscale[j], V(i,j)) is the value DSCAL would have stored, so results are unchanged.
+// un-normalised in HBM (U_j) and colscale[j] = 1/HJ1J is applied where a column is consumed:
+// v_j(i) = __dmul_rn(colscale[j], U_j(i)) is the value DSCAL would have stored.  The generator product is
+// taken on the UN-NORMALISED column, Y' = A U_j, and its scale moves to what is derived from it:
+//     H(J-1,J) = colscale[j] * <v_{j-1}, Y'>,   AVNORM = colscale[j] * ||Y'||,   w(i) = colscale[j] * Y'(i) - ...
+// so that the SpMV of column j does not need ||U_j|| while it runs -- which is what allows the lattice kernel
+// (lattice.cuh) to finalise U_j = w - h*v_{j-1}, take its norm, multiply by A and take the next dot product in
+// ONE pass.  This is the canonical arithmetic of oracle/kfsp_oracle.cpp (canonical_sweep), bit for bit.
 struct SweepCtl {
     double scal[8];
     int32_t brk;                // happy-breakdown column (1-based), 0 = none
@@ -184,30 +189,48 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
 
 // What to do with a finished reduction (same code on one GPU, inside the reducing kernel, and on
 // several GPUs, in k_dist_finalize after the ranks' double-double partials were gathered).
-enum RKind { RK_SPMV_DOT = 0, RK_SPMV_NRM, RK_AXPY_DOT, RK_AXPY_NRM, RK_NORMS, RK_SUM_BELOW };
-__device__ __forceinline__ void reduce_epilogue(int kind, const double* tot, SweepCtl* ctl, double* h_out, double break_tol, int column) {
+enum RKind { RK_SPMV_DOT = 0, RK_SPMV_NRM, RK_AXPY_DOT, RK_AXPY_NRM, RK_NORMS, RK_SUM_BELOW, RK_FUSED_DOT, RK_FUSED_NRM };
+// column: the basis column (0-based) the reduction belongs to -- for RK_SPMV_*: the SpMV's operand column (its scale
+// multiplies the result, -1 = scale 1); for RK_AXPY_NRM / RK_FUSED_*: the column whose norm HJ1J was taken (its
+// 0-based index equals the 1-based Arnoldi index J of KrylovSolver.f90:236-258, so it is also the breakdown column).
+__device__ __forceinline__ bool epilogue_norm(double ssq, SweepCtl* ctl, double* hn_out, double break_tol, int column, double* inv) {
+    const double hn = sqrt(ssq);                            // HJ1J (KrylovSolver.f90:247)
+    ctl->scal[SC_HN] = hn;
+    if (hn <= break_tol) {
+        ctl->brk = column;                                  // happy breakdown (:249-256)
+        return false;
+    }
+    *hn_out = hn;
+    *inv = 1.0 / hn;
+    ctl->scal[SC_INV_HN] = *inv;
+    ctl->colscale[column] = *inv;                           // column `column` of V stays un-normalised
+    return true;
+}
+__device__ __forceinline__ void reduce_epilogue(int kind, const double* tot, SweepCtl* ctl, double* h_out, double* hn_out, double break_tol,
+                                                int column) {
+    double inv = 0.0;
     switch (kind) {
-    case RK_SPMV_DOT: ctl->scal[SC_H1] = tot[0]; if (h_out) *h_out = tot[0]; break;
-    case RK_SPMV_NRM: ctl->scal[SC_AVNORM] = sqrt(tot[0]); break;
+    case RK_SPMV_DOT: { const double h = __dmul_rn(col_scale(ctl, column), tot[0]); ctl->scal[SC_H1] = h; if (h_out) *h_out = h; } break;
+    case RK_SPMV_NRM: ctl->scal[SC_AVNORM] = __dmul_rn(col_scale(ctl, column), sqrt(tot[0])); break;
     case RK_AXPY_DOT: ctl->scal[SC_H2] = tot[0]; if (h_out) *h_out = tot[0]; break;
-    case RK_AXPY_NRM: {
-        const double hn = sqrt(tot[0]);                     // HJ1J (KrylovSolver.f90:247)
-        ctl->scal[SC_HN] = hn;
-        if (hn <= break_tol) {
-            ctl->brk = column;                              // happy breakdown (:249-256)
-        } else {
-            *h_out = hn;
-            ctl->scal[SC_INV_HN] = 1.0 / hn;
-            ctl->colscale[column] = 1.0 / hn;               // column `column` (0-based) of V holds w un-normalised
+    case RK_AXPY_NRM: epilogue_norm(tot[0], ctl, hn_out, break_tol, column, &inv); break;
+    case RK_FUSED_DOT:                                      // tot[0] = ||U_c||^2, tot[1] = <v_{c-1}, A U_c>
+        if (epilogue_norm(tot[0], ctl, hn_out, break_tol, column, &inv)) {
+            const double h = __dmul_rn(inv, tot[1]);
+            ctl->scal[SC_H1] = h;
+            if (h_out) *h_out = h;
         }
-    } break;
+        break;
+    case RK_FUSED_NRM:                                      // tot[0] = ||U_c||^2, tot[1] = ||A U_c||^2
+        if (epilogue_norm(tot[0], ctl, hn_out, break_tol, column, &inv)) ctl->scal[SC_AVNORM] = __dmul_rn(inv, sqrt(tot[1]));
+        break;
     case RK_NORMS: ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; break;
     case RK_SUM_BELOW: ctl->scal[SC_WSUM] = tot[0]; break;
     }
 }
 // multi-GPU: merge the P gathered (hi,lo) partials in rank order, round once, run the epilogue
 __global__ void k_dist_finalize(int kind, int nv, const double* __restrict__ recv /*[P][4]*/, int nranks, SweepCtl* ctl,
-                                double* h_out, double break_tol, int column) {
+                                double* h_out, double* hn_out, double break_tol, int column) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (kind != RK_NORMS && kind != RK_SUM_BELOW && ctl->brk != 0) return;
     double tot[2] = {0.0, 0.0};
@@ -219,13 +242,14 @@ __global__ void k_dist_finalize(int kind, int nv, const double* __restrict__ rec
         }
         tot[q] = __dadd_rn(s.hi, s.lo);
     }
-    reduce_epilogue(kind, tot, ctl, h_out, break_tol, column);
+    reduce_epilogue(kind, tot, ctl, h_out, hn_out, break_tol, column);
 }
 
 // ---------------------------------------------------------------------------------------
-// FMATVEC (KrylovSolver.f90:577-607) in gather form: y_i = -DIAG_i x_i + sum_k coef_ki x[pred_ki].
-// Fused epilogue (optional): dot = <first, y> written to H and ctl->scal[SC_H1]  (the first
-// DDOT of the IOP window, :243), or ssq = <y,y> -> AVNORM (:263).
+// FMATVEC (KrylovSolver.f90:577-607) in gather form: y_i = -DIAG_i x_i + sum_k coef_ki x[pred_ki], on the stored
+// (un-normalised) column x; the column's scale colscale[cx] is applied to the reduction result in the epilogue.
+// Fused epilogue (optional): dot = <v_first, y> -> H and ctl->scal[SC_H1]  (the first DDOT of the IOP
+// window, :243), or ssq = <y,y> -> AVNORM (:263).
 //   mode 0: plain   mode 1: dot with `first`   mode 2: norm of y
 // Algorithmic traffic per row: R*(4+8) matrix + 8 diag + 8 x_i + 8 y_i  = 12R+24 bytes.
 // ---------------------------------------------------------------------------------------
@@ -247,7 +271,6 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
     // HALO 2: it is loaded straight from the owning GPU's basis column over NVLink (peer memory).
     const int R = RT > 0 ? RT : R_rt;
     if (MODE != 0 && ctl->brk != 0) return;
-    const double xs = col_scale(ctl, cx);                  // x = xs * (stored column)
     const double fs = MODE == 1 ? col_scale(ctl, cf) : 1.0;
     DD acc0; acc0.hi = 0.0; acc0.lo = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -261,7 +284,7 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
             const int64_t i = i0 + u * stride;
             if (i < n) {
                 if (MODE == 1) f[u] = __dmul_rn(fs, __ldcs(first + i));
-                s[u] = -__dmul_rn(__ldcs(diag + i), __dmul_rn(xs, x[i]));
+                s[u] = -__dmul_rn(__ldcs(diag + i), x[i]);
                 if (RT > 0) {
 #pragma unroll
                     for (int k = 0; k < RT; ++k) {
@@ -279,12 +302,12 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
                 if (RT > 0) {
 #pragma unroll
                     for (int k = 0; k < RT; ++k)
-                        if (j[u][k] >= 0) sv = fma(a[u][k], __dmul_rn(xs, halo_load<HALO>(x, xh, rd.peers, j[u][k], nloc, coloff)), sv);
+                        if (j[u][k] >= 0) sv = fma(a[u][k], halo_load<HALO>(x, xh, rd.peers, j[u][k], nloc, coloff), sv);
                 } else {
                     for (int k = 0; k < R; ++k) {
                         const int32_t jj = __ldcs(pred + (int64_t)k * ld + i);
                         const double aa = __ldcs(coef + (int64_t)k * ld + i);
-                        if (jj >= 0) sv = fma(aa, __dmul_rn(xs, halo_load<HALO>(x, xh, rd.peers, jj, nloc, coloff)), sv);
+                        if (jj >= 0) sv = fma(aa, halo_load<HALO>(x, xh, rd.peers, jj, nloc, coloff), sv);
                     }
                 }
                 __stcs(y + i, sv);
@@ -296,12 +319,15 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
     if (MODE == 0) return;
     DD v[1] = {acc0};
     double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, 0.0, 0);
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0)
+        reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, nullptr, 0.0, cx);
 }
 
-// w -= h1*a ; dot = <b, w>   (DAXPY + the next DDOT, KrylovSolver.f90:243-245)
+// out = cb*y - h1*v_a ; dot = <v_b, out>   (DAXPY + the next DDOT, KrylovSolver.f90:243-245).  y = A U_b is the
+// un-normalised product, so it carries b's scale.  out == y (in place) except on the fused lattice path, where the
+// result goes to the scratch column T that the next SpMV launch finalises (lattice.cuh).
 __global__ void __launch_bounds__(VEC_THREADS) k_axpy_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
-                                                          double* __restrict__ w, Reducer rd, SweepCtl* ctl, double* h_out,
+                                                          const double* y, double* out, Reducer rd, SweepCtl* ctl, double* h_out,
                                                           int ca, int cb) {
     if (ctl->brk != 0) return;
     const double h1 = ctl->scal[SC_H1];
@@ -309,19 +335,19 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy_dot(int64_t n, const doubl
     DD acc; acc.hi = 0.0; acc.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double ai = __dmul_rn(sa, __ldcs(a + i)), bi = __dmul_rn(sb, __ldcs(b + i));
-        const double wi = fma(-h1, ai, w[i]);
-        w[i] = wi;
+        const double wi = fma(-h1, ai, __dmul_rn(sb, y[i]));
+        __stcs(out + i, wi);
         dd_add_prod(acc, bi, wi);
     }
     DD v[1] = {acc};
     double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_AXPY_DOT, tot, ctl, h_out, 0.0, 0);
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_AXPY_DOT, tot, ctl, h_out, nullptr, 0.0, 0);
 }
 
-// w -= h*a ; ssq = <w,w>; then HJ1J = sqrt(ssq), happy-breakdown test, H(J+1,J) (KrylovSolver.f90:244-257)
-// which = SC_H1 or SC_H2: the scalar holding h.
+// w -= h*v_a ; ssq = <w,w>; then HJ1J = sqrt(ssq), happy-breakdown test, H(J+1,J) (KrylovSolver.f90:244-257)
+// which = SC_H1 or SC_H2: the scalar holding h.  (The fused lattice path does this inside the next SpMV launch.)
 __global__ void __launch_bounds__(VEC_THREADS) k_axpy_nrm(int64_t n, const double* __restrict__ a, double* __restrict__ w, int which,
-                                                          Reducer rd, SweepCtl* ctl, double* h_out, double break_tol, int column,
+                                                          Reducer rd, SweepCtl* ctl, double* hn_out, double break_tol, int column,
                                                           int ca) {
     if (ctl->brk != 0) return;
     const double h = ctl->scal[which];
@@ -334,7 +360,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy_nrm(int64_t n, const doubl
     }
     DD v[1] = {acc};
     double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_AXPY_NRM, tot, ctl, h_out, break_tol, column);
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_AXPY_NRM, tot, ctl, nullptr, hn_out, break_tol, column);
 }
 
 // V(:,1) = (1/BETA) * W (KrylovSolver.f90:223-226)
@@ -353,7 +379,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_scale_copy_nrm(int64_t n, doubl
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, 0.0, 0);
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, nullptr, 0.0, 0);
 }
 // ||w||_1 and ||w||_2^2 of a vector (BETA = DNRM2(N_NOW, W), KrylovSolver.f90:177,540)
 __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
@@ -365,7 +391,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* 
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, 0.0, 0);
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, nullptr, 0.0, 0);
 }
 
 // W = BETA * V(:,1:mx) * e ; W = max(W,0) ; WSUM = ||W||_1 ; also ||W||_2^2 for the next BETA
@@ -394,7 +420,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, 
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, 0.0, 0);
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, nullptr, 0.0, 0);
 }
 
 // FIND_DROPTOL's inner sum (StateSpace.f90:418-423): sum of W_i with 0 < W_i < droptol
@@ -406,7 +432,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_sum_below(int64_t n, const doub
     }
     DD vv[1] = {a};
     double tot[1];
-    if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_SUM_BELOW, tot, ctl, nullptr, 0.0, 0);
+    if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_SUM_BELOW, tot, ctl, nullptr, nullptr, 0.0, 0);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -433,13 +459,13 @@ __device__ __forceinline__ double cta_dd_total(DD v, DD* sh, double* bc) {
 }
 template <int RT>
 __device__ __forceinline__ double spmv_row(int64_t i, int64_t ld, int R, const int32_t* __restrict__ pred, const double* __restrict__ coef,
-                                           const double* __restrict__ diag, const double* x, double xs) {
-    double sv = -__dmul_rn(diag[i], __dmul_rn(xs, x[i]));
+                                           const double* __restrict__ diag, const double* x) {
+    double sv = -__dmul_rn(diag[i], x[i]);
 #pragma unroll
     for (int k = 0; k < (RT > 0 ? RT : R); ++k) {
         const int32_t j = pred[(int64_t)k * ld + i];
         const double a = coef[(int64_t)k * ld + i];
-        if (j >= 0) sv = fma(a, __dmul_rn(xs, x[j]), sv);
+        if (j >= 0) sv = fma(a, x[j], sv);
     }
     return sv;
 }
@@ -468,18 +494,18 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
         // FMATVEC + first DDOT of the IOP window
         DD acc; acc.hi = 0.0; acc.lo = 0.0;
         for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
-            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x, xs);
+            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x);     // A U_{J-1}: un-normalised
             y[i] = sv;
             dd_add_prod(acc, __dmul_rn(fs, first[i]), sv);
         }
-        const double h1 = cta_dd_total(acc, sh, &bc);
+        const double h1 = __dmul_rn(xs, cta_dd_total(acc, sh, &bc));
         double h = h1;
         if (J >= 2) {
             if (tid == 0) hcol[J - 2] = h1;                                  // H(J-1,J)
             acc.hi = 0.0; acc.lo = 0.0;
             for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
                 const double ai = __dmul_rn(fs, first[i]), bi = __dmul_rn(xs, x[i]);
-                const double wi = fma(-h1, ai, y[i]);
+                const double wi = fma(-h1, ai, __dmul_rn(xs, y[i]));
                 y[i] = wi;
                 dd_add_prod(acc, bi, wi);
             }
@@ -507,11 +533,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
         const double xs = cs[m];
         DD acc; acc.hi = 0.0; acc.lo = 0.0;
         for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
-            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x, xs);
+            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x);
             y[i] = sv;
             dd_add_prod(acc, sv, sv);
         }
-        const double av = sqrt(cta_dd_total(acc, sh, &bc));
+        const double av = __dmul_rn(xs, sqrt(cta_dd_total(acc, sh, &bc)));
         if (tid == 0) ctl->scal[SC_AVNORM] = av;
     }
     __syncthreads();

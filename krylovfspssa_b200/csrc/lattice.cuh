@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
                                                                 SweepCtl* ctl, double* h_out, int cx, int cf, int64_t coloff) {
     constexpr int R = RT;
     if (MODE != 0 && ctl->brk != 0) return;
-    const double xs = col_scale(ctl, cx);
     const double fs = MODE == 1 ? col_scale(ctl, cf) : 1.0;
     const int S = ST > 0 ? ST : L.S;
     const int64_t plane = L.plane;
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
                 }
                 d = __dadd_rn(d, ad[k]);
             }
-            double sv = -__dmul_rn(d, __dmul_rn(xs, x0));
+            double sv = -__dmul_rn(d, x0);
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 const int32_t zz = z - L.nu[k][S - 1];
@@ -169,7 +168,7 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
                     } else {
                         xv = x[(uint32_t)(i + off[k])];
                     }
-                    sv = fma(ac[k], __dmul_rn(xs, xv), sv);
+                    sv = fma(ac[k], xv, sv);
                 }
             }
             __stcs(y + i, sv);
@@ -181,7 +180,8 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
     if (MODE == 0) return;
     DD v[1] = {acc};
     double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, 0.0, 0);
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0)
+        reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, nullptr, 0.0, cx);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -194,8 +194,20 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
 // With the stencil known at compile time nothing is re-read from memory: rows z-1, z, z+1 of a column live in a
 // rolling register window fed by ONE first-touch load per row (issued PF rows before its use through a register
 // ring), the +-1 neighbours in x are the adjacent lanes' registers (warp shuffle: a warp covers 30 columns plus
-// one halo lane on each side, which loads but does not store), the y-tables of a chunk sit in shared memory.  ncu on the generic kernel
-// showed 43 % of all stall samples on the re-read of x(c-1, z) through L1 (hit rate 51 %).
+// one halo lane on each side, which loads but does not store), the y-tables of a chunk sit in shared memory.
+//
+// FIN = 1 fuses the tail of the previous Arnoldi column into the load stage (KrylovSolver.f90:244-258 + :240-243):
+// the operand is finalised on the fly,  U(i) = fma(-h, v_first(i), T(i)),  stored once, its norm^2 accumulated beside the
+// dot product, and the generator product is taken on U un-normalised (krylov.cuh: the column scale 1/||U|| is only
+// known when the pass ends, so it is applied to the two scalars in the epilogue).  T is the scratch column the
+// preceding k_axpy_dot wrote: the finalised column cannot be written over its own source because other warps (and,
+// on several GPUs, the neighbours) still gather rows of T for their stencil.  Per state the launch moves
+// T + v_first + U + y = 32 bytes and replaces k_axpy_nrm (24) + SpMV-with-dot (24).
+//
+// Rows are walked in three pieces so that the hot loop carries no bounds checks: a head (first PF rows when the chunk
+// starts at the box boundary z = 0), the main loop (every ring refill is a local, in-range row), and a tail (refills
+// that leave the chunk / the slab / the box, read through the general loader, which on several GPUs takes the halo
+// row from the owner's HBM over NVLink).
 // Same operation order as k_spmv_box / k_spmv (reactions in model order): bit-identical results
 // (tests/test_gpu_lattice.py runs all three).
 // ---------------------------------------------------------------------------------------
@@ -219,41 +231,55 @@ inline int lattice_bd2_order(const Lattice& L) {
 }
 constexpr int BD2_WCOLS = 30;                                  // live columns per warp (lanes 1..30; lanes 0 and 31 are halo)
 constexpr int BD2_CBW = BD2_WCOLS * (VEC_THREADS / 32);        // live columns per CTA
-constexpr int BD2_L2AHEAD = 10;                                // rows ahead of the walk that are prefetched into L2
+constexpr int BD2_L2AHEAD = 10;                                // rows ahead of the ring that are prefetched into L2
+constexpr int BD2_PF = 4;                                      // depth of the register ring (rows in flight per thread and stream)
+constexpr int BD2_MINB = 4;                                    // resident CTAs per SM the kernel is compiled for
 constexpr int BD2_ZT = 256;                                    // longest z-chunk (rows of the y-tables staged in shared memory)
-template <int ORD, int TS, int MODE, int PF, int MINB>
-__global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_constant__ Lattice L, int zc, int halo,
-                                                                const double* __restrict__ x, double* __restrict__ y,
-                                                                const double* __restrict__ first, Reducer rd, SweepCtl* ctl, double* h_out,
-                                                                int cx, int cf, int64_t coloff) {
-    if (MODE != 0 && ctl->brk != 0) return;
-    const double xs = col_scale(ctl, cx);
-    const double fs = MODE == 1 ? col_scale(ctl, cf) : 1.0;
+struct Bd2Args {
+    const double* src;        // operand column: FIN ? T (un-finalised) : the column itself
+    double* xout;             // FIN: the finalised column is stored here
+    double* y;                // A * column
+    const double* first;      // v_{j-1}: operand of the finalising axpy (FIN) and of the fused dot product (MODE 1)
+    double* h_out;            // MODE 1: H(J-1,J)
+    double* hn_out;           // FIN: H(J,J-1) = ||U||
+    double break_tol;
+    int32_t cx, cf;           // basis column of the operand / of `first` (-1: scale 1)
+    int32_t hsel;             // FIN: ctl->scal[hsel] is the axpy coefficient
+    int32_t zc, halo;         // rows per z-chunk; 1 = several GPUs (rows outside the slab come from the owner's HBM)
+    int64_t off_src, off_first;   // offsets of src / first inside the basis allocation (peer addressing)
+};
+template <int ORD, int TS, int MODE, int FIN, int PF, int MINB>
+__global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_constant__ Lattice L, const __grid_constant__ Bd2Args A,
+                                                                Reducer rd, SweepCtl* ctl) {
+    constexpr bool NEEDF = FIN || MODE == 1;
+    if ((MODE != 0 || FIN) && ctl->brk != 0) return;
+    const double fs = NEEDF ? col_scale(ctl, A.cf) : 1.0;
+    const double hf = FIN ? ctl->scal[A.hsel] : 0.0;
+    const double* __restrict__ src = A.src;
+    const double* __restrict__ first = A.first;
+    double* __restrict__ xout = A.xout;
+    double* __restrict__ y = A.y;
     const int32_t Bx = L.B[0], nz = L.nz;
+    const int zc = A.zc;
     const int nzl = L.zhi - L.zlo;
     const int64_t ncb = (Bx + BD2_CBW - 1) / BD2_CBW;
     const int64_t nzc = (nzl + zc - 1) / zc;
     const DistPeers* __restrict__ dp = rd.peers;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // x(c, zz) for any plane zz of the box: this rank's slab, or (several GPUs) the owner's basis column over NVLink
-    auto row = [&](int32_t c, int32_t zz) -> double {
-        if (!halo || (zz >= L.zlo && zz < L.zhi)) return x[(uint32_t)(c + Bx * (zz - L.zlo))];
-        int r = 0;
-        while (zz >= L.zb[r + 1]) ++r;
-        return __ldcg(dp->V[r] + coloff + c + (int64_t)Bx * (zz - L.zb[r]));
-    };
     // y-tables of the chunk, staged once per work item: ztab[k][j] = T_k[z0 - 1 + j].  (Read per row straight from global
-    // memory they missed the streaming-thrashed L1 half of the time: 62 % of all stall samples sat on the fma waiting for
-    // T[z+1], profiles/r1_summary.md.)
+    // memory they missed the streaming-thrashed L1 half of the time, profiles/r1_summary.md.)
     __shared__ double ztab[4][BD2_ZT + 2];
-    DD acc; acc.hi = 0.0; acc.lo = 0.0;
+    DD accx, accd;
+    accx.hi = accx.lo = accd.hi = accd.lo = 0.0;
     for (int64_t item = blockIdx.x; item < ncb * nzc; item += gridDim.x) {
+        const int32_t z0 = L.zlo + (int32_t)(item / ncb) * zc;
+        const int32_t z1 = min(z0 + zc, L.zhi);
         {
-            const int32_t zs = L.zlo + (int32_t)(item / ncb) * zc - 1, cnt = min(zc, L.zhi - (zs + 1)) + 2;
+            const int32_t cnt = z1 - z0 + 2;
             __syncthreads();
             for (int q = threadIdx.x; q < 4 * cnt; q += VEC_THREADS) {
                 const int k = q / cnt, j = q - k * cnt;
-                const int32_t zz = zs + j;
+                const int32_t zz = z0 - 1 + j;
                 ztab[k][j] = (((TS >> k) & 1) && zz >= 0 && zz < nz) ? __ldg(L.tab[k] + zz) : 0.0;
             }
             __syncthreads();
@@ -263,8 +289,6 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
         const int32_t c_raw = (int32_t)((item % ncb) * BD2_CBW) + warp * BD2_WCOLS + lane - 1;
         const bool live = lane >= 1 && lane <= BD2_WCOLS && c_raw < Bx;
         const int32_t c = c_raw < 0 ? 0 : (c_raw >= Bx ? Bx - 1 : c_raw);
-        const int32_t z0 = L.zlo + (int32_t)(item / ncb) * zc;
-        const int32_t z1 = min(z0 + zc, L.zhi);
         const bool okl = c >= 1, okr = c + 1 < Bx;
         // per reaction: a_k(x) for the diagonal and a_k(x - nu_k) for the off-diagonal term.  Tables over x are constant
         // along the walk; tables over y come from the staged chunk (ztab).
@@ -279,79 +303,132 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                 acn[k] = dir == BD_XP ? (okl ? __ldg(L.tab[k] + c - 1) : 0.0) : dir == BD_XM ? (okr ? __ldg(L.tab[k] + c + 1) : 0.0) : adc[k];
             }
         }
+        // raw operand(s) of row zz (0 <= zz < nz) of this lane's column: from this rank's slab, or (several GPUs) from the
+        // owner's basis over NVLink -- the owner's T and v_first are complete: the reduction exchange of the kernel that
+        // wrote them has passed on every rank (krylov.cuh, grid_reduce)
+        auto load_raw = [&](int32_t zz, double& t, double& fr) {
+            fr = 0.0;
+            if (!A.halo || (zz >= L.zlo && zz < L.zhi)) {
+                const uint32_t e = (uint32_t)(c + Bx * (zz - L.zlo));
+                t = src[e];
+                if (NEEDF) fr = first[e];
+            } else {
+                int r = 0;
+                while (zz >= L.zb[r + 1]) ++r;
+                const int64_t e = c + (int64_t)Bx * (zz - L.zb[r]);
+                t = __ldcg(dp->V[r] + A.off_src + e);
+                if (NEEDF) fr = __ldcg(dp->V[r] + A.off_first + e);
+            }
+        };
+        // x = the operand finalised (FIN), f = v_first
+        auto finish = [&](double t, double fr, double& xv, double& fv) {
+            fv = NEEDF ? __dmul_rn(fs, fr) : 0.0;
+            xv = FIN ? fma(-hf, fv, t) : t;
+        };
+        const int32_t zlast = min(z1, nz - 1);                  // last row whose operand this work item needs
         uint32_t i = (uint32_t)(c + Bx * (z0 - L.zlo));
-        // the window holds xs * x (the column scale DSCAL would have applied, krylov.cuh): one multiplication per element
-        // instead of one per use -- FP64 issue, not HBM, is what bounds this kernel on B200 (profiles/r1_summary.md)
-        double xm = z0 >= 1 ? __dmul_rn(xs, row(c, z0 - 1)) : 0.0;
-        double x0 = __dmul_rn(xs, x[i]);
-        // software pipeline in registers: slot u holds x(c, z+1) and first(c, z) of the row that will be evaluated
+        double xm = 0.0, x0, f0;
+        {
+            double t, fr, fdummy;
+            if (z0 >= 1) { load_raw(z0 - 1, t, fr); finish(t, fr, xm, fdummy); }
+            load_raw(z0, t, fr);
+            finish(t, fr, x0, f0);
+        }
+        // software pipeline in registers: slot u holds the raw operands of row z+1 of the row z that will be evaluated
         // PF rows after the slot was filled, so a row never waits for its own first-touch loads
-        double xq[PF], fq[PF];
+        double rt[PF], rf[PF];
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-            const int32_t z = z0 + u;
-            xq[u] = (z < z1 && z + 1 < nz) ? row(c, z + 1) : 0.0;
-            fq[u] = (MODE == 1 && live && z < z1) ? __ldcs(first + (i + (uint32_t)(Bx * u))) : 0.0;
+            rt[u] = 0.0; rf[u] = 0.0;
+            if (z0 + 1 + u <= zlast) load_raw(z0 + 1 + u, rt[u], rf[u]);
         }
-        for (int32_t zb = z0; zb < z1; zb += PF) {
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int32_t z = zb + u;
-                if (z < z1) {                                   // uniform over the CTA: the shuffles below are convergent
-                    const bool up = z + 1 < nz;
-                    const double xp = __dmul_rn(xs, xq[u]);
-                    const double f = __dmul_rn(fs, fq[u]);
-                    {   // refill the slot for row z + PF; rows further ahead are pulled into L2 (costs no registers)
-                        const int32_t zn = z + PF;
-                        xq[u] = (zn < z1 && zn + 1 < nz) ? row(c, zn + 1) : 0.0;
-                        if (MODE == 1) fq[u] = (live && zn < z1) ? __ldcs(first + (i + (uint32_t)(Bx * PF))) : 0.0;
-                        if (MODE == 1 && z + BD2_L2AHEAD + 1 < L.zhi) {      // measured: helps the two-stream (dot-fused) variant only
-                            lattice_prefetch<1>(x + (i + (uint32_t)(Bx * (BD2_L2AHEAD + 1))));
-                            lattice_prefetch<1>(first + (i + (uint32_t)(Bx * BD2_L2AHEAD)));
-                        }
+        // one row: GEN = false is the hot path (z >= 1, z + 1 < nz, the refill row is local and needed)
+        auto do_row = [&](const int32_t z, const int u, const bool gen) {
+            double xp, fp;
+            finish(rt[u], rf[u], xp, fp);
+            const bool yp_ok = gen ? z >= 1 : true, ym_ok = gen ? z + 1 < nz : true;
+            {   // refill the slot with row z + 1 + PF; two-stream variants also pull rows further ahead into L2
+                const int32_t zn = z + 1 + PF;
+                if (!gen) {
+                    const uint32_t e = i + (uint32_t)(Bx * (1 + PF));
+                    rt[u] = src[e];
+                    if (NEEDF) rf[u] = first[e];
+                    if (NEEDF && zn + BD2_L2AHEAD <= z1) {
+                        lattice_prefetch<1>(src + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
+                        lattice_prefetch<1>(first + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
                     }
-                    const double xl = __shfl_up_sync(0xffffffffu, x0, 1);
-                    const double xr = __shfl_down_sync(0xffffffffu, x0, 1);
-                    double ad[4], ac[4];
-                    const int jz = z - z0 + 1;                  // row z in the staged y-tables
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int dir = bd2_dir(ORD, k);
-                        const bool tz = (TS >> k) & 1;
-                        if (tz) {
-                            ad[k] = ztab[k][jz];
-                            ac[k] = dir == BD_YP ? ztab[k][jz - 1] : dir == BD_YM ? ztab[k][jz + 1] : ad[k];
-                        } else {
-                            ad[k] = adc[k];
-                            ac[k] = acn[k];
-                        }
-                    }
-                    double d = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) d = __dadd_rn(d, ad[k]);
-                    double sv = -__dmul_rn(d, x0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int dir = bd2_dir(ORD, k);
-                        const bool ok = dir == BD_XP ? okl : dir == BD_XM ? okr : dir == BD_YP ? z >= 1 : up;
-                        const double xv = dir == BD_XP ? xl : dir == BD_XM ? xr : dir == BD_YP ? xm : xp;
-                        if (ok) sv = fma(ac[k], xv, sv);
-                    }
-                    if (live) {
-                        __stcs(y + i, sv);
-                        if (MODE == 1) dd_add_prod(acc, f, sv);
-                        if (MODE == 2) dd_add_prod(acc, sv, sv);
-                    }
-                    xm = x0; x0 = xp;
-                    i += (uint32_t)Bx;
+                } else {
+                    rt[u] = 0.0; rf[u] = 0.0;
+                    if (zn <= zlast) load_raw(zn, rt[u], rf[u]);
                 }
             }
+            const double xl = __shfl_up_sync(0xffffffffu, x0, 1);
+            const double xr = __shfl_down_sync(0xffffffffu, x0, 1);
+            double ad[4], ac[4];
+            const int jz = z - z0 + 1;                          // row z in the staged y-tables
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int dir = bd2_dir(ORD, k);
+                const bool tz = (TS >> k) & 1;
+                if (tz) {
+                    ad[k] = ztab[k][jz];
+                    ac[k] = dir == BD_YP ? ztab[k][jz - 1] : dir == BD_YM ? ztab[k][jz + 1] : ad[k];
+                } else {
+                    ad[k] = adc[k];
+                    ac[k] = acn[k];
+                }
+            }
+            double d = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d = __dadd_rn(d, ad[k]);
+            double sv = -__dmul_rn(d, x0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int dir = bd2_dir(ORD, k);
+                const bool ok = dir == BD_XP ? okl : dir == BD_XM ? okr : dir == BD_YP ? yp_ok : ym_ok;
+                const double xv = dir == BD_XP ? xl : dir == BD_XM ? xr : dir == BD_YP ? xm : xp;
+                if (ok) sv = fma(ac[k], xv, sv);
+            }
+            if (live) {
+                if (FIN) { __stcs(xout + i, x0); dd_add_prod(accx, x0, x0); }
+                __stcs(y + i, sv);
+                if (MODE == 1) dd_add_prod(accd, f0, sv);
+                if (MODE == 2) dd_add_prod(accd, sv, sv);
+            }
+            xm = x0; x0 = xp; f0 = fp;
+            i += (uint32_t)Bx;
+        };
+        // rows [z0, zm) run the hot path in whole groups of PF: they need z >= 1 and the refill row z + 1 + PF <= zlast local
+        int32_t z = z0;
+        const int32_t zloc = min(zlast, L.zhi - 1);
+        if (z0 == 0) {                                          // the box boundary row goes through the general path
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (z + u < z1) do_row(z + u, u, true);
+            z += PF;
+        }
+        for (; z + PF - 1 + 1 + PF <= zloc && z + PF <= z1; z += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) do_row(z + u, u, false);
+        }
+        for (; z < z1; z += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (z + u < z1) do_row(z + u, u, true);       // uniform over the CTA: the shuffles are convergent
         }
     }
-    if (MODE == 0) return;
-    DD v[1] = {acc};
-    double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, 0.0, 0);
+    if (MODE == 0 && !FIN) return;
+    if (FIN) {
+        DD v[2] = {accx, accd};
+        double tot[2];
+        if (grid_reduce<2>(v, tot, rd) && threadIdx.x == 0)
+            reduce_epilogue(MODE == 1 ? RK_FUSED_DOT : RK_FUSED_NRM, tot, ctl, A.h_out, A.hn_out, A.break_tol, A.cx);
+    } else {
+        DD v[1] = {accd};
+        double tot[1];
+        if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0)
+            reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, A.h_out, nullptr, 0.0, A.cx);
+    }
 }
 
 // The reference's column form ADJ/OFFDIAG/DIAG (StateSpace.f90:13-17) of local rows [0, count), computed from

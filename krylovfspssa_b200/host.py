@@ -273,14 +273,15 @@ class KrylovFspHandle:
         check(lib().kfsp_expm(self._h, m, t, _f64(H), ldh, _f64(out), C.byref(ns), C.byref(hn)), "DGPADM")
         return out, ns.value, hn.value
 
-    def combine(self, V, e, beta):
+    def combine(self, V, e, beta, colscale=None, with_ssq=False):
         V = np.asfortranarray(V, dtype=np.float64)
         e = np.ascontiguousarray(e, dtype=np.float64)
         n, mx = V.shape
         w = np.zeros(n)
-        ws = C.c_double()
-        check(lib().kfsp_combine(self._h, n, mx, beta, _f64(V), _f64(e), _f64(w), C.byref(ws)))
-        return w, ws.value
+        ws, ssq = C.c_double(), C.c_double()
+        cs = None if colscale is None else _f64(np.ascontiguousarray(colscale, dtype=np.float64))
+        check(lib().kfsp_combine(self._h, n, mx, beta, _f64(V), _f64(e), cs, _f64(w), C.byref(ws), C.byref(ssq)))
+        return (w, ws.value, ssq.value) if with_ssq else (w, ws.value)
 
     # ---- solve ------------------------------------------------------------------------
     def solve(self, t, states_in, p_in, fsp_tol, kry_tol, verbosity=0, max_out=None):

@@ -81,6 +81,8 @@ def lib():
         "ko_stats_get": (None, [vp, C.POINTER(Stats)]),
         "ko_arnoldi_sweep": (C.c_double, [vp, dp, C.c_int, dp, dp, i32p]),
         "ko_time_matvec": (C.c_double, [vp, dp, dp, C.c_int]),
+        "ko_last_sweep": (C.c_int, [dp, C.c_int, dp]),
+        "ko_combine_reproducible": (C.c_double, [C.c_long, C.c_int, C.c_double, dp, C.c_long, dp, dp, dp, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -253,6 +255,35 @@ def dot_reproducible(x, y):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
     return lib().ko_dot_reproducible(len(x), _f64(x), _f64(y))
+
+
+def arnoldi_sweep(fsp, v, m):
+    """One IOP-2 sweep (KrylovSolver.f90:236-263) from v on the oracle's matrix.  Canonical mode (the Fsp was made with
+    reproducible=1): returns H ((m+2)^2, Fortran order, unit entry set), the UN-NORMALISED basis (n x (m+2), Fortran
+    order), its column scales, AVNORM and the happy-breakdown column."""
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    n = len(v)
+    work = np.zeros((n, m + 2), order="F")
+    H = np.zeros((m + 2, m + 2), order="F")
+    nm = C.c_int32()
+    lib().ko_arnoldi_sweep(fsp.h, _f64(v), m, _f64(work), _f64(H), C.byref(nm))
+    cs = np.ones(m + 2)
+    av = C.c_double(0)
+    brk = lib().ko_last_sweep(_f64(cs), m + 2, C.byref(av))
+    H[m + 1, m] = 1.0
+    return dict(H=H, basis=work, colscale=cs, avnorm=av.value, brk=brk, nmult=nm.value)
+
+
+def combine_reproducible(V, e, beta, colscale=None):
+    """W = max(beta * sum_j e_j (cs_j V_j), 0) in canonical arithmetic; returns (w, ||w||_1, sum w^2)."""
+    V = np.asfortranarray(V, dtype=np.float64)
+    n, mx = V.shape
+    e = np.ascontiguousarray(e, dtype=np.float64)
+    cs = np.ones(mx) if colscale is None else np.ascontiguousarray(colscale, dtype=np.float64)
+    w = np.zeros(n)
+    ssq = C.c_double(0)
+    ws = lib().ko_combine_reproducible(n, mx, beta, _f64(V), n, _f64(e), _f64(cs), _f64(w), C.byref(ssq))
+    return w, ws, ssq.value
 
 
 def dgpadm(H, t, ideg=6, m=None, reproducible=0):

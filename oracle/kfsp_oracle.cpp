@@ -172,6 +172,14 @@ static int b_dgesv(int m, double* A, double* B) {
 //   * element-wise updates and short fixed-length sums are IEEE fma chains in a fixed order
 //     (SpMV row: -(d*x_i) then reactions in order; axpy: fma(-h,a,w); GEMV row: columns in order;
 //     dense products: k ascending from 0);
+//   * the Krylov basis is held UN-NORMALISED with one scale factor per column (canonical_sweep
+//     below): DSCAL(1/HJ1J) (KrylovSolver.f90:258) is never a pass over the column, the factor
+//     cs_j = 1/HJ1J is applied where the column is consumed (v_j(i) = cs_j * U_j(i), one rounding),
+//     and the generator product of a column is taken on the un-normalised column, its scale moving
+//     to the two scalars derived from it (H(J-1,J) = cs * <v_{J-1}, A U>, AVNORM = cs * ||A U||)
+//     and to the element of the next axpy (cs * (A U)(i)).  This is what lets the device compute
+//     x = w - h*v, ||x||^2, A x and <v, A x> in ONE pass over HBM: the norm of x is not known
+//     while that pass runs;
 //   * every reduction over N elements (dot, sum of squares, 1-norm, FIND_DROPTOL sums) is
 //     accumulated in double-double and rounded once, which makes the rounded value independent
 //     of the summation order (up to a ~2^-47 chance per reduction of a double rounding tie);
@@ -210,6 +218,12 @@ static double r_asum(long n, const double* x) {
     return dd_round(s);
 }
 static double r_nrm2(long n, const double* x) { return sqrt(r_dot(n, x, x)); }
+// sum_i (sx*x_i)*y_i: dot product with a column of the un-normalised basis (one rounding for the scale)
+static double r_dot_scaled(long n, double sx, const double* x, const double* y) {
+    dd s{0.0, 0.0};
+    for (long i = 0; i < n; ++i) dd_add_prod(s, sx * x[i], y[i]);
+    return dd_round(s);
+}
 // C = A * (alpha*B), n x n, k ascending fma chains; C has leading dimension n
 static void r_gemm(int n, const double* A, int lda, const double* B, int ldb, double alpha, double* C) {
     std::vector<double> Bs((size_t)n * n);
@@ -817,6 +831,44 @@ static void fmatvec(Fsp& f, const double* x, double* y) {
     }
 }
 
+// Canonical IOP-2 sweep (KrylovSolver.f90:236-263 on the un-normalised basis, see CANONICAL ARITHMETIC):
+// columns J = jold..m and the extra product.  V holds U_0..U_{m+1} (leading dimension N), cs the column
+// scales (v_j = cs[j]*U_j, cs[0] = 1 from the caller), H the Hessenberg matrix (leading dimension mh).
+// Returns the happy-breakdown column (1-based, KrylovSolver.f90:249-256) or 0; *nmult = SpMVs the
+// reference would have counted.
+static int canonical_sweep(Fsp& f, long N, double* V, double* cs, double* H, int mh, int jold, int m, double break_tol,
+                           double* avnorm, int* nmult) {
+    int nm = 0;
+    for (int J = jold; J <= m; ++J) {
+        const int c = J - 1;
+        const double* x = V + (size_t)c * N;
+        double* y = V + (size_t)J * N;
+        fmatvec(f, x, y); ++nm;                                             // Y' = A U_c, un-normalised
+        double h;
+        if (J >= 2) {
+            const double* fi = V + (size_t)(c - 1) * N;
+            const double fs = cs[c - 1];
+            const double h1 = cs[c] * r_dot_scaled(N, fs, fi, y);           // H(J-1,J) = <v_{J-1}, A v_J>
+            H[(size_t)(J - 1) * mh + (J - 2)] = h1;
+            for (long i = 0; i < N; ++i) y[i] = std::fma(-h1, fs * fi[i], cs[c] * y[i]);
+            h = r_dot_scaled(N, cs[c], x, y);                               // H(J,J)
+        } else {
+            h = cs[c] * r_dot_scaled(N, cs[c], x, y);                       // H(1,1); cs[0] = 1: y is A v_1 itself
+        }
+        H[(size_t)(J - 1) * mh + (J - 1)] = h;
+        for (long i = 0; i < N; ++i) y[i] = std::fma(-h, cs[c] * x[i], y[i]);
+        const double hn = r_nrm2(N, y);                                     // HJ1J
+        if (hn <= break_tol) { *nmult = nm; return J; }
+        H[(size_t)(J - 1) * mh + J] = hn;
+        cs[J] = 1.0 / hn;                                                   // DSCAL deferred to the consumers
+    }
+    double* y = V + (size_t)(m + 1) * N;
+    fmatvec(f, V + (size_t)m * N, y); ++nm;
+    *avnorm = cs[m] * r_nrm2(N, y);
+    *nmult = nm;
+    return 0;
+}
+
 // FIND_DROPTOL -- StateSpace.f90:398-427
 static double find_droptol(long n, const double* w, double dsum, bool repro) {
     double droptol = 1.0e-8;
@@ -928,13 +980,14 @@ struct Solver {
         if (repro) { for (long i = 0; i < n; ++i) y[i] = std::fma(a, x[i], y[i]); }
         else b_daxpy((int)n, a, x, y);
     }
-    void n_gemv(long n, int m, double alpha, const double* A, long lda, const double* x, double* y) const {
+    // cs: column scales of the un-normalised basis (canonical mode only)
+    void n_gemv(long n, int m, double alpha, const double* A, long lda, const double* x, double* y, const double* cs) const {
         if (!repro) { b_dgemv_n((int)n, m, alpha, A, lda, x, y); return; }
         std::vector<double> c(m);
         for (int j = 0; j < m; ++j) c[j] = alpha * x[j];
         for (long i = 0; i < n; ++i) {
             double s = 0.0;
-            for (int j = 0; j < m; ++j) s = std::fma(c[j], A[(size_t)j * lda + i], s);
+            for (int j = 0; j < m; ++j) s = std::fma(c[j], cs[j] * A[(size_t)j * lda + i], s);
             y[i] = s;
         }
     }
@@ -1014,7 +1067,7 @@ struct Solver {
         double HNORM = 0.0, ERR_LOC = 0.0, AVNORM = 0.0, T_STEP = 0.0, WSUM = 0.0;
         double ERROR_ = 0.0, ERROROLD = 1.0, TAU_OLD = 1.0, FSPORDER = 2.0, TFSP = 0.0, T_SSA = 0.0;
         int MBRKDWN = M, K1 = 2, MH = 0, MX = 0, NS = 0, IREJECT = 0;
-        std::vector<double> V, H, HTMP, EXPH;
+        std::vector<double> V, H, HTMP, EXPH, CS;
         long n_expand = 0, n_drop = 0;
 
         while (T_NOW < T_OUT) {                                          // label 100
@@ -1034,7 +1087,22 @@ struct Solver {
             IREJECT = 0;
             bool to_404 = false;
         L101:
-            {
+            if (repro) {                                                  // canonical arithmetic: un-normalised basis
+                if ((int)CS.size() < M_MAX + 2) CS.assign(M_MAX + 2, 1.0);
+                if (JOLD == 1) CS[0] = 1.0;
+                int nm = 0;
+                const int brk = canonical_sweep(fsp, N, V.data(), CS.data(), H.data(), MH, JOLD, M, BREAK_TOL, &AVNORM, &nm);
+                NMULT += nm;
+                if (brk > 0) {                                            // happy breakdown (:249-256)
+                    K1 = 0;
+                    IBRKFLAG = 1;
+                    MBRKDWN = brk;
+                    TBRKDWN = T_NOW;
+                    T_STEP = T_OUT - T_NOW;
+                    flags |= 8;
+                }
+                H[(size_t)M * MH + (M + 1)] = 1.0;                        // label 300 (:266)
+            } else {
                 bool broke = false;
                 for (int J = JOLD; J <= M; ++J) {                         // DO 200
                     NMULT += 1;
@@ -1178,7 +1246,7 @@ struct Solver {
             IREJECTFSP = 0;
             // FSP criterion loop (:442-495)
             for (;;) {
-                n_gemv(N, MX, BETA, V.data(), N, EXPH.data(), W);
+                n_gemv(N, MX, BETA, V.data(), N, EXPH.data(), W, CS.data());
                 for (long i = 0; i < fsp.size; ++i) if (W[i] < 0.0) W[i] = 0.0;
                 WSUM = n_asum(fsp.size, W);
                 ERROR_ = WSUM_OLD - WSUM;
@@ -1415,6 +1483,9 @@ void ko_stats_get(void* sp, Stats* out) { *out = ((Solver*)sp)->stats; }
 
 // One Arnoldi/IOP sweep + FMATVEC timing helper for the CPU baseline (KrylovSolver.f90:236-263):
 // runs `m` columns on the fsp's matrix from v (length size), returns seconds; H (m+2)^2 optional.
+static std::vector<double> g_last_cs;       // column scales / AVNORM / breakdown column of the last canonical ko_arnoldi_sweep
+static double g_last_avnorm = 0.0;
+static int g_last_brk = 0;
 double ko_arnoldi_sweep(void* fp, const double* v, int m, double* work /*size*(m+2)*/, double* Hout, int* nmult) {
     Fsp& f = *(Fsp*)fp;
     long N = f.size;
@@ -1424,6 +1495,16 @@ double ko_arnoldi_sweep(void* fp, const double* v, int m, double* work /*size*(m
     double t0 = now_s();
     { const double ib = 1.0 / beta; for (long i = 0; i < N; ++i) work[i] = ib * v[i]; }
     int nm = 0;
+    if (f.repro) {
+        // canonical arithmetic: `work` receives the UN-NORMALISED basis, its column scales are read with ko_last_sweep()
+        g_last_cs.assign(m + 2, 1.0);
+        g_last_avnorm = 0.0;
+        g_last_brk = canonical_sweep(f, N, work, g_last_cs.data(), H.data(), MH, 1, m, 1e-7, &g_last_avnorm, &nm);
+        double dt = now_s() - t0;
+        if (Hout) memcpy(Hout, H.data(), sizeof(double) * H.size());
+        if (nmult) *nmult = nm;
+        return dt;
+    }
     for (int J = 1; J <= m; ++J) {
         double* vn = &work[(size_t)J * N];
         fmatvec(f, &work[(size_t)(J - 1) * N], vn); ++nm;
@@ -1443,6 +1524,30 @@ double ko_arnoldi_sweep(void* fp, const double* v, int m, double* work /*size*(m
     if (Hout) memcpy(Hout, H.data(), sizeof(double) * H.size());
     if (nmult) *nmult = nm;
     return dt;
+}
+// column scales (m+2 entries), AVNORM and breakdown column of the last canonical ko_arnoldi_sweep
+int ko_last_sweep(double* cs, int ncs, double* avnorm) {
+    for (int j = 0; j < ncs && j < (int)g_last_cs.size(); ++j) cs[j] = g_last_cs[j];
+    if (avnorm) *avnorm = g_last_avnorm;
+    return g_last_brk;
+}
+// Basis combination in canonical arithmetic (KrylovSolver.f90:444-450): w = max(beta * sum_j e_j (cs_j U_j), 0),
+// returns ||w||_1; *wssq = sum w^2 (both double-double, rounded once)
+double ko_combine_reproducible(long n, int mx, double beta, const double* V, long lda, const double* e, const double* cs, double* w,
+                               double* wssq) {
+    std::vector<double> c(mx);
+    for (int j = 0; j < mx; ++j) c[j] = beta * e[j];
+    dd a1{0.0, 0.0}, a2{0.0, 0.0};
+    for (long i = 0; i < n; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < mx; ++j) s = std::fma(c[j], cs[j] * V[(size_t)j * lda + i], s);
+        if (s < 0.0) s = 0.0;
+        w[i] = s;
+        dd_add(a1, s);
+        dd_add_prod(a2, s, s);
+    }
+    if (wssq) *wssq = dd_round(a2);
+    return dd_round(a1);
 }
 double ko_time_matvec(void* fp, const double* x, double* y, int reps) {
     Fsp& f = *(Fsp*)fp;

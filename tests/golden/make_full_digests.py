@@ -2,7 +2,9 @@
 commit as arrays, so tests/golden/full_digests.json keeps sizes, counters and SHA-256 digests of the
 state list, the decision trace and the probability vector.  The GPU test (tests/test_gpu_full_configs.py)
 must reproduce the digests, i.e. be bit-identical at full scale.
-Usage: python tests/golden/make_full_digests.py [tag ...]   (goutsias_full takes ~1-2 h of CPU)"""
+Usage: python tests/golden/make_full_digests.py [tag ...]   (goutsias_full takes ~1 h of CPU)
+Tags are independent: to use several cores run one process per tag with KFSP_DIGEST_OUT=<part file> each and merge
+the part files with `python tests/golden/make_full_digests.py --merge part1.json part2.json ...`."""
 import hashlib
 import json
 import os
@@ -40,6 +42,14 @@ def digest(out_states, out_vector, trace_i, trace_d, stats):
 
 def main():
     path = os.path.join(HERE, "full_digests.json")
+    if len(sys.argv) > 1 and sys.argv[1] == "--merge":
+        db = json.load(open(path)) if os.path.exists(path) else {}
+        for part in sys.argv[2:]:
+            db.update(json.load(open(part)))
+        json.dump(db, open(path, "w"), indent=1, sort_keys=True)
+        print("merged", len(sys.argv) - 2, "part files ->", sorted(db))
+        return
+    path = os.environ.get("KFSP_DIGEST_OUT", path)
     db = json.load(open(path)) if os.path.exists(path) else {}
     tags = sys.argv[1:] or list(FULL_RUNS) + list(DRIVER_RUNS)
     for tag in tags:

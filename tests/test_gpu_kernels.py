@@ -42,16 +42,16 @@ def test_arnoldi_hessenberg(name, steps, m):
     n = of.size
     v = np.zeros(n); v[0] = 1.0; v[1:5] = 0.3
     H, av, brk, _ = h.arnoldi(v, m)
-    work = np.zeros(n * (m + 2))
-    Ho = np.zeros((m + 2, m + 2), order="F")
-    nm = C.c_int32()
-    oracle.lib().ko_arnoldi_sweep(of.h, v.ctypes.data_as(C.POINTER(C.c_double)), m, work.ctypes.data_as(C.POINTER(C.c_double)),
-                                  Ho.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nm))
-    Ho[m + 1, m] = 1.0
-    assert brk == 0
-    assert np.array_equal(H, Ho)                                       # every Hessenberg entry bit-exact
-    avo = np.sqrt(oracle.dot_reproducible(work[(m + 1) * n:(m + 2) * n], work[(m + 1) * n:(m + 2) * n]))
-    assert av == avo
+    ref = oracle.arnoldi_sweep(of, v, m)                               # canonical sweep on the un-normalised basis
+    assert brk == 0 and ref["brk"] == 0
+    assert np.array_equal(H, ref["H"])                                 # every Hessenberg entry bit-exact
+    assert av == ref["avnorm"]
+    # against the reference's own operation order (netlib BLAS order, DSCAL as a pass): rounding level
+    lib = oracle.lib()
+    lib.ko_fsp_set_reproducible(of.h, 0)
+    net = oracle.arnoldi_sweep(of, v, m)
+    lib.ko_fsp_set_reproducible(of.h, 1)
+    assert np.abs(H - net["H"]).max() <= 1e-12 * np.abs(net["H"]).max()
     # IOP-2: H is tridiagonal apart from the unit entry
     assert np.count_nonzero(np.triu(H[:m, :m], 2)) == 0
     h.close()
@@ -118,4 +118,11 @@ def test_combine(n, mx):
     assert np.abs(w - wo).max() <= 1e-13 * max(1.0, np.abs(wo).max())
     assert abs(ws - wo.sum()) <= 1e-12 * max(1.0, wo.sum())
     assert w.min() >= 0.0
+    # SURVEY a6/a7 against the oracle, bit for bit, with the per-column scales of the un-normalised basis
+    cs = 1.0 / np.abs(rng.standard_normal(mx) * 3.0 + 0.1)
+    for scale in (None, cs):
+        w, ws, ssq = h.combine(V, e, 0.7, colscale=scale, with_ssq=True)
+        wr, wsr, ssqr = oracle.combine_reproducible(V, e, 0.7, colscale=scale)
+        assert np.array_equal(w, wr)
+        assert ws == wsr and ssq == ssqr
     h.close()

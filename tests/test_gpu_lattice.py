@@ -170,3 +170,32 @@ def test_stencil_kernel_every_table_role(order):
         Hb, avb, _, _ = b.arnoldi(v, 10)
         assert np.array_equal(Ha, Hb) and ava == avb, (order, mask)              # dot-fused and norm-fused variants
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("zc", [1, 5, 9, 17, 64, 256])
+def test_stencil_kernel_chunk_lengths(zc, monkeypatch):
+    """The stencil kernel walks a z-chunk in three pieces (head at the box boundary, a hot loop without bounds checks, a
+    general tail).  At test sizes the automatic chunking gives chunks shorter than the hot loop needs, so the chunk length
+    is forced (KFSP_BD2_ZC) to run every piece: plain, dot-fused, finalising (FIN) and norm variants against the explicit path."""
+    monkeypatch.setenv("KFSP_BD2_ZC", str(zc))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    bounds = (301, 257)
+    model = file_model("toggle_test.input", bench.PARAMS)
+    states, p0 = bench.synthetic(*bounds)
+    a, b, _ = pair(model, bounds)
+    rng = np.random.default_rng(zc)
+    x = rng.standard_normal(len(p0))
+    assert np.array_equal(a.matvec(x), b.matvec(x))
+    v = np.abs(rng.standard_normal(len(p0)))
+    Ha, ava, brka, _ = a.arnoldi(v, 12)
+    Hb, avb, brkb, _ = b.arnoldi(v, 12)
+    assert np.array_equal(Ha, Hb) and ava == avb and brka == brkb
+    a.set_vector(p0); b.set_vector(p0)
+    rca, sa = a.solve_resident(0.05, 1e-6, 1e-8)
+    rcb, sb = b.solve_resident(0.05, 1e-6, 1e-8)
+    assert rca == rcb == 0
+    assert np.array_equal(a.trace()["i"], b.trace()["i"])
+    assert np.array_equal(a.get(matrix=False)["vector"], b.get(matrix=False)["vector"])
+    a.close(); b.close()
