@@ -9,20 +9,22 @@ two discretised Gaussians centred mid-box (sigma = B/16), fixed state set (FSP a
 KRYTOL 1e-8, Krylov dimension adapting in [10, 30].
 
 The generator SpMV runs matrix-free on the lattice by default (--spmv-variant 1, csrc/lattice.cuh: FMATVEC recomputed
-from the integer state, 16 B/state, bit-identical to the explicit matrix); the same line carries a companion measurement
-of the identical solves on the explicit gather-ELL matrix (--spmv-variant 0 makes that one the main measurement).
+from the integer state, bit-identical to the explicit matrix); the same line carries a companion measurement
+of the identical solves on the explicit gather-ELL matrix (--spmv-variant 0 makes that one the main measurement)
+and a `parity` object: the two final vectors compared bit for bit at the benchmarked size.
 
 A "step" is one complete adaptive expv solve exp(t_final*A) p0 over the whole state space.
 `value` = generator state updates per second = N * NMULT / time with the state space and p0
 resident in HBM (kfsp_solve_resident); `e2e` is the same quantity through the reference-facing
 C-ABI call kfsp_solve() with HOST buffers (pinned): H2D of states and p0, MATRIX_STARTER on the
-device, the solve, D2H of states and p -- all inside the timed region.
+device, the solve, D2H of states and p -- all inside the timed region, at every GPU count.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, netlib-order arithmetic,
 1 thread -- the reference is serial) on a bounded sample of the same workload.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -40,12 +42,21 @@ PARAMS = [5000.0, 1600.0, 1.0, 1.0]
 METRIC = "expv_generator_state_updates_per_s"
 UNIT = "state-updates/s"
 R_TOGGLE = 4
-# algorithmic bytes per state of one generator SpMV and measured DRAM traffic per state of the
-# dot-fused launch (ncu --set full, profiles/), per SpMV variant: 0 explicit gather-ELL, 1 matrix-free lattice
-BYTES_PER_STATE = {0: 12 * R_TOGGLE + 24, 1: 16}
-TRAFFIC_PER_STATE = {0: 80.9, 1: 27.2}
-KERNEL_NAME = {0: "k_spmv (generator SpMV, explicit gather ELL; per GPU, rank 0)",
-               1: "k_spmv_bd2 (generator SpMV, matrix-free stencil kernel on the lattice; per GPU, rank 0)"}
+# Algorithmic bytes per state a launch of each kernel class must move, per SpMV variant.
+# explicit gather-ELL: 12R+24 for FMATVEC, +8 for the operand of the fused DDOT.
+# matrix-free lattice: x + y = 16 for FMATVEC; +8 for a DDOT operand that is not x itself; the finalising launches read the
+# un-finalised column T and v_first and write the finalised column and y = 32 (they replace k_axpy_nrm's 24 + the SpMV's 24).
+KERNEL_BYTES = {
+    0: {"spmv_plain": 12 * R_TOGGLE + 24, "spmv_dot": 12 * R_TOGGLE + 32, "spmv_nrm": 12 * R_TOGGLE + 24, "axpy_dot": 32, "axpy_nrm": 24,
+        "scale_copy": 16},
+    1: {"spmv_plain": 16, "spmv_dot": 24, "spmv_nrm": 16, "spmv_fin_dot": 32, "spmv_fin_nrm": 32, "axpy_dot": 32, "axpy_nrm": 24,
+        "scale_copy": 16},
+}
+SPMV_CLASSES = ("spmv_plain", "spmv_dot", "spmv_nrm", "spmv_fin_dot", "spmv_fin_nrm")
+KERNEL_NAME = {0: "k_spmv (generator SpMV, explicit gather ELL, first IOP dot fused; per GPU, rank 0)",
+               1: "k_spmv_bd2 (matrix-free generator SpMV on the lattice with the previous Arnoldi column's DAXPY+DNRM2 fused into "
+                  "its load stage and the first IOP dot into its epilogue; per GPU, rank 0)"}
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")     # dram__bytes per launch from the round's ncu --set full pass
 
 
 def synthetic(bx, by):
@@ -69,6 +80,17 @@ def measured_peak():
             return float(json.load(fh)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def measured_traffic(variant, states):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the ncu pass recorded in
+    profiles/traffic.json (bytes per state at the recorded size, scaled to this run's local states); None if absent."""
+    try:
+        with open(TRAFFIC_FILE) as fh:
+            t = json.load(fh)[str(variant)]
+        return t["dram_bytes_per_state"] * states, t["source"]
+    except Exception:
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -124,7 +146,8 @@ def cpu_sample(bx, by, m):
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the CPU restatement of the reference's own path, serial like the reference."""
+    """Reference arm: the CPU restatement of the reference's own path, serial like the reference, same t_final and Krylov
+    dimension range as the repo arm, on a bounded rectangle of the same workload."""
     if rank != 0:
         return
     import oracle
@@ -134,7 +157,7 @@ def run_reference(args, rank, world):
     n = len(p0)
     times, mults = [], []
     for it in range(args.warmup_ref + args.steps):
-        out = oracle.solve(om, states, p0, args.ref_t_final, 1e-6, 1e-8, max_size=n + 64, m_max=args.m_max, m_min=10,
+        out = oracle.solve(om, states, p0, args.t_final, 1e-6, 1e-8, max_size=n + 64, m_max=args.m_max, m_min=10,
                            n_init_onestep=0, enable_drop=0, enable_expand=0)
         if it >= args.warmup_ref:
             times.append(out["stats"]["wall_seconds"])
@@ -145,15 +168,21 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup_ref, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic toggle rectangle %dx%d (bounded sample of config 5), expv to t=%g, fixed state set"
-                               % (bx, by, args.ref_t_final), "states": n, "m_range": [10, args.m_max]},
+        "config": {"workload": "synthetic toggle rectangle %dx%d (bounded sample of config 5), expv to t_final=%g, KRYTOL 1e-8, "
+                               "Krylov dimension in [10,%d], fixed state set" % (bx, by, args.t_final, args.m_max),
+                   "states": n, "m_range": [10, args.m_max]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": "full expv solve on a %dx%d rectangle (%d states), %d SpMVs per solve; oracle port of the "
-                                   "serial Fortran reference (no Fortran compiler in this image)" % (bx, by, n, mults[0])},
+                                   "serial Fortran reference (no Fortran compiler in this image or on the GPU box: "
+                                   "profiles/r2_fortran_probe_gpu_box.txt), 1 of %d host cores" % (bx, by, n, mults[0], os.cpu_count())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def sha_of(arr):
+    return hashlib.sha256(np.ascontiguousarray(arr).view(np.uint8)).hexdigest()
 
 
 def main():
@@ -167,13 +196,13 @@ def main():
     ap.add_argument("--t-final", type=float, default=0.01)
     ap.add_argument("--m-max", type=int, default=30)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-bx", type=int, default=2000)
-    ap.add_argument("--cpu-by", type=int, default=2000)
+    ap.add_argument("--cpu-bx", type=int, default=3200)
+    ap.add_argument("--cpu-by", type=int, default=3200)
     ap.add_argument("--ref-bx", type=int, default=1500)
     ap.add_argument("--ref-by", type=int, default=1500)
-    ap.add_argument("--ref-t-final", type=float, default=0.05)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the bit-for-bit comparisons (profiling runs)")
     ap.add_argument("--scattered", action="store_true",
                     help="SURVEY 8d scattered-order variant: the same state set with its indices permuted by a fixed Philox permutation "
                          "(seed 12345) -- the irregular gather a real FSP ordering produces; explicit matrix only")
@@ -209,6 +238,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(v):
+        tt = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def new_uid():
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(k.KrylovFspHandle.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        return uid.cpu().numpy().tobytes()
+
     L = lib()
     bx, by = args.bx, args.by
     states_np, p0_np = synthetic(bx, by)
@@ -223,14 +265,13 @@ def main():
     # pinned host buffers (inputs and outputs of the C-ABI call)
     states_h = torch.from_numpy(states_np).pin_memory()
     p0_h = torch.from_numpy(p0_np).pin_memory()
-    states_out = torch.empty((n, 2), dtype=torch.int32).pin_memory()
     p_out = torch.empty(n, dtype=torch.float64).pin_memory()
     del states_np
 
     model = k.CME_MODEL().load(os.path.join(k.models_dir(), "toggle_test.input"))
     model.reset_parameters(PARAMS)
-    h = k.KrylovFspHandle(model, max_states=n + 64, m_max=args.m_max, m_min=10, n_init_onestep=0, enable_drop=0,
-                          enable_expand=0, device=local_rank, spmv_variant=args.spmv_variant)
+    hopts = dict(max_states=n + 64, m_max=args.m_max, m_min=10, n_init_onestep=0, enable_drop=0, enable_expand=0, device=local_rank)
+    h = k.KrylovFspHandle(model, spmv_variant=args.spmv_variant, **hopts)
     variant = args.spmv_variant
     i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
     fsp_tol, kry_tol = 1e-6, 1e-8
@@ -238,11 +279,7 @@ def main():
     if world > 1:
         # rows of the state space are block-partitioned over the ranks (one process per GPU); the NCCL
         # communicator of the library is bootstrapped through torch.distributed
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(k.KrylovFspHandle.dist_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        h.dist_init(rank, world, uid.cpu().numpy().tobytes())
+        h.dist_init(rank, world, new_uid())
 
     # ---- resident setup (not timed for `value`): MATRIX_STARTER on the device, p0 in HBM -------------
     t_setup = time.time()
@@ -256,67 +293,109 @@ def main():
     check(L.kfsp_device_upload(h._h, p0_dev, C.c_void_p(p0_h.data_ptr() + 8 * lo), 8 * nloc))
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
-    check(L.kfsp_set_profiling(h._h, 1))
+    h.set_profiling(True)
 
-    def resident_step():
-        check(L.kfsp_fsp_set_vector_device(h._h, p0_dev, nloc))
+    def resident_step(hh, pdev, cnt):
+        check(L.kfsp_fsp_set_vector_device(hh._h, pdev, cnt))
         st = Stats()
-        rc = L.kfsp_solve_resident(h._h, args.t_final, fsp_tol, kry_tol, 0, C.byref(st))
+        rc = L.kfsp_solve_resident(hh._h, args.t_final, fsp_tol, kry_tol, 0, C.byref(st))
         if rc < 0:
             raise k.KfspError(rc, "kfsp_solve_resident")
         return st
 
-    for _ in range(args.warmup):
-        resident_step()
+    def timed_solves(hh, pdev, cnt):
+        """warm-up, then K timed resident solves: device seconds (this rank), counters, per-class kernel times"""
+        for _ in range(args.warmup):
+            resident_step(hh, pdev, cnt)
+        barrier()
+        out = dict(dev_s=0.0, nmult=0, launches=0, nstep=0, classes={})
+        t0 = time.time()
+        for _ in range(args.steps):
+            st = resident_step(hh, pdev, cnt)
+            out["dev_s"] += st.device_seconds
+            out["nmult"] += st.nmult
+            out["launches"] += st.kernel_launches
+            out["nstep"] += st.nstep
+            for name, (sec, c) in hh.profile().items():
+                a = out["classes"].setdefault(name, [0.0, 0])
+                a[0] += sec
+                a[1] += c
+        barrier()
+        out["wall"] = time.time() - t0
+        return out
+
+    def kernel_table(res, var, rows):
+        """per kernel class: launches, mean ms, algorithmic GB/s and fraction of the measured HBM peak (this rank's rows)"""
+        tab = {}
+        for name, (sec, c) in res["classes"].items():
+            if c == 0:
+                continue
+            b = KERNEL_BYTES[var].get(name)
+            if name == "combine":
+                b = None
+            e = {"launches": c, "avg_ms": 1e3 * sec / c, "share_of_step": sec / res["dev_s"] if res["dev_s"] > 0 else None}
+            if b:
+                e["algorithmic_bytes_per_state"] = b
+                e["gbs"] = b * rows / (sec / c) / 1e9
+                e["frac_of_peak"] = e["gbs"] / peak
+            tab[name] = e
+        return tab
+
+    def spmv_roofline(res, var, rows):
+        """the generator SpMV (all its fused variants) against the HBM roofline: bytes the timed launches must move / their time"""
+        tot_b = tot_b16 = tot_s = 0.0
+        cnt = 0
+        for name in SPMV_CLASSES:
+            sec, c = res["classes"].get(name, (0.0, 0))
+            tot_b += KERNEL_BYTES[var].get(name, 0) * rows * c
+            tot_b16 += KERNEL_BYTES[var]["spmv_plain"] * rows * c
+            tot_s += sec
+            cnt += c
+        return tot_b, tot_b16, tot_s, cnt
+
+    peak, peak_kind = measured_peak()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    t0 = time.time()
-    dev_s = spmv_s = 0.0
-    nmult = launches = spmv_launches = nstep = 0
-    for _ in range(args.steps):
-        st = resident_step()
-        dev_s += st.device_seconds
-        spmv_s += st.spmv_seconds
-        nmult += st.nmult
-        launches += st.kernel_launches
-        spmv_launches += st.spmv_launches
-        nstep += st.nstep
-    barrier()
-    wall = time.time() - t0
+    res = timed_solves(h, p0_dev, nloc)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    # device-timed, max over ranks
-    tt = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_s_rank = dev_s
-    dev_s = float(tt.item())
+    dev_s = allmax(res["dev_s"])                          # device-timed, max over ranks
+    nmult, launches, nstep = res["nmult"], res["launches"], res["nstep"]
     units = float(n) * nmult                              # the whole job: all ranks together update N states per SpMV
     value = units / dev_s
     dinfo = h.dist_info() if world > 1 else None
 
-    # ---- end to end through the C ABI with host buffers ----------------------------------------------
+    # plain FMATVEC (mode 0, no fused reduction) on this rank's rows, device-timed: the SURVEY 8d "generator SpMV" number
+    plain = None
+    if not args.scattered and world == 1:
+        ybuf = C.c_void_p()
+        check(L.kfsp_device_alloc(h._h, 8 * nloc, C.byref(ybuf)))
+        sec = C.c_double()
+        check(L.kfsp_matvec_device(h._h, p0_dev, ybuf, 3, C.byref(sec)))
+        barrier()
+        check(L.kfsp_matvec_device(h._h, p0_dev, ybuf, 10, C.byref(sec)))
+        barrier()
+        pb = KERNEL_BYTES[variant]["spmv_plain"]
+        plain = {"avg_ms": 1e3 * sec.value, "algorithmic_bytes_per_state": pb, "gbs": pb * nloc / sec.value / 1e9,
+                 "frac_of_peak": pb * nloc / sec.value / 1e9 / peak, "launches_timed": 10,
+                 "what": "kfsp_matvec_device: FMATVEC alone (KrylovSolver.f90:577-607), no fused reduction, this rank's rows"}
+        check(L.kfsp_device_free(h._h, ybuf))
+
+    # ---- end to end through the C ABI with host buffers: kfsp_solve at every GPU count -------------------------------
+    # states_out is the same array as states_in, as in the reference (FSP_OUT is in/out, KrylovSolver.f90:7-36)
     def e2e_step():
         st = Stats()
-        if world == 1:
-            n_out = C.c_int64()
-            rc = L.kfsp_solve(h._h, args.t_final, n, C.cast(states_h.data_ptr(), i32p), C.cast(p0_h.data_ptr(), f64p), fsp_tol,
-                              kry_tol, 0, C.byref(n_out), C.cast(states_out.data_ptr(), i32p), C.cast(p_out.data_ptr(), f64p),
-                              n, C.byref(st))
-        else:
-            # the same call sequence the single-GPU kfsp_solve performs, spelled out for a partitioned state set:
-            # global states and p0 from the host, this rank's rows of states and p back to the host
-            check(L.kfsp_fsp_init(h._h, n, C.cast(states_h.data_ptr(), i32p)), "MATRIX_STARTER")
-            check(L.kfsp_fsp_set_vector(h._h, C.cast(p0_h.data_ptr(), f64p), n))
-            rc = L.kfsp_solve_resident(h._h, args.t_final, fsp_tol, kry_tol, 0, C.byref(st))
-            if rc >= 0:
-                check(L.kfsp_fsp_get(h._h, C.cast(states_out.data_ptr(), i32p), None, None, None, C.cast(p_out.data_ptr(), f64p)))
+        n_out = C.c_int64()
+        rc = L.kfsp_solve(h._h, args.t_final, n, C.cast(states_h.data_ptr(), i32p), C.cast(p0_h.data_ptr(), f64p), fsp_tol,
+                          kry_tol, 0, C.byref(n_out), C.cast(states_h.data_ptr(), i32p), C.cast(p_out.data_ptr(), f64p),
+                          n, C.byref(st))
         if rc < 0:
             raise k.KfspError(rc, "kfsp_solve")
+        assert n_out.value == nloc
         return st
 
     e2e = None
+    total_mass = None
     if args.e2e_steps > 0:
         e2e_step()                                        # warm-up
         barrier()
@@ -325,58 +404,48 @@ def main():
         for _ in range(args.e2e_steps):
             e_mult += e2e_step().nmult
         barrier()
-        e_wall = time.time() - t0
-        tt = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e_wall = float(tt.item())
+        e_wall = allmax(time.time() - t0)
         # the lattice variant ships only this rank's slab of the state list; the explicit one needs the global list for its hash table
-        h2d = int((states_h.numel() if (world == 1 or variant == 0) else nloc * 2) * 4 + (p0_h.numel() if world == 1 else nloc) * 8)
-        d2h = int(nloc * 2 * 4 + nloc * 8)
+        h2d = int((n if variant == 0 else nloc) * 2 * 4 + nloc * 8)
+        d2h = int(nloc * 8)
         e2e = {"value": float(n) * e_mult / e_wall, "unit": UNIT,
-               "h2d_bytes_per_step": h2d * world if world > 1 else h2d, "d2h_bytes_per_step": int(n * 2 * 4 + n * 8),
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "ms_per_step": 1e3 * e_wall / args.e2e_steps,
-               "timed": "host wall clock around the C-ABI calls with pinned host buffers (H2D of states and p0, device "
-                        "MATRIX_STARTER, solve, D2H of states and p), barrier on both sides, max over ranks"}
+               "timed": "host wall clock around kfsp_solve with pinned host buffers (H2D of states and p0, device MATRIX_STARTER, "
+                        "solve, D2H of p; the state list is in/out as in the reference and, the set being fixed, is not copied "
+                        "back), barrier on both sides, max over ranks; on N GPUs every rank calls kfsp_solve on its partitioned handle"}
         mass = torch.tensor([float(p_out[:nloc].sum())], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(mass)
         total_mass = float(mass.item())
-    else:
-        total_mass = None
 
-    peak, peak_kind = measured_peak()
-    spmv_avg = spmv_s / max(spmv_launches, 1)
-    bps = BYTES_PER_STATE[variant]
-    achieved = bps * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0
+    tot_b, tot_b16, tot_s, spmv_launches = spmv_roofline(res, variant, nloc)
+    achieved = tot_b / tot_s / 1e9 if tot_s > 0 else 0.0
+    traffic, traffic_src = measured_traffic(variant, nloc)
     roofline = {"bound": "hbm", "kernel": KERNEL_NAME[variant], "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": TRAFFIC_PER_STATE[variant] * nloc if TRAFFIC_PER_STATE[variant] else None,
-                "traffic_source": "ncu --set full of the dot-fused launch at 1e8 states, profiles/r1_summary.md",
-                "algorithmic_bytes_per_state": bps,
-                "algorithmic_bytes_per_launch": bps * nloc,
-                "algorithmic_bytes_per_launch_incl_fused_dot_operand": (bps + 8) * nloc,
-                "achieved_incl_fused_dot_operand": (bps + 8) * nloc / spmv_avg / 1e9 if spmv_avg > 0 else 0.0,
-                "frac_incl_fused_dot_operand": (bps + 8) * nloc / spmv_avg / 1e9 / peak if spmv_avg > 0 else 0.0,
-                "note": "achieved/frac count the SpMV's own algorithmic bytes (SURVEY 8d); 10 of every 11 timed launches also "
-                        "compute the first IOP dot product in the same pass, which reads 8 B/state more (the *_incl_fused_dot_operand fields)",
-                "states_per_s_per_launch": nloc / spmv_avg if spmv_avg > 0 else 0.0,
-                "avg_launch_ms": 1e3 * spmv_avg,
-                "launches_timed": spmv_launches, "share_of_step": spmv_s / dev_s_rank if dev_s_rank > 0 else None,
-                "frac_of_nominal_8TBs": achieved / 8000.0}
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": tot_b / max(spmv_launches, 1),
+                "algorithmic_bytes_per_state_per_launch": tot_b / max(spmv_launches, 1) / nloc,
+                "spmv_only_bytes_per_state": KERNEL_BYTES[variant]["spmv_plain"],
+                "achieved_spmv_only_bytes": tot_b16 / tot_s / 1e9 if tot_s > 0 else 0.0,
+                "frac_spmv_only_bytes": tot_b16 / tot_s / 1e9 / peak if tot_s > 0 else 0.0,
+                "note": "achieved = bytes the timed SpMV launches must move (operand, result, and the operands/results of the "
+                        "vector work fused into the same pass: DESIGN.md section 4, per class in `kernels`) / their CUDA-event time; "
+                        "*_spmv_only_bytes counts FMATVEC's own bytes alone (SURVEY 8d) for the same launches",
+                "avg_launch_ms": 1e3 * tot_s / max(spmv_launches, 1),
+                "launches_timed": spmv_launches, "share_of_step": tot_s / res["dev_s"] if res["dev_s"] > 0 else None,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "plain_spmv": plain}
+    kernels = kernel_table(res, variant, nloc)
 
     # ---- companion: the same resident solves on the EXPLICIT gather-ELL matrix (the reference's data model), so that one
     # line shows both generator-SpMV kernels against the HBM roofline; results of the two variants are bit-identical
     companion = None
+    parity = None
     if variant == 1 and not args.no_companion:
-        h0 = k.KrylovFspHandle(model, max_states=n + 64, m_max=args.m_max, m_min=10, n_init_onestep=0, enable_drop=0,
-                               enable_expand=0, device=local_rank, spmv_variant=0)
+        h0 = k.KrylovFspHandle(model, spmv_variant=0, **hopts)
         if world > 1:
-            uid0 = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                uid0.copy_(torch.frombuffer(bytearray(k.KrylovFspHandle.dist_unique_id()), dtype=torch.uint8))
-            dist.broadcast(uid0, 0)
-            h0.dist_init(rank, world, uid0.cpu().numpy().tobytes())
+            h0.dist_init(rank, world, new_uid())
         check(L.kfsp_fsp_init(h0._h, n, C.cast(states_h.data_ptr(), i32p)), "MATRIX_STARTER")
         lo0, hi0 = 0, n
         if world > 1:
@@ -385,37 +454,54 @@ def main():
         p0_dev0 = C.c_void_p()
         check(L.kfsp_device_alloc(h0._h, 8 * (hi0 - lo0), C.byref(p0_dev0)))
         check(L.kfsp_device_upload(h0._h, p0_dev0, C.c_void_p(p0_h.data_ptr() + 8 * lo0), 8 * (hi0 - lo0)))
-        check(L.kfsp_set_profiling(h0._h, 1))
-        c_dev = c_spmv = 0.0
-        c_mult = c_launch = 0
-        for it in range(args.warmup + args.steps):
-            if it == args.warmup:
-                barrier()
-            check(L.kfsp_fsp_set_vector_device(h0._h, p0_dev0, hi0 - lo0))
-            st = Stats()
-            rc = L.kfsp_solve_resident(h0._h, args.t_final, fsp_tol, kry_tol, 0, C.byref(st))
-            if rc < 0:
-                raise k.KfspError(rc, "kfsp_solve_resident (explicit companion)")
-            if it >= args.warmup:
-                c_dev += st.device_seconds
-                c_spmv += st.spmv_seconds
-                c_mult += st.nmult
-                c_launch += st.spmv_launches
-        barrier()
-        same = bool(c_mult == nmult)
-        tt = torch.tensor([c_dev], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        c_avg = c_spmv / max(c_launch, 1)
-        c_ach = BYTES_PER_STATE[0] * (hi0 - lo0) / c_avg / 1e9 if c_avg > 0 else 0.0
-        companion = {"spmv_variant": "explicit gather-ELL matrix", "value": float(n) * c_mult / float(tt.item()), "unit": UNIT,
-                     "ms_per_step": 1e3 * float(tt.item()) / args.steps, "same_spmv_count_as_main": same,
-                     "roofline": {"bound": "hbm", "kernel": KERNEL_NAME[0], "achieved": c_ach, "peak": peak, "unit": "GB/s",
-                                  "frac": c_ach / peak, "algorithmic_bytes_per_state": BYTES_PER_STATE[0],
-                                  "avg_launch_ms": 1e3 * c_avg, "launches_timed": c_launch,
-                                  "share_of_step": c_spmv / c_dev if c_dev > 0 else None,
-                                  "traffic": TRAFFIC_PER_STATE[0] * (hi0 - lo0)}}
+        h0.set_profiling(True)
+        cres = timed_solves(h0, p0_dev0, hi0 - lo0)
+        c_dev = allmax(cres["dev_s"])
+        cb, cb16, cs_, cl = spmv_roofline(cres, 0, hi0 - lo0)
+        c_tr, c_src = measured_traffic(0, hi0 - lo0)
+        companion = {"spmv_variant": "explicit gather-ELL matrix", "value": float(n) * cres["nmult"] / c_dev, "unit": UNIT,
+                     "ms_per_step": 1e3 * c_dev / args.steps, "same_spmv_count_as_main": bool(cres["nmult"] == nmult),
+                     "roofline": {"bound": "hbm", "kernel": KERNEL_NAME[0], "achieved": cb / cs_ / 1e9 if cs_ > 0 else 0.0, "peak": peak,
+                                  "unit": "GB/s", "frac": cb / cs_ / 1e9 / peak if cs_ > 0 else 0.0,
+                                  "frac_spmv_only_bytes": cb16 / cs_ / 1e9 / peak if cs_ > 0 else 0.0,
+                                  "avg_launch_ms": 1e3 * cs_ / max(cl, 1), "launches_timed": cl,
+                                  "share_of_step": cs_ / cres["dev_s"] if cres["dev_s"] > 0 else None, "traffic": c_tr,
+                                  "traffic_source": c_src},
+                     "kernels": kernel_table(cres, 0, hi0 - lo0)}
+        # parity at the benchmarked size: this rank's rows of the two final vectors, bit for bit.  The lattice handle's last
+        # solve was the e2e one (same inputs), its result sits in p_out; the companion's is fetched now.
+        if not args.no_parity and (hi0 - lo0) == nloc and lo0 == lo:
+            if args.e2e_steps == 0:
+                resident_step(h, p0_dev, nloc)
+                check(L.kfsp_fsp_get(h._h, None, None, None, None, C.cast(p_out.data_ptr(), f64p)))
+            pc = torch.empty(nloc, dtype=torch.float64).pin_memory()
+            check(L.kfsp_fsp_get(h0._h, None, None, None, None, C.cast(pc.data_ptr(), f64p)))
+            a, b = p_out[:nloc].numpy(), pc.numpy()
+            same = bool(np.array_equal(a.view(np.int64), b.view(np.int64)))
+            maxabs = allmax(float(np.abs(a - b).max()))
+            allsame = allmax(0.0 if same else 1.0) == 0.0
+            digests = [None] * world
+            mine = sha_of(a)
+            if world > 1:
+                dist.all_gather_object(digests, mine)
+            else:
+                digests = [mine]
+            parity = {"lattice_vs_explicit_bit_identical": allsame, "lattice_vs_explicit_max_abs": maxabs,
+                      "vector_sha256": hashlib.sha256("".join(digests).encode()).hexdigest() if world > 1 else mine,
+                      "states_compared": n, "what": "final probability vectors of the matrix-free and the explicit-matrix solves at the "
+                                                    "benchmarked size, compared bit for bit on every rank's rows (sha256 over the ranks' digests)"}
+            del pc
         h0.close()
+
+    # ---- multi-GPU parity inside the bench run: a reduced rectangle solved alone on every rank and partitioned over all of
+    # them (both SpMV variants, kfsp_solve and kfsp_matvec on the partitioned handles): tests/dist_check.py
+    dist_parity = None
+    if world > 1 and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import dist_check
+        ok = dist_check.run_case(rank, world, local_rank, 1200, 800, 0.03, quiet=True)
+        dist_parity = {"dist_bit_identical": bool(ok), "case": "1200x800 rectangle, t=0.03: solo on each GPU vs partitioned over %d GPUs, "
+                       "explicit and lattice variants, resident solve + kfsp_solve + kfsp_matvec (tests/dist_check.py)" % world}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -424,7 +510,7 @@ def main():
                "sample": "FMATVEC + one IOP-2 Arnoldi sweep (m=10, %d SpMVs) on a %dx%d rectangle of the same workload "
                          "(%d states); oracle port of the serial Fortran reference, 1 of %d host cores"
                          % (cm, args.cpu_bx, args.cpu_by, cn, os.cpu_count()),
-               "spmv_states_per_s": cn / t_mv, "spmv_gbs": BYTES_PER_STATE[0] * cn / t_mv / 1e9}
+               "spmv_states_per_s": cn / t_mv, "spmv_gbs": KERNEL_BYTES[0]["spmv_plain"] * cn / t_mv / 1e9}
 
     if rank == 0:
         line = {
@@ -444,9 +530,10 @@ def main():
                        "reduction the double-double partials are exchanged inside the reducing kernel (cudaIpc peer memory over "
                        "NVLink/NVSwitch; NCCL only bootstraps, KFSP_DIST_P2P=0 selects the NCCL send/recv + all-gather path)" % world},
             "expv_wall_s_to_t_final": dev_s / args.steps, "krylov_steps_per_solve": nstep / args.steps,
-            "spmv_per_solve": nmult / args.steps, "setup_s": t_setup, "host_wall_s": wall,
-            "roofline": roofline, "explicit_matrix_companion": companion, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "probability_mass_out": total_mass,
+            "spmv_per_solve": nmult / args.steps, "setup_s": t_setup, "host_wall_s": res["wall"],
+            "roofline": roofline, "kernels": kernels, "explicit_matrix_companion": companion, "parity": parity,
+            "dist_parity": dist_parity, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "probability_mass_out": total_mass,
             "dist": dinfo,
         }
         print(json.dumps(line))

@@ -145,7 +145,11 @@ int kfsp_set_model(kfsp_handle h, kfsp_model m);
 /* CME_SOLVE / DGEXPV_FSP  src/fsp/KrylovSolver.f90:7-36, 40-573.
  * states_in/p_in are FSP_OUT%STATE(:,1:n_in) and FSP_IN%VECTOR(1:n_in) (zero padded beyond).
  * On return *n_out = FSP%SIZE, states_out (S*n_out) and p_out (n_out) hold FSP%STATE and W.
- * max_out is the caller's capacity in states.  stats may be NULL. */
+ * max_out is the caller's capacity in states.  stats may be NULL.
+ * states_out may be the same array as states_in (the reference's FSP_OUT is in/out); when the state set is fixed
+ * (enable_expand = enable_drop = n_init_onestep = 0) an aliased list is left as it is instead of being copied back.
+ * On a partitioned handle (kfsp_dist_init, all ranks call together): states_in / p_in are the GLOBAL list and vector
+ * on every rank; the call returns THIS rank's rows, *n_out = hi - lo of kfsp_dist_info, in states_out / p_out. */
 int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, const double* p_in,
                double fsp_tol, double kry_tol, int32_t verbosity,
                int64_t* n_out, int32_t* states_out, double* p_out, int64_t max_out, kfsp_stats* stats);
@@ -230,9 +234,20 @@ int kfsp_set_profiling(kfsp_handle h, int32_t on);
 /* FSP%VECTOR(1:n) = src (device pointer), rest zero: device-to-device reset between benchmark steps */
 int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src_device, int64_t n);
 int kfsp_launch_count(kfsp_handle h, int64_t* n);
+/* Device time of the last solve by kernel class (kfsp_set_profiling on: CUDA events on the solver's stream around every
+ * launch of the time-stepping loop).  The four SPMV_* classes + FIN_* are the generator SpMV (FMATVEC, KrylovSolver.f90:577-607)
+ * in its variants: plain; fused with the first IOP DDOT (:240-243); fused with the norm of the extra product (:261-263);
+ * FIN_*: the same two with the previous column's DAXPY + DNRM2 (:244-247) fused into the load stage. */
+enum {
+    KFSP_PROF_SPMV_PLAIN = 0, KFSP_PROF_SPMV_DOT = 1, KFSP_PROF_SPMV_NRM = 2, KFSP_PROF_SPMV_FIN_DOT = 3, KFSP_PROF_SPMV_FIN_NRM = 4,
+    KFSP_PROF_AXPY_DOT = 5, KFSP_PROF_AXPY_NRM = 6, KFSP_PROF_COMBINE = 7, KFSP_PROF_SCALE_COPY = 8, KFSP_PROF_EXPM = 9,
+    KFSP_PROF_CLASSES = 12
+};
+int kfsp_profile_get(kfsp_handle h, double seconds[KFSP_PROF_CLASSES], int64_t launches[KFSP_PROF_CLASSES]);
 /* Generator-SpMV launches of the last solve by kind: [0] plain FMATVEC, [1] fused with the first IOP DDOT
- * (KrylovSolver.f90:240-243), [2] fused with the norm of the extra product (AVNORM, :261-263). */
-int kfsp_spmv_launch_counts(kfsp_handle h, int64_t out[3]);
+ * (KrylovSolver.f90:240-243), [2] fused with the norm of the extra product (AVNORM, :261-263), [3] how many of [1]+[2]
+ * also finalised the previous Arnoldi column in their load stage (DAXPY + DNRM2 of :244-247; lattice stencil kernel). */
+int kfsp_spmv_launch_counts(kfsp_handle h, int64_t out[4]);
 /* Host wall clock of the last solve by phase: [0] Arnoldi sweep + Pade, [1] basis combination + norms,
  * [2] SSA_EXTENDER, [3] DROP_STATES, [4] ONESTEP_EXTENDER, [5] host propensity callbacks (CUSTOMPROP; included in 2 and 4), [6] SSA side-cache rounds and [7] host propensity evaluations (counts) (each phase ends in a stream synchronisation). */
 int kfsp_phase_seconds(kfsp_handle h, double out[8]);

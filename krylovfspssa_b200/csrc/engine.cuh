@@ -97,8 +97,29 @@ struct Engine {
     double spmv_seconds = 0.0;
     int64_t spmv_timed = 0;
     int64_t spmv_by_mode[3] = {0, 0, 0};    // generator SpMV launches of the last solve: plain, dot-fused, norm-fused
-    std::vector<cudaEvent_t> ev_pool;   // pairs of events bracketing SpMV launches (profiling only)
+    int64_t spmv_fused = 0;                 // ... of which also finalised the previous column (lattice.cuh, FIN = 1)
+    std::vector<cudaEvent_t> ev_pool;   // pairs of events bracketing the launches of the solve, by kernel class (profiling only)
+    std::vector<int> ev_cls;
     size_t ev_used = 0;
+    long ev_cur = -1;
+    double prof_sec[KFSP_PROF_CLASSES] = {0};
+    int64_t prof_cnt[KFSP_PROF_CLASSES] = {0};
+    // kernel classes of the time-stepping loop (kfsp_profile_get): CUDA events on the solver's stream around every launch
+    int prof_begin(int cls) {
+        ev_cur = -1;
+        if (!profile_spmv || ev_used + 2 > ev_pool.size()) return KFSP_OK;
+        KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
+        ev_cls[ev_used / 2] = cls;
+        ev_cur = (long)ev_used;
+        return KFSP_OK;
+    }
+    int prof_end() {
+        if (ev_cur < 0) return KFSP_OK;
+        KFSP_CUDA(cudaEventRecord(ev_pool[ev_cur + 1], stream));
+        ev_used += 2;
+        ev_cur = -1;
+        return KFSP_OK;
+    }
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 
     // ---------------------------------------------------------------- lifetime
@@ -759,16 +780,11 @@ struct Engine {
                 x = stage;
             }
         }
-        const bool timed = profile_spmv && ev_used + 2 <= ev_pool.size();
-        if (timed) KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
+        KFSP_TRY(prof_begin(MODE == 0 ? KFSP_PROF_SPMV_PLAIN : MODE == 1 ? KFSP_PROF_SPMV_DOT : KFSP_PROF_SPMV_NRM));
         spmv_by_mode[MODE] += 1;
         if (box) {
             KFSP_TRY(spmv_box<MODE>(x, y, first, h_out, cx, cf));
-            if (timed) {
-                KFSP_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
-                ev_used += 2;
-            }
-            return KFSP_OK;
+            return prof_end();
         }
         void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
                      Reducer, SweepCtl*, double*, int, int, const double*, int64_t, int64_t);
@@ -795,16 +811,13 @@ struct Engine {
                                            (int64_t)(d_V ? x - d_V : 0));
         KFSP_TRY(check_launch());
         if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, 1, h_out, nullptr, cx));
-        if (timed) {
-            KFSP_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
-            ev_used += 2;
-        }
-        return KFSP_OK;
+        return prof_end();
     }
     int set_profiling(bool on) {
         profile_spmv = on;
         if (on && ev_pool.empty()) {
-            ev_pool.resize(2 * 4096);
+            ev_pool.resize(2 * 8192);
+            ev_cls.assign(8192, 0);
             for (auto& e : ev_pool) KFSP_CUDA(cudaEventCreate(&e));
         }
         ev_used = 0;
@@ -817,8 +830,13 @@ struct Engine {
         for (size_t i = 0; i + 1 < ev_used; i += 2) {
             float ms = 0.f;
             KFSP_CUDA(cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]));
-            spmv_seconds += 1e-3 * ms;
-            spmv_timed += 1;
+            const int cls = ev_cls[i / 2];
+            prof_sec[cls] += 1e-3 * ms;
+            prof_cnt[cls] += 1;
+            if (cls <= KFSP_PROF_SPMV_FIN_NRM) {                 // the generator SpMV in all its variants
+                spmv_seconds += 1e-3 * ms;
+                spmv_timed += 1;
+            }
         }
         ev_used = 0;
         return KFSP_OK;
@@ -926,15 +944,21 @@ struct Engine {
             if (J >= 2) {
                 const double* vp = d_V + (size_t)(J - 2) * ld;
                 KFSP_TRY(spmv<1>(vj, vn, vp, hcol + (J - 2), J - 1, J - 2));                       // H(J-1,J)
+                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_DOT));
                 KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, vj, (const double*)vn, vn, next_rd(), d_ctl,
                             hcol + (J - 1), J - 2, J - 1);                                        // H(J,J)
                 KFSP_TRY(dist_finalize(RK_AXPY_DOT, 1, hcol + (J - 1), nullptr, 0));
+                KFSP_TRY(prof_end());
+                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_NRM));
                 KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H2, next_rd(), d_ctl, hcol + J, opt.break_tol, J, J - 1);
                 KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, nullptr, hcol + J, J));
+                KFSP_TRY(prof_end());
             } else {
                 KFSP_TRY(spmv<1>(vj, vn, vj, hcol + 0, 0, 0));                                       // H(1,1)
+                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_NRM));
                 KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H1, next_rd(), d_ctl, hcol + J, opt.break_tol, J, 0);
                 KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, nullptr, hcol + J, J));
+                KFSP_TRY(prof_end());
             }
         }
         KFSP_TRY(spmv<2>(d_V + (size_t)m * ld, d_V + (size_t)(m + 1) * ld, nullptr, nullptr, m, -1));    // AVNORM
@@ -965,20 +989,28 @@ struct Engine {
             a.h_out = extra ? nullptr : d_H + (size_t)c * LDH + (J >= 2 ? c - 1 : 0);        // H(J-1,J); H(1,1)
             a.hn_out = fin ? d_H + (size_t)(c - 1) * LDH + c : nullptr;                      // H(c+1,c) = ||U_c||
             a.break_tol = opt.break_tol;
+            KFSP_TRY(prof_begin(extra ? KFSP_PROF_SPMV_FIN_NRM : fin ? KFSP_PROF_SPMV_FIN_DOT : KFSP_PROF_SPMV_DOT));
+            spmv_by_mode[extra ? 2 : 1] += 1;
+            if (fin) spmv_fused += 1;
             if (extra) KFSP_TRY(spmv_bd2<2>(a, true));
             else KFSP_TRY(spmv_bd2<1>(a, fin));
+            KFSP_TRY(prof_end());
             if (J >= 2 && !extra) {
                 const double* vp = d_V + (size_t)(c - 1) * ld;
+                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_DOT));
                 KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, (const double*)vj, (const double*)vn, T, next_rd(), d_ctl,
                             d_H + (size_t)c * LDH + c, c - 1, c);                             // H(J,J)
+                KFSP_TRY(prof_end());
             }
         }
         return KFSP_OK;
     }
     // exp(t*H) on the device; result struct copied to pinned memory (synchronises)
     int expm_step(int mx_ok, double t_ok, int use_brk, double t_brk, int set_one) {
+        KFSP_TRY(prof_begin(KFSP_PROF_EXPM));
         KFSP_LAUNCH(k_expm, 1, EXPM_THREADS, EXPM_SMEM, d_H, LDH, mx_ok, t_ok, use_brk, t_brk, set_one, (const SweepCtl*)d_ctl,
                     d_expm_work, d_res, (double*)nullptr);
+        KFSP_TRY(prof_end());
         KFSP_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(ExpmResult), cudaMemcpyDeviceToHost, stream));
         KFSP_TRY(dist.nranks > 1 ? sync_check_peers() : sync());
         return h_res->info;

@@ -55,9 +55,11 @@ struct GpuBackend {
         KFSP_CUDA(cudaMemsetAsync(e.d_H, 0, sizeof(double) * e.LDH * e.LDH, e.stream));
         k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);
         KFSP_TRY(e.check_launch());
+        KFSP_TRY(e.prof_begin(KFSP_PROF_SCALE_COPY));
         k_scale_copy<<<e.wave_grid((const void*)k_scale_copy, e.n), VEC_THREADS, 0, e.stream>>>(e.n, inv_beta, e.d_w, e.d_V);
         KFSP_TRY(e.check_launch());
-        return e.dist_barrier();           // neighbours gather column 0 straight from this GPU's HBM
+        KFSP_TRY(e.dist_barrier());        // neighbours gather column 0 straight from this GPU's HBM
+        return e.prof_end();
     }
     int arnoldi(int jold, int m) { Tick t(e.phase_s[0]); return e.arnoldi(jold, m); }
     int expm(int mx_ok, double t_ok, int use_brk, double t_brk, int set_one, StepScalars* out) {
@@ -74,9 +76,11 @@ struct GpuBackend {
     }
     int combine(int mx, double beta, double* wsum, double* wssq) {
         Tick t(e.phase_s[1]);
+        KFSP_TRY(e.prof_begin(KFSP_PROF_COMBINE));
         k_combine<<<e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, nullptr, 0));
+        KFSP_TRY(e.prof_end());
         KFSP_TRY(e.read_ctl());
         *wsum = e.h_ctl->scal[SC_WSUM];
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
@@ -103,9 +107,11 @@ int Engine::solve(double T, double fsptol, double krytol, int itrace, kfsp_stats
     for (double& v : phase_s) v = 0.0;
     host_prop_rounds = host_prop_evals = 0;
     spmv_by_mode[0] = spmv_by_mode[1] = spmv_by_mode[2] = 0;
+    spmv_fused = 0;
     spmv_seconds = 0.0;
     spmv_timed = 0;
     ev_used = 0;
+    for (int i = 0; i < KFSP_PROF_CLASSES; ++i) { prof_sec[i] = 0.0; prof_cnt[i] = 0; }
     cudaEvent_t e0, e1;
     KFSP_CUDA(cudaEventCreate(&e0));
     KFSP_CUDA(cudaEventCreate(&e1));
@@ -448,13 +454,27 @@ int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, 
     if (verbosity) std::printf(" CALLING DGEXPV_FSP\n");                              // KrylovSolver.f90:32
     cudaSetDevice(e.device);
     KFSP_TRY(e.fsp_init(n_in, states_in));
-    KFSP_CUDA(cudaMemcpyAsync(e.d_w, p_in, sizeof(double) * n_in, cudaMemcpyHostToDevice, e.stream));
+    // Partitioned handle (kfsp_dist_init): states_in / p_in are the GLOBAL list and vector on every rank; this rank keeps
+    // rows [lo, hi) and returns them (n_out = hi - lo).  fsp_init has zeroed W.
+    const bool part = e.dist.nranks > 1;
+    const int64_t lo = part ? e.dist.lo : 0;
+    if (n_in > lo) {
+        const int64_t cnt = std::min<int64_t>(n_in - lo, e.n);
+        KFSP_CUDA(cudaMemcpyAsync(e.d_w, p_in + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, e.stream));
+    }
     int st = e.solve(t, fsp_tol, kry_tol, verbosity, stats);
     *n_out = e.n;
     if (st == KFSP_OK || st == KFSP_IFLAG_MXSTEP) {
         if (e.n > max_out) return KFSP_ERR_OUT_TOO_SMALL;
-        if (e.box && states_out) KFSP_TRY(e.box_states());
-        if (states_out) KFSP_CUDA(cudaMemcpyAsync(states_out, e.d_states, sizeof(int32_t) * e.n * e.S, cudaMemcpyDeviceToHost, e.stream));
+        // FSP_OUT supplies the initial states and receives the final ones (KrylovSolver.f90:7-36): when the caller passes the
+        // same array for both and the state set cannot have changed, the list is already what it would receive
+        const bool fixed_set = !e.opt.enable_expand && !e.opt.enable_drop && e.opt.n_init_onestep == 0;
+        const bool in_place = states_out == states_in && fixed_set;
+        if (states_out && !in_place) {
+            if (e.box) KFSP_TRY(e.box_states());
+            const int64_t row0 = (part && !e.box) ? lo : 0;          // the explicit partitioned variant keeps the global list
+            KFSP_CUDA(cudaMemcpyAsync(states_out, e.d_states + row0 * e.S, sizeof(int32_t) * e.n * e.S, cudaMemcpyDeviceToHost, e.stream));
+        }
         if (p_out) KFSP_CUDA(cudaMemcpyAsync(p_out, e.d_w, sizeof(double) * e.n, cudaMemcpyDeviceToHost, e.stream));
         KFSP_TRY(e.sync());
     }
@@ -701,9 +721,15 @@ int kfsp_phase_seconds(kfsp_handle h, double out[8]) {
     out[7] = (double)h->e.host_prop_evals;
     return KFSP_OK;
 }
-int kfsp_spmv_launch_counts(kfsp_handle h, int64_t out[3]) {
+int kfsp_spmv_launch_counts(kfsp_handle h, int64_t out[4]) {
     if (!h || !out) return KFSP_ERR_ARG;
     for (int i = 0; i < 3; ++i) out[i] = h->e.spmv_by_mode[i];
+    out[3] = h->e.spmv_fused;
+    return KFSP_OK;
+}
+int kfsp_profile_get(kfsp_handle h, double seconds[KFSP_PROF_CLASSES], int64_t launches[KFSP_PROF_CLASSES]) {
+    if (!h || !seconds || !launches) return KFSP_ERR_ARG;
+    for (int i = 0; i < KFSP_PROF_CLASSES; ++i) { seconds[i] = h->e.prof_sec[i]; launches[i] = h->e.prof_cnt[i]; }
     return KFSP_OK;
 }
 int kfsp_launch_count(kfsp_handle h, int64_t* n) {

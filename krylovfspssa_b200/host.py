@@ -318,6 +318,19 @@ class KrylovFspHandle:
         i = np.array([[r.m, r.n_step, r.n_after, r.flags, r.nmult, r.nexph] for r in rows[:n.value]], dtype=np.int32).reshape(-1, 6)
         return dict(d=d, i=i)
 
+    PROF_CLASSES = ("spmv_plain", "spmv_dot", "spmv_nrm", "spmv_fin_dot", "spmv_fin_nrm", "axpy_dot", "axpy_nrm", "combine",
+                    "scale_copy", "expm")
+
+    def profile(self):
+        """Device seconds and launches of the last solve by kernel class (set_profiling(True) before the solve)."""
+        sec = (C.c_double * 12)()
+        cnt = (C.c_int64 * 12)()
+        check(lib().kfsp_profile_get(self._h, sec, cnt))
+        return {name: (sec[i], cnt[i]) for i, name in enumerate(self.PROF_CLASSES)}
+
+    def set_profiling(self, on=True):
+        check(lib().kfsp_set_profiling(self._h, 1 if on else 0))
+
     def phase_seconds(self):
         buf = (C.c_double * 8)()
         check(lib().kfsp_phase_seconds(self._h, buf))

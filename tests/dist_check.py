@@ -35,7 +35,7 @@ def main():
         print("DIST CHECK OK")
 
 
-def run_case(rank, world, local, bx, by, t_final):
+def run_case(rank, world, local, bx, by, t_final, quiet=False):
     states, p0 = bench.synthetic(bx, by)
     n = len(p0)
     model = k.CME_MODEL().load(os.path.join(k.models_dir(), "toggle_test.input"))
@@ -79,15 +79,37 @@ def run_case(rank, world, local, bx, by, t_final):
     okb = okb and len(bmine) == binfo["hi"] - binfo["lo"] and np.array_equal(bmine, ref[binfo["lo"]:binfo["hi"]])
     box.close()
 
-    ok = rc1 == rc2 == 0 and okb
+    # the reference-facing call on partitioned handles (global list and vector in, this rank's rows out), and FMATVEC on an
+    # operand that is not a column of the basis (staged for the peer-memory halo) -- both variants
+    okc = True
+    xg = np.random.default_rng(7).standard_normal(n)
+    yref = solo.matvec(xg)
+    for variant in (0, 1):
+        uid3 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid3.copy_(torch.frombuffer(bytearray(k.KrylovFspHandle.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid3, 0)
+        hh = k.KrylovFspHandle(model, spmv_variant=variant, **opts)
+        hh.dist_init(rank, world, bytes(uid3.cpu().numpy().tobytes()))
+        out = hh.solve(t_final, states, p0, 1e-6, 1e-8)
+        inf = hh.dist_info()
+        lo, hi = inf["lo"], inf["hi"]
+        okc = okc and out["iflag"] == 0 and len(out["vector"]) == hi - lo
+        okc = okc and np.array_equal(out["vector"], ref[lo:hi]) and np.array_equal(out["states"], states[lo:hi])
+        okc = okc and np.array_equal(out["trace"]["i"], tr1["i"])
+        okc = okc and np.array_equal(hh.matvec(xg[lo:hi]), yref[lo:hi])
+        hh.close()
+
+    ok = rc1 == rc2 == 0 and okb and okc
     ok = ok and np.array_equal(tr1["i"], tr2["i"]) and np.array_equal(tr1["d"], tr2["d"])
     ok = ok and all(st1[key] == st2[key] for key in ("nmult", "nexph", "nscale", "nstep", "nreject"))
     ok = ok and len(mine) == info["hi"] - info["lo"] and np.array_equal(mine, ref[info["lo"]:info["hi"]])
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    print("%dx%d rank %d/%d rows [%d,%d) halo %d send %d steps %d nmult %d bit-identical=%s lattice[%d,%d)=%s max|diff|=%.3e" %
+    if not quiet:
+      print("%dx%d rank %d/%d rows [%d,%d) halo %d send %d steps %d nmult %d bit-identical=%s lattice[%d,%d)=%s kfsp_solve+matvec=%s max|diff|=%.3e" %
           (bx, by, rank, world, info["lo"], info["hi"], info["n_halo"], info["n_send"], st2["nstep"], st2["nmult"], ok,
-           binfo["lo"], binfo["hi"], okb,
+           binfo["lo"], binfo["hi"], okb, okc,
            float(np.abs(mine - ref[info["lo"]:info["hi"]]).max()) if len(mine) == info["hi"] - info["lo"] else -1.0), flush=True)
     solo.close()
     part.close()
