@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkfsp.so")
+LIB_PATH = os.environ.get("KFSP_LIB", os.path.join(_HERE, "libkfsp.so"))     # KFSP_LIB: an alternative build (A/B measurements)
 NCCL_ID_BYTES = 128
 
 

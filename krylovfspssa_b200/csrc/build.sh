@@ -3,7 +3,7 @@
 # without a GPU.  Usage: build.sh [extra nvcc flags]
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="$HERE/../libkfsp.so"
+OUT="${KFSP_OUT:-$HERE/../libkfsp.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 NCCL_FLAGS=()
 # NCCL (torch-bundled wheel): needed for the multi-GPU path only; found automatically when importable

@@ -51,6 +51,7 @@ struct Engine {
     DeviceModel h_dm{};               // host mirror of *d_model (table pointers, stoichiometry)
     int box_tune = 0;                 // KFSP_BOX_TUNE: rows per batch / CTAs per SM of the lattice SpMV (A/B)
     int bd2_zc = 0;                   // KFSP_BD2_ZC: forced rows per z-chunk of the stencil kernel (0 = automatic)
+    int bd2_sync = 8;                 // KFSP_BD2_SYNC: the stencil kernel's CTAs re-align their warps every so many rows (power of two; 0 = never)
 
     // state space
     int64_t ld = 0;                   // capacity in states (multiple of 64)
@@ -128,6 +129,7 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_SPMV_TUNE")) spmv_tune = std::atoi(ev);
         if (const char* ev = std::getenv("KFSP_BOX_TUNE")) box_tune = std::atoi(ev);
         if (const char* ev = std::getenv("KFSP_BD2_ZC")) bd2_zc = std::atoi(ev);
+        if (const char* ev = std::getenv("KFSP_BD2_SYNC")) { bd2_sync = std::atoi(ev); if (bd2_sync & (bd2_sync - 1)) bd2_sync = 0; }
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
         if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
             opt.max_states > 2000000000LL)
@@ -1330,6 +1332,7 @@ struct Engine {
         }
         a.zc = zc;
         a.halo = halo ? 1 : 0;
+        a.sync_every = bd2_sync;
         a.off_src = d_V ? (int64_t)(a.src - d_V) : 0;
         a.off_first = (d_V && a.first) ? (int64_t)(a.first - d_V) : 0;
         if (!a.first) a.first = a.src;

@@ -234,6 +234,21 @@ constexpr int BD2_CBW = BD2_WCOLS * (VEC_THREADS / 32);        // live columns p
 constexpr int BD2_L2AHEAD = 10;                                // rows ahead of the ring that are prefetched into L2
 constexpr int BD2_PF = 4;                                      // depth of the register ring (rows in flight per thread and stream)
 constexpr int BD2_MINB = 4;                                    // resident CTAs per SM the kernel is compiled for
+#ifndef KFSP_BD2_RING
+#define KFSP_BD2_RING 1
+#endif
+// KFSP_BD2_RING 1: the rows in flight live in a shared-memory ring filled by per-thread asynchronous copies (cp.async,
+// 8 bytes per thread and stream: every lane copies and later reads its own element, so no barrier is involved), BD2_DEPTH
+// rows deep; 0: in a register ring PF rows deep (the depth is then bounded by the register file: ncu showed 50 % of all
+// stall cycles on the scoreboard of the first-touch loads at PF = 4, profiles/r2_summary.md).
+constexpr int BD2_DEPTH = 8;
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int BD2_ZT = 256;                                    // longest z-chunk (rows of the y-tables staged in shared memory)
 struct Bd2Args {
     const double* src;        // operand column: FIN ? T (un-finalised) : the column itself
@@ -246,6 +261,8 @@ struct Bd2Args {
     int32_t cx, cf;           // basis column of the operand / of `first` (-1: scale 1)
     int32_t hsel;             // FIN: ctl->scal[hsel] is the axpy coefficient
     int32_t zc, halo;         // rows per z-chunk; 1 = several GPUs (rows outside the slab come from the owner's HBM)
+    int32_t sync_every;       // 0, or a power of two: the CTA's warps re-align every so many rows of the hot loop, which keeps the
+                              // sectors two neighbouring warps share (a warp's 256-byte row segment is not sector-aligned) in L1
     int64_t off_src, off_first;   // offsets of src / first inside the basis allocation (peer addressing)
 };
 template <int ORD, int TS, int MODE, int FIN, int PF, int MINB>
@@ -334,26 +351,80 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
             load_raw(z0, t, fr);
             finish(t, fr, x0, f0);
         }
-        // software pipeline in registers: slot u holds the raw operands of row z+1 of the row z that will be evaluated
-        // PF rows after the slot was filled, so a row never waits for its own first-touch loads
+        // software pipeline: slot u holds the raw operands of row z+1 of the row z that will be evaluated DEPTH rows after
+        // the slot was filled, so a row never waits for its own first-touch loads
+        const int32_t zloc = min(zlast, L.zhi - 1);             // ... and the last such row that is local
+#if KFSP_BD2_RING
+        constexpr int DEPTH = BD2_DEPTH;
+        constexpr int SLOT = (NEEDF ? 2 : 1) * VEC_THREADS;     // doubles per ring slot
+        __shared__ double ring[DEPTH * SLOT];
+        double* const rbase = ring + threadIdx.x;
+        int rs = 0;                                             // slot of the row about to be consumed
+        cp_async_wait<0>();                                     // (nothing of the previous work item is still landing)
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+            const int32_t zn = z0 + 1 + u;
+            double* slot = rbase + u * SLOT;
+            if (zn <= zloc) {
+                const uint32_t e = i + (uint32_t)(Bx * (1 + u));
+                cp_async8(slot, src + e);
+                if (NEEDF) cp_async8(slot + VEC_THREADS, first + e);
+            } else {
+                double t = 0.0, fr = 0.0;
+                if (zn <= zlast) load_raw(zn, t, fr);
+                slot[0] = t;
+                if (NEEDF) slot[VEC_THREADS] = fr;
+            }
+            cp_async_commit();
+        }
+#else
+        constexpr int DEPTH = PF;
         double rt[PF], rf[PF];
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
             rt[u] = 0.0; rf[u] = 0.0;
             if (z0 + 1 + u <= zlast) load_raw(z0 + 1 + u, rt[u], rf[u]);
         }
+#endif
         // one row: GEN = false is the hot path (z >= 1, z + 1 < nz, the refill row is local and needed)
         auto do_row = [&](const int32_t z, const int u, const bool gen) {
             double xp, fp;
-            finish(rt[u], rf[u], xp, fp);
             const bool yp_ok = gen ? z >= 1 : true, ym_ok = gen ? z + 1 < nz : true;
+            const int32_t zn = z + 1 + DEPTH;                   // the row the freed slot is refilled with
+#if KFSP_BD2_RING
+            {
+                (void)u;
+                double* slot = rbase + rs * SLOT;
+                cp_async_wait<DEPTH - 1>();                     // this thread's copy of row z+1 has landed
+                finish(slot[0], NEEDF ? slot[VEC_THREADS] : 0.0, xp, fp);
+                const uint32_t e = i + (uint32_t)(Bx * (1 + DEPTH));
+                if (!gen) {
+                    cp_async8(slot, src + e);
+                    if (NEEDF) cp_async8(slot + VEC_THREADS, first + e);
+                } else if (zn <= zloc) {
+                    cp_async8(slot, src + e);
+                    if (NEEDF) cp_async8(slot + VEC_THREADS, first + e);
+                } else {
+                    double t = 0.0, fr = 0.0;
+                    if (zn <= zlast) load_raw(zn, t, fr);
+                    slot[0] = t;
+                    if (NEEDF) slot[VEC_THREADS] = fr;
+                }
+                cp_async_commit();
+                rs = rs + 1 == DEPTH ? 0 : rs + 1;
+                if (!gen && NEEDF && zn + BD2_L2AHEAD <= zloc) {  // two-stream variants also pull rows further ahead into L2
+                    lattice_prefetch<1>(src + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
+                    lattice_prefetch<1>(first + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
+                }
+            }
+#else
+            finish(rt[u], rf[u], xp, fp);
             {   // refill the slot with row z + 1 + PF; two-stream variants also pull rows further ahead into L2
-                const int32_t zn = z + 1 + PF;
                 if (!gen) {
                     const uint32_t e = i + (uint32_t)(Bx * (1 + PF));
                     rt[u] = src[e];
                     if (NEEDF) rf[u] = first[e];
-                    if (NEEDF && zn + BD2_L2AHEAD <= z1) {
+                    if (NEEDF && zn + BD2_L2AHEAD <= zloc) {
                         lattice_prefetch<1>(src + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
                         lattice_prefetch<1>(first + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
                     }
@@ -362,6 +433,7 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                     if (zn <= zlast) load_raw(zn, rt[u], rf[u]);
                 }
             }
+#endif
             const double xl = __shfl_up_sync(0xffffffffu, x0, 1);
             const double xr = __shfl_down_sync(0xffffffffu, x0, 1);
             double ad[4], ac[4];
@@ -398,16 +470,16 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
             xm = x0; x0 = xp; f0 = fp;
             i += (uint32_t)Bx;
         };
-        // rows [z0, zm) run the hot path in whole groups of PF: they need z >= 1 and the refill row z + 1 + PF <= zlast local
+        // the hot path runs in whole groups of PF rows: they need z >= 1 and a refill row z + 1 + DEPTH <= zloc (local, needed)
         int32_t z = z0;
-        const int32_t zloc = min(zlast, L.zhi - 1);
         if (z0 == 0) {                                          // the box boundary row goes through the general path
 #pragma unroll
             for (int u = 0; u < PF; ++u)
                 if (z + u < z1) do_row(z + u, u, true);
             z += PF;
         }
-        for (; z + PF - 1 + 1 + PF <= zloc && z + PF <= z1; z += PF) {
+        for (; z + PF - 1 + 1 + DEPTH <= zloc && z + PF <= z1; z += PF) {
+            if (A.sync_every && ((z - z0) & (A.sync_every - 1)) == 0) __syncthreads();
 #pragma unroll
             for (int u = 0; u < PF; ++u) do_row(z + u, u, false);
         }

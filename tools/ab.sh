@@ -1,0 +1,10 @@
+run() { tag=$1; shift; env "$@" python bench.py --steps 2 --warmup 2 --e2e-steps 0 --no-cpu-baseline --no-companion --no-parity > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err; python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/ab_$tag.json"))
+    k=d["kernels"]
+    print("$tag", "ms/solve %.2f"%d["ms_per_step"], " ".join("%s=%.4f"%(n,k[n]["avg_ms"]) for n in ("spmv_dot","spmv_fin_dot","spmv_fin_nrm","axpy_dot") if n in k), "plain=%.4f"%d["roofline"]["plain_spmv"]["avg_ms"], d["clocks"]["sm_mhz"])
+except Exception as e:
+    print("$tag FAILED", e)
+PY
+}
