@@ -42,20 +42,14 @@ PARAMS = [5000.0, 1600.0, 1.0, 1.0]
 METRIC = "expv_generator_state_updates_per_s"
 UNIT = "state-updates/s"
 R_TOGGLE = 4
-# Algorithmic bytes per state a launch of each kernel class must move, per SpMV variant.
-# explicit gather-ELL: 12R+24 for FMATVEC, +8 for the operand of the fused DDOT.
-# matrix-free lattice: x + y = 16 for FMATVEC; +8 for a DDOT operand that is not x itself; the finalising launches read the
-# un-finalised column T and v_first and write the finalised column and y = 32 (they replace k_axpy_nrm's 24 + the SpMV's 24).
-KERNEL_BYTES = {
-    0: {"spmv_plain": 12 * R_TOGGLE + 24, "spmv_dot": 12 * R_TOGGLE + 32, "spmv_nrm": 12 * R_TOGGLE + 24, "axpy_dot": 32, "axpy_nrm": 24,
-        "scale_copy": 16},
-    1: {"spmv_plain": 16, "spmv_dot": 24, "spmv_nrm": 16, "spmv_fin_dot": 32, "spmv_fin_nrm": 32, "axpy_dot": 32, "axpy_nrm": 24,
-        "scale_copy": 16},
-}
+# Algorithmic bytes per state of FMATVEC alone, per SpMV variant: explicit gather-ELL 12R+24, matrix-free lattice
+# x + y = 16.  What each launch of the solve must move (the SpMV's operands and results plus those of the vector work fused
+# into the same pass) is counted by the library per launch (kfsp_profile_get).
+SPMV_ONLY_BYTES = {0: 12 * R_TOGGLE + 24, 1: 16}
 SPMV_CLASSES = ("spmv_plain", "spmv_dot", "spmv_nrm", "spmv_fin_dot", "spmv_fin_nrm")
-KERNEL_NAME = {0: "k_spmv (generator SpMV, explicit gather ELL, first IOP dot fused; per GPU, rank 0)",
-               1: "k_spmv_bd2 (matrix-free generator SpMV on the lattice with the previous Arnoldi column's DAXPY+DNRM2 fused into "
-                  "its load stage and the first IOP dot into its epilogue; per GPU, rank 0)"}
+KERNEL_NAME = {0: "k_spmv (generator SpMV, explicit gather ELL, inner products of the IOP window fused; per GPU, rank 0)",
+               1: "k_spmv_bd2 (matrix-free generator SpMV on the lattice = one whole Arnoldi column per launch: the previous column's two "
+                  "DAXPYs + DNRM2 in its load stage, FMATVEC, and the inner products of the IOP window in its epilogue; per GPU, rank 0)"}
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")     # dram__bytes per launch from the round's ncu --set full pass
 
 
@@ -316,10 +310,11 @@ def main():
             out["nmult"] += st.nmult
             out["launches"] += st.kernel_launches
             out["nstep"] += st.nstep
-            for name, (sec, c) in hh.profile().items():
-                a = out["classes"].setdefault(name, [0.0, 0])
+            for name, (sec, c, b) in hh.profile().items():
+                a = out["classes"].setdefault(name, [0.0, 0, 0])
                 a[0] += sec
                 a[1] += c
+                a[2] += b
         barrier()
         out["wall"] = time.time() - t0
         return out
@@ -327,16 +322,13 @@ def main():
     def kernel_table(res, var, rows):
         """per kernel class: launches, mean ms, algorithmic GB/s and fraction of the measured HBM peak (this rank's rows)"""
         tab = {}
-        for name, (sec, c) in res["classes"].items():
+        for name, (sec, c, b) in res["classes"].items():
             if c == 0:
                 continue
-            b = KERNEL_BYTES[var].get(name)
-            if name == "combine":
-                b = None
             e = {"launches": c, "avg_ms": 1e3 * sec / c, "share_of_step": sec / res["dev_s"] if res["dev_s"] > 0 else None}
             if b:
-                e["algorithmic_bytes_per_state"] = b
-                e["gbs"] = b * rows / (sec / c) / 1e9
+                e["algorithmic_bytes_per_state"] = b / c
+                e["gbs"] = b * rows / sec / 1e9
                 e["frac_of_peak"] = e["gbs"] / peak
             tab[name] = e
         return tab
@@ -346,9 +338,9 @@ def main():
         tot_b = tot_b16 = tot_s = 0.0
         cnt = 0
         for name in SPMV_CLASSES:
-            sec, c = res["classes"].get(name, (0.0, 0))
-            tot_b += KERNEL_BYTES[var].get(name, 0) * rows * c
-            tot_b16 += KERNEL_BYTES[var]["spmv_plain"] * rows * c
+            sec, c, b = res["classes"].get(name, (0.0, 0, 0))
+            tot_b += b * rows
+            tot_b16 += SPMV_ONLY_BYTES[var] * rows * c
             tot_s += sec
             cnt += c
         return tot_b, tot_b16, tot_s, cnt
@@ -375,7 +367,7 @@ def main():
         barrier()
         check(L.kfsp_matvec_device(h._h, p0_dev, ybuf, 10, C.byref(sec)))
         barrier()
-        pb = KERNEL_BYTES[variant]["spmv_plain"]
+        pb = SPMV_ONLY_BYTES[variant]
         plain = {"avg_ms": 1e3 * sec.value, "algorithmic_bytes_per_state": pb, "gbs": pb * nloc / sec.value / 1e9,
                  "frac_of_peak": pb * nloc / sec.value / 1e9 / peak, "launches_timed": 10,
                  "what": "kfsp_matvec_device: FMATVEC alone (KrylovSolver.f90:577-607), no fused reduction, this rank's rows"}
@@ -427,7 +419,7 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": tot_b / max(spmv_launches, 1),
                 "algorithmic_bytes_per_state_per_launch": tot_b / max(spmv_launches, 1) / nloc,
-                "spmv_only_bytes_per_state": KERNEL_BYTES[variant]["spmv_plain"],
+                "spmv_only_bytes_per_state": SPMV_ONLY_BYTES[variant],
                 "achieved_spmv_only_bytes": tot_b16 / tot_s / 1e9 if tot_s > 0 else 0.0,
                 "frac_spmv_only_bytes": tot_b16 / tot_s / 1e9 / peak if tot_s > 0 else 0.0,
                 "note": "achieved = bytes the timed SpMV launches must move (operand, result, and the operands/results of the "
@@ -510,7 +502,7 @@ def main():
                "sample": "FMATVEC + one IOP-2 Arnoldi sweep (m=10, %d SpMVs) on a %dx%d rectangle of the same workload "
                          "(%d states); oracle port of the serial Fortran reference, 1 of %d host cores"
                          % (cm, args.cpu_bx, args.cpu_by, cn, os.cpu_count()),
-               "spmv_states_per_s": cn / t_mv, "spmv_gbs": KERNEL_BYTES[0]["spmv_plain"] * cn / t_mv / 1e9}
+               "spmv_states_per_s": cn / t_mv, "spmv_gbs": SPMV_ONLY_BYTES[0] * cn / t_mv / 1e9}
 
     if rank == 0:
         line = {

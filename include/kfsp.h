@@ -235,15 +235,18 @@ int kfsp_set_profiling(kfsp_handle h, int32_t on);
 int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src_device, int64_t n);
 int kfsp_launch_count(kfsp_handle h, int64_t* n);
 /* Device time of the last solve by kernel class (kfsp_set_profiling on: CUDA events on the solver's stream around every
- * launch of the time-stepping loop).  The four SPMV_* classes + FIN_* are the generator SpMV (FMATVEC, KrylovSolver.f90:577-607)
- * in its variants: plain; fused with the first IOP DDOT (:240-243); fused with the norm of the extra product (:261-263);
- * FIN_*: the same two with the previous column's DAXPY + DNRM2 (:244-247) fused into the load stage. */
+ * launch of the time-stepping loop).  SPMV_* and FIN_* are the generator SpMV (FMATVEC, KrylovSolver.f90:577-607) in its
+ * variants: plain; one Arnoldi column (FMATVEC + the inner products that give H(J-1,J) and H(J,J), :240-245); the extra
+ * product with its norm (:261-263); FIN_*: the same two with the previous column's two DAXPYs + DNRM2 (:243-247) fused
+ * into the load stage.  AXPY_NRM is that finalisation as a launch of its own (explicit-matrix path).
+ * bytes_per_state (optional): algorithmic bytes per state each launch had to move, summed over the class's launches. */
 enum {
     KFSP_PROF_SPMV_PLAIN = 0, KFSP_PROF_SPMV_DOT = 1, KFSP_PROF_SPMV_NRM = 2, KFSP_PROF_SPMV_FIN_DOT = 3, KFSP_PROF_SPMV_FIN_NRM = 4,
     KFSP_PROF_AXPY_DOT = 5, KFSP_PROF_AXPY_NRM = 6, KFSP_PROF_COMBINE = 7, KFSP_PROF_SCALE_COPY = 8, KFSP_PROF_EXPM = 9,
     KFSP_PROF_CLASSES = 12
 };
-int kfsp_profile_get(kfsp_handle h, double seconds[KFSP_PROF_CLASSES], int64_t launches[KFSP_PROF_CLASSES]);
+int kfsp_profile_get(kfsp_handle h, double seconds[KFSP_PROF_CLASSES], int64_t launches[KFSP_PROF_CLASSES],
+                     int64_t bytes_per_state[KFSP_PROF_CLASSES]);
 /* Generator-SpMV launches of the last solve by kind: [0] plain FMATVEC, [1] fused with the first IOP DDOT
  * (KrylovSolver.f90:240-243), [2] fused with the norm of the extra product (AVNORM, :261-263), [3] how many of [1]+[2]
  * also finalised the previous Arnoldi column in their load stage (DAXPY + DNRM2 of :244-247; lattice stencil kernel). */

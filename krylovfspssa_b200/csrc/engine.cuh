@@ -105,12 +105,16 @@ struct Engine {
     long ev_cur = -1;
     double prof_sec[KFSP_PROF_CLASSES] = {0};
     int64_t prof_cnt[KFSP_PROF_CLASSES] = {0};
+    int64_t prof_bps[KFSP_PROF_CLASSES] = {0};   // algorithmic bytes per state, summed over the launches of the class
+    std::vector<int> ev_bps;
     // kernel classes of the time-stepping loop (kfsp_profile_get): CUDA events on the solver's stream around every launch
-    int prof_begin(int cls) {
+    // bps: bytes per state the launch must move (operands read once + results written once)
+    int prof_begin(int cls, int bps = 0) {
         ev_cur = -1;
         if (!profile_spmv || ev_used + 2 > ev_pool.size()) return KFSP_OK;
         KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
         ev_cls[ev_used / 2] = cls;
+        ev_bps[ev_used / 2] = bps;
         ev_cur = (long)ev_used;
         return KFSP_OK;
     }
@@ -159,7 +163,7 @@ struct Engine {
         KFSP_CUDA(cudaMalloc(&d_ctl, sizeof(SweepCtl)));
         KFSP_CUDA(cudaMemset(d_ctl, 0, sizeof(SweepCtl)));
         KFSP_CUDA(cudaMallocHost(&h_ctl, sizeof(SweepCtl)));
-        KFSP_CUDA(cudaMalloc(&rd.partials, sizeof(double) * 4 * MAX_VEC_BLOCKS));
+        KFSP_CUDA(cudaMalloc(&rd.partials, sizeof(double) * RED_W * MAX_VEC_BLOCKS));
         KFSP_CUDA(cudaMalloc(&rd.counter, sizeof(unsigned int)));
         KFSP_CUDA(cudaMemset(rd.counter, 0, sizeof(unsigned int)));
         KFSP_CUDA(cudaFuncSetAttribute(k_expm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXPM_SMEM));
@@ -498,9 +502,10 @@ struct Engine {
     }
     int ensure_basis() {
         if (d_V) return KFSP_OK;
-        // m_max+2 basis columns, the scratch column T of the fused lattice sweep (lattice.cuh), and slack for its L2 prefetches
+        // m_max+2 basis columns, the two scratch columns of the fused lattice sweep (lattice.cuh; the first one also stages
+        // operands for the peer-memory halo), and slack for its L2 prefetches
         const size_t slack = box ? (size_t)(BD2_L2AHEAD + 8) * (size_t)lat.B[0] : 0;
-        KFSP_CUDA(cudaMalloc(&d_V, sizeof(double) * ((size_t)ld * (opt.m_max + 3) + slack)));
+        KFSP_CUDA(cudaMalloc(&d_V, sizeof(double) * ((size_t)ld * (opt.m_max + 4) + slack)));
         if (dist.nranks > 1) KFSP_TRY(dist_setup_p2p());       // collective: every rank allocates its basis here
         return KFSP_OK;
     }
@@ -767,14 +772,21 @@ struct Engine {
     }
 
     // ---------------------------------------------------------------- FMATVEC
+    // MODE 0: y = A x.  MODE 1: one Arnoldi column (x = U_c, g = U_{c-1} or null): ea says where H(J-1,J), H(J,J) go.
+    // MODE 2: the extra product (AVNORM).
+    static EpiArgs epi_none() {
+        EpiArgs e;
+        e.kind = RK_COLUMN; e.column = -1; e.fin = 0; e.has_g = 0; e.break_tol = 0.0; e.h1_out = e.h2_out = e.hn_out = nullptr;
+        return e;
+    }
     template <int MODE>
-    int spmv(const double* x, double* y, const double* first, double* h_out, int cx = -1, int cf = -1) {
+    int spmv(const double* x, double* y, const double* g = nullptr, EpiArgs ea = epi_none(), int cg = -1) {
         // several GPUs, peer-memory halo: remote rows are addressed as (peer's basis) + (x - d_V), which only means
         // something for a column of the basis.  Any other operand (kfsp_matvec, kfsp_matvec_device) is staged in the
         // scratch column first; the barrier makes every rank's copy visible before any rank gathers from it.
         if (dist.nranks > 1 && dist.p2p && dist.p2p_halo) {
             KFSP_TRY(ensure_basis());
-            const double* vend = d_V + (size_t)ld * (opt.m_max + 3);
+            const double* vend = d_V + (size_t)ld * (opt.m_max + 4);
             if (x < d_V || x >= vend) {
                 double* stage = d_V + (size_t)ld * (opt.m_max + 2);
                 KFSP_CUDA(cudaMemcpyAsync(stage, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
@@ -782,14 +794,16 @@ struct Engine {
                 x = stage;
             }
         }
-        KFSP_TRY(prof_begin(MODE == 0 ? KFSP_PROF_SPMV_PLAIN : MODE == 1 ? KFSP_PROF_SPMV_DOT : KFSP_PROF_SPMV_NRM));
+        ea.has_g = (MODE == 1 && g) ? 1 : 0;
+        KFSP_TRY(prof_begin(MODE == 0 ? KFSP_PROF_SPMV_PLAIN : MODE == 1 ? KFSP_PROF_SPMV_DOT : KFSP_PROF_SPMV_NRM,
+                            (box ? 16 : 12 * R + 24) + 8 * ea.has_g));
         spmv_by_mode[MODE] += 1;
         if (box) {
-            KFSP_TRY(spmv_box<MODE>(x, y, first, h_out, cx, cf));
+            KFSP_TRY(spmv_box<MODE>(x, y, g, ea, cg));
             return prof_end();
         }
         void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
-                     Reducer, SweepCtl*, double*, int, int, const double*, int64_t, int64_t);
+                     Reducer, SweepCtl*, EpiArgs, int, const double*, int64_t, int64_t);
         const int halo = dist.nranks > 1 ? ((dist.p2p && dist.p2p_halo) ? 2 : 1) : 0;
         if (halo == 1) KFSP_TRY(dist_halo_exchange(x));
         // tuning variant (KFSP_SPMV_TUNE): 0 = 1 row/iter, 1 = 2 rows/iter, 3/4/5 = 1 row/iter capped at 8/6/5 CTAs per SM
@@ -805,14 +819,14 @@ struct Engine {
         default: kern = halo == 2 ? k_spmv<0, MODE, 1, 4, 2> : halo == 1 ? k_spmv<0, MODE, 1, 4, 1> : k_spmv<0, MODE, 1, 1, 0>; break;
         }
 #undef KFSP_SPMV_PICK
-        const int g = wave_grid((const void*)kern, n);
+        const int gr = wave_grid((const void*)kern, n);
         const Reducer r = MODE != 0 ? next_rd() : rd;
         Reducer r2 = r;
         if (halo == 2 && !r2.peers) r2.peers = dist.d_peers;     // the peer table is also the halo address book
-        kern<<<g, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, first, r2, d_ctl, h_out, cx, cf, dist.halo, n,
-                                           (int64_t)(d_V ? x - d_V : 0));
+        kern<<<gr, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, g, r2, d_ctl, ea, cg, dist.halo, n,
+                                            (int64_t)(d_V ? x - d_V : 0));
         KFSP_TRY(check_launch());
-        if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, 1, h_out, nullptr, cx));
+        if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(ea, MODE == 1 ? 4 : 2));
         return prof_end();
     }
     int set_profiling(bool on) {
@@ -820,6 +834,7 @@ struct Engine {
         if (on && ev_pool.empty()) {
             ev_pool.resize(2 * 8192);
             ev_cls.assign(8192, 0);
+            ev_bps.assign(8192, 0);
             for (auto& e : ev_pool) KFSP_CUDA(cudaEventCreate(&e));
         }
         ev_used = 0;
@@ -835,6 +850,7 @@ struct Engine {
             const int cls = ev_cls[i / 2];
             prof_sec[cls] += 1e-3 * ms;
             prof_cnt[cls] += 1;
+            prof_bps[cls] += ev_bps[i / 2];
             if (cls <= KFSP_PROF_SPMV_FIN_NRM) {                 // the generator SpMV in all its variants
                 spmv_seconds += 1e-3 * ms;
                 spmv_timed += 1;
@@ -875,7 +891,7 @@ struct Engine {
         KFSP_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), stream));
         KFSP_LAUNCH(k_drop_mark, grid_for(lsize), VEC_THREADS, 0, (const double*)d_w, lsize, droptol, drop, d_cnt);
         double* aw = (double*)tmp;         // WTMP; the compaction scratch is not in use yet
-        KFSP_TRY(spmv<0>(d_w, aw, nullptr, nullptr));
+        KFSP_TRY(spmv<0>(d_w, aw));
         KFSP_LAUNCH(k_drop_unmark, grid_for(lsize), VEC_THREADS, 0, (const double*)aw, lsize, opt.drop_deriv_tol, drop, d_cnt + 1);
         unsigned long long c[2];
         KFSP_CUDA(cudaMemcpyAsync(c, d_cnt, sizeof c, cudaMemcpyDeviceToHost, stream));
@@ -939,71 +955,74 @@ struct Engine {
             return check_launch();
         }
         if (box && box_tune < 10 && lattice_bd2_order(lat) >= 0) return arnoldi_fused(jold, m);
-        for (int J = jold; J <= m; ++J) {
-            const double* vj = d_V + (size_t)(J - 1) * ld;      // column J-1 (0-based), scale colscale[J-1]
-            double* vn = d_V + (size_t)J * ld;                   // column J receives A U_{J-1}, then w, and stays un-normalised
-            double* hcol = d_H + (size_t)(J - 1) * LDH;
-            if (J >= 2) {
-                const double* vp = d_V + (size_t)(J - 2) * ld;
-                KFSP_TRY(spmv<1>(vj, vn, vp, hcol + (J - 2), J - 1, J - 2));                       // H(J-1,J)
-                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_DOT));
-                KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, vj, (const double*)vn, vn, next_rd(), d_ctl,
-                            hcol + (J - 1), J - 2, J - 1);                                        // H(J,J)
-                KFSP_TRY(dist_finalize(RK_AXPY_DOT, 1, hcol + (J - 1), nullptr, 0));
-                KFSP_TRY(prof_end());
-                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_NRM));
-                KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H2, next_rd(), d_ctl, hcol + J, opt.break_tol, J, J - 1);
-                KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, nullptr, hcol + J, J));
-                KFSP_TRY(prof_end());
-            } else {
-                KFSP_TRY(spmv<1>(vj, vn, vj, hcol + 0, 0, 0));                                       // H(1,1)
-                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_NRM));
-                KFSP_LAUNCH(k_axpy_nrm, wave_grid((const void*)k_axpy_nrm, n), VEC_THREADS, 0, n, vj, vn, (int)SC_H1, next_rd(), d_ctl, hcol + J, opt.break_tol, J, 0);
-                KFSP_TRY(dist_finalize(RK_AXPY_NRM, 1, nullptr, hcol + J, J));
-                KFSP_TRY(prof_end());
-            }
-        }
-        KFSP_TRY(spmv<2>(d_V + (size_t)m * ld, d_V + (size_t)(m + 1) * ld, nullptr, nullptr, m, -1));    // AVNORM
-        return KFSP_OK;
-    }
-    // The same sweep on the stencil lattice kernel with the tail of every column fused into the next SpMV launch
-    // (lattice.cuh, FIN = 1): per column one k_spmv_bd2 launch (finalise U_{J-1} = T - h v_{J-2}, its norm, A U_{J-1},
-    // <v_{J-2}, A U_{J-1}>) and one k_axpy_dot (w -> the scratch column T, <v_{J-1}, w>): 64 bytes per state and column
-    // instead of 80, two reductions instead of three.  The first column of a sweep has nothing to finalise (column 0 comes
-    // from k_scale_copy; on a resumed sweep, KrylovSolver.f90:400-433, column jold-1 is complete).
-    int arnoldi_fused(int jold, int m) {
-        double* T = d_V + (size_t)(opt.m_max + 2) * ld;
+        // Two launches per column: finalise U_c (the two axpys of the previous column + its norm), then the generator product
+        // with the three inner products of the window.  Column 0 and, on a resumed sweep (KrylovSolver.f90:400-433), column
+        // jold-1 are complete already.
         for (int J = jold; J <= m + 1; ++J) {                    // J = m+1: the extra product for AVNORM (:261-263)
             const int c = J - 1;
-            double* vj = d_V + (size_t)c * ld;
+            double* vc = d_V + (size_t)c * ld;                   // holds A U_{c-1} until finalised into U_c
             double* vn = d_V + (size_t)J * ld;
+            const double* vg = c >= 1 ? d_V + (size_t)(c - 1) * ld : nullptr;
+            if (J > jold) {
+                const double* vf = c >= 2 ? d_V + (size_t)(c - 2) * ld : vg;
+                EpiArgs ef = epi_none();
+                ef.kind = RK_FIN_NRM; ef.column = c; ef.fin = 1; ef.break_tol = opt.break_tol; ef.hn_out = d_H + (size_t)(c - 1) * LDH + c;   // H(c+1,c)
+                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_NRM, 24 + (c >= 2 ? 8 : 0)));
+                KFSP_LAUNCH(k_finalize, wave_grid((const void*)k_finalize, n), VEC_THREADS, 0, n, vg, vf, vc, c >= 2 ? 1 : 0, next_rd(), d_ctl, ef, c - 1, c - 2);
+                KFSP_TRY(dist_finalize(ef, 1));
+                KFSP_TRY(prof_end());
+            }
+            EpiArgs ea = epi_none();
+            ea.column = c;
+            if (J <= m) {
+                ea.kind = RK_COLUMN;
+                ea.h1_out = c >= 1 ? d_H + (size_t)c * LDH + (c - 1) : nullptr;          // H(J-1,J)
+                ea.h2_out = d_H + (size_t)c * LDH + c;                                    // H(J,J)
+                KFSP_TRY(spmv<1>(vc, vn, vg, ea, c - 1));
+            } else {
+                ea.kind = RK_EXTRA;
+                KFSP_TRY(spmv<2>(vc, vn, nullptr, ea, -1));
+            }
+        }
+        return KFSP_OK;
+    }
+    // The same sweep on the stencil lattice kernel with the tail of every column fused into the load stage of the next
+    // generator product (lattice.cuh, FIN = 1): ONE launch and one reduction point per Arnoldi column, 40 bytes per state.
+    // A U_c goes to one of two scratch columns (alternating), from where the next launch finalises it into column c+1.
+    int arnoldi_fused(int jold, int m) {
+        double* T[2] = {d_V + (size_t)(opt.m_max + 2) * ld, d_V + (size_t)(opt.m_max + 3) * ld};
+        for (int J = jold; J <= m + 1; ++J) {                    // J = m+1: the extra product for AVNORM (:261-263)
+            const int c = J - 1;
+            double* vc = d_V + (size_t)c * ld;
             const bool fin = J > jold;
             const bool extra = J == m + 1;
             Bd2Args a;
             std::memset(&a, 0, sizeof a);
-            a.src = fin ? T : vj;
-            a.xout = vj;
-            a.y = (J == 1) ? T : vn;                            // column 1 has no k_axpy_dot: A U_0 is finalised by the next launch
-            a.first = J >= 2 ? d_V + (size_t)(c - 1) * ld : vj;
-            a.cf = J >= 2 ? c - 1 : c;
-            a.cx = c;
-            a.hsel = c == 1 ? SC_H1 : SC_H2;                    // H(c,c): column 1's only coefficient is H(1,1)
-            a.h_out = extra ? nullptr : d_H + (size_t)c * LDH + (J >= 2 ? c - 1 : 0);        // H(J-1,J); H(1,1)
-            a.hn_out = fin ? d_H + (size_t)(c - 1) * LDH + c : nullptr;                      // H(c+1,c) = ||U_c||
-            a.break_tol = opt.break_tol;
-            KFSP_TRY(prof_begin(extra ? KFSP_PROF_SPMV_FIN_NRM : fin ? KFSP_PROF_SPMV_FIN_DOT : KFSP_PROF_SPMV_DOT));
+            a.src = fin ? T[c & 1] : vc;                         // A U_{c-1} was written to T[(J-1) & 1] by the previous launch
+            a.xout = vc;
+            a.y = T[J & 1];
+            a.has_g = c >= 1 ? 1 : 0;
+            a.has_f = (fin && c >= 2) ? 1 : 0;
+            a.g = c >= 1 ? d_V + (size_t)(c - 1) * ld : vc;
+            a.f = c >= 2 ? d_V + (size_t)(c - 2) * ld : a.g;
+            a.cg = c - 1; a.cf = c - 2;
+            a.ea = epi_none();
+            a.ea.column = c; a.ea.fin = fin ? 1 : 0; a.ea.has_g = a.has_g; a.ea.break_tol = opt.break_tol;
+            a.ea.hn_out = fin ? d_H + (size_t)(c - 1) * LDH + c : nullptr;               // H(c+1,c) = ||U_c||
+            if (!extra) {
+                a.ea.kind = RK_COLUMN;
+                a.ea.h1_out = c >= 1 ? d_H + (size_t)c * LDH + (c - 1) : nullptr;        // H(J-1,J)
+                a.ea.h2_out = d_H + (size_t)c * LDH + c;                                  // H(J,J)
+            } else {
+                a.ea.kind = RK_EXTRA;
+            }
+            KFSP_TRY(prof_begin(extra ? KFSP_PROF_SPMV_FIN_NRM : fin ? KFSP_PROF_SPMV_FIN_DOT : KFSP_PROF_SPMV_DOT,
+                                8 * (2 + a.has_g + a.has_f + (fin ? 1 : 0))));
             spmv_by_mode[extra ? 2 : 1] += 1;
             if (fin) spmv_fused += 1;
-            if (extra) KFSP_TRY(spmv_bd2<2>(a, true));
+            if (extra) KFSP_TRY(spmv_bd2<2>(a, fin));
             else KFSP_TRY(spmv_bd2<1>(a, fin));
             KFSP_TRY(prof_end());
-            if (J >= 2 && !extra) {
-                const double* vp = d_V + (size_t)(c - 1) * ld;
-                KFSP_TRY(prof_begin(KFSP_PROF_AXPY_DOT));
-                KFSP_LAUNCH(k_axpy_dot, wave_grid((const void*)k_axpy_dot, n), VEC_THREADS, 0, n, vp, (const double*)vj, (const double*)vn, T, next_rd(), d_ctl,
-                            d_H + (size_t)c * LDH + c, c - 1, c);                             // H(J,J)
-                KFSP_TRY(prof_end());
-            }
         }
         return KFSP_OK;
     }
@@ -1100,7 +1119,7 @@ struct Engine {
             }
             hp.V[r] = (const double*)pv;
             hp.part[r] = (double*)px;
-            hp.flag[r] = (unsigned long long*)(px + sizeof(double) * 2 * P * 4);
+            hp.flag[r] = (unsigned long long*)(px + sizeof(double) * 2 * P * RED_W);
         }
         // every rank must take the same path: agree on success
         long long* d_ok = (long long*)(d_info);
@@ -1139,9 +1158,9 @@ struct Engine {
             const int v = std::atoi(ev);
             dist.want_p2p = v != 0; dist.p2p_red = v == 1 || v == 2; dist.p2p_halo = v == 1 || v == 3;
         }
-        KFSP_CUDA(cudaMalloc(&dist.red_send, sizeof(double) * 4));
-        KFSP_CUDA(cudaMalloc(&dist.red_recv, sizeof(double) * 4 * nranks));
-        KFSP_CUDA(cudaMemset(dist.red_send, 0, sizeof(double) * 4));
+        KFSP_CUDA(cudaMalloc(&dist.red_send, sizeof(double) * RED_W));
+        KFSP_CUDA(cudaMalloc(&dist.red_recv, sizeof(double) * RED_W * nranks));
+        KFSP_CUDA(cudaMemset(dist.red_send, 0, sizeof(double) * RED_W));
         rd.dist_send = dist.red_send;
         return KFSP_OK;
 #else
@@ -1150,14 +1169,14 @@ struct Engine {
 #endif
     }
     // all-gather the ranks' double-double partials, merge in rank order, run the reduction's epilogue
-    int dist_finalize(int kind, int nv, double* h_out, double* hn_out, int column) {
+    int dist_finalize(const EpiArgs& ea, int nv) {
         if (dist.nranks == 1 || (dist.p2p && dist.p2p_red)) return KFSP_OK;     // peer-memory path: exchanged inside the reducing kernel
 #ifdef KFSP_WITH_NCCL
-        if (ncclAllGather(dist.red_send, dist.red_recv, 4, ncclFloat64, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
-        KFSP_LAUNCH(k_dist_finalize, 1, 32, 0, kind, nv, (const double*)dist.red_recv, dist.nranks, d_ctl, h_out, hn_out, opt.break_tol, column);
+        if (ncclAllGather(dist.red_send, dist.red_recv, RED_W, ncclFloat64, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+        KFSP_LAUNCH(k_dist_finalize, 1, 32, 0, ea, nv, (const double*)dist.red_recv, dist.nranks, d_ctl);
         dist.reductions += 1;
 #else
-        (void)kind; (void)nv; (void)h_out; (void)hn_out; (void)column;
+        (void)ea; (void)nv;
 #endif
         return KFSP_OK;
     }
@@ -1333,31 +1352,33 @@ struct Engine {
         a.zc = zc;
         a.halo = halo ? 1 : 0;
         a.sync_every = bd2_sync;
+        a.off_g = (d_V && a.g) ? (int64_t)(a.g - d_V) : 0;
+        a.off_f = (d_V && a.f) ? (int64_t)(a.f - d_V) : 0;
+        if (!a.g) { a.g = a.src; a.has_g = 0; }
+        if (!a.f) { a.f = a.g; a.has_f = 0; }
+        a.ea.has_g = a.has_g;
         a.off_src = d_V ? (int64_t)(a.src - d_V) : 0;
-        a.off_first = (d_V && a.first) ? (int64_t)(a.first - d_V) : 0;
-        if (!a.first) a.first = a.src;
         kb<<<g, VEC_THREADS, 0, stream>>>(lat, a, r, d_ctl);
         return check_launch();
     }
     template <int MODE>
-    int spmv_box(const double* x, double* y, const double* first, double* h_out, int cx, int cf) {
+    int spmv_box(const double* x, double* y, const double* g, const EpiArgs& ea, int cg) {
         const bool halo = dist.nranks > 1;
         // column blocks: the plane split evenly into the fewest blocks of at most 256 columns
         const int64_t ncb0 = (lat.plane + VEC_THREADS - 1) / VEC_THREADS;
         const int cbw = (int)((lat.plane + ncb0 - 1) / ncb0);
         const int64_t ncb = (lat.plane + cbw - 1) / cbw;
-        const int nzl = lat.zhi - lat.zlo;
         // 2-species one-molecule-step networks in the reference's reaction orders (config 5, the toggle models): stencil kernel
         if (box_tune < 10 && lattice_bd2_order(lat) >= 0) {
             Bd2Args a;
             std::memset(&a, 0, sizeof a);
-            a.src = x; a.y = y; a.first = first; a.h_out = h_out; a.cx = cx; a.cf = cf;
+            a.src = x; a.y = y; a.g = g; a.has_g = g ? 1 : 0; a.cg = cg; a.cf = -1; a.ea = ea;
             return spmv_bd2<MODE>(a, false);
         }
         const Reducer r = MODE != 0 ? next_rd() : rd;
         Reducer r2 = r;
         if (halo && !r2.peers) r2.peers = dist.d_peers;
-        void (*kern)(const Lattice, int, int, const double*, double*, const double*, Reducer, SweepCtl*, double*, int, int, int64_t) = nullptr;
+        void (*kern)(const Lattice, int, int, const double*, double*, const double*, Reducer, SweepCtl*, EpiArgs, int, int64_t) = nullptr;
         const int tune = box_tune >= 10 ? box_tune - 10 : box_tune;
 #define KFSP_BOX_PICK(RR)                                                                                                   \
         kern = halo ? (S == 2 ? k_spmv_box<RR, 2, MODE, 2, 1, 6, 3> : k_spmv_box<RR, 0, MODE, 2, 1, 6, 3>)                      \
@@ -1372,9 +1393,9 @@ struct Engine {
         }
 #undef KFSP_BOX_PICK
         const int wave = wave_grid((const void*)kern, (int64_t)1 << 40);
-        int zc, g;
-        lattice_chunking(wave, ncb, &zc, &g);
-        kern<<<g, VEC_THREADS, 0, stream>>>(lat, zc, cbw, x, y, first, r2, d_ctl, h_out, cx, cf, (int64_t)(d_V ? x - d_V : 0));
+        int zc, gsz;
+        lattice_chunking(wave, ncb, &zc, &gsz);
+        kern<<<gsz, VEC_THREADS, 0, stream>>>(lat, zc, cbw, x, y, g ? g : x, r2, d_ctl, ea, cg, (int64_t)(d_V ? x - d_V : 0));
         return check_launch();
     }
     // kfsp_fsp_init_box: the projection is the lattice [0,B_1) x ... x [0,B_S) in natural order.

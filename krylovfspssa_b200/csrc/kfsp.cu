@@ -45,7 +45,7 @@ struct GpuBackend {
         Tick t(e.phase_s[1]);
         k_norms<<<e.wave_grid((const void*)k_norms, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
-        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, nullptr, 0));
+        { EpiArgs en = Engine::epi_none(); en.kind = RK_NORMS; KFSP_TRY(e.dist_finalize(en, 2)); }
         KFSP_TRY(e.read_ctl());
         *wsum = e.h_ctl->scal[SC_WSUM];
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
@@ -55,7 +55,7 @@ struct GpuBackend {
         KFSP_CUDA(cudaMemsetAsync(e.d_H, 0, sizeof(double) * e.LDH * e.LDH, e.stream));
         k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);
         KFSP_TRY(e.check_launch());
-        KFSP_TRY(e.prof_begin(KFSP_PROF_SCALE_COPY));
+        KFSP_TRY(e.prof_begin(KFSP_PROF_SCALE_COPY, 16));
         k_scale_copy<<<e.wave_grid((const void*)k_scale_copy, e.n), VEC_THREADS, 0, e.stream>>>(e.n, inv_beta, e.d_w, e.d_V);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.dist_barrier());        // neighbours gather column 0 straight from this GPU's HBM
@@ -76,10 +76,10 @@ struct GpuBackend {
     }
     int combine(int mx, double beta, double* wsum, double* wssq) {
         Tick t(e.phase_s[1]);
-        KFSP_TRY(e.prof_begin(KFSP_PROF_COMBINE));
+        KFSP_TRY(e.prof_begin(KFSP_PROF_COMBINE, 8 * (mx + 1)));
         k_combine<<<e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
-        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, nullptr, 0));
+        { EpiArgs en = Engine::epi_none(); en.kind = RK_NORMS; KFSP_TRY(e.dist_finalize(en, 2)); }
         KFSP_TRY(e.prof_end());
         KFSP_TRY(e.read_ctl());
         *wsum = e.h_ctl->scal[SC_WSUM];
@@ -89,7 +89,7 @@ struct GpuBackend {
     int restore_w(double beta, double* wssq) {
         k_scale_copy_nrm<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, beta, e.d_V, e.d_w, e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
-        KFSP_TRY(e.dist_finalize(RK_NORMS, 2, nullptr, nullptr, 0));
+        { EpiArgs en = Engine::epi_none(); en.kind = RK_NORMS; KFSP_TRY(e.dist_finalize(en, 2)); }
         KFSP_TRY(e.read_ctl());
         *wssq = std::sqrt(e.h_ctl->scal[SC_WSSQ]);
         return KFSP_OK;
@@ -111,7 +111,7 @@ int Engine::solve(double T, double fsptol, double krytol, int itrace, kfsp_stats
     spmv_seconds = 0.0;
     spmv_timed = 0;
     ev_used = 0;
-    for (int i = 0; i < KFSP_PROF_CLASSES; ++i) { prof_sec[i] = 0.0; prof_cnt[i] = 0; }
+    for (int i = 0; i < KFSP_PROF_CLASSES; ++i) { prof_sec[i] = 0.0; prof_cnt[i] = 0; prof_bps[i] = 0; }
     cudaEvent_t e0, e1;
     KFSP_CUDA(cudaEventCreate(&e0));
     KFSP_CUDA(cudaEventCreate(&e1));
@@ -504,7 +504,7 @@ int kfsp_matvec(kfsp_handle h, const double* x, double* y) {
     double* dx = (double*)e.d_scratch;
     double* dy = (double*)(e.d_scratch + a);
     KFSP_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * e.n, cudaMemcpyHostToDevice, e.stream));
-    KFSP_TRY(e.spmv<0>(dx, dy, nullptr, nullptr));
+    KFSP_TRY(e.spmv<0>(dx, dy));
     KFSP_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * e.n, cudaMemcpyDeviceToHost, e.stream));
     return e.sync();
 }
@@ -514,7 +514,7 @@ int kfsp_matvec_device(kfsp_handle h, const double* xd, double* yd, int32_t reps
     if (e.n < 1) return KFSP_ERR_BAD_SIZES;
     cudaSetDevice(e.device);
     KFSP_CUDA(cudaEventRecord(e.ev_a, e.stream));
-    for (int r = 0; r < reps; ++r) KFSP_TRY(e.spmv<0>(xd, yd, nullptr, nullptr));
+    for (int r = 0; r < reps; ++r) KFSP_TRY(e.spmv<0>(xd, yd));
     KFSP_CUDA(cudaEventRecord(e.ev_b, e.stream));
     KFSP_CUDA(cudaEventSynchronize(e.ev_b));
     float ms = 0.f;
@@ -727,9 +727,13 @@ int kfsp_spmv_launch_counts(kfsp_handle h, int64_t out[4]) {
     out[3] = h->e.spmv_fused;
     return KFSP_OK;
 }
-int kfsp_profile_get(kfsp_handle h, double seconds[KFSP_PROF_CLASSES], int64_t launches[KFSP_PROF_CLASSES]) {
+int kfsp_profile_get(kfsp_handle h, double seconds[KFSP_PROF_CLASSES], int64_t launches[KFSP_PROF_CLASSES], int64_t bytes_per_state[KFSP_PROF_CLASSES]) {
     if (!h || !seconds || !launches) return KFSP_ERR_ARG;
-    for (int i = 0; i < KFSP_PROF_CLASSES; ++i) { seconds[i] = h->e.prof_sec[i]; launches[i] = h->e.prof_cnt[i]; }
+    for (int i = 0; i < KFSP_PROF_CLASSES; ++i) {
+        seconds[i] = h->e.prof_sec[i];
+        launches[i] = h->e.prof_cnt[i];
+        if (bytes_per_state) bytes_per_state[i] = h->e.prof_bps[i];
+    }
     return KFSP_OK;
 }
 int kfsp_launch_count(kfsp_handle h, int64_t* n) {

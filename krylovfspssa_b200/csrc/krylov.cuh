@@ -14,17 +14,22 @@ constexpr int VEC_THREADS = 256;
 constexpr int MAX_VEC_BLOCKS = 148 * 8;       // 148 SMs x 8 resident 256-thread CTAs
 
 // device scalars of the sweep
-enum Scal { SC_H1 = 0, SC_H2, SC_INV_HN, SC_AVNORM, SC_WSUM, SC_WSSQ, SC_HN, SC_COUNT };
+enum Scal { SC_H1 = 0, SC_H2, SC_INV_HN, SC_AVNORM, SC_WSUM, SC_WSSQ, SC_HN, SC_COUNT };   // SweepCtl::scal has 8 entries
 
 constexpr int MAX_COLS = 104;      // m_max + 2 basis columns
+constexpr int RED_NV = 4;          // a reduction point carries up to 4 double-double values
+constexpr int RED_W = 2 * RED_NV;  // ... = 8 doubles per rank
 // DSCAL(N, 1/HJ1J, v) (KrylovSolver.f90:258) is never run as a pass of its own: the basis columns stay
 // un-normalised in HBM (U_j) and colscale[j] = 1/HJ1J is applied where a column is consumed:
-// v_j(i) = __dmul_rn(colscale[j], U_j(i)) is the value DSCAL would have stored.  The generator product is
-// taken on the UN-NORMALISED column, Y' = A U_j, and its scale moves to what is derived from it:
-//     H(J-1,J) = colscale[j] * <v_{j-1}, Y'>,   AVNORM = colscale[j] * ||Y'||,   w(i) = colscale[j] * Y'(i) - ...
-// so that the SpMV of column j does not need ||U_j|| while it runs -- which is what allows the lattice kernel
-// (lattice.cuh) to finalise U_j = w - h*v_{j-1}, take its norm, multiply by A and take the next dot product in
-// ONE pass.  This is the canonical arithmetic of oracle/kfsp_oracle.cpp (canonical_sweep), bit for bit.
+// v_j(i) = __dmul_rn(colscale[j], U_j(i)) is the value DSCAL would have stored.  The generator product is taken on the
+// UN-NORMALISED column, Y' = A U_c, and the pass that forms it also accumulates (double-double)
+//     dA = <v_{c-1}, Y'>,   dB = <U_c, Y'>,   dC = <U_c, v_{c-1}>      (and ||U_c||^2 where U_c is finalised on the fly)
+// from which BOTH coefficients of the IOP window follow at one reduction point, with cs = colscale[c]:
+//     H(J-1,J) = h1 = cs*dA,      H(J,J) = h2 = cs*(cs*dB) - h1*(cs*dC)      ( = <v_J, A v_J - h1 v_{J-1}> by linearity )
+// and the next column is U_{c+1}(i) = fma(-h2, cs*U_c(i), fma(-h1, v_{c-1}(i), cs*Y'(i))).  One pass over HBM and one
+// (cross-GPU) reduction per Arnoldi column instead of three.  This is the canonical arithmetic of
+// oracle/kfsp_oracle.cpp (canonical_sweep), bit for bit; against the reference's operation order (two DDOTs on the
+// successively updated vector, KrylovSolver.f90:240-245) H agrees to rounding level (tests/test_gpu_kernels.py).
 struct SweepCtl {
     double scal[8];
     int32_t brk;                // happy-breakdown column (1-based), 0 = none
@@ -37,7 +42,7 @@ __device__ __forceinline__ double col_scale(const SweepCtl* ctl, int c) { return
 constexpr int MAX_RANKS = 8;
 struct DistPeers {
     int rank, nranks;
-    double* part[MAX_RANKS];                 // rank r's exchange area: part[r][(slot*nranks + src)*4 + v]
+    double* part[MAX_RANKS];                 // rank r's exchange area: part[r][(slot*nranks + src)*RED_W + v]
     unsigned long long* flag[MAX_RANKS];     // rank r's arrival flags: flag[r][slot*nranks + src] = sequence number
     const double* V[MAX_RANKS];              // rank r's Krylov basis (same leading dimension on every rank)
     const int32_t* halo_owner;               // for halo position h: owning rank ...
@@ -45,11 +50,11 @@ struct DistPeers {
     int32_t* err;
 };
 struct Reducer {
-    double* partials;           // [4 * MAX_VEC_BLOCKS]: (hi, lo) planes for up to two reductions
+    double* partials;           // [RED_W * MAX_VEC_BLOCKS]: (hi, lo) planes for up to RED_NV reductions
     unsigned int* counter;      // self-resetting ticket
     const DistPeers* peers;     // multi-GPU, peer-memory path: partials are exchanged INSIDE the reducing kernel
     unsigned long long seq;     // sequence number of this reduction (same on every rank)
-    double* dist_send;          // multi-GPU: this rank's double-double totals go here (4 doubles) and the
+    double* dist_send;          // multi-GPU: this rank's double-double totals go here (RED_W doubles) and the
                                 // epilogue runs in k_dist_finalize after the all-gather; nullptr on one GPU
 };
 
@@ -153,7 +158,7 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
         __syncthreads();
         if ((int)threadIdx.x < P) {
             const int r = threadIdx.x;
-            double* dst = dp->part[r] + ((size_t)slot * P + me) * 4;
+            double* dst = dp->part[r] + ((size_t)slot * P + me) * RED_W;
 #pragma unroll
             for (int v2 = 0; v2 < 2 * NV; ++v2) dst[v2] = mine[v2];
             __threadfence_system();
@@ -171,7 +176,7 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
             for (int q = 0; q < NV; ++q) {
                 DD s; s.hi = 0.0; s.lo = 0.0;
                 for (int r = 0; r < P; ++r) {
-                    const volatile double* src = dp->part[me] + ((size_t)slot * P + r) * 4;
+                    const volatile double* src = dp->part[me] + ((size_t)slot * P + r) * RED_W;
                     DD o; o.hi = src[2 * q]; o.lo = src[2 * q + 1];
                     dd_merge(s, o);
                 }
@@ -189,69 +194,85 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
 
 // What to do with a finished reduction (same code on one GPU, inside the reducing kernel, and on
 // several GPUs, in k_dist_finalize after the ranks' double-double partials were gathered).
-enum RKind { RK_SPMV_DOT = 0, RK_SPMV_NRM, RK_AXPY_DOT, RK_AXPY_NRM, RK_NORMS, RK_SUM_BELOW, RK_FUSED_DOT, RK_FUSED_NRM };
-// column: the basis column (0-based) the reduction belongs to -- for RK_SPMV_*: the SpMV's operand column (its scale
-// multiplies the result, -1 = scale 1); for RK_AXPY_NRM / RK_FUSED_*: the column whose norm HJ1J was taken (its
-// 0-based index equals the 1-based Arnoldi index J of KrylovSolver.f90:236-258, so it is also the breakdown column).
-__device__ __forceinline__ bool epilogue_norm(double ssq, SweepCtl* ctl, double* hn_out, double break_tol, int column, double* inv) {
+enum RKind { RK_COLUMN = 0, RK_EXTRA, RK_FIN_NRM, RK_NORMS, RK_SUM_BELOW };
+struct EpiArgs {
+    int kind;
+    int column;        // the SpMV's operand column c (0-based; -1: plain operand, scale 1).  c is also the 1-based Arnoldi index of
+                       // the step that produced U_c, i.e. the happy-breakdown column if ||U_c|| is tiny (KrylovSolver.f90:249-256)
+    int fin;           // tot[0] = ||U_c||^2 was accumulated by this launch (the column was finalised in its load stage)
+    int has_g;         // c >= 1: the window has a previous vector (tot[1] = dA, tot[3] = dC)
+    double break_tol;
+    double* h1_out;    // H(J-1,J)
+    double* h2_out;    // H(J,J)
+    double* hn_out;    // H(c+1,c) = ||U_c||
+};
+__device__ __forceinline__ bool epilogue_norm(double ssq, SweepCtl* ctl, double* hn_out, double break_tol, int column) {
     const double hn = sqrt(ssq);                            // HJ1J (KrylovSolver.f90:247)
     ctl->scal[SC_HN] = hn;
     if (hn <= break_tol) {
         ctl->brk = column;                                  // happy breakdown (:249-256)
         return false;
     }
-    *hn_out = hn;
-    *inv = 1.0 / hn;
-    ctl->scal[SC_INV_HN] = *inv;
-    ctl->colscale[column] = *inv;                           // column `column` of V stays un-normalised
+    if (hn_out) *hn_out = hn;
+    const double inv = 1.0 / hn;
+    ctl->scal[SC_INV_HN] = inv;
+    ctl->colscale[column] = inv;                            // column `column` of V stays un-normalised
     return true;
 }
-__device__ __forceinline__ void reduce_epilogue(int kind, const double* tot, SweepCtl* ctl, double* h_out, double* hn_out, double break_tol,
-                                                int column) {
-    double inv = 0.0;
-    switch (kind) {
-    case RK_SPMV_DOT: { const double h = __dmul_rn(col_scale(ctl, column), tot[0]); ctl->scal[SC_H1] = h; if (h_out) *h_out = h; } break;
-    case RK_SPMV_NRM: ctl->scal[SC_AVNORM] = __dmul_rn(col_scale(ctl, column), sqrt(tot[0])); break;
-    case RK_AXPY_DOT: ctl->scal[SC_H2] = tot[0]; if (h_out) *h_out = tot[0]; break;
-    case RK_AXPY_NRM: epilogue_norm(tot[0], ctl, hn_out, break_tol, column, &inv); break;
-    case RK_FUSED_DOT:                                      // tot[0] = ||U_c||^2, tot[1] = <v_{c-1}, A U_c>
-        if (epilogue_norm(tot[0], ctl, hn_out, break_tol, column, &inv)) {
-            const double h = __dmul_rn(inv, tot[1]);
-            ctl->scal[SC_H1] = h;
-            if (h_out) *h_out = h;
+// tot: RK_COLUMN {ssq, dA, dB, dC}; RK_EXTRA {ssq, ||Y'||^2}; RK_FIN_NRM {ssq}; RK_NORMS {||w||_1, ||w||^2}; RK_SUM_BELOW {sum}
+__device__ __forceinline__ void reduce_epilogue(const EpiArgs& ea, const double* tot, SweepCtl* ctl) {
+    switch (ea.kind) {
+    case RK_COLUMN: {
+        if (ea.fin && !epilogue_norm(tot[0], ctl, ea.hn_out, ea.break_tol, ea.column)) break;
+        const double sc = col_scale(ctl, ea.column);
+        double h1 = 0.0, h2 = __dmul_rn(sc, __dmul_rn(sc, tot[2]));
+        if (ea.has_g) {
+            h1 = __dmul_rn(sc, tot[1]);
+            h2 = fma(-h1, __dmul_rn(sc, tot[3]), h2);
+            if (ea.h1_out) *ea.h1_out = h1;
         }
+        ctl->scal[SC_H1] = h1;
+        ctl->scal[SC_H2] = h2;
+        if (ea.h2_out) *ea.h2_out = h2;
+    } break;
+    case RK_EXTRA:
+        if (ea.fin && !epilogue_norm(tot[0], ctl, ea.hn_out, ea.break_tol, ea.column)) break;
+        ctl->scal[SC_AVNORM] = __dmul_rn(col_scale(ctl, ea.column), sqrt(tot[1]));
         break;
-    case RK_FUSED_NRM:                                      // tot[0] = ||U_c||^2, tot[1] = ||A U_c||^2
-        if (epilogue_norm(tot[0], ctl, hn_out, break_tol, column, &inv)) ctl->scal[SC_AVNORM] = __dmul_rn(inv, sqrt(tot[1]));
-        break;
+    case RK_FIN_NRM: epilogue_norm(tot[0], ctl, ea.hn_out, ea.break_tol, ea.column); break;
     case RK_NORMS: ctl->scal[SC_WSUM] = tot[0]; ctl->scal[SC_WSSQ] = tot[1]; break;
     case RK_SUM_BELOW: ctl->scal[SC_WSUM] = tot[0]; break;
     }
 }
-// multi-GPU: merge the P gathered (hi,lo) partials in rank order, round once, run the epilogue
-__global__ void k_dist_finalize(int kind, int nv, const double* __restrict__ recv /*[P][4]*/, int nranks, SweepCtl* ctl,
-                                double* h_out, double* hn_out, double break_tol, int column) {
+__device__ __forceinline__ EpiArgs epi_simple(int kind) {
+    EpiArgs e;
+    e.kind = kind; e.column = -1; e.fin = 0; e.has_g = 0; e.break_tol = 0.0; e.h1_out = e.h2_out = e.hn_out = nullptr;
+    return e;
+}
+// multi-GPU, NCCL path: merge the P gathered (hi,lo) partials in rank order, round once, run the epilogue
+__global__ void k_dist_finalize(EpiArgs ea, int nv, const double* __restrict__ recv /*[P][RED_W]*/, int nranks, SweepCtl* ctl) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (kind != RK_NORMS && kind != RK_SUM_BELOW && ctl->brk != 0) return;
-    double tot[2] = {0.0, 0.0};
+    if (ea.kind != RK_NORMS && ea.kind != RK_SUM_BELOW && ctl->brk != 0) return;
+    double tot[RED_NV] = {0.0, 0.0, 0.0, 0.0};
     for (int q = 0; q < nv; ++q) {
         DD s; s.hi = 0.0; s.lo = 0.0;
         for (int r = 0; r < nranks; ++r) {
-            DD o; o.hi = recv[r * 4 + 2 * q]; o.lo = recv[r * 4 + 2 * q + 1];
+            DD o; o.hi = recv[r * RED_W + 2 * q]; o.lo = recv[r * RED_W + 2 * q + 1];
             dd_merge(s, o);
         }
         tot[q] = __dadd_rn(s.hi, s.lo);
     }
-    reduce_epilogue(kind, tot, ctl, h_out, hn_out, break_tol, column);
+    reduce_epilogue(ea, tot, ctl);
 }
 
 // ---------------------------------------------------------------------------------------
 // FMATVEC (KrylovSolver.f90:577-607) in gather form: y_i = -DIAG_i x_i + sum_k coef_ki x[pred_ki], on the stored
-// (un-normalised) column x; the column's scale colscale[cx] is applied to the reduction result in the epilogue.
-// Fused epilogue (optional): dot = <v_first, y> -> H and ctl->scal[SC_H1]  (the first DDOT of the IOP
-// window, :243), or ssq = <y,y> -> AVNORM (:263).
-//   mode 0: plain   mode 1: dot with `first`   mode 2: norm of y
-// Algorithmic traffic per row: R*(4+8) matrix + 8 diag + 8 x_i + 8 y_i  = 12R+24 bytes.
+// (un-normalised) column x = U_c.
+//   mode 0: plain
+//   mode 1: one Arnoldi column: also dA = <v_{c-1}, y>, dB = <x, y>, dC = <x, v_{c-1}> (g = U_{c-1} is the extra stream;
+//           has_g = 0 for the first column); the epilogue turns them into H(J-1,J) and H(J,J) (reduce_epilogue)
+//   mode 2: the extra product: ||y||^2 -> AVNORM (:261-263)
+// Algorithmic traffic per row: R*(4+8) matrix + 8 diag + 8 x_i + 8 y_i  = 12R+24 bytes (+8 for g).
 // ---------------------------------------------------------------------------------------
 template <int HALO>
 __device__ __forceinline__ double halo_load(const double* __restrict__ x, const double* __restrict__ xh, const DistPeers* __restrict__ dp,
@@ -265,26 +286,29 @@ template <int RT, int MODE, int UNROLL, int MINB, int HALO>
 __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
                                                              const double* __restrict__ coef, const double* __restrict__ diag,
                                                              const double* __restrict__ x, double* __restrict__ y,
-                                                             const double* __restrict__ first, Reducer rd, SweepCtl* ctl, double* h_out,
-                                                             int cx, int cf, const double* __restrict__ xh, int64_t nloc, int64_t coloff) {
+                                                             const double* __restrict__ g, Reducer rd, SweepCtl* ctl, EpiArgs ea,
+                                                             int cg, const double* __restrict__ xh, int64_t nloc, int64_t coloff) {
     // HALO 1: gathered index j >= nloc addresses the halo buffer xh filled by the NCCL exchange step;
     // HALO 2: it is loaded straight from the owning GPU's basis column over NVLink (peer memory).
     const int R = RT > 0 ? RT : R_rt;
     if (MODE != 0 && ctl->brk != 0) return;
-    const double fs = MODE == 1 ? col_scale(ctl, cf) : 1.0;
-    DD acc0; acc0.hi = 0.0; acc0.lo = 0.0;
+    const bool has_g = MODE == 1 && ea.has_g;
+    const double gs = has_g ? col_scale(ctl, cg) : 0.0;
+    DD accA, accB, accC;
+    accA.hi = accA.lo = accB.hi = accB.lo = accC.hi = accC.lo = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += stride * UNROLL) {
         // UNROLL independent rows per iteration: all streaming loads are issued before any gather is consumed
-        double s[UNROLL], f[UNROLL];
+        double s[UNROLL], gv[UNROLL], xi[UNROLL];
         int32_t j[UNROLL][RT > 0 ? RT : 1];
         double a[UNROLL][RT > 0 ? RT : 1];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < n) {
-                if (MODE == 1) f[u] = __dmul_rn(fs, __ldcs(first + i));
-                s[u] = -__dmul_rn(__ldcs(diag + i), x[i]);
+                gv[u] = has_g ? __dmul_rn(gs, __ldcs(g + i)) : 0.0;
+                xi[u] = x[i];
+                s[u] = -__dmul_rn(__ldcs(diag + i), xi[u]);
                 if (RT > 0) {
 #pragma unroll
                     for (int k = 0; k < RT; ++k) {
@@ -311,56 +335,47 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
                     }
                 }
                 __stcs(y + i, sv);
-                if (MODE == 1) dd_add_prod(acc0, f[u], sv);
-                if (MODE == 2) dd_add_prod(acc0, sv, sv);
+                if (MODE == 1) {
+                    dd_add_prod(accB, xi[u], sv);
+                    if (has_g) { dd_add_prod(accA, gv[u], sv); dd_add_prod(accC, xi[u], gv[u]); }
+                }
+                if (MODE == 2) dd_add_prod(accB, sv, sv);
             }
         }
     }
     if (MODE == 0) return;
-    DD v[1] = {acc0};
-    double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0)
-        reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, nullptr, 0.0, cx);
+    if (MODE == 1) {
+        DD z; z.hi = 0.0; z.lo = 0.0;
+        DD v[4] = {z, accA, accB, accC};
+        double tot[4];
+        if (grid_reduce<4>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(ea, tot, ctl);
+    } else {
+        DD z; z.hi = 0.0; z.lo = 0.0;
+        DD v[2] = {z, accB};
+        double tot[2];
+        if (grid_reduce<2>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(ea, tot, ctl);
+    }
 }
 
-// out = cb*y - h1*v_a ; dot = <v_b, out>   (DAXPY + the next DDOT, KrylovSolver.f90:243-245).  y = A U_b is the
-// un-normalised product, so it carries b's scale.  out == y (in place) except on the fused lattice path, where the
-// result goes to the scratch column T that the next SpMV launch finalises (lattice.cuh).
-__global__ void __launch_bounds__(VEC_THREADS) k_axpy_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
-                                                          const double* y, double* out, Reducer rd, SweepCtl* ctl, double* h_out,
-                                                          int ca, int cb) {
+// U_c = (cg*w - h1*v_f) - h2*v_g in place on w = A U_{c-1} (g = U_{c-1}, f = U_{c-2}; has_f = 0 for column 1), and its
+// norm: HJ1J = ||U_c||, happy-breakdown test, H(c+1,c), colscale[c] (the two DAXPYs, DNRM2 and the deferred DSCAL of
+// KrylovSolver.f90:244-258).  The fused lattice path does this inside the next SpMV launch (lattice.cuh).
+__global__ void __launch_bounds__(VEC_THREADS) k_finalize(int64_t n, const double* __restrict__ g, const double* __restrict__ f, double* __restrict__ w,
+                                                          int has_f, Reducer rd, SweepCtl* ctl, EpiArgs ea, int cg, int cf) {
     if (ctl->brk != 0) return;
-    const double h1 = ctl->scal[SC_H1];
-    const double sa = col_scale(ctl, ca), sb = col_scale(ctl, cb);
+    const double h1 = ctl->scal[SC_H1], h2 = ctl->scal[SC_H2];
+    const double sg = col_scale(ctl, cg), sf = has_f ? col_scale(ctl, cf) : 0.0;
     DD acc; acc.hi = 0.0; acc.lo = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double ai = __dmul_rn(sa, __ldcs(a + i)), bi = __dmul_rn(sb, __ldcs(b + i));
-        const double wi = fma(-h1, ai, __dmul_rn(sb, y[i]));
-        __stcs(out + i, wi);
-        dd_add_prod(acc, bi, wi);
+        double inner = __dmul_rn(sg, w[i]);
+        if (has_f) inner = fma(-h1, __dmul_rn(sf, __ldcs(f + i)), inner);
+        const double u = fma(-h2, __dmul_rn(sg, __ldcs(g + i)), inner);
+        w[i] = u;
+        dd_add_prod(acc, u, u);
     }
     DD v[1] = {acc};
     double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_AXPY_DOT, tot, ctl, h_out, nullptr, 0.0, 0);
-}
-
-// w -= h*v_a ; ssq = <w,w>; then HJ1J = sqrt(ssq), happy-breakdown test, H(J+1,J) (KrylovSolver.f90:244-257)
-// which = SC_H1 or SC_H2: the scalar holding h.  (The fused lattice path does this inside the next SpMV launch.)
-__global__ void __launch_bounds__(VEC_THREADS) k_axpy_nrm(int64_t n, const double* __restrict__ a, double* __restrict__ w, int which,
-                                                          Reducer rd, SweepCtl* ctl, double* hn_out, double break_tol, int column,
-                                                          int ca) {
-    if (ctl->brk != 0) return;
-    const double h = ctl->scal[which];
-    const double sa = col_scale(ctl, ca);
-    DD acc; acc.hi = 0.0; acc.lo = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double wi = fma(-h, __dmul_rn(sa, __ldcs(a + i)), w[i]);
-        w[i] = wi;
-        dd_add_prod(acc, wi, wi);
-    }
-    DD v[1] = {acc};
-    double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_AXPY_NRM, tot, ctl, nullptr, hn_out, break_tol, column);
+    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(ea, tot, ctl);
 }
 
 // V(:,1) = (1/BETA) * W (KrylovSolver.f90:223-226)
@@ -379,7 +394,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_scale_copy_nrm(int64_t n, doubl
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, nullptr, 0.0, 0);
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(epi_simple(RK_NORMS), tot, ctl);
 }
 // ||w||_1 and ||w||_2^2 of a vector (BETA = DNRM2(N_NOW, W), KrylovSolver.f90:177,540)
 __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
@@ -391,7 +406,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_norms(int64_t n, const double* 
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, nullptr, 0.0, 0);
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(epi_simple(RK_NORMS), tot, ctl);
 }
 
 // W = BETA * V(:,1:mx) * e ; W = max(W,0) ; WSUM = ||W||_1 ; also ||W||_2^2 for the next BETA
@@ -420,7 +435,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, 
     }
     DD vv[2] = {a1, a2};
     double tot[2];
-    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_NORMS, tot, ctl, nullptr, nullptr, 0.0, 0);
+    if (grid_reduce<2>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(epi_simple(RK_NORMS), tot, ctl);
 }
 
 // FIND_DROPTOL's inner sum (StateSpace.f90:418-423): sum of W_i with 0 < W_i < droptol
@@ -432,7 +447,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_sum_below(int64_t n, const doub
     }
     DD vv[1] = {a};
     double tot[1];
-    if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(RK_SUM_BELOW, tot, ctl, nullptr, nullptr, 0.0, 0);
+    if (grid_reduce<1>(vv, tot, rd) && threadIdx.x == 0) reduce_epilogue(epi_simple(RK_SUM_BELOW), tot, ctl);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -488,33 +503,38 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
         const double* x = V + (size_t)(J - 1) * ld;
         double* y = V + (size_t)J * ld;
         const double xs = cs[J - 1];
-        const double* first = J >= 2 ? V + (size_t)(J - 2) * ld : x;
-        const double fs = J >= 2 ? cs[J - 2] : xs;
+        const double* g = J >= 2 ? V + (size_t)(J - 2) * ld : x;
+        const double gs = J >= 2 ? cs[J - 2] : 0.0;
         double* hcol = H + (size_t)(J - 1) * ldh;
-        // FMATVEC + first DDOT of the IOP window
+        // FMATVEC on the un-normalised column and the three inner products of the window
+        DD accA, accB, accC;
+        accA.hi = accA.lo = accB.hi = accB.lo = accC.hi = accC.lo = 0.0;
+        for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
+            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x);
+            y[i] = sv;
+            const double xi = x[i];
+            dd_add_prod(accB, xi, sv);
+            if (J >= 2) {
+                const double gv = __dmul_rn(gs, g[i]);
+                dd_add_prod(accA, gv, sv);
+                dd_add_prod(accC, xi, gv);
+            }
+        }
+        const double dB = cta_dd_total(accB, sh, &bc);
+        double h1 = 0.0, h2 = __dmul_rn(xs, __dmul_rn(xs, dB));
+        if (J >= 2) {
+            const double dA = cta_dd_total(accA, sh, &bc);
+            const double dC = cta_dd_total(accC, sh, &bc);
+            h1 = __dmul_rn(xs, dA);
+            h2 = fma(-h1, __dmul_rn(xs, dC), h2);
+            if (tid == 0) hcol[J - 2] = h1;                                  // H(J-1,J)
+        }
+        if (tid == 0) hcol[J - 1] = h2;                                      // H(J,J)
         DD acc; acc.hi = 0.0; acc.lo = 0.0;
         for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
-            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x);     // A U_{J-1}: un-normalised
-            y[i] = sv;
-            dd_add_prod(acc, __dmul_rn(fs, first[i]), sv);
-        }
-        const double h1 = __dmul_rn(xs, cta_dd_total(acc, sh, &bc));
-        double h = h1;
-        if (J >= 2) {
-            if (tid == 0) hcol[J - 2] = h1;                                  // H(J-1,J)
-            acc.hi = 0.0; acc.lo = 0.0;
-            for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
-                const double ai = __dmul_rn(fs, first[i]), bi = __dmul_rn(xs, x[i]);
-                const double wi = fma(-h1, ai, __dmul_rn(xs, y[i]));
-                y[i] = wi;
-                dd_add_prod(acc, bi, wi);
-            }
-            h = cta_dd_total(acc, sh, &bc);
-        }
-        if (tid == 0) hcol[J - 1] = h;                                       // H(J,J)
-        acc.hi = 0.0; acc.lo = 0.0;
-        for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
-            const double wi = fma(-h, __dmul_rn(xs, x[i]), y[i]);
+            double inner = __dmul_rn(xs, y[i]);
+            if (J >= 2) inner = fma(-h1, __dmul_rn(gs, g[i]), inner);
+            const double wi = fma(-h2, __dmul_rn(xs, x[i]), inner);
             y[i] = wi;
             dd_add_prod(acc, wi, wi);
         }

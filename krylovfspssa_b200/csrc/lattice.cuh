@@ -79,7 +79,7 @@ __device__ __forceinline__ void lattice_prefetch(const void* p) {
     if (LEVEL == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
-// mode 0: y = A x   mode 1: + dot = <first, y>   mode 2: + ssq = <y, y>     (same contract as k_spmv)
+// mode 0: y = A x   mode 1: + dA, dB, dC of the Arnoldi column   mode 2: + ssq = <y, y>     (same contract as k_spmv)
 // Every reaction runs the same few instructions with per-thread data hoisted out of the walk over z: the
 // element offset of its predecessor, the bounds check of the column species, and the table entries that do
 // not depend on z.  The rows z-1, z, z+1 of x are re-read through L1 (the CTA touched them one and two
@@ -89,17 +89,19 @@ __device__ __forceinline__ void lattice_prefetch(const void* p) {
 template <int RT, int ST, int MODE, int HALO, int PFL, int PF, int MINB>
 __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_constant__ Lattice L, int zc, int cbw, const double* __restrict__ x,
                                                                 double* __restrict__ y, const double* __restrict__ first, Reducer rd,
-                                                                SweepCtl* ctl, double* h_out, int cx, int cf, int64_t coloff) {
+                                                                SweepCtl* ctl, EpiArgs ea, int cf, int64_t coloff) {
     constexpr int R = RT;
     if (MODE != 0 && ctl->brk != 0) return;
-    const double fs = MODE == 1 ? col_scale(ctl, cf) : 1.0;
+    const bool has_g = MODE == 1 && ea.has_g;             // `first` = g = U_{c-1}
+    const double fs = has_g ? col_scale(ctl, cf) : 0.0;
     const int S = ST > 0 ? ST : L.S;
     const int64_t plane = L.plane;
     const int nzl = L.zhi - L.zlo;
     const int64_t ncb = (plane + cbw - 1) / cbw;                 // column blocks of cbw <= 256 columns (even split of the plane)
     const int64_t nzc = (nzl + zc - 1) / zc;
     const DistPeers* __restrict__ dp = rd.peers;
-    DD acc; acc.hi = 0.0; acc.lo = 0.0;
+    DD acc, accA, accC;
+    acc.hi = acc.lo = accA.hi = accA.lo = accC.hi = accC.lo = 0.0;
     for (int64_t item = blockIdx.x; item < ncb * nzc; item += gridDim.x) {
         const int64_t c = (item % ncb) * cbw + threadIdx.x;
         if ((int)threadIdx.x >= cbw || c >= plane) continue;
@@ -137,13 +139,13 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
         if (PFL > 0) {
 #pragma unroll
             for (int q = 1; q < PF; ++q)
-                if (z0 + q < L.zhi) { lattice_prefetch<PFL>(x + (i + plane32 * q)); if (MODE == 1) lattice_prefetch<PFL>(first + (i + plane32 * q)); }
+                if (z0 + q < L.zhi) { lattice_prefetch<PFL>(x + (i + plane32 * q)); if (has_g) lattice_prefetch<PFL>(first + (i + plane32 * q)); }
         }
         for (int32_t z = z0; z < z1; ++z) {
-            if (PFL > 0 && z + PF < L.zhi) { lattice_prefetch<PFL>(x + (i + pfo)); if (MODE == 1) lattice_prefetch<PFL>(first + (i + pfo)); }
+            if (PFL > 0 && z + PF < L.zhi) { lattice_prefetch<PFL>(x + (i + pfo)); if (has_g) lattice_prefetch<PFL>(first + (i + pfo)); }
             const double x0 = x[i];
             double f = 0.0;
-            if (MODE == 1) f = __dmul_rn(fs, __ldcs(first + i));
+            if (has_g) f = __dmul_rn(fs, __ldcs(first + i));
             double d = 0.0;
 #pragma unroll
             for (int k = 0; k < R; ++k) {
@@ -172,16 +174,25 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
                 }
             }
             __stcs(y + i, sv);
-            if (MODE == 1) dd_add_prod(acc, f, sv);
+            if (MODE == 1) {
+                dd_add_prod(acc, x0, sv);
+                if (has_g) { dd_add_prod(accA, f, sv); dd_add_prod(accC, x0, f); }
+            }
             if (MODE == 2) dd_add_prod(acc, sv, sv);
             i += (uint32_t)plane32;
         }
     }
     if (MODE == 0) return;
-    DD v[1] = {acc};
-    double tot[1];
-    if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0)
-        reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, h_out, nullptr, 0.0, cx);
+    DD zz0; zz0.hi = 0.0; zz0.lo = 0.0;
+    if (MODE == 1) {
+        DD v[4] = {zz0, accA, acc, accC};
+        double tot[4];
+        if (grid_reduce<4>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(ea, tot, ctl);
+    } else {
+        DD v[2] = {zz0, acc};
+        double tot[2];
+        if (grid_reduce<2>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(ea, tot, ctl);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -196,13 +207,14 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
 // ring), the +-1 neighbours in x are the adjacent lanes' registers (warp shuffle: a warp covers 30 columns plus
 // one halo lane on each side, which loads but does not store), the y-tables of a chunk sit in shared memory.
 //
-// FIN = 1 fuses the tail of the previous Arnoldi column into the load stage (KrylovSolver.f90:244-258 + :240-243):
-// the operand is finalised on the fly,  U(i) = fma(-h, v_first(i), T(i)),  stored once, its norm^2 accumulated beside the
-// dot product, and the generator product is taken on U un-normalised (krylov.cuh: the column scale 1/||U|| is only
-// known when the pass ends, so it is applied to the two scalars in the epilogue).  T is the scratch column the
-// preceding k_axpy_dot wrote: the finalised column cannot be written over its own source because other warps (and,
-// on several GPUs, the neighbours) still gather rows of T for their stencil.  Per state the launch moves
-// T + v_first + U + y = 32 bytes and replaces k_axpy_nrm (24) + SpMV-with-dot (24).
+// FIN = 1 fuses the tail of the previous Arnoldi column into the load stage (KrylovSolver.f90:243-258): the operand is
+// finalised on the fly,  U_c(i) = fma(-h2, v_g(i), fma(-h1, v_f(i), cs*Yp(i)))  with Yp = A U_{c-1} (scratch column written
+// by the previous launch), g = U_{c-1}, f = U_{c-2}, stored once, its norm^2 accumulated beside the three inner products of
+// the new column (krylov.cuh: dA, dB, dC), and the generator product is taken on U_c un-normalised -- the column scale
+// 1/||U_c|| is only known when the pass ends, so it is applied to the scalars in the epilogue.  The finalised column cannot be
+// written over its own source because other warps (and, on several GPUs, the neighbours) still gather rows of Yp for their
+// stencil, hence the two scratch columns used alternately.  Per state and Arnoldi column ONE launch moves
+// Yp + g + f + U_c + y = 40 bytes and ends in ONE reduction point (the reference's BLAS sequence: 24 + 104 bytes, three).
 //
 // Rows are walked in three pieces so that the hot loop carries no bounds checks: a head (first PF rows when the chunk
 // starts at the box boundary z = 0), the main loop (every ring refill is a local, in-range row), and a tail (refills
@@ -234,14 +246,11 @@ constexpr int BD2_CBW = BD2_WCOLS * (VEC_THREADS / 32);        // live columns p
 constexpr int BD2_L2AHEAD = 10;                                // rows ahead of the ring that are prefetched into L2
 constexpr int BD2_PF = 4;                                      // depth of the register ring (rows in flight per thread and stream)
 constexpr int BD2_MINB = 4;                                    // resident CTAs per SM the kernel is compiled for
-#ifndef KFSP_BD2_RING
-#define KFSP_BD2_RING 1
-#endif
-// KFSP_BD2_RING 1: the rows in flight live in a shared-memory ring filled by per-thread asynchronous copies (cp.async,
-// 8 bytes per thread and stream: every lane copies and later reads its own element, so no barrier is involved), BD2_DEPTH
-// rows deep; 0: in a register ring PF rows deep (the depth is then bounded by the register file: ncu showed 50 % of all
-// stall cycles on the scoreboard of the first-touch loads at PF = 4, profiles/r2_summary.md).
-constexpr int BD2_DEPTH = 8;
+// The rows in flight live in a shared-memory ring filled by per-thread asynchronous copies (cp.async, 8 bytes per thread and
+// stream: every lane copies and later reads its own element, so no barrier is involved), BD2_DEPTH rows deep.  (A register
+// ring is bounded by the register file: at 4 rows ncu showed 50 % of all stall cycles on the scoreboard of the first-touch
+// loads, and the launch was 10 % slower; profiles/r2_summary.md.)
+constexpr int BD2_DEPTH = 6;                                   // 3 streams x 6 rows x 256 threads x 8 B = 36 KB per CTA, 4 CTAs per SM
 __device__ __forceinline__ void cp_async8(double* smem, const double* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
@@ -251,29 +260,33 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int BD2_ZT = 256;                                    // longest z-chunk (rows of the y-tables staged in shared memory)
 struct Bd2Args {
-    const double* src;        // operand column: FIN ? T (un-finalised) : the column itself
-    double* xout;             // FIN: the finalised column is stored here
-    double* y;                // A * column
-    const double* first;      // v_{j-1}: operand of the finalising axpy (FIN) and of the fused dot product (MODE 1)
-    double* h_out;            // MODE 1: H(J-1,J)
-    double* hn_out;           // FIN: H(J,J-1) = ||U||
-    double break_tol;
-    int32_t cx, cf;           // basis column of the operand / of `first` (-1: scale 1)
-    int32_t hsel;             // FIN: ctl->scal[hsel] is the axpy coefficient
+    const double* src;        // FIN: Yp = A U_{c-1} (scratch column); else: the operand column U_c itself
+    double* xout;             // FIN: the finalised column U_c is stored here
+    double* y;                // A U_c
+    const double* g;          // U_{c-1}: previous basis vector (finalising axpy and dA, dC); unused if !has_g
+    const double* f;          // U_{c-2}: FIN and has_f only
+    EpiArgs ea;               // what the reduction point produces (krylov.cuh)
+    int32_t cg, cf;           // basis columns of g and f (their scales)
+    int32_t has_g, has_f;
     int32_t zc, halo;         // rows per z-chunk; 1 = several GPUs (rows outside the slab come from the owner's HBM)
     int32_t sync_every;       // 0, or a power of two: the CTA's warps re-align every so many rows of the hot loop, which keeps the
                               // sectors two neighbouring warps share (a warp's 256-byte row segment is not sector-aligned) in L1
-    int64_t off_src, off_first;   // offsets of src / first inside the basis allocation (peer addressing)
+    int64_t off_src, off_g, off_f;    // offsets of src / g / f inside the basis allocation (peer addressing)
 };
+// MODE 0: plain product (FIN = 0).  MODE 1: an Arnoldi column.  MODE 2: the extra product (||y||^2).
 template <int ORD, int TS, int MODE, int FIN, int PF, int MINB>
 __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_constant__ Lattice L, const __grid_constant__ Bd2Args A,
                                                                 Reducer rd, SweepCtl* ctl) {
-    constexpr bool NEEDF = FIN || MODE == 1;
+    constexpr int NS = FIN ? 3 : (MODE == 1 ? 2 : 1);      // streams in flight: src [, g [, f]]
     if ((MODE != 0 || FIN) && ctl->brk != 0) return;
-    const double fs = NEEDF ? col_scale(ctl, A.cf) : 1.0;
-    const double hf = FIN ? ctl->scal[A.hsel] : 0.0;
+    const bool has_g = (FIN || MODE == 1) && A.has_g;       // FIN implies has_g (a finalised column has a predecessor)
+    const bool has_f = FIN && A.has_f;
+    const double sg = has_g ? col_scale(ctl, A.cg) : 0.0;
+    const double sf = has_f ? col_scale(ctl, A.cf) : 0.0;
+    const double h1 = FIN ? ctl->scal[SC_H1] : 0.0, h2 = FIN ? ctl->scal[SC_H2] : 0.0;
     const double* __restrict__ src = A.src;
-    const double* __restrict__ first = A.first;
+    const double* __restrict__ gp = A.g;
+    const double* __restrict__ fp_ = A.f;
     double* __restrict__ xout = A.xout;
     double* __restrict__ y = A.y;
     const int32_t Bx = L.B[0], nz = L.nz;
@@ -286,8 +299,8 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
     // y-tables of the chunk, staged once per work item: ztab[k][j] = T_k[z0 - 1 + j].  (Read per row straight from global
     // memory they missed the streaming-thrashed L1 half of the time, profiles/r1_summary.md.)
     __shared__ double ztab[4][BD2_ZT + 2];
-    DD accx, accd;
-    accx.hi = accx.lo = accd.hi = accd.lo = 0.0;
+    DD accx, accA, accB, accC;
+    accx.hi = accx.lo = accA.hi = accA.lo = accB.hi = accB.lo = accC.hi = accC.lo = 0.0;
     for (int64_t item = blockIdx.x; item < ncb * nzc; item += gridDim.x) {
         const int32_t z0 = L.zlo + (int32_t)(item / ncb) * zc;
         const int32_t z1 = min(z0 + zc, L.zhi);
@@ -320,120 +333,93 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                 acn[k] = dir == BD_XP ? (okl ? __ldg(L.tab[k] + c - 1) : 0.0) : dir == BD_XM ? (okr ? __ldg(L.tab[k] + c + 1) : 0.0) : adc[k];
             }
         }
-        // raw operand(s) of row zz (0 <= zz < nz) of this lane's column: from this rank's slab, or (several GPUs) from the
-        // owner's basis over NVLink -- the owner's T and v_first are complete: the reduction exchange of the kernel that
-        // wrote them has passed on every rank (krylov.cuh, grid_reduce)
-        auto load_raw = [&](int32_t zz, double& t, double& fr) {
-            fr = 0.0;
+        // raw operands of row zz (0 <= zz < nz) of this lane's column: from this rank's slab, or (several GPUs) from the
+        // owner's basis over NVLink -- the owner's scratch column and basis vectors are complete: the reduction exchange of
+        // the kernel that wrote them has passed on every rank (krylov.cuh, grid_reduce)
+        auto load_raw = [&](int32_t zz, double& t, double& gr, double& fr) {
+            gr = 0.0; fr = 0.0;
             if (!A.halo || (zz >= L.zlo && zz < L.zhi)) {
                 const uint32_t e = (uint32_t)(c + Bx * (zz - L.zlo));
                 t = src[e];
-                if (NEEDF) fr = first[e];
+                if (NS >= 2 && has_g) gr = gp[e];
+                if (NS >= 3 && has_f) fr = fp_[e];
             } else {
                 int r = 0;
                 while (zz >= L.zb[r + 1]) ++r;
                 const int64_t e = c + (int64_t)Bx * (zz - L.zb[r]);
                 t = __ldcg(dp->V[r] + A.off_src + e);
-                if (NEEDF) fr = __ldcg(dp->V[r] + A.off_first + e);
+                if (NS >= 2 && has_g) gr = __ldcg(dp->V[r] + A.off_g + e);
+                if (NS >= 3 && has_f) fr = __ldcg(dp->V[r] + A.off_f + e);
             }
         };
-        // x = the operand finalised (FIN), f = v_first
-        auto finish = [&](double t, double fr, double& xv, double& fv) {
-            fv = NEEDF ? __dmul_rn(fs, fr) : 0.0;
-            xv = FIN ? fma(-hf, fv, t) : t;
+        // x = the operand (finalised if FIN), gv = v_g = sg * g
+        auto finish = [&](double t, double gr, double fr, double& xv, double& gv) {
+            gv = (NS >= 2) ? __dmul_rn(sg, gr) : 0.0;
+            if (FIN) {
+                double inner = __dmul_rn(sg, t);
+                if (has_f) inner = fma(-h1, __dmul_rn(sf, fr), inner);
+                xv = fma(-h2, gv, inner);
+            } else {
+                xv = t;
+            }
         };
         const int32_t zlast = min(z1, nz - 1);                  // last row whose operand this work item needs
         uint32_t i = (uint32_t)(c + Bx * (z0 - L.zlo));
-        double xm = 0.0, x0, f0;
+        double xm = 0.0, x0, g0;
         {
-            double t, fr, fdummy;
-            if (z0 >= 1) { load_raw(z0 - 1, t, fr); finish(t, fr, xm, fdummy); }
-            load_raw(z0, t, fr);
-            finish(t, fr, x0, f0);
+            double t, gr, fr, gdummy;
+            if (z0 >= 1) { load_raw(z0 - 1, t, gr, fr); finish(t, gr, fr, xm, gdummy); }
+            load_raw(z0, t, gr, fr);
+            finish(t, gr, fr, x0, g0);
         }
         // software pipeline: slot u holds the raw operands of row z+1 of the row z that will be evaluated DEPTH rows after
         // the slot was filled, so a row never waits for its own first-touch loads
         const int32_t zloc = min(zlast, L.zhi - 1);             // ... and the last such row that is local
-#if KFSP_BD2_RING
         constexpr int DEPTH = BD2_DEPTH;
-        constexpr int SLOT = (NEEDF ? 2 : 1) * VEC_THREADS;     // doubles per ring slot
+        constexpr int SLOT = NS * VEC_THREADS;                  // doubles per ring slot
         __shared__ double ring[DEPTH * SLOT];
         double* const rbase = ring + threadIdx.x;
         int rs = 0;                                             // slot of the row about to be consumed
         cp_async_wait<0>();                                     // (nothing of the previous work item is still landing)
+        auto fill_async = [&](double* slot, uint32_t e) {
+            cp_async8(slot, src + e);
+            if (NS >= 2 && has_g) cp_async8(slot + VEC_THREADS, gp + e);
+            if (NS >= 3 && has_f) cp_async8(slot + 2 * VEC_THREADS, fp_ + e);
+        };
+        auto fill_general = [&](double* slot, int32_t zn) {
+            double t = 0.0, gr = 0.0, fr = 0.0;
+            if (zn <= zlast) load_raw(zn, t, gr, fr);
+            slot[0] = t;
+            if (NS >= 2) slot[VEC_THREADS] = gr;
+            if (NS >= 3) slot[2 * VEC_THREADS] = fr;
+        };
 #pragma unroll
         for (int u = 0; u < DEPTH; ++u) {
             const int32_t zn = z0 + 1 + u;
-            double* slot = rbase + u * SLOT;
-            if (zn <= zloc) {
-                const uint32_t e = i + (uint32_t)(Bx * (1 + u));
-                cp_async8(slot, src + e);
-                if (NEEDF) cp_async8(slot + VEC_THREADS, first + e);
-            } else {
-                double t = 0.0, fr = 0.0;
-                if (zn <= zlast) load_raw(zn, t, fr);
-                slot[0] = t;
-                if (NEEDF) slot[VEC_THREADS] = fr;
-            }
+            if (zn <= zloc) fill_async(rbase + u * SLOT, i + (uint32_t)(Bx * (1 + u)));
+            else fill_general(rbase + u * SLOT, zn);
             cp_async_commit();
         }
-#else
-        constexpr int DEPTH = PF;
-        double rt[PF], rf[PF];
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            rt[u] = 0.0; rf[u] = 0.0;
-            if (z0 + 1 + u <= zlast) load_raw(z0 + 1 + u, rt[u], rf[u]);
-        }
-#endif
-        // one row: GEN = false is the hot path (z >= 1, z + 1 < nz, the refill row is local and needed)
-        auto do_row = [&](const int32_t z, const int u, const bool gen) {
-            double xp, fp;
+        // one row: gen = false is the hot path (z >= 1, z + 1 < nz, the refill row is local and needed)
+        auto do_row = [&](const int32_t z, const bool gen) {
+            double xp, gn;
             const bool yp_ok = gen ? z >= 1 : true, ym_ok = gen ? z + 1 < nz : true;
             const int32_t zn = z + 1 + DEPTH;                   // the row the freed slot is refilled with
-#if KFSP_BD2_RING
             {
-                (void)u;
                 double* slot = rbase + rs * SLOT;
                 cp_async_wait<DEPTH - 1>();                     // this thread's copy of row z+1 has landed
-                finish(slot[0], NEEDF ? slot[VEC_THREADS] : 0.0, xp, fp);
+                finish(slot[0], NS >= 2 ? slot[VEC_THREADS] : 0.0, NS >= 3 ? slot[2 * VEC_THREADS] : 0.0, xp, gn);
                 const uint32_t e = i + (uint32_t)(Bx * (1 + DEPTH));
-                if (!gen) {
-                    cp_async8(slot, src + e);
-                    if (NEEDF) cp_async8(slot + VEC_THREADS, first + e);
-                } else if (zn <= zloc) {
-                    cp_async8(slot, src + e);
-                    if (NEEDF) cp_async8(slot + VEC_THREADS, first + e);
-                } else {
-                    double t = 0.0, fr = 0.0;
-                    if (zn <= zlast) load_raw(zn, t, fr);
-                    slot[0] = t;
-                    if (NEEDF) slot[VEC_THREADS] = fr;
-                }
+                if (!gen || zn <= zloc) fill_async(slot, e);
+                else fill_general(slot, zn);
                 cp_async_commit();
                 rs = rs + 1 == DEPTH ? 0 : rs + 1;
-                if (!gen && NEEDF && zn + BD2_L2AHEAD <= zloc) {  // two-stream variants also pull rows further ahead into L2
+                if (!gen && NS >= 2 && zn + BD2_L2AHEAD <= zloc) {  // multi-stream variants also pull rows further ahead into L2
                     lattice_prefetch<1>(src + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
-                    lattice_prefetch<1>(first + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
+                    if (has_g) lattice_prefetch<1>(gp + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
+                    if (NS >= 3 && has_f) lattice_prefetch<1>(fp_ + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
                 }
             }
-#else
-            finish(rt[u], rf[u], xp, fp);
-            {   // refill the slot with row z + 1 + PF; two-stream variants also pull rows further ahead into L2
-                if (!gen) {
-                    const uint32_t e = i + (uint32_t)(Bx * (1 + PF));
-                    rt[u] = src[e];
-                    if (NEEDF) rf[u] = first[e];
-                    if (NEEDF && zn + BD2_L2AHEAD <= zloc) {
-                        lattice_prefetch<1>(src + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
-                        lattice_prefetch<1>(first + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
-                    }
-                } else {
-                    rt[u] = 0.0; rf[u] = 0.0;
-                    if (zn <= zlast) load_raw(zn, rt[u], rf[u]);
-                }
-            }
-#endif
             const double xl = __shfl_up_sync(0xffffffffu, x0, 1);
             const double xr = __shfl_down_sync(0xffffffffu, x0, 1);
             double ad[4], ac[4];
@@ -464,10 +450,13 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
             if (live) {
                 if (FIN) { __stcs(xout + i, x0); dd_add_prod(accx, x0, x0); }
                 __stcs(y + i, sv);
-                if (MODE == 1) dd_add_prod(accd, f0, sv);
-                if (MODE == 2) dd_add_prod(accd, sv, sv);
+                if (MODE == 1) {
+                    dd_add_prod(accB, x0, sv);
+                    if (has_g) { dd_add_prod(accA, g0, sv); dd_add_prod(accC, x0, g0); }
+                }
+                if (MODE == 2) dd_add_prod(accB, sv, sv);
             }
-            xm = x0; x0 = xp; f0 = fp;
+            xm = x0; x0 = xp; g0 = gn;
             i += (uint32_t)Bx;
         };
         // the hot path runs in whole groups of PF rows: they need z >= 1 and a refill row z + 1 + DEPTH <= zloc (local, needed)
@@ -475,31 +464,29 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
         if (z0 == 0) {                                          // the box boundary row goes through the general path
 #pragma unroll
             for (int u = 0; u < PF; ++u)
-                if (z + u < z1) do_row(z + u, u, true);
+                if (z + u < z1) do_row(z + u, true);
             z += PF;
         }
         for (; z + PF - 1 + 1 + DEPTH <= zloc && z + PF <= z1; z += PF) {
             if (A.sync_every && ((z - z0) & (A.sync_every - 1)) == 0) __syncthreads();
 #pragma unroll
-            for (int u = 0; u < PF; ++u) do_row(z + u, u, false);
+            for (int u = 0; u < PF; ++u) do_row(z + u, false);
         }
         for (; z < z1; z += PF) {
 #pragma unroll
             for (int u = 0; u < PF; ++u)
-                if (z + u < z1) do_row(z + u, u, true);       // uniform over the CTA: the shuffles are convergent
+                if (z + u < z1) do_row(z + u, true);           // uniform over the CTA: the shuffles are convergent
         }
     }
-    if (MODE == 0 && !FIN) return;
-    if (FIN) {
-        DD v[2] = {accx, accd};
-        double tot[2];
-        if (grid_reduce<2>(v, tot, rd) && threadIdx.x == 0)
-            reduce_epilogue(MODE == 1 ? RK_FUSED_DOT : RK_FUSED_NRM, tot, ctl, A.h_out, A.hn_out, A.break_tol, A.cx);
+    if (MODE == 0) return;
+    if (MODE == 1) {
+        DD v[4] = {accx, accA, accB, accC};
+        double tot[4];
+        if (grid_reduce<4>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(A.ea, tot, ctl);
     } else {
-        DD v[1] = {accd};
-        double tot[1];
-        if (grid_reduce<1>(v, tot, rd) && threadIdx.x == 0)
-            reduce_epilogue(MODE == 1 ? RK_SPMV_DOT : RK_SPMV_NRM, tot, ctl, A.h_out, nullptr, 0.0, A.cx);
+        DD v[2] = {accx, accB};
+        double tot[2];
+        if (grid_reduce<2>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(A.ea, tot, ctl);
     }
 }
 

@@ -322,11 +322,13 @@ class KrylovFspHandle:
                     "scale_copy", "expm")
 
     def profile(self):
-        """Device seconds and launches of the last solve by kernel class (set_profiling(True) before the solve)."""
+        """Device seconds, launches and algorithmic bytes per state (summed over the launches) of the last solve by
+        kernel class (set_profiling(True) before the solve)."""
         sec = (C.c_double * 12)()
         cnt = (C.c_int64 * 12)()
-        check(lib().kfsp_profile_get(self._h, sec, cnt))
-        return {name: (sec[i], cnt[i]) for i, name in enumerate(self.PROF_CLASSES)}
+        bps = (C.c_int64 * 12)()
+        check(lib().kfsp_profile_get(self._h, sec, cnt, bps))
+        return {name: (sec[i], cnt[i], bps[i]) for i, name in enumerate(self.PROF_CLASSES)}
 
     def set_profiling(self, on=True):
         check(lib().kfsp_set_profiling(self._h, 1 if on else 0))

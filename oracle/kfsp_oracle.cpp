@@ -836,6 +836,16 @@ static void fmatvec(Fsp& f, const double* x, double* y) {
 // scales (v_j = cs[j]*U_j, cs[0] = 1 from the caller), H the Hessenberg matrix (leading dimension mh).
 // Returns the happy-breakdown column (1-based, KrylovSolver.f90:249-256) or 0; *nmult = SpMVs the
 // reference would have counted.
+//
+// One reduction point per column.  With x = U_c, g = v_{c-1} (the previous basis vector) and Y' = A U_c, the pass that
+// forms Y' also accumulates, each in double-double,
+//     dA = <g, Y'>,   dB = <U_c, Y'>,   dC = <U_c, g>,   ssq = <U_c, U_c>
+// and both coefficients of the IOP window follow from them with cs = 1/sqrt(ssq):
+//     H(J-1,J) = h1 = cs*dA                          ( = <v_{J-1}, A v_J>,            KrylovSolver.f90:243 )
+//     H(J,J)   = h2 = cs*(cs*dB) - h1*(cs*dC)        ( = <v_J, A v_J - h1 v_{J-1}>,   the second DDOT of the window )
+// The second line is the reference's DDOT of v_J with the already updated w = A v_J - h1 v_{J-1}, expanded by linearity;
+// the inner products being accurate to double-double, it differs from the dot product of the rounded w by less than
+// the rounding of w itself.  The next column is then U_{c+1} = (cs*Y' - h1*g) - h2*(cs*U_c), element by element.
 static int canonical_sweep(Fsp& f, long N, double* V, double* cs, double* H, int mh, int jold, int m, double break_tol,
                            double* avnorm, int* nmult) {
     int nm = 0;
@@ -844,19 +854,23 @@ static int canonical_sweep(Fsp& f, long N, double* V, double* cs, double* H, int
         const double* x = V + (size_t)c * N;
         double* y = V + (size_t)J * N;
         fmatvec(f, x, y); ++nm;                                             // Y' = A U_c, un-normalised
-        double h;
+        const double sc = cs[c];
+        const double dB = r_dot(N, x, y);
+        double h1 = 0.0, h2;
         if (J >= 2) {
-            const double* fi = V + (size_t)(c - 1) * N;
-            const double fs = cs[c - 1];
-            const double h1 = cs[c] * r_dot_scaled(N, fs, fi, y);           // H(J-1,J) = <v_{J-1}, A v_J>
+            const double* g = V + (size_t)(c - 1) * N;
+            const double gs = cs[c - 1];
+            const double dA = r_dot_scaled(N, gs, g, y);
+            const double dC = r_dot_scaled(N, gs, g, x);
+            h1 = sc * dA;                                                   // H(J-1,J)
             H[(size_t)(J - 1) * mh + (J - 2)] = h1;
-            for (long i = 0; i < N; ++i) y[i] = std::fma(-h1, fs * fi[i], cs[c] * y[i]);
-            h = r_dot_scaled(N, cs[c], x, y);                               // H(J,J)
+            h2 = std::fma(-h1, sc * dC, sc * (sc * dB));                    // H(J,J)
+            for (long i = 0; i < N; ++i) y[i] = std::fma(-h2, sc * x[i], std::fma(-h1, gs * g[i], sc * y[i]));
         } else {
-            h = cs[c] * r_dot_scaled(N, cs[c], x, y);                       // H(1,1); cs[0] = 1: y is A v_1 itself
+            h2 = sc * (sc * dB);                                            // H(1,1)
+            for (long i = 0; i < N; ++i) y[i] = std::fma(-h2, sc * x[i], sc * y[i]);
         }
-        H[(size_t)(J - 1) * mh + (J - 1)] = h;
-        for (long i = 0; i < N; ++i) y[i] = std::fma(-h, cs[c] * x[i], y[i]);
+        H[(size_t)(J - 1) * mh + (J - 1)] = h2;
         const double hn = r_nrm2(N, y);                                     // HJ1J
         if (hn <= break_tol) { *nmult = nm; return J; }
         H[(size_t)(J - 1) * mh + J] = hn;
