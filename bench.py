@@ -287,7 +287,10 @@ def main():
     check(L.kfsp_device_upload(h._h, p0_dev, C.c_void_p(p0_h.data_ptr() + 8 * lo), 8 * nloc))
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
-    h.set_profiling(True)
+    # Timed solves: the lattice variant's Arnoldi sweep is nothing but SpMV-class launches (one per column), so ONE event pair
+    # per sweep times them without putting anything between the launches (programmatic dependent launch stays effective);
+    # the explicit variant interleaves k_finalize and k_spmv, so its launches are bracketed one by one.
+    h.set_profiling(1 if args.spmv_variant == 1 else 2)
 
     def resident_step(hh, pdev, cnt):
         check(L.kfsp_fsp_set_vector_device(hh._h, pdev, cnt))
@@ -337,7 +340,7 @@ def main():
         """the generator SpMV (all its fused variants) against the HBM roofline: bytes the timed launches must move / their time"""
         tot_b = tot_b16 = tot_s = 0.0
         cnt = 0
-        for name in SPMV_CLASSES:
+        for name in SPMV_CLASSES + (("sweep",) if var == 1 else ()):
             sec, c, b = res["classes"].get(name, (0.0, 0, 0))
             tot_b += b * rows
             tot_b16 += SPMV_ONLY_BYTES[var] * rows * c
@@ -422,13 +425,24 @@ def main():
                 "spmv_only_bytes_per_state": SPMV_ONLY_BYTES[variant],
                 "achieved_spmv_only_bytes": tot_b16 / tot_s / 1e9 if tot_s > 0 else 0.0,
                 "frac_spmv_only_bytes": tot_b16 / tot_s / 1e9 / peak if tot_s > 0 else 0.0,
+                "timing": "CUDA events on the solver's stream inside the timed solves: " + ("one pair around each Arnoldi sweep, which in this "
+                          "variant consists of the column launches of this kernel only (avg = sweep time / launches, gaps between launches included)"
+                          if variant == 1 else "one pair around every launch"),
                 "note": "achieved = bytes the timed SpMV launches must move (operand, result, and the operands/results of the "
                         "vector work fused into the same pass: DESIGN.md section 4, per class in `kernels`) / their CUDA-event time; "
                         "*_spmv_only_bytes counts FMATVEC's own bytes alone (SURVEY 8d) for the same launches",
                 "avg_launch_ms": 1e3 * tot_s / max(spmv_launches, 1),
                 "launches_timed": spmv_launches, "share_of_step": tot_s / res["dev_s"] if res["dev_s"] > 0 else None,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "plain_spmv": plain}
-    kernels = kernel_table(res, variant, nloc)
+    if variant == 1:                                      # one more solve with every launch bracketed: the per-class table
+        h.set_profiling(2)
+        saved_steps, saved_warm = args.steps, args.warmup
+        args.steps, args.warmup = 1, 0
+        kernels = kernel_table(timed_solves(h, p0_dev, nloc), variant, nloc)
+        args.steps, args.warmup = saved_steps, saved_warm
+        h.set_profiling(0)
+    else:
+        kernels = kernel_table(res, variant, nloc)
 
     # ---- companion: the same resident solves on the EXPLICIT gather-ELL matrix (the reference's data model), so that one
     # line shows both generator-SpMV kernels against the HBM roofline; results of the two variants are bit-identical
@@ -446,7 +460,7 @@ def main():
         p0_dev0 = C.c_void_p()
         check(L.kfsp_device_alloc(h0._h, 8 * (hi0 - lo0), C.byref(p0_dev0)))
         check(L.kfsp_device_upload(h0._h, p0_dev0, C.c_void_p(p0_h.data_ptr() + 8 * lo0), 8 * (hi0 - lo0)))
-        h0.set_profiling(True)
+        h0.set_profiling(2)
         cres = timed_solves(h0, p0_dev0, hi0 - lo0)
         c_dev = allmax(cres["dev_s"])
         cb, cb16, cs_, cl = spmv_roofline(cres, 0, hi0 - lo0)

@@ -228,9 +228,11 @@ int kfsp_device_upload(kfsp_handle h, void* dst_device, const void* src_host, in
 int kfsp_device_download(kfsp_handle h, void* dst_host, const void* src_device, int64_t bytes);
 int kfsp_device_vector(kfsp_handle h, double** fsp_vector_device);
 int kfsp_flush_l2(kfsp_handle h);
-/* Bracket every generator-SpMV launch of the next solves with CUDA events on the solver's stream
- * (no synchronisation inside the solve); the sum is reported in kfsp_stats.spmv_seconds. */
-int kfsp_set_profiling(kfsp_handle h, int32_t on);
+/* CUDA events on the solver's stream around the launches of the time-stepping loop of the next solves (no synchronisation
+ * inside the solve).  level 0: off; 1: one event pair around each Arnoldi sweep (class KFSP_PROF_SWEEP: nothing is recorded
+ * between the sweep's launches); 2: one pair around every launch (per-class table).  The generator SpMV's share is reported
+ * in kfsp_stats.spmv_seconds / spmv_launches, everything by class through kfsp_profile_get. */
+int kfsp_set_profiling(kfsp_handle h, int32_t level);
 /* FSP%VECTOR(1:n) = src (device pointer), rest zero: device-to-device reset between benchmark steps */
 int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src_device, int64_t n);
 int kfsp_launch_count(kfsp_handle h, int64_t* n);
@@ -243,6 +245,7 @@ int kfsp_launch_count(kfsp_handle h, int64_t* n);
 enum {
     KFSP_PROF_SPMV_PLAIN = 0, KFSP_PROF_SPMV_DOT = 1, KFSP_PROF_SPMV_NRM = 2, KFSP_PROF_SPMV_FIN_DOT = 3, KFSP_PROF_SPMV_FIN_NRM = 4,
     KFSP_PROF_AXPY_DOT = 5, KFSP_PROF_AXPY_NRM = 6, KFSP_PROF_COMBINE = 7, KFSP_PROF_SCALE_COPY = 8, KFSP_PROF_EXPM = 9,
+    KFSP_PROF_SWEEP = 10,      /* profiling level 1: one event pair around each Arnoldi sweep (all its launches together) */
     KFSP_PROF_CLASSES = 12
 };
 int kfsp_profile_get(kfsp_handle h, double seconds[KFSP_PROF_CLASSES], int64_t launches[KFSP_PROF_CLASSES],

@@ -51,6 +51,9 @@ struct Engine {
     DeviceModel h_dm{};               // host mirror of *d_model (table pointers, stoichiometry)
     int box_tune = 0;                 // KFSP_BOX_TUNE: rows per batch / CTAs per SM of the lattice SpMV (A/B)
     int bd2_zc = 0;                   // KFSP_BD2_ZC: forced rows per z-chunk of the stencil kernel (0 = automatic)
+    int bd2_ahead = 0;                // KFSP_BD2_AHEAD: rows beyond the ring prefetched into L2 by the multi-stream stencil launches.  Off:
+                                      // with the cp.async ring 6 rows deep it only adds traffic (ncu: 2.86 GB instead of 2.45 GB of
+                                      // DRAM reads per launch at 1e8 states, 0.85 instead of 0.73 ms; profiles/r2_summary.md)
     int bd2_sync = 8;                 // KFSP_BD2_SYNC: the stencil kernel's CTAs re-align their warps every so many rows (power of two; 0 = never)
 
     // state space
@@ -94,7 +97,10 @@ struct Engine {
     double phase_s[8] = {0};          // host wall clock per phase of the last solve: 0 sweep+Pade, 1 combine/norms, 2 expand, 3 drop
     int64_t launches = 0;
     std::vector<kfsp_trace_row> trace;
-    bool profile_spmv = false;
+    bool profile_spmv = false;        // kfsp_set_profiling: CUDA events around the launches of the time-stepping loop
+    int profile_level = 0;            // 1: one event pair per Arnoldi sweep (class SWEEP; nothing between the sweep's launches, so
+                                      //    programmatic dependent launch stays effective), 2: one pair per launch (per-class table)
+    bool in_sweep = false;
     double spmv_seconds = 0.0;
     int64_t spmv_timed = 0;
     int64_t spmv_by_mode[3] = {0, 0, 0};    // generator SpMV launches of the last solve: plain, dot-fused, norm-fused
@@ -106,19 +112,46 @@ struct Engine {
     double prof_sec[KFSP_PROF_CLASSES] = {0};
     int64_t prof_cnt[KFSP_PROF_CLASSES] = {0};
     int64_t prof_bps[KFSP_PROF_CLASSES] = {0};   // algorithmic bytes per state, summed over the launches of the class
-    std::vector<int> ev_bps;
+    std::vector<int> ev_bps, ev_n, ev_nspmv;
     // kernel classes of the time-stepping loop (kfsp_profile_get): CUDA events on the solver's stream around every launch
     // bps: bytes per state the launch must move (operands read once + results written once)
     int prof_begin(int cls, int bps = 0) {
+        if (in_sweep && profile_level == 1) {              // inside a sweep bracket: only count
+            sweep_launches += 1;
+            sweep_bps += bps;
+            if (cls <= KFSP_PROF_SPMV_FIN_NRM) sweep_spmv += 1;
+            return KFSP_OK;
+        }
         ev_cur = -1;
         if (!profile_spmv || ev_used + 2 > ev_pool.size()) return KFSP_OK;
         KFSP_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
         ev_cls[ev_used / 2] = cls;
         ev_bps[ev_used / 2] = bps;
+        ev_n[ev_used / 2] = 1;
+        ev_nspmv[ev_used / 2] = cls <= KFSP_PROF_SPMV_FIN_NRM ? 1 : 0;
         ev_cur = (long)ev_used;
         return KFSP_OK;
     }
+    int64_t sweep_launches = 0, sweep_bps = 0, sweep_spmv = 0;
+    int sweep_begin() {
+        if (!profile_spmv || profile_level != 1) return KFSP_OK;
+        KFSP_TRY(prof_begin(KFSP_PROF_SWEEP, 0));
+        in_sweep = true;
+        sweep_launches = sweep_bps = sweep_spmv = 0;
+        return KFSP_OK;
+    }
+    int sweep_end() {
+        if (!in_sweep) return KFSP_OK;
+        in_sweep = false;
+        if (ev_cur >= 0) {
+            ev_bps[ev_cur / 2] = (int)sweep_bps;
+            ev_n[ev_cur / 2] = (int)sweep_launches;
+            ev_nspmv[ev_cur / 2] = (int)sweep_spmv;
+        }
+        return prof_end();
+    }
     int prof_end() {
+        if (in_sweep && profile_level == 1) return KFSP_OK;
         if (ev_cur < 0) return KFSP_OK;
         KFSP_CUDA(cudaEventRecord(ev_pool[ev_cur + 1], stream));
         ev_used += 2;
@@ -133,6 +166,8 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_SPMV_TUNE")) spmv_tune = std::atoi(ev);
         if (const char* ev = std::getenv("KFSP_BOX_TUNE")) box_tune = std::atoi(ev);
         if (const char* ev = std::getenv("KFSP_BD2_ZC")) bd2_zc = std::atoi(ev);
+        if (const char* ev = std::getenv("KFSP_PDL")) use_pdl = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_BD2_AHEAD")) bd2_ahead = std::min(std::max(std::atoi(ev), 0), BD2_L2AHEAD);
         if (const char* ev = std::getenv("KFSP_BD2_SYNC")) { bd2_sync = std::atoi(ev); if (bd2_sync & (bd2_sync - 1)) bd2_sync = 0; }
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
         if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
@@ -231,6 +266,26 @@ struct Engine {
         kernel<<<(grid), (block), (smem), stream>>>(__VA_ARGS__); \
         KFSP_TRY(check_launch());                              \
     } while (0)
+
+    // Launch with programmatic stream serialization (KFSP_PDL=0 switches it off): the kernel may be scheduled while its
+    // predecessor drains; it calls pdl_wait() before touching anything the predecessor wrote (krylov.cuh).
+    bool use_pdl = true;
+    template <typename... KArgs, typename... Args>
+    int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, Args&&... args) {
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)grid, 1, 1);
+        cfg.blockDim = dim3((unsigned)block, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        KFSP_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+        return check_launch();
+    }
 
     int ensure_scratch(size_t bytes) {
         if (bytes <= scratch_bytes) return KFSP_OK;
@@ -823,18 +878,21 @@ struct Engine {
         const Reducer r = MODE != 0 ? next_rd() : rd;
         Reducer r2 = r;
         if (halo == 2 && !r2.peers) r2.peers = dist.d_peers;     // the peer table is also the halo address book
-        kern<<<gr, VEC_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, x, y, g, r2, d_ctl, ea, cg, dist.halo, n,
-                                            (int64_t)(d_V ? x - d_V : 0));
-        KFSP_TRY(check_launch());
+        KFSP_TRY(launch_pdl(kern, gr, VEC_THREADS, 0, n, ld, R, (const int32_t*)d_pred, (const double*)d_coef, (const double*)d_diag, x, y, g, r2, d_ctl, ea, cg,
+                            (const double*)dist.halo, n, (int64_t)(d_V ? x - d_V : 0)));
         if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(ea, MODE == 1 ? 4 : 2));
         return prof_end();
     }
-    int set_profiling(bool on) {
+    int set_profiling(int level) {
+        const bool on = level != 0;
+        profile_level = level;
         profile_spmv = on;
         if (on && ev_pool.empty()) {
             ev_pool.resize(2 * 8192);
             ev_cls.assign(8192, 0);
             ev_bps.assign(8192, 0);
+            ev_n.assign(8192, 1);
+            ev_nspmv.assign(8192, 0);
             for (auto& e : ev_pool) KFSP_CUDA(cudaEventCreate(&e));
         }
         ev_used = 0;
@@ -849,11 +907,14 @@ struct Engine {
             KFSP_CUDA(cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]));
             const int cls = ev_cls[i / 2];
             prof_sec[cls] += 1e-3 * ms;
-            prof_cnt[cls] += 1;
+            prof_cnt[cls] += ev_n[i / 2];
             prof_bps[cls] += ev_bps[i / 2];
             if (cls <= KFSP_PROF_SPMV_FIN_NRM) {                 // the generator SpMV in all its variants
                 spmv_seconds += 1e-3 * ms;
                 spmv_timed += 1;
+            } else if (cls == KFSP_PROF_SWEEP && ev_nspmv[i / 2] == ev_n[i / 2]) {   // a sweep of SpMV-class launches only
+                spmv_seconds += 1e-3 * ms;
+                spmv_timed += ev_n[i / 2];
             }
         }
         ev_used = 0;
@@ -954,7 +1015,12 @@ struct Engine {
             kern<<<1, SWEEP_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, d_V, d_H, LDH, jold, m, d_ctl, opt.break_tol);
             return check_launch();
         }
-        if (box && box_tune < 10 && lattice_bd2_order(lat) >= 0) return arnoldi_fused(jold, m);
+        KFSP_TRY(sweep_begin());
+        const int st = (box && box_tune < 10 && lattice_bd2_order(lat) >= 0) ? arnoldi_fused(jold, m) : arnoldi_unfused(jold, m);
+        KFSP_TRY(sweep_end());
+        return st;
+    }
+    int arnoldi_unfused(int jold, int m) {
         // Two launches per column: finalise U_c (the two axpys of the previous column + its norm), then the generator product
         // with the three inner products of the window.  Column 0 and, on a resumed sweep (KrylovSolver.f90:400-433), column
         // jold-1 are complete already.
@@ -968,7 +1034,7 @@ struct Engine {
                 EpiArgs ef = epi_none();
                 ef.kind = RK_FIN_NRM; ef.column = c; ef.fin = 1; ef.break_tol = opt.break_tol; ef.hn_out = d_H + (size_t)(c - 1) * LDH + c;   // H(c+1,c)
                 KFSP_TRY(prof_begin(KFSP_PROF_AXPY_NRM, 24 + (c >= 2 ? 8 : 0)));
-                KFSP_LAUNCH(k_finalize, wave_grid((const void*)k_finalize, n), VEC_THREADS, 0, n, vg, vf, vc, c >= 2 ? 1 : 0, next_rd(), d_ctl, ef, c - 1, c - 2);
+                KFSP_TRY(launch_pdl(k_finalize, wave_grid((const void*)k_finalize, n), VEC_THREADS, 0, n, vg, vf, vc, c >= 2 ? 1 : 0, next_rd(), d_ctl, ef, c - 1, c - 2));
                 KFSP_TRY(dist_finalize(ef, 1));
                 KFSP_TRY(prof_end());
             }
@@ -1061,7 +1127,7 @@ struct Engine {
     int dist_barrier() {
         if (!(dist.p2p && dist.p2p_halo)) return KFSP_OK;       // the NCCL exchange step is ordered by NCCL itself
         if (!dist.p2p_red) return KFSP_ERR_UNSUPPORTED;         // flags are shared with the reduction exchange
-        KFSP_LAUNCH(k_dist_barrier, 1, 32, 0, (const DistPeers*)dist.d_peers, ++dist.seq);
+        KFSP_TRY(launch_pdl(k_dist_barrier, 1, 32, 0, (const DistPeers*)dist.d_peers, (unsigned long long)(++dist.seq)));
         return KFSP_OK;
     }
     // Map every peer's basis and exchange area into this process (cudaIpc over NVLink).  Collective.
@@ -1352,14 +1418,14 @@ struct Engine {
         a.zc = zc;
         a.halo = halo ? 1 : 0;
         a.sync_every = bd2_sync;
+        a.l2_ahead = bd2_ahead;
         a.off_g = (d_V && a.g) ? (int64_t)(a.g - d_V) : 0;
         a.off_f = (d_V && a.f) ? (int64_t)(a.f - d_V) : 0;
         if (!a.g) { a.g = a.src; a.has_g = 0; }
         if (!a.f) { a.f = a.g; a.has_f = 0; }
         a.ea.has_g = a.has_g;
         a.off_src = d_V ? (int64_t)(a.src - d_V) : 0;
-        kb<<<g, VEC_THREADS, 0, stream>>>(lat, a, r, d_ctl);
-        return check_launch();
+        return launch_pdl(kb, g, VEC_THREADS, 0, lat, a, r, d_ctl);
     }
     template <int MODE>
     int spmv_box(const double* x, double* y, const double* g, const EpiArgs& ea, int cg) {
@@ -1395,8 +1461,7 @@ struct Engine {
         const int wave = wave_grid((const void*)kern, (int64_t)1 << 40);
         int zc, gsz;
         lattice_chunking(wave, ncb, &zc, &gsz);
-        kern<<<gsz, VEC_THREADS, 0, stream>>>(lat, zc, cbw, x, y, g ? g : x, r2, d_ctl, ea, cg, (int64_t)(d_V ? x - d_V : 0));
-        return check_launch();
+        return launch_pdl(kern, gsz, VEC_THREADS, 0, lat, zc, cbw, x, y, g ? g : x, r2, d_ctl, ea, cg, (int64_t)(d_V ? x - d_V : 0));
     }
     // kfsp_fsp_init_box: the projection is the lattice [0,B_1) x ... x [0,B_S) in natural order.
     int fsp_init_box(const int32_t* bounds) {

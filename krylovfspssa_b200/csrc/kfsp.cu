@@ -56,8 +56,7 @@ struct GpuBackend {
         k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.prof_begin(KFSP_PROF_SCALE_COPY, 16));
-        k_scale_copy<<<e.wave_grid((const void*)k_scale_copy, e.n), VEC_THREADS, 0, e.stream>>>(e.n, inv_beta, e.d_w, e.d_V);
-        KFSP_TRY(e.check_launch());
+        KFSP_TRY(e.launch_pdl(k_scale_copy, e.wave_grid((const void*)k_scale_copy, e.n), VEC_THREADS, 0, e.n, inv_beta, (const double*)e.d_w, e.d_V));
         KFSP_TRY(e.dist_barrier());        // neighbours gather column 0 straight from this GPU's HBM
         return e.prof_end();
     }
@@ -77,8 +76,8 @@ struct GpuBackend {
     int combine(int mx, double beta, double* wsum, double* wssq) {
         Tick t(e.phase_s[1]);
         KFSP_TRY(e.prof_begin(KFSP_PROF_COMBINE, 8 * (mx + 1)));
-        k_combine<<<e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.ld, mx, beta, e.d_V, e.d_res->e, e.d_w, e.next_rd(), e.d_ctl);
-        KFSP_TRY(e.check_launch());
+        KFSP_TRY(e.launch_pdl(k_combine, e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.n, e.ld, mx, beta, (const double*)e.d_V, (const double*)e.d_res->e, e.d_w,
+                              e.next_rd(), e.d_ctl));
         { EpiArgs en = Engine::epi_none(); en.kind = RK_NORMS; KFSP_TRY(e.dist_finalize(en, 2)); }
         KFSP_TRY(e.prof_end());
         KFSP_TRY(e.read_ctl());
@@ -703,7 +702,7 @@ int kfsp_flush_l2(kfsp_handle h) {
 int kfsp_set_profiling(kfsp_handle h, int32_t on) {
     if (!h) return KFSP_ERR_ARG;
     cudaSetDevice(h->e.device);
-    return h->e.set_profiling(on != 0);
+    return h->e.set_profiling(on);
 }
 int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src, int64_t cnt) {
     if (!h || !src || cnt < 0) return KFSP_ERR_ARG;

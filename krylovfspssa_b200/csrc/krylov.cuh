@@ -107,20 +107,46 @@ __device__ __forceinline__ DD block_sum(DD v, DD* sh /*>= 32*/) {
     }
     return v;
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may be
+// scheduled while its predecessor in the stream is still running (its CTAs take the SM slots the predecessor's CTAs free);
+// pdl_wait() blocks until the predecessor grid has completed and its writes are visible, so everything that reads a
+// predecessor's output comes after it; pdl_trigger() (issued by every CTA of the predecessor, at its start) allows the
+// dependent launch.  What this hides is the launch latency and the ramp of the next kernel behind the tail of the current
+// one -- on several GPUs that tail is the cross-GPU reduction exchange.  Both are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Grid-wide reduction of NV double-double values.  Returns true in ALL threads of the last block to
 // finish, with the totals rounded once to double in out[].
 template <int NV>
 __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV], const Reducer& rd) {
-    __shared__ DD sh[32];
+    __shared__ DD sh[NV][32];
     __shared__ bool last;
     __shared__ double tot[NV];
     __shared__ double mine[2 * NV];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // block totals of all NV values with one pair of barriers
+    {
+        DD w[NV];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        const DD s = block_sum(v[q], sh);
-        if (threadIdx.x == 0) {
-            rd.partials[(2 * q) * MAX_VEC_BLOCKS + blockIdx.x] = s.hi;
-            rd.partials[(2 * q + 1) * MAX_VEC_BLOCKS + blockIdx.x] = s.lo;
+        for (int q = 0; q < NV; ++q) w[q] = warp_sum(v[q]);
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sh[q][wid] = w[q];
+        }
+        __syncthreads();
+        if (wid == 0) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                DD z; z.hi = 0.0; z.lo = 0.0;
+                DD t = lane < nw ? sh[q][lane] : z;
+                t = warp_sum(t);
+                if (lane == 0) {
+                    rd.partials[(2 * q) * MAX_VEC_BLOCKS + blockIdx.x] = t.hi;
+                    rd.partials[(2 * q + 1) * MAX_VEC_BLOCKS + blockIdx.x] = t.lo;
+                }
+            }
         }
     }
     if (threadIdx.x == 0) {
@@ -131,20 +157,39 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
     __syncthreads();
     if (!last) return false;
     __threadfence();
+    {   // the last block merges the per-block partials (block order does not matter: double-double, rounded once at the end)
+        DD s[NV];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        DD s; s.hi = 0.0; s.lo = 0.0;
+        for (int q = 0; q < NV; ++q) { s[q].hi = 0.0; s[q].lo = 0.0; }
         for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-            DD o;
-            o.hi = __ldcg(&rd.partials[(2 * q) * MAX_VEC_BLOCKS + b]);
-            o.lo = __ldcg(&rd.partials[(2 * q + 1) * MAX_VEC_BLOCKS + b]);
-            dd_merge(s, o);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                DD o;
+                o.hi = __ldcg(&rd.partials[(2 * q) * MAX_VEC_BLOCKS + b]);
+                o.lo = __ldcg(&rd.partials[(2 * q + 1) * MAX_VEC_BLOCKS + b]);
+                dd_merge(s[q], o);
+            }
         }
-        s = block_sum(s, sh);
-        if (threadIdx.x == 0) {
-            if (rd.peers && rd.seq) { mine[2 * q] = s.hi; mine[2 * q + 1] = s.lo; }
-            else if (rd.dist_send) { rd.dist_send[2 * q] = s.hi; rd.dist_send[2 * q + 1] = s.lo; }
-            else tot[q] = __dadd_rn(s.hi, s.lo);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) s[q] = warp_sum(s[q]);
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sh[q][wid] = s[q];
+        }
+        __syncthreads();
+        if (wid == 0) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                DD z; z.hi = 0.0; z.lo = 0.0;
+                DD t = lane < nw ? sh[q][lane] : z;
+                t = warp_sum(t);
+                if (lane == 0) {
+                    if (rd.peers && rd.seq) { mine[2 * q] = t.hi; mine[2 * q + 1] = t.lo; }
+                    else if (rd.dist_send) { rd.dist_send[2 * q] = t.hi; rd.dist_send[2 * q + 1] = t.lo; }
+                    else tot[q] = __dadd_rn(t.hi, t.lo);
+                }
+            }
         }
     }
     if (rd.peers && rd.seq) {
@@ -165,23 +210,23 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
             *((volatile unsigned long long*)(dp->flag[r] + (size_t)slot * P + me)) = rd.seq;
             const volatile unsigned long long* fl = dp->flag[me] + (size_t)slot * P + r;
             const long long t0 = clock64();
+            const volatile int32_t* gone = dp->err;
             while (*fl != rd.seq) {
+                if (*gone & 32) break;                                                    // a peer timed out earlier: do not spin again
                 if (clock64() - t0 > 8000000000LL) { atomicOr(dp->err, 32); break; }      // ~4 s: a rank is gone
             }
             __threadfence_system();
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-                DD s; s.hi = 0.0; s.lo = 0.0;
-                for (int r = 0; r < P; ++r) {
-                    const volatile double* src = dp->part[me] + ((size_t)slot * P + r) * RED_W;
-                    DD o; o.hi = src[2 * q]; o.lo = src[2 * q + 1];
-                    dd_merge(s, o);
-                }
-                tot[q] = __dadd_rn(s.hi, s.lo);
+        if ((int)threadIdx.x < NV) {                        // one thread per value merges the P ranks' partials in rank order
+            const int q = threadIdx.x;
+            DD s; s.hi = 0.0; s.lo = 0.0;
+            for (int r = 0; r < P; ++r) {
+                const volatile double* src = dp->part[me] + ((size_t)slot * P + r) * RED_W;
+                DD o; o.hi = src[2 * q]; o.lo = src[2 * q + 1];
+                dd_merge(s, o);
             }
+            tot[q] = __dadd_rn(s.hi, s.lo);
         }
     } else if (rd.dist_send) {
         return false;                        // uniform: totals are combined across ranks by NCCL first
@@ -291,6 +336,8 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
     // HALO 1: gathered index j >= nloc addresses the halo buffer xh filled by the NCCL exchange step;
     // HALO 2: it is loaded straight from the owning GPU's basis column over NVLink (peer memory).
     const int R = RT > 0 ? RT : R_rt;
+    pdl_trigger();
+    pdl_wait();
     if (MODE != 0 && ctl->brk != 0) return;
     const bool has_g = MODE == 1 && ea.has_g;
     const double gs = has_g ? col_scale(ctl, cg) : 0.0;
@@ -362,6 +409,8 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
 // KrylovSolver.f90:244-258).  The fused lattice path does this inside the next SpMV launch (lattice.cuh).
 __global__ void __launch_bounds__(VEC_THREADS) k_finalize(int64_t n, const double* __restrict__ g, const double* __restrict__ f, double* __restrict__ w,
                                                           int has_f, Reducer rd, SweepCtl* ctl, EpiArgs ea, int cg, int cf) {
+    pdl_trigger();
+    pdl_wait();
     if (ctl->brk != 0) return;
     const double h1 = ctl->scal[SC_H1], h2 = ctl->scal[SC_H2];
     const double sg = col_scale(ctl, cg), sf = has_f ? col_scale(ctl, cf) : 0.0;
@@ -380,6 +429,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_finalize(int64_t n, const doubl
 
 // V(:,1) = (1/BETA) * W (KrylovSolver.f90:223-226)
 __global__ void __launch_bounds__(VEC_THREADS) k_scale_copy(int64_t n, double s, const double* __restrict__ w, double* __restrict__ v) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = __dmul_rn(s, w[i]);
 }
 // W = BETA * V(:,1) (KrylovSolver.f90:467)
@@ -415,6 +466,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_combine(int64_t n, int64_t ld, 
                                                          const double* __restrict__ e, double* __restrict__ w, Reducer rd, SweepCtl* ctl) {
     __shared__ double coef[128];
     __shared__ double cs[128];
+    pdl_trigger();
+    pdl_wait();
     for (int j = threadIdx.x; j < mx; j += blockDim.x) { coef[j] = __dmul_rn(beta, e[j]); cs[j] = ctl->colscale[j]; }   // temp = alpha*x(j)
     __syncthreads();
     DD a1, a2; a1.hi = a1.lo = a2.hi = a2.lo = 0.0;
@@ -568,6 +621,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
 // of them.  Needed where a kernel without a reduction (k_scale_copy writing basis column 0) is followed by a
 // SpMV that gathers that column from the neighbours' HBM.
 __global__ void k_dist_barrier(const DistPeers* __restrict__ dp, unsigned long long seq) {
+    pdl_trigger();
+    pdl_wait();
     const int P = dp->nranks, me = dp->rank, r = threadIdx.x;
     const int slot = (int)(seq & 1ull);
     if (r < P) {
@@ -575,7 +630,9 @@ __global__ void k_dist_barrier(const DistPeers* __restrict__ dp, unsigned long l
         *((volatile unsigned long long*)(dp->flag[r] + (size_t)slot * P + me)) = seq;
         const volatile unsigned long long* fl = dp->flag[me] + (size_t)slot * P + r;
         const long long t0 = clock64();
+        const volatile int32_t* gone = dp->err;
         while (*fl != seq) {
+            if (*gone & 32) break;
             if (clock64() - t0 > 8000000000LL) { atomicOr(dp->err, 32); break; }
         }
         __threadfence_system();

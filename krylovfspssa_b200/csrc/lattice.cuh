@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_box(const __grid_con
                                                                 double* __restrict__ y, const double* __restrict__ first, Reducer rd,
                                                                 SweepCtl* ctl, EpiArgs ea, int cf, int64_t coloff) {
     constexpr int R = RT;
+    pdl_trigger();
+    pdl_wait();
     if (MODE != 0 && ctl->brk != 0) return;
     const bool has_g = MODE == 1 && ea.has_g;             // `first` = g = U_{c-1}
     const double fs = has_g ? col_scale(ctl, cf) : 0.0;
@@ -269,6 +271,7 @@ struct Bd2Args {
     int32_t cg, cf;           // basis columns of g and f (their scales)
     int32_t has_g, has_f;
     int32_t zc, halo;         // rows per z-chunk; 1 = several GPUs (rows outside the slab come from the owner's HBM)
+    int32_t l2_ahead;         // rows beyond the ring that are prefetched into L2 (0: none; at most BD2_L2AHEAD)
     int32_t sync_every;       // 0, or a power of two: the CTA's warps re-align every so many rows of the hot loop, which keeps the
                               // sectors two neighbouring warps share (a warp's 256-byte row segment is not sector-aligned) in L1
     int64_t off_src, off_g, off_f;    // offsets of src / g / f inside the basis allocation (peer addressing)
@@ -278,6 +281,8 @@ template <int ORD, int TS, int MODE, int FIN, int PF, int MINB>
 __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_constant__ Lattice L, const __grid_constant__ Bd2Args A,
                                                                 Reducer rd, SweepCtl* ctl) {
     constexpr int NS = FIN ? 3 : (MODE == 1 ? 2 : 1);      // streams in flight: src [, g [, f]]
+    pdl_trigger();
+    pdl_wait();
     if ((MODE != 0 || FIN) && ctl->brk != 0) return;
     const bool has_g = (FIN || MODE == 1) && A.has_g;       // FIN implies has_g (a finalised column has a predecessor)
     const bool has_f = FIN && A.has_f;
@@ -414,10 +419,11 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv_bd2(const __grid_con
                 else fill_general(slot, zn);
                 cp_async_commit();
                 rs = rs + 1 == DEPTH ? 0 : rs + 1;
-                if (!gen && NS >= 2 && zn + BD2_L2AHEAD <= zloc) {  // multi-stream variants also pull rows further ahead into L2
-                    lattice_prefetch<1>(src + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
-                    if (has_g) lattice_prefetch<1>(gp + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
-                    if (NS >= 3 && has_f) lattice_prefetch<1>(fp_ + (e + (uint32_t)(Bx * BD2_L2AHEAD)));
+                if (!gen && NS >= 2 && A.l2_ahead > 0 && zn + A.l2_ahead <= zloc) {  // multi-stream variants also pull rows further ahead into L2
+                    const uint32_t ea = e + (uint32_t)(Bx * A.l2_ahead);
+                    lattice_prefetch<1>(src + ea);
+                    if (has_g) lattice_prefetch<1>(gp + ea);
+                    if (NS >= 3 && has_f) lattice_prefetch<1>(fp_ + ea);
                 }
             }
             const double xl = __shfl_up_sync(0xffffffffu, x0, 1);

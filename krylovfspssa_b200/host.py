@@ -319,7 +319,7 @@ class KrylovFspHandle:
         return dict(d=d, i=i)
 
     PROF_CLASSES = ("spmv_plain", "spmv_dot", "spmv_nrm", "spmv_fin_dot", "spmv_fin_nrm", "axpy_dot", "axpy_nrm", "combine",
-                    "scale_copy", "expm")
+                    "scale_copy", "expm", "sweep")
 
     def profile(self):
         """Device seconds, launches and algorithmic bytes per state (summed over the launches) of the last solve by
@@ -330,8 +330,9 @@ class KrylovFspHandle:
         check(lib().kfsp_profile_get(self._h, sec, cnt, bps))
         return {name: (sec[i], cnt[i], bps[i]) for i, name in enumerate(self.PROF_CLASSES)}
 
-    def set_profiling(self, on=True):
-        check(lib().kfsp_set_profiling(self._h, 1 if on else 0))
+    def set_profiling(self, level=2):
+        """0 off, 1 one event pair per Arnoldi sweep, 2 one pair per launch"""
+        check(lib().kfsp_set_profiling(self._h, int(level)))
 
     def phase_seconds(self):
         buf = (C.c_double * 8)()
