@@ -149,12 +149,16 @@ def run_reference(args, rank, world):
     om = oracle.Model.load(os.path.join(ROOT, "krylovfspssa_b200", "models", "toggle_test.input"), PARAMS)
     states, p0 = synthetic(bx, by)
     n = len(p0)
-    times, mults = [], []
+    times, mults, setups = [], [], []
     for it in range(args.warmup_ref + args.steps):
         out = oracle.solve(om, states, p0, args.t_final, 1e-6, 1e-8, max_size=n + 64, m_max=args.m_max, m_min=10,
                            n_init_onestep=0, enable_drop=0, enable_expand=0)
         if it >= args.warmup_ref:
-            times.append(out["stats"]["wall_seconds"])
+            # the time-stepping loop only: MATRIX_STARTER (the reference builds its hash table of big-integer keys there) is left
+            # out of the reference's time although this repo's e2e figure includes its own set-up -- on a bounded sample the
+            # set-up would otherwise dominate and flatter the comparison
+            times.append(out["stats"]["wall_seconds"] - out["stats"]["setup_seconds"])
+            setups.append(out["stats"]["setup_seconds"])
             mults.append(out["stats"]["nmult"])
     total = sum(times)
     value = n * sum(mults) / total
@@ -166,7 +170,8 @@ def run_reference(args, rank, world):
                                "Krylov dimension in [10,%d], fixed state set" % (bx, by, args.t_final, args.m_max),
                    "states": n, "m_range": [10, args.m_max]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": "full expv solve on a %dx%d rectangle (%d states), %d SpMVs per solve; oracle port of the "
+                         "setup_seconds_not_counted": sum(setups) / len(setups),
+                         "sample": "time-stepping loop of a full expv solve (MATRIX_STARTER excluded) on a %dx%d rectangle (%d states), %d SpMVs per solve; oracle port of the "
                                    "serial Fortran reference (no Fortran compiler in this image or on the GPU box: "
                                    "profiles/r2_fortran_probe_gpu_box.txt), 1 of %d host cores" % (bx, by, n, mults[0], os.cpu_count())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -192,8 +197,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-bx", type=int, default=3200)
     ap.add_argument("--cpu-by", type=int, default=3200)
-    ap.add_argument("--ref-bx", type=int, default=1500)
-    ap.add_argument("--ref-by", type=int, default=1500)
+    ap.add_argument("--ref-bx", type=int, default=2500)
+    ap.add_argument("--ref-by", type=int, default=2500)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the bit-for-bit comparisons (profiling runs)")

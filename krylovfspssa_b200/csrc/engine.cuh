@@ -28,6 +28,10 @@ struct Engine {
     kfsp_options opt{};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // side stream: uploads that the solve does not depend on (the lattice's state-list check)
+    cudaEvent_t ev_side = nullptr;
+    int32_t* d_chk = nullptr;         // result of the deferred lattice check
+    bool box_check_pending = false;
     bool have_model = false;
     DeviceModel* d_model = nullptr;
     double* d_tables = nullptr;       // host-built propensity tables
@@ -184,6 +188,9 @@ struct Engine {
         KFSP_CUDA(cudaSetDevice(device));
         KFSP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         KFSP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        KFSP_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+        KFSP_CUDA(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+        KFSP_CUDA(cudaMalloc(&d_chk, sizeof(int32_t)));
         KFSP_CUDA(cudaEventCreate(&ev_a));
         KFSP_CUDA(cudaEventCreate(&ev_b));
         KFSP_CUDA(cudaMalloc(&d_model, sizeof(DeviceModel)));
@@ -207,6 +214,9 @@ struct Engine {
     void destroy() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
+        if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
+        if (ev_side) cudaEventDestroy(ev_side);
+        cudaFree(d_chk);
         free_state_space();
         free_prop_cache();
         cudaFree(d_model); cudaFree(d_tables); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
@@ -641,8 +651,8 @@ struct Engine {
         if (e) { n = 0; return err_to_status(e); }
         return KFSP_OK;
     }
-    int fsp_init(int64_t count, const int32_t* states_host) {
-        if (opt.spmv_variant == 1) return box_init_from_states(count, states_host);
+    int fsp_init(int64_t count, const int32_t* states_host, bool defer_check = false) {
+        if (opt.spmv_variant == 1) return box_init_from_states(count, states_host, defer_check);
         if (dist.nranks > 1) return dist_fsp_init(count, states_host);
         KFSP_TRY(ensure_state_space());
         if (count < 1 || count > opt.max_states) return KFSP_ERR_BAD_SIZES;
@@ -1524,9 +1534,13 @@ struct Engine {
     }
     // kfsp_fsp_init / kfsp_solve with spmv_variant = 1: the caller's state list must be a lattice in natural
     // order.  Bounds come from the last state; this rank's rows are verified on the device.
-    int box_init_from_states(int64_t count, const int32_t* states_host) {
+    // defer = true (kfsp_solve): the list is uploaded and verified on the side stream WHILE the solve runs -- the lattice
+    // arithmetic does not read it -- and box_check_finish() delivers the verdict afterwards; `after` (optional) is an event
+    // of the main stream the upload should wait for (the p0 upload, which the solve does need, goes over the same link first).
+    int box_init_from_states(int64_t count, const int32_t* states_host, bool defer = false) {
         if (!have_model) return KFSP_ERR_NO_MODEL;
         if (count < 1) return KFSP_ERR_BAD_SIZES;
+        KFSP_TRY(box_check_finish());
         int32_t bounds[KFSP_MAX_SPECIES];
         int64_t total = 1;
         for (int s = 0; s < S; ++s) {
@@ -1539,11 +1553,38 @@ struct Engine {
         if (total != count) return KFSP_ERR_UNSUPPORTED;          // not a full box: use spmv_variant = 0
         KFSP_TRY(fsp_init_box(bounds));
         if (!d_states) KFSP_CUDA(cudaMalloc(&d_states, sizeof(int32_t) * n * S));     // n is fixed while ld is (fsp_init_box)
-        KFSP_CUDA(cudaMemcpyAsync(d_states, states_host + dist.lo * S, sizeof(int32_t) * n * S, cudaMemcpyHostToDevice, stream));
-        KFSP_LAUNCH(k_box_check_states, grid_for(n), VEC_THREADS, 0, lat, dist.lo, n, (const int32_t*)d_states, d_err);
-        int32_t e = 0;
-        KFSP_TRY(read_err(&e));
-        if (e) { n = 0; box = false; return KFSP_ERR_UNSUPPORTED; }
+        box_src = states_host + dist.lo * S;
+        if (defer) { box_check_pending = true; box_check_started = false; return KFSP_OK; }
+        KFSP_TRY(box_check_start(stream));
+        return box_check_finish();
+    }
+    const int32_t* box_src = nullptr;
+    bool box_check_started = false;
+    int box_check_start(cudaStream_t st) {
+        KFSP_CUDA(cudaMemsetAsync(d_chk, 0, sizeof(int32_t), st));
+        KFSP_CUDA(cudaMemcpyAsync(d_states, box_src, sizeof(int32_t) * n * S, cudaMemcpyHostToDevice, st));
+        k_box_check_states<<<grid_for(n), VEC_THREADS, 0, st>>>(lat, dist.lo, n, (const int32_t*)d_states, d_chk);
+        KFSP_TRY(check_launch());
+        box_check_pending = true;
+        box_check_started = true;
+        return KFSP_OK;
+    }
+    // start the deferred upload on the side stream once everything enqueued so far on the main stream has gone over the link
+    int box_check_overlap() {
+        if (!box_check_pending || box_check_started) return KFSP_OK;
+        KFSP_CUDA(cudaEventRecord(ev_side, stream));
+        KFSP_CUDA(cudaStreamWaitEvent(stream2, ev_side, 0));
+        return box_check_start(stream2);
+    }
+    int box_check_finish() {
+        if (!box_check_pending) return KFSP_OK;
+        if (!box_check_started) KFSP_TRY(box_check_start(stream));
+        box_check_pending = false;
+        int32_t bad = 0;
+        KFSP_CUDA(cudaStreamSynchronize(stream2));
+        KFSP_CUDA(cudaMemcpyAsync(&bad, d_chk, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        if (bad) { n = 0; box = false; return KFSP_ERR_UNSUPPORTED; }
         return KFSP_OK;
     }
 

@@ -452,7 +452,7 @@ int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, 
     const double w0 = wall_now();
     if (verbosity) std::printf(" CALLING DGEXPV_FSP\n");                              // KrylovSolver.f90:32
     cudaSetDevice(e.device);
-    KFSP_TRY(e.fsp_init(n_in, states_in));
+    KFSP_TRY(e.fsp_init(n_in, states_in, /*defer_check=*/true));
     // Partitioned handle (kfsp_dist_init): states_in / p_in are the GLOBAL list and vector on every rank; this rank keeps
     // rows [lo, hi) and returns them (n_out = hi - lo).  fsp_init has zeroed W.
     const bool part = e.dist.nranks > 1;
@@ -461,7 +461,12 @@ int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, 
         const int64_t cnt = std::min<int64_t>(n_in - lo, e.n);
         KFSP_CUDA(cudaMemcpyAsync(e.d_w, p_in + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, e.stream));
     }
+    KFSP_TRY(e.box_check_overlap());                       // lattice variant: the state list is uploaded and verified beside the solve
     int st = e.solve(t, fsp_tol, kry_tol, verbosity, stats);
+    {
+        const int chk = e.box_check_finish();               // ... and a list that is not the lattice voids the result
+        if (chk != KFSP_OK) { *n_out = 0; return chk; }
+    }
     *n_out = e.n;
     if (st == KFSP_OK || st == KFSP_IFLAG_MXSTEP) {
         if (e.n > max_out) return KFSP_ERR_OUT_TOO_SMALL;

@@ -27,7 +27,7 @@ class Stats(C.Structure):
                 ("nmult", "nexph", "nscale", "nstep", "nreject", "ibrkflag", "mbrkdwn", "iflag")] + \
                [(n, C.c_double) for n in
                 ("step_min", "step_max", "x_error", "s_error", "tbrkdwn", "t_now", "hump", "beta_ratio")] + \
-               [("n_expand", C.c_int64), ("n_drop", C.c_int64), ("wall_seconds", C.c_double)]
+               [("n_expand", C.c_int64), ("n_drop", C.c_int64), ("wall_seconds", C.c_double), ("setup_seconds", C.c_double)]
 
 
 def build(force=False):

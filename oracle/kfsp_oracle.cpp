@@ -977,6 +977,7 @@ struct Stats {
     double step_min, step_max, x_error, s_error, tbrkdwn, t_now, hump, beta_ratio;
     int64_t n_expand, n_drop;
     double wall_seconds;
+    double setup_seconds;           // MATRIX_STARTER + the initial ONESTEP_EXTENDER calls (KrylovSolver.f90:130-134), part of wall_seconds
 };
 
 static double now_s() {
@@ -1037,6 +1038,7 @@ struct Solver {
             rc = onestep_extender(fsp);
             if (rc) return rc;
         }
+        const double t_setup_done = now_s();
         int M = M_MIN, ISTART = 1;
         long N = fsp.max_size;
         if ((M >= N) || (M <= 0)) return -3;
@@ -1343,6 +1345,7 @@ struct Solver {
         stats.tbrkdwn = TBRKDWN; stats.t_now = SGN * T_NOW; stats.hump = HUMP / VNORM; stats.beta_ratio = BETA / VNORM;
         stats.n_expand = n_expand; stats.n_drop = n_drop;
         stats.wall_seconds = now_s() - t0;
+        stats.setup_seconds = t_setup_done - t0;
         (void)T_SSA; (void)XM; (void)ISTART;
         return iflag;
     }

@@ -127,6 +127,9 @@ def test_lattice_rejects_what_it_cannot_do():
         h.fsp_init(st[::-1].copy())
     with pytest.raises(k.KfspError):
         h.fsp_init(st[:-3])
+    p0 = np.zeros(len(st)); p0[0] = 1.0
+    with pytest.raises(k.KfspError):                      # kfsp_solve verifies the list beside the solve: same verdict
+        h.solve(0.01, st[::-1].copy(), p0, 1e-6, 1e-8)
     h.fsp_init(st)                                        # a lattice given as a list is accepted
     with pytest.raises(k.KfspError):
         h.onestep()                                       # fixed state set
