@@ -52,6 +52,27 @@ struct DeviceModel {
     const double* table[KFSP_MAX_REACTIONS];         // device pointers, max_molecules+1 entries each
 };
 
+// Factored propensities of the index-only SpMV (spmv_variant = 2, krylov.cuh: k_spmv_idx).  model_host.h: factor_program
+// splits a_k into terms that read at most one species each -- tabulated on the host over the count 0..max_molecules --
+// combined by + - * (postfix).  The common shapes are decided at set-up time:
+//   FAC_ONE  a = T0[x_s0]                         (every single-species propensity: c*x, c*x*(x-1)/2, Hill functions ...)
+//   FAC_MUL2 a = T0[x_s0] * T1[x_s1]              (bimolecular mass action c*x*y)
+//   FAC_MUL3 a = (T0[x_s0] * T1[x_s1]) * T2[x_s2]
+//   FAC_GEN  the postfix program over up to FAC_MAX_TERMS terms
+constexpr int FAC_MAX_TERMS = 4;
+constexpr int FAC_MAX_OPS = 8;
+enum FacShape : int8_t { FAC_ONE = 0, FAC_MUL2, FAC_MUL3, FAC_GEN };
+struct FacModel {
+    int32_t S, R;
+    int8_t shape[KFSP_MAX_REACTIONS];
+    int8_t nops[KFSP_MAX_REACTIONS];
+    int8_t sp[KFSP_MAX_REACTIONS][FAC_MAX_TERMS];        // species the term's table runs over (constants: species 0, stride 0)
+    int8_t use[KFSP_MAX_REACTIONS][FAC_MAX_TERMS];       // 1: index by the species count, 0: constant (entry 0)
+    int8_t ops[KFSP_MAX_REACTIONS][FAC_MAX_OPS];         // FAC_GEN: t >= 0 pushes term t, -3/-4/-5 = add/sub/mul, -2 = neg
+    int8_t nu[KFSP_MAX_REACTIONS][KFSP_MAX_SPECIES];     // stoichiometry
+    const double* tab[KFSP_MAX_REACTIONS][FAC_MAX_TERMS];
+};
+
 // Philox4x32-10 (Salmon et al., SC'11): one counter-based sub-stream per SSA trajectory.
 // counter = (jump, j0 (1-based start index), call number, 0), key = 64-bit seed.
 __host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {

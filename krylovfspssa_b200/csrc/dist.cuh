@@ -49,10 +49,10 @@ __global__ void k_dist_build_rows(FspView f, int64_t lo, int64_t nloc) {
             double c = 0.0;
             if (!neg) {
                 j = table_lookup(f, nb);
-                if (j >= 0) c = eval_propensity(m, k, nb);
+                if (j >= 0 && f.coef) c = eval_propensity(m, k, nb);
             }
             f.pred[(int64_t)k * f.ld + il] = j;
-            f.coef[(int64_t)k * f.ld + il] = c;
+            if (f.coef) f.coef[(int64_t)k * f.ld + il] = c;
             f.succ[(int64_t)k * f.ld + il] = IDX_ABSENT;
         }
         f.diag[il] = d;

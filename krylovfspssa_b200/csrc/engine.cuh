@@ -60,6 +60,13 @@ struct Engine {
                                       // DRAM reads per launch at 1e8 states, 0.85 instead of 0.73 ms; profiles/r2_summary.md)
     int bd2_sync = 8;                 // KFSP_BD2_SYNC: the stencil kernel's CTAs re-align their warps every so many rows (power of two; 0 = never)
 
+    // index-only SpMV (opt.spmv_variant == 2, krylov.cuh: k_spmv_idx): coef is never stored, a_k(x - nu_k) is recomputed
+    // from the row's integer state through the factored propensity tables
+    bool idx = false;
+    FacModel fac{};
+    double* d_factabs = nullptr;
+    int idx_drec = 0;                 // KFSP_IDX_DREC=1: DIAG is recomputed as well instead of streamed (A/B)
+
     // state space
     int64_t ld = 0;                   // capacity in states (multiple of 64)
     int64_t n = 0;
@@ -174,6 +181,8 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_BD2_AHEAD")) bd2_ahead = std::min(std::max(std::atoi(ev), 0), BD2_L2AHEAD);
         if (const char* ev = std::getenv("KFSP_BD2_SYNC")) { bd2_sync = std::atoi(ev); if (bd2_sync & (bd2_sync - 1)) bd2_sync = 0; }
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_IDX_DREC")) idx_drec = std::atoi(ev) != 0;
+        if (opt.spmv_variant < 0 || opt.spmv_variant > 2) return KFSP_ERR_ARG;
         if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
             opt.max_states > 2000000000LL)
             return KFSP_ERR_ARG;
@@ -221,6 +230,7 @@ struct Engine {
         free_prop_cache();
         cudaFree(d_model); cudaFree(d_tables); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
         cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush); cudaFree(hp_dev);
+        cudaFree(d_factabs);
         if (hp_host) cudaFreeHost(hp_host);
         if (h_res) cudaFreeHost(h_res);
         if (h_ctl) cudaFreeHost(h_ctl);
@@ -386,6 +396,7 @@ struct Engine {
             for (size_t q = 0; q < tab_k.size(); ++q) dm.table[tab_k[q]] = d_tables + q * tlen;
             n_tabulated = (int)tab_k.size();
         }
+        if (opt.spmv_variant == 2) KFSP_TRY(build_factored(m));
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
         KFSP_CUDA(cudaStreamSynchronize(stream));
         h_dm = dm;
@@ -399,11 +410,67 @@ struct Engine {
         return KFSP_OK;
     }
 
+    // spmv_variant = 2: factor every propensity into single-species terms (model_host.h: factor_program), tabulate the terms
+    // on the host over the counts 0..max_molecules and hand the tables to the index-only SpMV.  A model whose propensities
+    // combine several species by anything but + - * (or whose terms hit a division by zero / domain error inside a
+    // multi-term propensity) cannot take this variant: KFSP_ERR_UNSUPPORTED, never a silent switch.
+    int build_factored(const HostModel& m) {
+        FacModel F;
+        std::memset(&F, 0, sizeof F);
+        F.S = m.S; F.R = m.R;
+        const int64_t tlen = (int64_t)opt.max_molecules + 1;
+        std::vector<double> host;
+        std::vector<size_t> off;                         // start of table (k,t) in `host`, row-major over [k][t]
+        std::vector<double> val((size_t)m.S + m.P, 0.0);
+        for (int i = 0; i < m.P; ++i) val[m.S + i] = m.params[i];
+        for (int k = 0; k < m.R; ++k) {
+            Factored fp;
+            if (!factor_program(m.programs[k], m.S, fp)) return KFSP_ERR_UNSUPPORTED;
+            if (fp.terms.empty() || (int)fp.terms.size() > FAC_MAX_TERMS || (int)fp.ops.size() > FAC_MAX_OPS) return KFSP_ERR_UNSUPPORTED;
+            const bool multi = fp.terms.size() > 1;
+            for (size_t t = 0; t < fp.terms.size(); ++t) {
+                const FactoredTerm& tm = fp.terms[t];
+                const int64_t len = tm.species >= 0 ? tlen : 1;
+                off.push_back(host.size());
+                for (int64_t c = 0; c < len; ++c) {
+                    for (int s2 = 0; s2 < m.S; ++s2) val[s2] = 0.0;
+                    if (tm.species >= 0) val[tm.species] = (double)c;
+                    bool ab = false;
+                    host.push_back(evaluate_program_checked(tm.prog, val.data(), &ab));
+                    if (ab && multi) return KFSP_ERR_UNSUPPORTED;      // the whole propensity would be 0 there, not the term
+                }
+                F.sp[k][t] = (int8_t)(tm.species >= 0 ? tm.species : 0);
+                F.use[k][t] = tm.species >= 0 ? 1 : 0;
+            }
+            for (size_t t = fp.terms.size(); t < (size_t)FAC_MAX_TERMS; ++t) off.push_back(host.size());
+            F.nops[k] = (int8_t)fp.ops.size();
+            for (size_t q = 0; q < fp.ops.size(); ++q) F.ops[k][q] = (int8_t)fp.ops[q];
+            const std::vector<int32_t>& o = fp.ops;
+            if (o.size() == 1) F.shape[k] = FAC_ONE;
+            else if (o.size() == 3 && o[0] == 0 && o[1] == 1 && o[2] == -cMul) F.shape[k] = FAC_MUL2;
+            else if (o.size() == 5 && o[0] == 0 && o[1] == 1 && o[2] == -cMul && o[3] == 2 && o[4] == -cMul) F.shape[k] = FAC_MUL3;
+            else F.shape[k] = FAC_GEN;
+            for (int s2 = 0; s2 < m.S; ++s2) {
+                const int32_t v = m.stoich[(size_t)k * m.S + s2];
+                if (v < -127 || v > 127) return KFSP_ERR_UNSUPPORTED;
+                F.nu[k][s2] = (int8_t)v;
+            }
+        }
+        if (d_factabs) { KFSP_CUDA(cudaFree(d_factabs)); d_factabs = nullptr; }
+        KFSP_CUDA(cudaMalloc(&d_factabs, sizeof(double) * std::max<size_t>(host.size(), 1)));
+        KFSP_CUDA(cudaMemcpy(d_factabs, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
+        for (int k = 0; k < m.R; ++k)
+            for (int t = 0; t < FAC_MAX_TERMS; ++t) F.tab[k][t] = d_factabs + off[(size_t)k * FAC_MAX_TERMS + t];
+        fac = F;
+        idx = true;
+        return KFSP_OK;
+    }
+
     // CUSTOMPROP: the propensity is an opaque host function.  Sizes, stoichiometry and parameters go to the
     // device; a_k(x) is evaluated on the host in batches (propensities_host) and, inside SSA walks, served
     // from the device side cache (fsp_ssa_hostprop).
     int set_model_hostprop(const HostModel& m) {
-        if (dist.nranks > 1 || opt.spmv_variant == 1) return KFSP_ERR_UNSUPPORTED;   // those rows are built from device byte code / tables
+        if (dist.nranks > 1 || opt.spmv_variant != 0) return KFSP_ERR_UNSUPPORTED;   // those rows are built from device byte code / tables
         DeviceModel dm;
         std::memset(&dm, 0, sizeof dm);
         dm.S = m.S; dm.R = m.R; dm.P = m.P; dm.max_molecules = opt.max_molecules;
@@ -554,7 +621,7 @@ struct Engine {
         KFSP_CUDA(cudaMalloc(&d_succ, sizeof(int32_t) * cap * R));
         KFSP_CUDA(cudaMalloc(&d_pred, sizeof(int32_t) * cap * R));
         KFSP_CUDA(cudaMalloc(&d_prop, sizeof(double) * cap * R));
-        KFSP_CUDA(cudaMalloc(&d_coef, sizeof(double) * cap * R));
+        if (opt.spmv_variant != 2) KFSP_CUDA(cudaMalloc(&d_coef, sizeof(double) * cap * R));      // index-only variant: recomputed
         KFSP_CUDA(cudaMalloc(&d_diag, sizeof(double) * cap));
         KFSP_CUDA(cudaMalloc(&d_w, sizeof(double) * cap));
         KFSP_CUDA(cudaMalloc(&d_table, sizeof(int32_t) * ts));
@@ -861,7 +928,7 @@ struct Engine {
         }
         ea.has_g = (MODE == 1 && g) ? 1 : 0;
         KFSP_TRY(prof_begin(MODE == 0 ? KFSP_PROF_SPMV_PLAIN : MODE == 1 ? KFSP_PROF_SPMV_DOT : KFSP_PROF_SPMV_NRM,
-                            (box ? 16 : 12 * R + 24) + 8 * ea.has_g));
+                            (box ? 16 : idx ? 4 * R + 4 * S + (idx_drec ? 16 : 24) : 12 * R + 24) + 8 * ea.has_g));
         spmv_by_mode[MODE] += 1;
         if (box) {
             KFSP_TRY(spmv_box<MODE>(x, y, g, ea, cg));
@@ -871,6 +938,11 @@ struct Engine {
                      Reducer, SweepCtl*, EpiArgs, int, const double*, int64_t, int64_t);
         const int halo = dist.nranks > 1 ? ((dist.p2p && dist.p2p_halo) ? 2 : 1) : 0;
         if (halo == 1) KFSP_TRY(dist_halo_exchange(x));
+        if (idx) {
+            KFSP_TRY(spmv_idx<MODE>(x, y, g, ea, cg, halo));
+            if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(ea, MODE == 1 ? 4 : 2));
+            return prof_end();
+        }
         // tuning variant (KFSP_SPMV_TUNE): 0 = 1 row/iter, 1 = 2 rows/iter, 3/4/5 = 1 row/iter capped at 8/6/5 CTAs per SM
 #define KFSP_SPMV_PICK(RR)                                                                                              \
         kern = halo == 2 ? k_spmv<RR, MODE, 1, 4, 2> : halo == 1 ? k_spmv<RR, MODE, 1, 4, 1>                             \
@@ -892,6 +964,27 @@ struct Engine {
                             (const double*)dist.halo, n, (int64_t)(d_V ? x - d_V : 0)));
         if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(ea, MODE == 1 ? 4 : 2));
         return prof_end();
+    }
+    // index-only variant (krylov.cuh: k_spmv_idx); local rows' states start at d_states + lo*S on a partitioned handle
+    template <int MODE>
+    int spmv_idx(const double* x, double* y, const double* g, const EpiArgs& ea, int cg, int halo) {
+        void (*kern)(const FacModel, int64_t, int64_t, const int32_t*, const int32_t*, const double*, const double*, double*, const double*,
+                     Reducer, SweepCtl*, EpiArgs, int, const double*, int64_t, int64_t) = nullptr;
+#define KFSP_IDX_PICK(RR, SS)                                                                                           \
+        kern = halo == 2 ? (idx_drec ? k_spmv_idx<RR, SS, MODE, 2, 1> : k_spmv_idx<RR, SS, MODE, 2, 0>)                  \
+             : halo == 1 ? (idx_drec ? k_spmv_idx<RR, SS, MODE, 1, 1> : k_spmv_idx<RR, SS, MODE, 1, 0>)                  \
+             : (idx_drec ? k_spmv_idx<RR, SS, MODE, 0, 1> : k_spmv_idx<RR, SS, MODE, 0, 0>)
+        if (R == 4 && S == 2) { KFSP_IDX_PICK(4, 2); }
+        else if (R == 6 && S == 3) { KFSP_IDX_PICK(6, 3); }
+        else if (R == 10 && S == 6) { KFSP_IDX_PICK(10, 6); }
+        else { KFSP_IDX_PICK(0, 0); }
+#undef KFSP_IDX_PICK
+        const int gr = wave_grid((const void*)kern, n);
+        Reducer r2 = MODE != 0 ? next_rd() : rd;
+        if (halo == 2 && !r2.peers) r2.peers = dist.d_peers;
+        const int32_t* st = d_states + (dist.nranks > 1 ? dist.lo * S : 0);
+        return launch_pdl(kern, gr, VEC_THREADS, 0, fac, n, ld, (const int32_t*)d_pred, st, (const double*)d_diag, x, y, g, r2, d_ctl, ea, cg,
+                          (const double*)dist.halo, n, (int64_t)(d_V ? x - d_V : 0));
     }
     int set_profiling(int level) {
         const bool on = level != 0;
@@ -1015,14 +1108,16 @@ struct Engine {
     int arnoldi(int jold, int m) {
         // small state spaces: the whole sweep in one single-CTA launch (bit-identical, see k_sweep_small)
         if (dist.nranks == 1 && !box && !profile_spmv && small_sweep && n * (int64_t)(12 * R + 88) <= (1 << 20)) {
-            void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, double*, double*, int, int, int, SweepCtl*, double);
+            void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, double*, double*, int, int, int, SweepCtl*, double,
+                         const FacModel, const int32_t*);
             switch (R) {
-            case 4: kern = k_sweep_small<4>; break;
-            case 6: kern = k_sweep_small<6>; break;
-            case 10: kern = k_sweep_small<10>; break;
-            default: kern = k_sweep_small<0>; break;
+            case 4: kern = idx ? k_sweep_small<4, 1> : k_sweep_small<4, 0>; break;
+            case 6: kern = idx ? k_sweep_small<6, 1> : k_sweep_small<6, 0>; break;
+            case 10: kern = idx ? k_sweep_small<10, 1> : k_sweep_small<10, 0>; break;
+            default: kern = idx ? k_sweep_small<0, 1> : k_sweep_small<0, 0>; break;
             }
-            kern<<<1, SWEEP_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, d_V, d_H, LDH, jold, m, d_ctl, opt.break_tol);
+            kern<<<1, SWEEP_THREADS, 0, stream>>>(n, ld, R, d_pred, d_coef, d_diag, d_V, d_H, LDH, jold, m, d_ctl, opt.break_tol, fac,
+                                                  (const int32_t*)d_states);
             return check_launch();
         }
         KFSP_TRY(sweep_begin());
@@ -1407,8 +1502,13 @@ struct Engine {
                      : (bd_ord == 0 ? k_spmv_bd2<0, T, MODE, 0, BD2_PF, BD2_MINB> : k_spmv_bd2<1, T, MODE, 0, BD2_PF, BD2_MINB>);            \
             break
         switch (ts) {
+#ifdef KFSP_FAST_BUILD                                      // developer builds: only the table pattern of the toggle models
+            KFSP_BD2(9);
+            default: return KFSP_ERR_UNSUPPORTED;
+#else
             KFSP_BD2(0); KFSP_BD2(1); KFSP_BD2(2); KFSP_BD2(3); KFSP_BD2(4); KFSP_BD2(5); KFSP_BD2(6); KFSP_BD2(7);
             KFSP_BD2(8); KFSP_BD2(9); KFSP_BD2(10); KFSP_BD2(11); KFSP_BD2(12); KFSP_BD2(13); KFSP_BD2(14); KFSP_BD2(15);
+#endif
         }
 #undef KFSP_BD2
         if (fin && MODE == 0) return KFSP_ERR_ARG;

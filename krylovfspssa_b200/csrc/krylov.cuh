@@ -404,6 +404,130 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// FMATVEC without the coefficient array (spmv_variant = 2, "index-only"): the row streams pred (4R bytes) and the integer
+// state of the row (4S bytes) and RECOMPUTES  coef_ki = a_k(x_i - nu_k)  from it -- the stored value was produced by the
+// same evaluation of the same state (StateSpace.f90:207-212, 240-244: OFFDIAG(K,J) is a_K of state J), so the product is
+// bit-identical to k_spmv -- for 4R + 4S + 24 bytes per state instead of 12R + 24 (Goutsias: 88 instead of 144;
+// DREC = 1 also recomputes DIAG_i = ((a_1 + a_2) + ...)(x_i): 4R + 4S + 16).  Works on ANY state set (irregular,
+// adaptively grown, row-partitioned); propensities are the factored tables of common.cuh (FacModel).
+// The thread's state sits in shared memory (column threadIdx.x) because the species a term reads is a run-time index.
+// ---------------------------------------------------------------------------------------
+template <int ST, int STRIDE>
+__device__ __forceinline__ void idx_load_state(const int32_t* __restrict__ states, int64_t row, int S, int32_t* sst) {
+    if (ST > 0 && ST % 2 == 0) {
+        const int2* __restrict__ p = reinterpret_cast<const int2*>(states + row * ST);
+#pragma unroll
+        for (int q = 0; q < ST / 2; ++q) {
+            const int2 v = __ldcs(p + q);
+            sst[(2 * q) * STRIDE] = v.x;
+            sst[(2 * q + 1) * STRIDE] = v.y;
+        }
+    } else {
+        const int SS = ST > 0 ? ST : S;
+#pragma unroll
+        for (int q = 0; q < (ST > 0 ? ST : KFSP_MAX_SPECIES); ++q)
+            if (q < SS) sst[q * STRIDE] = __ldcs(states + row * SS + q);
+    }
+}
+// a_k at the row's state (sgn = 0) or at its predecessor x - nu_k (sgn = 1)
+template <int STRIDE>
+__device__ __forceinline__ double fac_term(const FacModel& F, int k, int t, const int32_t* sst, int sgn) {
+    const int sp = F.sp[k][t];
+    const int c = (sst[sp * STRIDE] - sgn * (int)F.nu[k][sp]) * (int)F.use[k][t];
+    return __ldg(F.tab[k][t] + c);
+}
+template <int STRIDE>
+__device__ __forceinline__ double fac_eval(const FacModel& F, int k, const int32_t* sst, int sgn) {
+    const int shp = F.shape[k];
+    if (shp != FAC_GEN) {
+        double a = fac_term<STRIDE>(F, k, 0, sst, sgn);
+        if (shp >= FAC_MUL2) a = __dmul_rn(a, fac_term<STRIDE>(F, k, 1, sst, sgn));
+        if (shp >= FAC_MUL3) a = __dmul_rn(a, fac_term<STRIDE>(F, k, 2, sst, sgn));
+        return a;
+    }
+    double stk[FAC_MAX_OPS];
+    int top = -1;
+    for (int q = 0; q < F.nops[k]; ++q) {
+        const int op = F.ops[k][q];
+        if (op >= 0) stk[++top] = fac_term<STRIDE>(F, k, op, sst, sgn);
+        else if (op == -2) stk[top] = -stk[top];
+        else {
+            const double b = stk[top--];
+            stk[top] = op == -3 ? __dadd_rn(stk[top], b) : op == -4 ? __dsub_rn(stk[top], b) : __dmul_rn(stk[top], b);
+        }
+    }
+    return stk[0];
+}
+template <int RT, int ST, int MODE, int HALO, int DREC>
+__global__ void __launch_bounds__(VEC_THREADS) k_spmv_idx(const __grid_constant__ FacModel F, int64_t n, int64_t ld, const int32_t* __restrict__ pred,
+                                                          const int32_t* __restrict__ states, const double* __restrict__ diag,
+                                                          const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ g,
+                                                          Reducer rd, SweepCtl* ctl, EpiArgs ea, int cg, const double* __restrict__ xh,
+                                                          int64_t nloc, int64_t coloff) {
+    __shared__ int32_t sstate[KFSP_MAX_SPECIES * VEC_THREADS];
+    int32_t* const sst = sstate + threadIdx.x;
+    const int R = RT > 0 ? RT : F.R;
+    pdl_trigger();
+    pdl_wait();
+    if (MODE != 0 && ctl->brk != 0) return;
+    const bool has_g = MODE == 1 && ea.has_g;
+    const double gs = has_g ? col_scale(ctl, cg) : 0.0;
+    DD accA, accB, accC;
+    accA.hi = accA.lo = accB.hi = accB.lo = accC.hi = accC.lo = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t j[RT > 0 ? RT : 1];
+        if (RT > 0) {
+#pragma unroll
+            for (int k = 0; k < RT; ++k) j[k] = __ldcs(pred + (int64_t)k * ld + i);
+        }
+        idx_load_state<ST, VEC_THREADS>(states, i, F.S, sst);
+        const double xi = x[i];
+        const double gv = has_g ? __dmul_rn(gs, __ldcs(g + i)) : 0.0;
+        double d;
+        if (DREC) {
+            d = 0.0;
+#pragma unroll
+            for (int k = 0; k < (RT > 0 ? RT : 1); ++k) {
+                if (RT > 0) d = __dadd_rn(d, fac_eval<VEC_THREADS>(F, k, sst, 0));
+            }
+            if (RT == 0) for (int k = 0; k < R; ++k) d = __dadd_rn(d, fac_eval<VEC_THREADS>(F, k, sst, 0));
+        } else {
+            d = __ldcs(diag + i);
+        }
+        double sv = -__dmul_rn(d, xi);
+        if (RT > 0) {
+#pragma unroll
+            for (int k = 0; k < RT; ++k)
+                if (j[k] >= 0) sv = fma(fac_eval<VEC_THREADS>(F, k, sst, 1), halo_load<HALO>(x, xh, rd.peers, j[k], nloc, coloff), sv);
+        } else {
+            for (int k = 0; k < R; ++k) {
+                const int32_t jj = __ldcs(pred + (int64_t)k * ld + i);
+                if (jj >= 0) sv = fma(fac_eval<VEC_THREADS>(F, k, sst, 1), halo_load<HALO>(x, xh, rd.peers, jj, nloc, coloff), sv);
+            }
+        }
+        __stcs(y + i, sv);
+        if (MODE == 1) {
+            dd_add_prod(accB, xi, sv);
+            if (has_g) { dd_add_prod(accA, gv, sv); dd_add_prod(accC, xi, gv); }
+        }
+        if (MODE == 2) dd_add_prod(accB, sv, sv);
+    }
+    if (MODE == 0) return;
+    if (MODE == 1) {
+        DD z; z.hi = 0.0; z.lo = 0.0;
+        DD v[4] = {z, accA, accB, accC};
+        double tot[4];
+        if (grid_reduce<4>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(ea, tot, ctl);
+    } else {
+        DD z; z.hi = 0.0; z.lo = 0.0;
+        DD v[2] = {z, accB};
+        double tot[2];
+        if (grid_reduce<2>(v, tot, rd) && threadIdx.x == 0) reduce_epilogue(ea, tot, ctl);
+    }
+}
+
 // U_c = (cg*w - h1*v_f) - h2*v_g in place on w = A U_{c-1} (g = U_{c-1}, f = U_{c-2}; has_f = 0 for column 1), and its
 // norm: HJ1J = ||U_c||, happy-breakdown test, H(c+1,c), colscale[c] (the two DAXPYs, DNRM2 and the deferred DSCAL of
 // KrylovSolver.f90:244-258).  The fused lattice path does this inside the next SpMV launch (lattice.cuh).
@@ -525,23 +649,30 @@ __device__ __forceinline__ double cta_dd_total(DD v, DD* sh, double* bc) {
     __syncthreads();
     return *bc;
 }
-template <int RT>
+template <int RT, int IDX>
 __device__ __forceinline__ double spmv_row(int64_t i, int64_t ld, int R, const int32_t* __restrict__ pred, const double* __restrict__ coef,
-                                           const double* __restrict__ diag, const double* x) {
+                                           const double* __restrict__ diag, const double* x, const FacModel& F,
+                                           const int32_t* __restrict__ states, int32_t* sst) {
     double sv = -__dmul_rn(diag[i], x[i]);
+    if (IDX) idx_load_state<0, SWEEP_THREADS>(states, i, F.S, sst);      // index-only variant: coef is recomputed (k_spmv_idx)
 #pragma unroll
     for (int k = 0; k < (RT > 0 ? RT : R); ++k) {
         const int32_t j = pred[(int64_t)k * ld + i];
-        const double a = coef[(int64_t)k * ld + i];
-        if (j >= 0) sv = fma(a, x[j], sv);
+        if (j >= 0) {
+            const double a = IDX ? fac_eval<SWEEP_THREADS>(F, k, sst, 1) : coef[(int64_t)k * ld + i];
+            sv = fma(a, x[j], sv);
+        }
     }
     return sv;
 }
-template <int RT>
+template <int RT, int IDX>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
                                                                    const double* __restrict__ coef, const double* __restrict__ diag,
                                                                    double* V, double* H, int ldh, int jold, int m, SweepCtl* ctl,
-                                                                   double break_tol) {
+                                                                   double break_tol, const __grid_constant__ FacModel F,
+                                                                   const int32_t* __restrict__ states) {
+    __shared__ int32_t sstate[IDX ? KFSP_MAX_SPECIES * SWEEP_THREADS : 1];
+    int32_t* const sst = sstate + (IDX ? threadIdx.x : 0);
     __shared__ DD sh[32];
     __shared__ double bc;
     __shared__ double cs[MAX_COLS];
@@ -563,7 +694,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
         DD accA, accB, accC;
         accA.hi = accA.lo = accB.hi = accB.lo = accC.hi = accC.lo = 0.0;
         for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
-            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x);
+            const double sv = spmv_row<RT, IDX>(i, ld, R, pred, coef, diag, x, F, states, sst);
             y[i] = sv;
             const double xi = x[i];
             dd_add_prod(accB, xi, sv);
@@ -606,7 +737,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
         const double xs = cs[m];
         DD acc; acc.hi = 0.0; acc.lo = 0.0;
         for (int64_t i = tid; i < n; i += SWEEP_THREADS) {
-            const double sv = spmv_row<RT>(i, ld, R, pred, coef, diag, x);
+            const double sv = spmv_row<RT, IDX>(i, ld, R, pred, coef, diag, x, F, states, sst);
             y[i] = sv;
             dd_add_prod(acc, sv, sv);
         }

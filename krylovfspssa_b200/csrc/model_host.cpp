@@ -246,10 +246,12 @@ bool compile_expression(const std::string& expr, const std::vector<std::string>&
     return true;
 }
 
-double evaluate_program(const Program& p, const double* val) {
+double evaluate_program_checked(const Program& p, const double* val, bool* aborted) {
     double st[64];
     int sp = -1;
     size_t dp = 0;
+    if (aborted) *aborted = false;
+#define KFSP_ABORT() do { if (aborted) *aborted = true; return 0.0; } while (0)
     for (int32_t op : p.code) {
         switch (op) {
         case cImmed: st[++sp] = p.immed[dp++]; break;
@@ -257,26 +259,88 @@ double evaluate_program(const Program& p, const double* val) {
         case cAdd: st[sp - 1] = st[sp - 1] + st[sp]; --sp; break;
         case cSub: st[sp - 1] = st[sp - 1] - st[sp]; --sp; break;
         case cMul: st[sp - 1] = st[sp - 1] * st[sp]; --sp; break;
-        case cDiv: if (st[sp] == 0.0) return 0.0; st[sp - 1] = st[sp - 1] / st[sp]; --sp; break;
+        case cDiv: if (st[sp] == 0.0) KFSP_ABORT(); st[sp - 1] = st[sp - 1] / st[sp]; --sp; break;
         case cPow: st[sp - 1] = std::pow(st[sp - 1], st[sp]); --sp; break;
         case cAbs: st[sp] = std::fabs(st[sp]); break;
         case cExp: st[sp] = std::exp(st[sp]); break;
-        case cLog10: if (st[sp] <= 0.0) return 0.0; st[sp] = std::log10(st[sp]); break;
-        case cLog: if (st[sp] <= 0.0) return 0.0; st[sp] = std::log(st[sp]); break;
-        case cSqrt: if (st[sp] < 0.0) return 0.0; st[sp] = std::sqrt(st[sp]); break;
+        case cLog10: if (st[sp] <= 0.0) KFSP_ABORT(); st[sp] = std::log10(st[sp]); break;
+        case cLog: if (st[sp] <= 0.0) KFSP_ABORT(); st[sp] = std::log(st[sp]); break;
+        case cSqrt: if (st[sp] < 0.0) KFSP_ABORT(); st[sp] = std::sqrt(st[sp]); break;
         case cSinh: st[sp] = std::sinh(st[sp]); break;
         case cCosh: st[sp] = std::cosh(st[sp]); break;
         case cTanh: st[sp] = std::tanh(st[sp]); break;
         case cSin: st[sp] = std::sin(st[sp]); break;
         case cCos: st[sp] = std::cos(st[sp]); break;
         case cTan: st[sp] = std::tan(st[sp]); break;
-        case cAsin: if (st[sp] < -1.0 || st[sp] > 1.0) return 0.0; st[sp] = std::asin(st[sp]); break;
-        case cAcos: if (st[sp] < -1.0 || st[sp] > 1.0) return 0.0; st[sp] = std::acos(st[sp]); break;
+        case cAsin: if (st[sp] < -1.0 || st[sp] > 1.0) KFSP_ABORT(); st[sp] = std::asin(st[sp]); break;
+        case cAcos: if (st[sp] < -1.0 || st[sp] > 1.0) KFSP_ABORT(); st[sp] = std::acos(st[sp]); break;
         case cAtan: st[sp] = std::atan(st[sp]); break;
         default: st[++sp] = val[op - VarBegin]; break;
         }
     }
+#undef KFSP_ABORT
     return st[0];
+}
+double evaluate_program(const Program& p, const double* val) { return evaluate_program_checked(p, val, nullptr); }
+
+bool factor_program(const Program& p, int S, Factored& out) {
+    // postfix -> tree: a sub-expression is a contiguous range of the code (and of the immediates)
+    struct TNode { int32_t op; int a, b; int c0, c1, i0, i1; uint32_t mask; };
+    std::vector<TNode> nodes;
+    std::vector<int> stack;
+    int imm = 0;
+    for (int ip = 0; ip < (int)p.code.size(); ++ip) {
+        const int32_t op = p.code[ip];
+        TNode n{op, -1, -1, ip, ip + 1, imm, imm, 0u};
+        if (op == cImmed) {
+            if (imm >= (int)p.immed.size()) return false;
+            n.i1 = ++imm;
+        } else if (op == cNeg || (op >= cAbs && op <= cAtan)) {
+            if (stack.empty()) return false;
+            n.a = stack.back(); stack.pop_back();
+        } else if (op >= cAdd && op <= cPow) {
+            if (stack.size() < 2) return false;
+            n.b = stack.back(); stack.pop_back();
+            n.a = stack.back(); stack.pop_back();
+        } else if (op >= VarBegin) {
+            if (op - VarBegin < S) n.mask = 1u << (op - VarBegin);
+        } else {
+            return false;
+        }
+        if (n.a >= 0) { n.c0 = nodes[n.a].c0; n.i0 = nodes[n.a].i0; n.mask |= nodes[n.a].mask; }
+        if (n.b >= 0) n.mask |= nodes[n.b].mask;
+        n.i1 = imm;
+        nodes.push_back(n);
+        stack.push_back((int)nodes.size() - 1);
+    }
+    if (stack.size() != 1) return false;
+    out = Factored();
+    bool ok = true;
+    auto single = [](uint32_t m) { return (m & (m - 1)) == 0; };
+    auto reduce = [&](auto&& self, int id) -> void {
+        const TNode& n = nodes[id];
+        if (single(n.mask)) {
+            FactoredTerm t;
+            uint32_t m = n.mask;
+            while (m > 1) { m >>= 1; ++t.species; }
+            if (n.mask) ++t.species;
+            t.prog.code.assign(p.code.begin() + n.c0, p.code.begin() + n.c1);
+            t.prog.immed.assign(p.immed.begin() + n.i0, p.immed.begin() + n.i1);
+            out.ops.push_back((int32_t)out.terms.size());
+            out.terms.push_back(t);
+            return;
+        }
+        if (n.op == cNeg) { self(self, n.a); out.ops.push_back(-cNeg); return; }
+        if (n.op == cAdd || n.op == cSub || n.op == cMul) {
+            self(self, n.a);
+            self(self, n.b);
+            out.ops.push_back(-n.op);
+            return;
+        }
+        ok = false;
+    };
+    reduce(reduce, stack.back());
+    return ok;
 }
 
 double HostModel::propensity(const int32_t* state, int reaction1) const {

@@ -44,6 +44,27 @@ double evaluate_program(const Program& p, const double* val);
 // Which species a program reads (bit mask over the first S variables) and whether it contains an
 // operation that is not correctly rounded on every platform (pow, exp, log, trigonometric ...).
 void program_profile(const Program& p, int S, uint32_t* species_mask, bool* inexact);
+// evaluate_program with the interpreter's early exits reported: *aborted is set when a division by zero or a domain
+// error (log of a non-positive number, sqrt of a negative one, asin/acos out of range) ended the evaluation with 0.
+double evaluate_program_checked(const Program& p, const double* val, bool* aborted);
+
+// Partial evaluation of a propensity program for the index-only SpMV (spmv_variant = 2): every maximal sub-expression
+// that reads AT MOST ONE species becomes a `term` (tabulated on the host over that species' count, same libm and same
+// operation order as the whole program), and what is left above the terms -- the nodes that combine several species --
+// must consist of + - * and unary minus only (IEEE-exact operations the device reproduces bit for bit).  c5*DNA*D
+// becomes T1[DNA] * T2[D] with T1 = c5*DNA, T2 = D.  ops is the postfix program over the terms: a value t >= 0 pushes
+// term t, a negative value -op applies the byte-code operation op (cNeg, cAdd, cSub, cMul).
+struct FactoredTerm {
+    int species = -1;                        // -1: reads no species (a constant)
+    Program prog;                            // the sub-expression, variables numbered as in the full program
+};
+struct Factored {
+    std::vector<FactoredTerm> terms;
+    std::vector<int32_t> ops;
+};
+// false if the program is malformed or a multi-species node is not one of + - * neg
+bool factor_program(const Program& p, int S, Factored& out);
+
 bool load_model_file(const std::string& path, HostModel& m, std::string& err);
 bool parse_reaction(const std::string& line, const std::vector<std::string>& species, int32_t* vec, std::string& err);
 

@@ -190,7 +190,7 @@ __global__ void k_reset_links(FspView f, int64_t first, int64_t count) {
         const int64_t k = t / count, i = first + t % count;
         f.succ[k * f.ld + i] = IDX_ABSENT;
         f.pred[k * f.ld + i] = IDX_ABSENT;
-        f.coef[k * f.ld + i] = 0.0;
+        if (f.coef) f.coef[k * f.ld + i] = 0.0;                      // no coefficient array in the index-only variant
     }
 }
 
@@ -220,7 +220,7 @@ __global__ void k_resolve_links(FspView f) {
             } else {
                 const int32_t j = table_lookup(f, nb);
                 f.pred[e] = j;
-                if (j >= 0) f.coef[e] = f.prop[k * f.ld + j];
+                if (j >= 0 && f.coef) f.coef[e] = f.prop[k * f.ld + j];
             }
         }
     }
