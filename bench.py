@@ -45,9 +45,11 @@ R_TOGGLE = 4
 # Algorithmic bytes per state of FMATVEC alone, per SpMV variant: explicit gather-ELL 12R+24, matrix-free lattice
 # x + y = 16.  What each launch of the solve must move (the SpMV's operands and results plus those of the vector work fused
 # into the same pass) is counted by the library per launch (kfsp_profile_get).
-SPMV_ONLY_BYTES = {0: 12 * R_TOGGLE + 24, 1: 16}
+SPMV_ONLY_BYTES = {0: 12 * R_TOGGLE + 24, 1: 16, 2: 4 * R_TOGGLE + 4 * 2 + 24}
 SPMV_CLASSES = ("spmv_plain", "spmv_dot", "spmv_nrm", "spmv_fin_dot", "spmv_fin_nrm")
 KERNEL_NAME = {0: "k_spmv (generator SpMV, explicit gather ELL, inner products of the IOP window fused; per GPU, rank 0)",
+               2: "k_spmv_idx (index-only generator SpMV: pred + integer state streamed, a_k(x - nu_k) recomputed from factored tables, inner "
+                  "products of the IOP window fused; per GPU, rank 0)",
                1: "k_spmv_bd2 (matrix-free generator SpMV on the lattice = one whole Arnoldi column per launch: the previous column's two "
                   "DAXPYs + DNRM2 in its load stage, FMATVEC, and the inner products of the IOP window in its epilogue; per GPU, rank 0)"}
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")     # dram__bytes per launch from the round's ncu --set full pass
@@ -108,7 +110,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
@@ -187,7 +189,7 @@ def sha_of(arr):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bx", type=int, default=10000)
@@ -207,9 +209,10 @@ def main():
                          "(seed 12345) -- the irregular gather a real FSP ordering produces; explicit matrix only")
     ap.add_argument("--no-companion", action="store_true",
                     help="skip the explicit-matrix companion measurement that a --spmv-variant 1 run adds to its line")
-    ap.add_argument("--spmv-variant", type=int, default=1, choices=[0, 1],
+    ap.add_argument("--spmv-variant", type=int, default=1, choices=[0, 1, 2],
                     help="0: explicit gather-ELL matrix (the reference's data model); 1: matrix-free lattice SpMV "
-                         "(bit-identical results, 16 instead of 72 bytes per state)")
+                         "(bit-identical results, 16 instead of 72 bytes per state); 2: index-only SpMV for any state set "
+                         "(coefficients recomputed from the integer state, 48 instead of 72 bytes per state)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -255,8 +258,8 @@ def main():
     states_np, p0_np = synthetic(bx, by)
     n = len(p0_np)
     if args.scattered:
-        if args.spmv_variant != 0:
-            raise SystemExit("--scattered needs --spmv-variant 0: the lattice variant requires the natural order")
+        if args.spmv_variant == 1:
+            raise SystemExit("--scattered needs --spmv-variant 0 or 2: the lattice variant requires the natural order")
         perm = np.random.Generator(np.random.Philox(12345)).permutation(n)
         states_np = np.ascontiguousarray(states_np[perm])
         p0_np = np.ascontiguousarray(p0_np[perm])
@@ -406,7 +409,7 @@ def main():
         barrier()
         e_wall = allmax(time.time() - t0)
         # the lattice variant ships only this rank's slab of the state list; the explicit one needs the global list for its hash table
-        h2d = int((n if variant == 0 else nloc) * 2 * 4 + nloc * 8)
+        h2d = int((nloc if variant == 1 else n) * 2 * 4 + nloc * 8)
         d2h = int(nloc * 8)
         e2e = {"value": float(n) * e_mult / e_wall, "unit": UNIT,
                "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -533,8 +536,9 @@ def main():
                                    % (bx, by, n, args.t_final, args.m_max, ", indices in scattered (Philox-permuted) order" if args.scattered else ""),
                        "states": n, "reactions": R_TOGGLE,
                        "spmv_variant": "matrix-free lattice (FMATVEC recomputed from the integer state, bit-identical to the explicit "
-                                       "matrix)" if variant == 1 else "explicit gather-ELL matrix (ADJ/OFFDIAG/DIAG in HBM)",
-                       "l2": "inputs (%.2f GB per vector%s) %s the 126 MB L2" % (8e-9 * n, ", %.1f GB matrix" % (56e-9 * n) if variant == 0 else "",
+                                       "matrix)" if variant == 1 else "explicit gather-ELL matrix (ADJ/OFFDIAG/DIAG in HBM)" if variant == 0 else
+                                       "index-only (pred + integer state in HBM, coefficients recomputed; bit-identical to the explicit matrix)",
+                       "l2": "inputs (%.2f GB per vector%s) %s the 126 MB L2" % (8e-9 * n, ", %.1f GB matrix" % ((56e-9 if variant == 0 else 32e-9) * n) if variant != 1 else "",
                                                                                "exceed" if 8 * n > 126e6 else "DO NOT exceed"),
                        "parallelism": "1 GPU" if world == 1 else
                        "rows block-partitioned over %d GPUs; per SpMV the halo is gathered straight from the neighbours' HBM and per "

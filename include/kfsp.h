@@ -72,7 +72,12 @@ typedef struct {
     int32_t device;            /* CUDA device ordinal; -1 = current device                       */
     int32_t spmv_variant;      /* 0 explicit gather-ELL (reference data model); 1 matrix-free on a lattice:
                                   the state set must be a full box in natural order (first species fastest),
-                                  every propensity must read at most one species, the state set is fixed   */
+                                  every propensity must read at most one species, the state set is fixed;
+                                  2 index-only: any (adaptive, irregular, partitioned) state set; OFFDIAG's gather
+                                  form is never stored, a_k(x - nu_k) is recomputed from the row's integer state
+                                  (4R+4S+24 instead of 12R+24 bytes per state and SpMV); every propensity must be
+                                  sums/products of sub-expressions that read one species each (mass action, Hill
+                                  terms): kfsp_set_model returns KFSP_ERR_UNSUPPORTED otherwise                */
     int64_t max_states;        /* 6291469  NMAX, StateSpace.f90:10                               */
     double delta;              /* 1.2      KrylovSolver.f90:85                                   */
     double gamma;              /* 0.9      KrylovSolver.f90:87                                   */

@@ -113,6 +113,16 @@ __global__ void k_dist_halo_owner(const int32_t* __restrict__ halo_g, int64_t nh
 
 struct Dist {
     int rank = 0, nranks = 1;
+    // Adaptive state sets (expansion / pruning enabled): every rank keeps the single-GPU layout of the WHOLE state space
+    // (states, hash table, both orientations of the generator, W, basis) and computes the rows [rb[rank], rb[rank+1]) of
+    // every N-sized operation of the Krylov loop; expansion and pruning run on the gathered W, identically on every rank
+    // (Engine::repl_enter / repartition).  Fixed sets (config 5) use the memory-scaled layout instead: local rows only.
+    bool repl = false;
+    bool suspended = false;             // inside repl_enter/repl_leave: kernels see the whole state space, reductions stay local
+    bool whole = false;                 // the state set is still too small for a split to pay (Engine::repartition): every rank
+                                        // computes every row, nothing is exchanged; rows are split once it has grown
+    int64_t repl_min_rows = 1 << 22;    // KFSP_REPL_MIN_ROWS
+    int64_t rb[9] = {0};                // row bounds of the replicated-layout partition
     bool p2p = false;                   // peer-memory path active (cudaIpc over NVLink); else NCCL path
     bool want_p2p = true;
     bool p2p_red = true, p2p_halo = true;   // which halves use peer memory (KFSP_DIST_P2P: 1 both, 2 reductions only, 3 halo only)

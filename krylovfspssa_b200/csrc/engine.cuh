@@ -45,6 +45,7 @@ struct Engine {
     HostModel hm;                     // copy of the host model (callback, parameters, programs)
     PropCache pc;                     // device side cache used by SSA walks in host_prop mode
     int64_t pc_n = 0;                 // cached states
+    int64_t pc_budget = 16 << 20;     // ... the cache is emptied when it holds more (KFSP_PROP_CACHE_STATES)
     char* hp_dev = nullptr;           // device staging of the host-propensity path (grows on demand)
     char* hp_host = nullptr;          // pinned host staging
     size_t hp_dev_bytes = 0, hp_host_bytes = 0;
@@ -65,7 +66,6 @@ struct Engine {
     bool idx = false;
     FacModel fac{};
     double* d_factabs = nullptr;
-    int idx_drec = 0;                 // KFSP_IDX_DREC=1: DIAG is recomputed as well instead of streamed (A/B)
 
     // state space
     int64_t ld = 0;                   // capacity in states (multiple of 64)
@@ -181,7 +181,9 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_BD2_AHEAD")) bd2_ahead = std::min(std::max(std::atoi(ev), 0), BD2_L2AHEAD);
         if (const char* ev = std::getenv("KFSP_BD2_SYNC")) { bd2_sync = std::atoi(ev); if (bd2_sync & (bd2_sync - 1)) bd2_sync = 0; }
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
-        if (const char* ev = std::getenv("KFSP_IDX_DREC")) idx_drec = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_PROP_CACHE_STATES")) pc_budget = std::atoll(ev);
+        if (const char* ev = std::getenv("KFSP_DEBUG_REPL")) repl_debug = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_REPL_MIN_ROWS")) dist.repl_min_rows = std::atoll(ev);
         if (opt.spmv_variant < 0 || opt.spmv_variant > 2) return KFSP_ERR_ARG;
         if (opt.m_max < opt.m_min || opt.m_min < 1 || opt.m_max > EXPM_MAXN - 4 || opt.ideg != 6 || opt.max_states < 2 ||
             opt.max_states > 2000000000LL)
@@ -207,7 +209,7 @@ struct Engine {
         KFSP_CUDA(cudaMemset(d_err, 0, sizeof(int32_t)));
         LDH = opt.m_max + 2;
         KFSP_CUDA(cudaMalloc(&d_H, sizeof(double) * LDH * LDH));
-        KFSP_CUDA(cudaMalloc(&d_expm_work, sizeof(double) * 4 * EXPM_MAXN * EXPM_MAXN));
+        KFSP_CUDA(cudaMalloc(&d_expm_work, sizeof(double) * 7 * EXPM_MAXN * EXPM_MAXN));
         KFSP_CUDA(cudaMalloc(&d_expm_full, sizeof(double) * EXPM_MAXN * EXPM_MAXN));
         KFSP_CUDA(cudaMalloc(&d_res, sizeof(ExpmResult)));
         KFSP_CUDA(cudaMallocHost(&h_res, sizeof(ExpmResult)));
@@ -218,10 +220,13 @@ struct Engine {
         KFSP_CUDA(cudaMalloc(&rd.counter, sizeof(unsigned int)));
         KFSP_CUDA(cudaMemset(rd.counter, 0, sizeof(unsigned int)));
         KFSP_CUDA(cudaFuncSetAttribute(k_expm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXPM_SMEM));
+        KFSP_CUDA(cudaFuncSetAttribute(k_expm_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXPM_SMEM));
+        if (const char* ev = std::getenv("KFSP_EXPM_CLUSTER")) expm_cluster_from = std::atoi(ev);
         return KFSP_OK;
     }
     void destroy() {
         cudaSetDevice(device);
+        if (repl_debug) std::fprintf(stderr, "libkfsp rank %d: %g gathers of W %.3f s, re-partitions %.3f s\n", dist.rank, repl_s[2], repl_s[0], repl_s[1]);
         if (stream) cudaStreamSynchronize(stream);
         if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
         if (ev_side) cudaEventDestroy(ev_side);
@@ -276,6 +281,11 @@ struct Engine {
         KFSP_CUDA(cudaStreamSynchronize(stream));
         return KFSP_OK;
     }
+    // rows the Krylov kernels of this rank work on: everything, or this rank's slice of the replicated layout
+    bool sliced() const { return dist.repl && !dist.suspended && !dist.whole; }
+    bool dist_active() const { return dist.nranks > 1 && !dist.suspended && !dist.whole; }     // kernels exchange with the other ranks
+    int64_t kr0() const { return sliced() ? dist.lo : 0; }
+    int64_t kn() const { return sliced() ? dist.hi - dist.lo : n; }
     int check_launch() {
         ++launches;
         KFSP_CUDA(cudaGetLastError());
@@ -292,8 +302,7 @@ struct Engine {
     bool use_pdl = true;
     template <typename... KArgs, typename... Args>
     int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, Args&&... args) {
-        cudaLaunchConfig_t cfg;
-        std::memset(&cfg, 0, sizeof cfg);
+        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid, 1, 1);
         cfg.blockDim = dim3((unsigned)block, 1, 1);
         cfg.dynamicSmemBytes = smem;
@@ -614,7 +623,7 @@ struct Engine {
         KFSP_CUDA(cudaSetDevice(device));
         const int64_t gcap = ((opt.max_states + 63) / 64) * 64;
         // row arrays (matrix, vectors, basis) hold only this rank's rows when the state space is partitioned
-        const int64_t cap = dist.nranks > 1 ? (((opt.max_states + dist.nranks - 1) / dist.nranks + 1 + 63) / 64) * 64 : gcap;
+        const int64_t cap = (dist.nranks > 1 && !dist.repl) ? (((opt.max_states + dist.nranks - 1) / dist.nranks + 1 + 63) / 64) * 64 : gcap;
         int64_t ts = 1024;
         while (ts < 2 * gcap) ts <<= 1;
         KFSP_CUDA(cudaMalloc(&d_states, sizeof(int32_t) * gcap * S));
@@ -720,12 +729,13 @@ struct Engine {
     }
     int fsp_init(int64_t count, const int32_t* states_host, bool defer_check = false) {
         if (opt.spmv_variant == 1) return box_init_from_states(count, states_host, defer_check);
-        if (dist.nranks > 1) return dist_fsp_init(count, states_host);
+        if (dist.nranks > 1 && !dist.repl) return dist_fsp_init(count, states_host);
         KFSP_TRY(ensure_state_space());
         if (count < 1 || count > opt.max_states) return KFSP_ERR_BAD_SIZES;
         KFSP_CUDA(cudaMemcpyAsync(d_states, states_host, sizeof(int32_t) * count * S, cudaMemcpyHostToDevice, stream));
         KFSP_CUDA(cudaMemsetAsync(d_w, 0, sizeof(double) * count, stream));
-        return fsp_init_device(count);
+        KFSP_TRY(fsp_init_device(count));
+        return repartition();
     }
 
     // Insert `ncand` candidate states (in visiting order) that sit in scratch at `cand`;
@@ -761,8 +771,88 @@ struct Engine {
     static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
     // ---------------------------------------------------------------- ONESTEP_EXTENDER
+    // Several GPUs, adaptive state set: the three routines that change the state space run on the whole (replicated) state
+    // space with W gathered from the ranks' slices, identically on every rank -- SSA draws are counter-based per start
+    // state, reductions are double-double -- and the rows are re-partitioned afterwards.
+    double repl_s[3] = {0, 0, 0};     // KFSP_DEBUG_REPL=1: host wall time of the W gather (synchronised) / re-partition, printed by destroy()
+    bool repl_debug = false;
+    int repl_enter() {
+        if (!dist.repl) return KFSP_OK;
+        const double t0 = repl_debug ? wall_now() : 0.0;
+        KFSP_TRY(gather_rows(d_w));
+        if (repl_debug) { KFSP_TRY(sync()); repl_s[0] += wall_now() - t0; repl_s[2] += 1; }
+        dist.suspended = true;
+        return KFSP_OK;
+    }
+    int repl_leave() {
+        if (!dist.repl) return KFSP_OK;
+        dist.suspended = false;
+        const double t0 = repl_debug ? wall_now() : 0.0;
+        const int st = repartition();
+        if (repl_debug) { sync(); repl_s[1] += wall_now() - t0; }
+        return st;
+    }
+    // in-place all-gather of a vector in the replicated layout: rank r's slice [rb[r], rb[r+1]) becomes valid everywhere
+    int gather_rows(double* base) {
+#ifdef KFSP_WITH_NCCL
+        if (!dist.repl || dist.nranks == 1 || dist.whole) return KFSP_OK;       // `whole`: every rank computed every row
+        if (ncclGroupStart() != ncclSuccess) return KFSP_ERR_NCCL;
+        for (int r = 0; r < dist.nranks; ++r) {
+            const int64_t cnt = dist.rb[r + 1] - dist.rb[r];
+            if (cnt > 0 && ncclBroadcast(base + dist.rb[r], base + dist.rb[r], (size_t)cnt, ncclFloat64, r, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
+        }
+        if (ncclGroupEnd() != ncclSuccess) return KFSP_ERR_NCCL;
+        dist.halo_exchanges += 1;
+        dist.halo_bytes += 8 * (n - (dist.hi - dist.lo));
+        return KFSP_OK;
+#else
+        (void)base;
+        return KFSP_OK;
+#endif
+    }
+    // new row bounds after the state set changed (block partition of [0, n) over the ranks)
+    int repartition() {
+        dist.n_global = n;
+        if (!dist.repl) return KFSP_OK;
+        // Below repl_min_rows a column of the sweep is launch latency, not bandwidth, and a cross-GPU exchange per launch only
+        // adds to it (measured: Goutsias, 5e5 states on average, sweep 1.99 s on one GPU, 3.46 s split over two): every
+        // rank then computes every row and nothing is exchanged.  W is complete on every rank at both transitions (the
+        // caller gathered it before the state set changed).
+        dist.whole = n < dist.repl_min_rows;
+        for (int r = 0; r <= dist.nranks; ++r) dist.rb[r] = part_lo(n, dist.nranks, r);
+        dist.lo = dist.rb[dist.rank];
+        dist.hi = dist.rb[dist.rank + 1];
+        if (dist.d_peers) {
+            int64_t rb[MAX_RANKS + 1] = {0};
+            for (int r = 0; r <= dist.nranks; ++r) rb[r] = dist.rb[r];
+            KFSP_CUDA(cudaMemcpyAsync(dist.d_peers->rb, rb, sizeof rb, cudaMemcpyHostToDevice, stream));   // pageable source: staged before the call returns
+        }
+        return KFSP_OK;
+    }
     int fsp_onestep() {
-        if (dist.nranks > 1 || box) return KFSP_ERR_UNSUPPORTED;     // partitioned / lattice state sets are fixed
+        if (dist.nranks > 1 && !dist.repl) return KFSP_ERR_UNSUPPORTED;     // memory-scaled partitioned sets are fixed
+        KFSP_TRY(repl_enter());
+        const int st = fsp_onestep_1();
+        const int st2 = repl_leave();
+        return st != KFSP_OK ? st : st2;
+    }
+    int fsp_ssa(double timestep) {
+        if (dist.nranks > 1 && !dist.repl) return KFSP_ERR_UNSUPPORTED;
+        KFSP_TRY(repl_enter());
+        const int st = fsp_ssa_1(timestep);
+        const int st2 = repl_leave();
+        return st != KFSP_OK ? st : st2;
+    }
+    int fsp_drop(double dsum, int32_t* dropped, double* droptol_out, int64_t* count_out) {
+        *dropped = 0;
+        if (dist.nranks > 1 && !dist.repl) return KFSP_ERR_UNSUPPORTED;
+        KFSP_TRY(repl_enter());
+        const int st = fsp_drop_1(dsum, dropped, droptol_out, count_out);
+        const int st2 = repl_leave();
+        return st != KFSP_OK ? st : st2;
+    }
+    int fsp_onestep_1() {
+        if (box) return KFSP_ERR_UNSUPPORTED;                        // lattice state sets are fixed
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         // scratch: cnt[n_old], off[n_old], tiles
@@ -824,8 +914,8 @@ struct Engine {
     }
 
     // ---------------------------------------------------------------- SSA_EXTENDER
-    int fsp_ssa(double timestep) {
-        if (dist.nranks > 1 || box) return KFSP_ERR_UNSUPPORTED;
+    int fsp_ssa_1(double timestep) {
+        if (box) return KFSP_ERR_UNSUPPORTED;
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         ssa_calls += 1;
@@ -841,8 +931,12 @@ struct Engine {
         if (host_prop) {
             // Rounds: walks that step onto a state the host has not evaluated yet are suspended (cnt = -1) and
             // replayed once the host has put a_k of the requested states into the side cache.
+            // The side cache PERSISTS across expansions (and across the drops in between): a_k of a state never changes while
+            // the model stands, walks of successive expansions leave the projection through the same boundary region, and
+            // dropped states come back -- config 4 asked the host 3.0e8 times for 970k final states when the cache was
+            // emptied per call.  It is emptied by set_model, and here if it outgrows its budget.
             KFSP_TRY(ensure_prop_cache(1));
-            KFSP_TRY(clear_prop_cache());
+            if (pc_n > pc_budget) KFSP_TRY(clear_prop_cache());
             KFSP_LAUNCH(k_fill_i32, grid_for(n_old), VEC_THREADS, 0, cnt, n_old, (int32_t)-1);
             const size_t a_r = align_up(sizeof(int32_t) * (size_t)pc.req_cap * S), a_v = align_up(sizeof(double) * (size_t)pc.req_cap * (R + 1));
             KFSP_TRY(ensure_hp(256, 256 + 2 * a_r + a_v));
@@ -898,9 +992,7 @@ struct Engine {
         if (e) return err_to_status(e);
         if (ncand == 0) return KFSP_OK;
         if (ncand > 2000000000LL - n_old) return KFSP_ERR_OVERFLOW;
-        const int st = expand_with(ncand, n_old, /*ssa=*/true, timestep);
-        if (host_prop) KFSP_TRY(clear_prop_cache());
-        return st;
+        return expand_with(ncand, n_old, /*ssa=*/true, timestep);
     }
 
     // ---------------------------------------------------------------- FMATVEC
@@ -913,78 +1005,80 @@ struct Engine {
     }
     template <int MODE>
     int spmv(const double* x, double* y, const double* g = nullptr, EpiArgs ea = epi_none(), int cg = -1) {
+        const bool multi = dist_active();
+        const int64_t rows = kn(), r0 = kr0();
         // several GPUs, peer-memory halo: remote rows are addressed as (peer's basis) + (x - d_V), which only means
         // something for a column of the basis.  Any other operand (kfsp_matvec, kfsp_matvec_device) is staged in the
         // scratch column first; the barrier makes every rank's copy visible before any rank gathers from it.
-        if (dist.nranks > 1 && dist.p2p && dist.p2p_halo) {
+        if (multi && dist.p2p && dist.p2p_halo) {
             KFSP_TRY(ensure_basis());
             const double* vend = d_V + (size_t)ld * (opt.m_max + 4);
             if (x < d_V || x >= vend) {
-                double* stage = d_V + (size_t)ld * (opt.m_max + 2);
-                KFSP_CUDA(cudaMemcpyAsync(stage, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+                double* stage = d_V + (size_t)ld * (opt.m_max + 2) + r0;
+                KFSP_CUDA(cudaMemcpyAsync(stage, x, sizeof(double) * rows, cudaMemcpyDeviceToDevice, stream));
                 KFSP_TRY(dist_barrier());
                 x = stage;
             }
         }
         ea.has_g = (MODE == 1 && g) ? 1 : 0;
         KFSP_TRY(prof_begin(MODE == 0 ? KFSP_PROF_SPMV_PLAIN : MODE == 1 ? KFSP_PROF_SPMV_DOT : KFSP_PROF_SPMV_NRM,
-                            (box ? 16 : idx ? 4 * R + 4 * S + (idx_drec ? 16 : 24) : 12 * R + 24) + 8 * ea.has_g));
+                            (box ? 16 : idx ? 4 * R + 4 * S + 24 : 12 * R + 24) + 8 * ea.has_g));
         spmv_by_mode[MODE] += 1;
         if (box) {
             KFSP_TRY(spmv_box<MODE>(x, y, g, ea, cg));
             return prof_end();
         }
-        void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
-                     Reducer, SweepCtl*, EpiArgs, int, const double*, int64_t, int64_t);
-        const int halo = dist.nranks > 1 ? ((dist.p2p && dist.p2p_halo) ? 2 : 1) : 0;
+        // 1 / 2: memory-scaled partition (local rows + halo plan; NCCL exchange / peer loads); 3 / 4: replicated layout
+        // (global indices; peer loads / column completed by an all-gather first)
+        int halo = 0;
+        if (multi) halo = dist.repl ? ((dist.p2p && dist.p2p_halo) ? 3 : 4) : ((dist.p2p && dist.p2p_halo) ? 2 : 1);
         if (halo == 1) KFSP_TRY(dist_halo_exchange(x));
-        if (idx) {
-            KFSP_TRY(spmv_idx<MODE>(x, y, g, ea, cg, halo));
-            if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(ea, MODE == 1 ? 4 : 2));
-            return prof_end();
-        }
-        // tuning variant (KFSP_SPMV_TUNE): 0 = 1 row/iter, 1 = 2 rows/iter, 3/4/5 = 1 row/iter capped at 8/6/5 CTAs per SM
-#define KFSP_SPMV_PICK(RR)                                                                                              \
-        kern = halo == 2 ? k_spmv<RR, MODE, 1, 4, 2> : halo == 1 ? k_spmv<RR, MODE, 1, 4, 1>                             \
-             : spmv_tune == 1 ? k_spmv<RR, MODE, 2, 1, 0> : spmv_tune == 3 ? k_spmv<RR, MODE, 1, 8, 0>                   \
-             : spmv_tune == 4 ? k_spmv<RR, MODE, 1, 6, 0> : spmv_tune == 5 ? k_spmv<RR, MODE, 1, 5, 0>                   \
-             : k_spmv<RR, MODE, 1, 1, 0>
-        switch (R) {
-        case 4: KFSP_SPMV_PICK(4); break;
-        case 6: KFSP_SPMV_PICK(6); break;
-        case 10: KFSP_SPMV_PICK(10); break;
-        default: kern = halo == 2 ? k_spmv<0, MODE, 1, 4, 2> : halo == 1 ? k_spmv<0, MODE, 1, 4, 1> : k_spmv<0, MODE, 1, 1, 0>; break;
-        }
-#undef KFSP_SPMV_PICK
-        const int gr = wave_grid((const void*)kern, n);
+        if (halo == 4) KFSP_TRY(gather_rows(const_cast<double*>(x) - r0));
         const Reducer r = MODE != 0 ? next_rd() : rd;
         Reducer r2 = r;
-        if (halo == 2 && !r2.peers) r2.peers = dist.d_peers;     // the peer table is also the halo address book
-        KFSP_TRY(launch_pdl(kern, gr, VEC_THREADS, 0, n, ld, R, (const int32_t*)d_pred, (const double*)d_coef, (const double*)d_diag, x, y, g, r2, d_ctl, ea, cg,
-                            (const double*)dist.halo, n, (int64_t)(d_V ? x - d_V : 0)));
-        if (halo == 1 && MODE != 0) KFSP_TRY(dist_finalize(ea, MODE == 1 ? 4 : 2));
-        return prof_end();
-    }
-    // index-only variant (krylov.cuh: k_spmv_idx); local rows' states start at d_states + lo*S on a partitioned handle
-    template <int MODE>
-    int spmv_idx(const double* x, double* y, const double* g, const EpiArgs& ea, int cg, int halo) {
-        void (*kern)(const FacModel, int64_t, int64_t, const int32_t*, const int32_t*, const double*, const double*, double*, const double*,
-                     Reducer, SweepCtl*, EpiArgs, int, const double*, int64_t, int64_t) = nullptr;
+        if ((halo == 2 || halo == 3) && !r2.peers) r2.peers = dist.d_peers;     // the peer table is also the halo address book
+        if (!multi) { r2.peers = nullptr; r2.dist_send = nullptr; r2.seq = 0; }
+        const int64_t coloff = d_V ? x - d_V : 0;
+        if (idx) {
+            void (*ki)(const FacModel, int64_t, int64_t, const int32_t*, const int32_t*, const double*, const double*, double*, const double*,
+                       Reducer, SweepCtl*, EpiArgs, int, const double*, int64_t, int64_t, int64_t) = nullptr;
 #define KFSP_IDX_PICK(RR, SS)                                                                                           \
-        kern = halo == 2 ? (idx_drec ? k_spmv_idx<RR, SS, MODE, 2, 1> : k_spmv_idx<RR, SS, MODE, 2, 0>)                  \
-             : halo == 1 ? (idx_drec ? k_spmv_idx<RR, SS, MODE, 1, 1> : k_spmv_idx<RR, SS, MODE, 1, 0>)                  \
-             : (idx_drec ? k_spmv_idx<RR, SS, MODE, 0, 1> : k_spmv_idx<RR, SS, MODE, 0, 0>)
-        if (R == 4 && S == 2) { KFSP_IDX_PICK(4, 2); }
-        else if (R == 6 && S == 3) { KFSP_IDX_PICK(6, 3); }
-        else if (R == 10 && S == 6) { KFSP_IDX_PICK(10, 6); }
-        else { KFSP_IDX_PICK(0, 0); }
+            ki = halo == 4 ? k_spmv_idx<RR, SS, MODE, 4, 0> : halo == 3 ? k_spmv_idx<RR, SS, MODE, 3, 0>                   \
+               : halo == 2 ? k_spmv_idx<RR, SS, MODE, 2, 0> : halo == 1 ? k_spmv_idx<RR, SS, MODE, 1, 0> : k_spmv_idx<RR, SS, MODE, 0, 0>
+            bool gen = false;                                   // a reaction that needs the postfix program: generic kernel only
+            for (int k = 0; k < R; ++k) gen = gen || fac.shape[k] == FAC_GEN;
+            if (!gen && R == 4 && S == 2) { KFSP_IDX_PICK(4, 2); }
+            else if (!gen && R == 6 && S == 3) { KFSP_IDX_PICK(6, 3); }
+            else if (!gen && R == 10 && S == 6) { KFSP_IDX_PICK(10, 6); }
+            else { KFSP_IDX_PICK(0, 0); }
 #undef KFSP_IDX_PICK
-        const int gr = wave_grid((const void*)kern, n);
-        Reducer r2 = MODE != 0 ? next_rd() : rd;
-        if (halo == 2 && !r2.peers) r2.peers = dist.d_peers;
-        const int32_t* st = d_states + (dist.nranks > 1 ? dist.lo * S : 0);
-        return launch_pdl(kern, gr, VEC_THREADS, 0, fac, n, ld, (const int32_t*)d_pred, st, (const double*)d_diag, x, y, g, r2, d_ctl, ea, cg,
-                          (const double*)dist.halo, n, (int64_t)(d_V ? x - d_V : 0));
+            // the rows' states: this rank's rows start at lo in the state list on a partitioned handle
+            const int32_t* st = d_states + (multi ? dist.lo * S : 0);
+            KFSP_TRY(launch_pdl(ki, wave_grid((const void*)ki, rows), VEC_THREADS, 0, fac, rows, ld, (const int32_t*)d_pred + r0, st,
+                                (const double*)d_diag + r0, x, y, g, r2, d_ctl, ea, cg, (const double*)dist.halo, rows, coloff, r0));
+        } else {
+            void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, const double*, double*, const double*,
+                         Reducer, SweepCtl*, EpiArgs, int, const double*, int64_t, int64_t, int64_t);
+            // tuning variant (KFSP_SPMV_TUNE): 0 = 1 row/iter, 1 = 2 rows/iter, 3/4/5 = 1 row/iter capped at 8/6/5 CTAs per SM
+#define KFSP_SPMV_PICK(RR)                                                                                              \
+            kern = halo == 4 ? k_spmv<RR, MODE, 1, 4, 4> : halo == 3 ? k_spmv<RR, MODE, 1, 4, 3>                             \
+                 : halo == 2 ? k_spmv<RR, MODE, 1, 4, 2> : halo == 1 ? k_spmv<RR, MODE, 1, 4, 1>                             \
+                 : spmv_tune == 1 ? k_spmv<RR, MODE, 2, 1, 0> : spmv_tune == 3 ? k_spmv<RR, MODE, 1, 8, 0>                   \
+                 : spmv_tune == 4 ? k_spmv<RR, MODE, 1, 6, 0> : spmv_tune == 5 ? k_spmv<RR, MODE, 1, 5, 0>                   \
+                 : k_spmv<RR, MODE, 1, 1, 0>
+            switch (R) {
+            case 4: KFSP_SPMV_PICK(4); break;
+            case 6: KFSP_SPMV_PICK(6); break;
+            case 10: KFSP_SPMV_PICK(10); break;
+            default: kern = halo == 4 ? k_spmv<0, MODE, 1, 4, 4> : halo == 3 ? k_spmv<0, MODE, 1, 4, 3> : halo == 2 ? k_spmv<0, MODE, 1, 4, 2>
+                          : halo == 1 ? k_spmv<0, MODE, 1, 4, 1> : k_spmv<0, MODE, 1, 1, 0>; break;
+            }
+#undef KFSP_SPMV_PICK
+            KFSP_TRY(launch_pdl(kern, wave_grid((const void*)kern, rows), VEC_THREADS, 0, rows, ld, R, (const int32_t*)d_pred + r0, (const double*)d_coef + r0,
+                                (const double*)d_diag + r0, x, y, g, r2, d_ctl, ea, cg, (const double*)dist.halo, rows, coloff, r0));
+        }
+        if (multi && MODE != 0) KFSP_TRY(dist_finalize(ea, MODE == 1 ? 4 : 2));      // NCCL reduction path only (no-op with peer memory)
+        return prof_end();
     }
     int set_profiling(int level) {
         const bool on = level != 0;
@@ -1025,9 +1119,9 @@ struct Engine {
     }
 
     // ---------------------------------------------------------------- DROP_STATES
-    int fsp_drop(double dsum, int32_t* dropped, double* droptol_out, int64_t* count_out) {
+    int fsp_drop_1(double dsum, int32_t* dropped, double* droptol_out, int64_t* count_out) {
         *dropped = 0;
-        if (dist.nranks > 1 || box) return KFSP_ERR_UNSUPPORTED;
+        if (box) return KFSP_ERR_UNSUPPORTED;
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t lsize = n;
         // FIND_DROPTOL (StateSpace.f90:398-427): thresholds by repeated division
@@ -1045,7 +1139,7 @@ struct Engine {
         char* tmp = p;
         // one double-double reduction per candidate threshold, exactly the reference's loop
         for (int it = 0; it < 400; ++it) {
-            KFSP_LAUNCH(k_sum_below, grid_for(lsize), VEC_THREADS, 0, lsize, (const double*)d_w, droptol, rd, d_ctl);
+            KFSP_LAUNCH(k_sum_below, grid_for(lsize), VEC_THREADS, 0, lsize, (const double*)d_w, droptol, next_rd(), d_ctl);
             KFSP_TRY(read_ctl());
             if (h_ctl->scal[SC_WSUM] < dsum) break;
             droptol = droptol / 10.0;
@@ -1107,7 +1201,7 @@ struct Engine {
     // columns J = jold..m (1-based) then the extra product (KrylovSolver.f90:236-266). No host sync.
     int arnoldi(int jold, int m) {
         // small state spaces: the whole sweep in one single-CTA launch (bit-identical, see k_sweep_small)
-        if (dist.nranks == 1 && !box && !profile_spmv && small_sweep && n * (int64_t)(12 * R + 88) <= (1 << 20)) {
+        if (!dist_active() && !box && !profile_spmv && small_sweep && n * (int64_t)(12 * R + 88) <= (1 << 20)) {
             void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, double*, double*, int, int, int, SweepCtl*, double,
                          const FacModel, const int32_t*);
             switch (R) {
@@ -1128,18 +1222,19 @@ struct Engine {
     int arnoldi_unfused(int jold, int m) {
         // Two launches per column: finalise U_c (the two axpys of the previous column + its norm), then the generator product
         // with the three inner products of the window.  Column 0 and, on a resumed sweep (KrylovSolver.f90:400-433), column
-        // jold-1 are complete already.
+        // jold-1 are complete already.  (Replicated layout on several GPUs: this rank's slice of every column.)
+        const int64_t rows = kn(), r0 = kr0();
         for (int J = jold; J <= m + 1; ++J) {                    // J = m+1: the extra product for AVNORM (:261-263)
             const int c = J - 1;
-            double* vc = d_V + (size_t)c * ld;                   // holds A U_{c-1} until finalised into U_c
-            double* vn = d_V + (size_t)J * ld;
-            const double* vg = c >= 1 ? d_V + (size_t)(c - 1) * ld : nullptr;
+            double* vc = d_V + (size_t)c * ld + r0;              // holds A U_{c-1} until finalised into U_c
+            double* vn = d_V + (size_t)J * ld + r0;
+            const double* vg = c >= 1 ? d_V + (size_t)(c - 1) * ld + r0 : nullptr;
             if (J > jold) {
-                const double* vf = c >= 2 ? d_V + (size_t)(c - 2) * ld : vg;
+                const double* vf = c >= 2 ? d_V + (size_t)(c - 2) * ld + r0 : vg;
                 EpiArgs ef = epi_none();
                 ef.kind = RK_FIN_NRM; ef.column = c; ef.fin = 1; ef.break_tol = opt.break_tol; ef.hn_out = d_H + (size_t)(c - 1) * LDH + c;   // H(c+1,c)
                 KFSP_TRY(prof_begin(KFSP_PROF_AXPY_NRM, 24 + (c >= 2 ? 8 : 0)));
-                KFSP_TRY(launch_pdl(k_finalize, wave_grid((const void*)k_finalize, n), VEC_THREADS, 0, n, vg, vf, vc, c >= 2 ? 1 : 0, next_rd(), d_ctl, ef, c - 1, c - 2));
+                KFSP_TRY(launch_pdl(k_finalize, wave_grid((const void*)k_finalize, rows), VEC_THREADS, 0, rows, vg, vf, vc, c >= 2 ? 1 : 0, next_rd(), d_ctl, ef, c - 1, c - 2));
                 KFSP_TRY(dist_finalize(ef, 1));
                 KFSP_TRY(prof_end());
             }
@@ -1197,11 +1292,30 @@ struct Engine {
         }
         return KFSP_OK;
     }
+    // orders >= expm_cluster_from run the squarings on a cluster of 8 CTAs (expm.cuh); KFSP_EXPM_CLUSTER=1000 keeps everything on one CTA (A/B)
+    int expm_cluster_from = 36;
+    int launch_expm(int mx_ok, double t_ok, int use_brk, double t_brk, int set_one, const SweepCtl* ctl, double* full_out) {
+        if (mx_ok < expm_cluster_from) {
+            KFSP_LAUNCH(k_expm, 1, EXPM_THREADS, EXPM_SMEM, d_H, LDH, mx_ok, t_ok, use_brk, t_brk, set_one, ctl, d_expm_work, d_res, full_out);
+            return KFSP_OK;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(EXPM_CLUSTER, 1, 1);
+        cfg.blockDim = dim3(EXPM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = EXPM_SMEM;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = EXPM_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        KFSP_CUDA(cudaLaunchKernelEx(&cfg, k_expm_cluster, d_H, LDH, mx_ok, t_ok, use_brk, t_brk, set_one, ctl, d_expm_work, d_res, full_out));
+        return check_launch();
+    }
     // exp(t*H) on the device; result struct copied to pinned memory (synchronises)
     int expm_step(int mx_ok, double t_ok, int use_brk, double t_brk, int set_one) {
         KFSP_TRY(prof_begin(KFSP_PROF_EXPM));
-        KFSP_LAUNCH(k_expm, 1, EXPM_THREADS, EXPM_SMEM, d_H, LDH, mx_ok, t_ok, use_brk, t_brk, set_one, (const SweepCtl*)d_ctl,
-                    d_expm_work, d_res, (double*)nullptr);
+        KFSP_TRY(launch_expm(mx_ok, t_ok, use_brk, t_brk, set_one, (const SweepCtl*)d_ctl, nullptr));
         KFSP_TRY(prof_end());
         KFSP_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(ExpmResult), cudaMemcpyDeviceToHost, stream));
         KFSP_TRY(dist.nranks > 1 ? sync_check_peers() : sync());
@@ -1225,12 +1339,13 @@ struct Engine {
     // (identical on all ranks: the controller is SPMD) that tags the exchanged partials.
     Reducer next_rd() {
         Reducer r = rd;
+        if (dist.suspended || dist.whole) { r.peers = nullptr; r.dist_send = nullptr; r.seq = 0; return r; }   // whole state space on this GPU: no exchange
         if (dist.p2p && dist.p2p_red) r.seq = ++dist.seq;
         return r;
     }
     // all ranks: everything enqueued so far on every GPU is complete and visible before anything enqueued later starts
     int dist_barrier() {
-        if (!(dist.p2p && dist.p2p_halo)) return KFSP_OK;       // the NCCL exchange step is ordered by NCCL itself
+        if (!dist_active() || !(dist.p2p && dist.p2p_halo)) return KFSP_OK;       // the NCCL exchange step is ordered by NCCL itself
         if (!dist.p2p_red) return KFSP_ERR_UNSUPPORTED;         // flags are shared with the reduction exchange
         KFSP_TRY(launch_pdl(k_dist_barrier, 1, 32, 0, (const DistPeers*)dist.d_peers, (unsigned long long)(++dist.seq)));
         return KFSP_OK;
@@ -1306,6 +1421,7 @@ struct Engine {
             return KFSP_OK;
         }
         hp.halo_owner = dist.halo_owner; hp.halo_lidx = dist.halo_lidx; hp.err = d_err;
+        for (int r = 0; r <= P; ++r) hp.rb[r] = dist.rb[r];
         if (!dist.d_peers) KFSP_CUDA(cudaMalloc(&dist.d_peers, sizeof(DistPeers)));
         KFSP_CUDA(cudaMemcpy(dist.d_peers, &hp, sizeof hp, cudaMemcpyHostToDevice));
         if (dist.p2p_red) { rd.peers = dist.d_peers; rd.dist_send = nullptr; }
@@ -1325,6 +1441,8 @@ struct Engine {
         std::memcpy(&u, id, sizeof u);
         if (ncclCommInitRank(&dist.comm, nranks, u, rank) != ncclSuccess) return KFSP_ERR_NCCL;
         dist.rank = rank; dist.nranks = nranks;
+        // adaptive state sets keep the whole state space on every rank and partition the rows of the Krylov loop (dist.cuh)
+        dist.repl = opt.spmv_variant != 1 && (opt.enable_expand || opt.enable_drop || opt.n_init_onestep > 0);
         if (const char* ev = std::getenv("KFSP_DIST_P2P")) {
             const int v = std::atoi(ev);
             dist.want_p2p = v != 0; dist.p2p_red = v == 1 || v == 2; dist.p2p_halo = v == 1 || v == 3;
@@ -1341,7 +1459,7 @@ struct Engine {
     }
     // all-gather the ranks' double-double partials, merge in rank order, run the reduction's epilogue
     int dist_finalize(const EpiArgs& ea, int nv) {
-        if (dist.nranks == 1 || (dist.p2p && dist.p2p_red)) return KFSP_OK;     // peer-memory path: exchanged inside the reducing kernel
+        if (!dist_active() || (dist.p2p && dist.p2p_red)) return KFSP_OK;     // peer-memory path: exchanged inside the reducing kernel
 #ifdef KFSP_WITH_NCCL
         if (ncclAllGather(dist.red_send, dist.red_recv, RED_W, ncclFloat64, dist.comm, stream) != ncclSuccess) return KFSP_ERR_NCCL;
         KFSP_LAUNCH(k_dist_finalize, 1, 32, 0, ea, nv, (const double*)dist.red_recv, dist.nranks, d_ctl);

@@ -83,17 +83,11 @@ __device__ __forceinline__ void expm_store(double* C, int ldc, int n, const doub
         }
 }
 
-// One CTA of 1024 threads.
-//   H, ldh        : the device Hessenberg matrix (column-major)
-//   mx_ok, t_ok   : order and step when the sweep did not break down
-//   use_brk,t_brk : if use_brk and ctl->brk > 0, order = ctl->brk and step = t_brk (KrylovSolver.f90:249-256, 271)
-//   set_one       : if >= 0, first set H(set_one+2, set_one+1) = 1 (label 300, KrylovSolver.f90:266; set_one = M)
-//   work          : 4 * EXPM_MAXN^2 doubles of global scratch
-//   full_out      : optional mx*mx output of the whole exponential (tests)
-__global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, int mx_ok, double t_ok, int use_brk, double t_brk,
-                                                          int set_one, const SweepCtl* ctl, double* work, ExpmResult* res,
-                                                          double* full_out) {
-    extern __shared__ __align__(16) double smem[];
+// Everything of DGPADM up to the squarings, on ONE CTA of 1024 threads: ||H||_inf, ns, the Pade numerator and denominator by
+// Horner, the linear solve, E = I + 2 X.  Returns info (uniform over the CTA); on success E (n x n, zero padded to a multiple
+// of 4) is in sB.  smem: the dynamic shared memory of the kernel (EXPM_SMEM bytes); work: 4 * EXPM_MAXN^2 doubles of global scratch.
+__device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, int n, double t, double* work, double* smem, int* ns_out,
+                                         double* hnorm_out) {
     double* sA = smem;
     double* sB = smem + (size_t)EXPM_LDS * EXPM_MAXN;
     double* sx = sB + (size_t)EXPM_LDS * EXPM_MAXN;       // 64 doubles of scratch
@@ -103,32 +97,23 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     __shared__ int s_piv, s_info, s_ns, s_kb;
     __shared__ double s_scale, s_hnorm, s_coef[8];
     const int tid = threadIdx.x;
-
-    int n = mx_ok;
-    double t = t_ok;
-    const int brk = ctl ? ctl->brk : 0;
-    if (use_brk && brk > 0) { n = brk; t = t_brk; }
-    if (set_one >= 0 && tid == 0) H[(size_t)set_one * ldh + set_one + 1] = 1.0;
     if (tid == 0) s_info = 0;
     __syncthreads();
     const int np = (n + 3) & ~3;
-    const size_t nn = (size_t)EXPM_MAXN * EXPM_MAXN;
-    double* gH2 = work;            // scale2*H*H
-    double* gP = work + nn;
-    double* gQ = work + 2 * nn;
-    double* gF = work + 3 * nn;
+    double* gQ = work;             // the finished denominator polynomial q, parked while p is formed (thread-private tiles)
 
-    // ---- ||H||_inf by row sums in column order (dgpadm.f:241-253) -------------------------
+    // ---- stage H once; ||H||_inf by row sums in column order (dgpadm.f:241-253) from the staged copy ----------
+    expm_load(sA, H, ldh, n, np, 1.0);
+    if (tid == 0) s_kb = 0;
+    __syncthreads();
     double rs = 0.0;
     int kb_row = 0;                                        // widest |i-j| of a non-zero entry in this row
     if (tid < n)
         for (int j = 0; j < n; ++j) {
-            const double v = H[(size_t)j * ldh + tid];
+            const double v = sA[(size_t)j * EXPM_LDS + tid];
             rs += fabs(v);
             if (v != 0.0) kb_row = max(kb_row, abs(j - tid));
         }
-    if (tid == 0) s_kb = 0;
-    __syncthreads();
     if (kb_row) atomicMax(&s_kb, kb_row);
     {
         // block max through shared scratch
@@ -162,11 +147,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
         }
         __syncthreads();
     }
-    if (s_info != 0) {
-        if (tid == 0) { res->info = s_info; res->ns = 0; res->mx = n; res->brk = brk; res->hnorm = s_hnorm; res->t_used = t;
-                        res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0; }
-        return;
-    }
+    if (s_info != 0) { *ns_out = 0; *hnorm_out = s_hnorm; return s_info; }
     const double scale = s_scale, scale2 = __dmul_rn(scale, scale);
     double acc[4][4];
     // The Krylov H of IOP-2 is tridiagonal (plus the unit sub-diagonal entry): every Pade factor is banded
@@ -174,56 +155,73 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     const bool tri = s_kb <= 1 && n > 2 * (EXPM_KL + EXPM_KU);
     const int DENSE = 1 << 20;
     const int bH = tri ? 1 : DENSE, bH2 = tri ? 2 : DENSE;
+    const int ti = tid & 31, tj = tid >> 5;
+    // one tile of a polynomial value lives in the registers of the thread that computed it: it goes to shared memory as the
+    // left operand of the next product and comes back as that product's accumulator -- nothing of the Horner recurrence
+    // passes through global memory (it used to: ~14 round trips of L2 latency per call, a third of the kernel at n = 100)
+    auto add_diag = [&](double c) {
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2)
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2)
+                if (4 * ti + a2 == 4 * tj + b2) acc[a2][b2] = __dadd_rn(acc[a2][b2], c);
+    };
 
     // ---- H2 = scale2*H*H (dgpadm.f:270): alpha multiplies the right operand, as DGEMM does ----
-    expm_load(sA, H, ldh, n, np, 1.0);
-    expm_load(sB, H, ldh, n, np, scale2);
+    for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) sB[t2] = __dmul_rn(scale2, sA[t2]);     // the padding stays 0
     __syncthreads();
     expm_mma(sA, sB, n, acc, bH, bH);
-    expm_store(gH2, n, n, acc, 0.0);
     __syncthreads();
-    // sB <- H2 (stays for the whole Horner recurrence)
-    expm_load(sB, gH2, n, n, np, 1.0);
-    // ---- p = c5*I, q = c6*I ; Horner (dgpadm.f:274-301) -----------------------------------
-    // k = 5: q = q*H2 + c4 I ; k = 4: p = p*H2 + c3 I ; k = 3: q ; k = 2: p ; k = 1: q = q*H2 + c0 I
-    // The first two products have diagonal left operands: (c*I)*H2 = c*H2.
-    double* bufP = gP; double* bufQ = gQ; double* bufF = gF;
-    for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) {
-        const int j = t2 / n, i = t2 % n;
-        const double h2 = gH2[t2];
-        bufF[t2] = fma(s_coef[6], h2, (i == j ? s_coef[4] : 0.0));   // new q
-        bufP[t2] = (i == j) ? s_coef[5] : 0.0;                      // p = c5 I
+    expm_store(sB, EXPM_LDS, n, acc, 0.0);                 // sB <- H2 (stays for both Horner recurrences)
+    // ---- Horner (dgpadm.f:274-301): q = ((c6 H2 + c4 I) H2 + c2 I) H2 + c0 I and p = ((c5 I) H2 + c3 I) H2 + c1 I are
+    // independent of each other: one after the other instead of interleaved, so that a single register tile is live.
+    // The first product of each has a diagonal left operand: (c I) H2 = c H2.
+#pragma unroll
+    for (int b2 = 0; b2 < 4; ++b2)
+#pragma unroll
+        for (int a2 = 0; a2 < 4; ++a2) acc[a2][b2] = fma(s_coef[6], acc[a2][b2], (4 * ti + a2 == 4 * tj + b2) ? s_coef[4] : 0.0);
+    int bQ = tri ? 2 : DENSE;
+    for (int k = 2; k >= 0; k -= 2) {                      // q = q*H2 + c2 I ; q = q*H2 + c0 I
+        __syncthreads();
+        expm_store(sA, EXPM_LDS, n, acc, 0.0);
+        __syncthreads();
+        expm_mma(sA, sB, n, acc, bQ, bH2);
+        if (tri) bQ += 2;
+        add_diag(s_coef[k]);
     }
+#pragma unroll
+    for (int b2 = 0; b2 < 4; ++b2)
+#pragma unroll
+        for (int a2 = 0; a2 < 4; ++a2) {
+            const int i = 4 * ti + a2, j = 4 * tj + b2;
+            if (i < n && j < n) gQ[(size_t)j * EXPM_LDS + i] = acc[a2][b2];
+            acc[a2][b2] = (i == j) ? s_coef[5] : 0.0;      // p = c5 I
+        }
+    int bP = tri ? 0 : DENSE;
+    for (int k = 3; k >= 1; k -= 2) {                      // p = p*H2 + c3 I ; p = p*H2 + c1 I
+        __syncthreads();
+        expm_store(sA, EXPM_LDS, n, acc, 0.0);
+        __syncthreads();
+        expm_mma(sA, sB, n, acc, bP, bH2);
+        if (tri) bP += 2;
+        add_diag(s_coef[k]);
+    }
+    // p = scale * p * H (dgpadm.f:309-312)
     __syncthreads();
-    { double* tmp = bufQ; bufQ = bufF; bufF = tmp; }               // q is now in old F; old Q buffer is free
-    int iodd = 0;
-    int bP = tri ? 0 : DENSE, bQ = tri ? 2 : DENSE;         // p = c5 I, q = c6 H2 + c4 I
-    for (int k = 4; k >= 1; --k) {
-        double* used = iodd ? bufQ : bufP;
-        expm_load(sA, used, n, n, np, 1.0);
-        __syncthreads();
-        expm_mma(sA, sB, n, acc, iodd ? bQ : bP, bH2);
-        if (tri) { if (iodd) bQ += 2; else bP += 2; }
-        expm_store(bufF, n, n, acc, s_coef[k - 1]);
-        __syncthreads();
-        if (iodd) { bufQ = bufF; } else { bufP = bufF; }
-        bufF = used;
-        iodd = 1 - iodd;
-    }
-    // here iodd == 0: p = scale * p * H (dgpadm.f:309-312)
-    expm_load(sA, bufP, n, n, np, 1.0);
+    expm_store(sA, EXPM_LDS, n, acc, 0.0);
     expm_load(sB, H, ldh, n, np, scale);
     __syncthreads();
     expm_mma(sA, sB, n, acc, bP, bH);
     __syncthreads();
     // ---- sA <- q - p ; sB <- p ; solve (q-p) X = p (dgpadm.f:314-315) ----------------------
     expm_store(sB, EXPM_LDS, n, acc, 0.0);
-    expm_load(sA, bufQ, n, n, np, 1.0);
-    __syncthreads();
-    for (int t2 = tid; t2 < n * EXPM_LDS; t2 += EXPM_THREADS) {
-        const int i = t2 % EXPM_LDS;
-        if (i < n) sA[t2] = __dsub_rn(sA[t2], sB[t2]);
-    }
+#pragma unroll
+    for (int b2 = 0; b2 < 4; ++b2)
+#pragma unroll
+        for (int a2 = 0; a2 < 4; ++a2) {
+            const int i = 4 * ti + a2, j = 4 * tj + b2;
+            if (i < n && j < n) sA[(size_t)j * EXPM_LDS + i] = __dsub_rn(gQ[(size_t)j * EXPM_LDS + i], acc[a2][b2]);
+        }
     __syncthreads();
     if (tri) {
         // ---- banded path: q-p has lower bandwidth 6; with partial pivoting U has upper bandwidth 12 ---------
@@ -272,11 +270,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
             }
         }
         __syncthreads();
-        if (s_info != 0) {
-            if (tid == 0) { res->info = s_info; res->ns = s_ns; res->mx = n; res->brk = brk; res->hnorm = s_hnorm; res->t_used = t;
-                            res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0; }
-            return;
-        }
+        if (s_info != 0) { *ns_out = s_ns; *hnorm_out = s_hnorm; return s_info; }
         // Phase B: the n right-hand sides are independent -> transpose B so that thread j owns column j with
         // conflict-free shared-memory accesses, then forward and backward substitution without any barrier.
         for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) {
@@ -351,11 +345,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
         }
         __syncthreads();
     }
-    if (s_info != 0) {
-        if (tid == 0) { res->info = s_info; res->ns = s_ns; res->mx = n; res->brk = brk; res->hnorm = s_hnorm; res->t_used = t;
-                        res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0; }
-        return;
-    }
+    if (s_info != 0) { *ns_out = s_ns; *hnorm_out = s_hnorm; return s_info; }
     // back substitution U X = Y, column oriented
     for (int k = n - 1; k >= 0; --k) {
         const double ukk = sA[(size_t)k * EXPM_LDS + k];
@@ -375,8 +365,46 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     }
     __syncthreads();
     }   // dense path
+    *ns_out = s_ns;
+    *hnorm_out = s_hnorm;
+    return 0;
+}
+
+// One CTA of 1024 threads.
+//   H, ldh        : the device Hessenberg matrix (column-major)
+//   mx_ok, t_ok   : order and step when the sweep did not break down
+//   use_brk,t_brk : if use_brk and ctl->brk > 0, order = ctl->brk and step = t_brk (KrylovSolver.f90:249-256, 271)
+//   set_one       : if >= 0, first set H(set_one+2, set_one+1) = 1 (label 300, KrylovSolver.f90:266; set_one = M)
+//   work          : 6 * EXPM_MAXN^2 doubles of global scratch (the last two: E ping-pong of the cluster variant)
+//   full_out      : optional mx*mx output of the whole exponential (tests)
+__device__ __forceinline__ void expm_result(ExpmResult* res, int info, int ns, int n, int brk, double hnorm, double t, const SweepCtl* ctl) {
+    res->info = info; res->ns = ns; res->mx = n; res->brk = brk; res->hnorm = hnorm; res->t_used = t;
+    res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0;
+}
+__global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, int mx_ok, double t_ok, int use_brk, double t_brk,
+                                                          int set_one, const SweepCtl* ctl, double* work, ExpmResult* res,
+                                                          double* full_out) {
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;
+    double* sB = smem + (size_t)EXPM_LDS * EXPM_MAXN;
+    const int tid = threadIdx.x;
+    int n = mx_ok;
+    double t = t_ok;
+    const int brk = ctl ? ctl->brk : 0;
+    if (use_brk && brk > 0) { n = brk; t = t_brk; }
+    if (set_one >= 0 && tid == 0) H[(size_t)set_one * ldh + set_one + 1] = 1.0;
+    __syncthreads();
+    const int np = (n + 3) & ~3;
+    int ns = 0;
+    double hnorm = 0.0;
+    const int info = expm_pade(H, ldh, n, t, work, smem, &ns, &hnorm);
+    if (info != 0) {
+        if (tid == 0) expm_result(res, info, ns, n, brk, hnorm, t, ctl);
+        return;
+    }
+    double acc[4][4];
     // ---- squarings (dgpadm.f:329-336) ------------------------------------------------------
-    for (int s = 0; s < s_ns; ++s) {
+    for (int s = 0; s < ns; ++s) {
         for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) sA[t2] = sB[t2];
         __syncthreads();
         expm_mma(sA, sB, n, acc);
@@ -388,10 +416,101 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     for (int i = tid; i < EXPM_MAXN; i += EXPM_THREADS) res->e[i] = i < n ? sB[i] : 0.0;
     if (full_out)
         for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) full_out[t2] = sB[(size_t)(t2 / n) * EXPM_LDS + t2 % n];
-    if (tid == 0) {
-        res->info = 0; res->ns = s_ns; res->mx = n; res->brk = brk; res->hnorm = s_hnorm; res->t_used = t;
-        res->avnorm = ctl ? ctl->scal[SC_AVNORM] : 0.0;
+    if (tid == 0) expm_result(res, 0, ns, n, brk, hnorm, t, ctl);
+}
+
+// The same on a thread-block CLUSTER of EXPM_CLUSTER CTAs (one per SM): CTA 0 runs expm_pade, then the ns squarings -- which
+// are dense (n x n x n each) and at n ~ 100 cost 55 us apiece at the FP64 rate of a single SM, 5-10 of them per call -- are
+// split by column tiles over the CTAs: every CTA stages the current E in its shared memory, computes its tiles of E*E with the
+// same per-element operation order (k ascending from an accumulator that starts at 0: bit-identical to k_expm), writes them to
+// the other E buffer in global memory (L2-resident, 85 KB), and a cluster barrier (release/acquire) separates the squarings.
+constexpr int EXPM_CLUSTER = 8;
+__device__ __forceinline__ void cluster_barrier() {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm_cluster(double* H, int ldh, int mx_ok, double t_ok, int use_brk, double t_brk,
+                                                                  int set_one, const SweepCtl* ctl, double* work, ExpmResult* res,
+                                                                  double* full_out) {
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;
+    double* sB = smem + (size_t)EXPM_LDS * EXPM_MAXN;
+    const int tid = threadIdx.x;
+    const int cta = (int)cluster_cta_rank();
+    int n = mx_ok;
+    double t = t_ok;
+    const int brk = ctl ? ctl->brk : 0;
+    if (use_brk && brk > 0) { n = brk; t = t_brk; }
+    const int np = (n + 3) & ~3;
+    const size_t nn = (size_t)EXPM_MAXN * EXPM_MAXN;
+    double* gE[2] = {work + 4 * nn, work + 5 * nn};
+    volatile int* hdr = reinterpret_cast<volatile int*>(work + 6 * nn);      // {info, ns} for the other CTAs
+    int ns = 0;
+    double hnorm = 0.0;
+    if (cta == 0) {
+        if (set_one >= 0 && tid == 0) H[(size_t)set_one * ldh + set_one + 1] = 1.0;
+        __syncthreads();
+        const int info = expm_pade(H, ldh, n, t, work, smem, &ns, &hnorm);
+        if (info == 0)
+            for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) gE[0][t2] = sB[t2];
+        if (tid == 0) { hdr[0] = info; hdr[1] = ns; }
+        if (info != 0 && tid == 0) expm_result(res, info, ns, n, brk, hnorm, t, ctl);
     }
+    cluster_barrier();
+    if (hdr[0] != 0) return;                                               // uniform over the cluster
+    ns = hdr[1];
+    // column tiles of this CTA: tj in [cta*TJ, (cta+1)*TJ), one warp per column tile, 32 row tiles per warp
+    const int ntile = np / 4;
+    const int TJ = (ntile + EXPM_CLUSTER - 1) / EXPM_CLUSTER;
+    for (int s = 0; s < ns; ++s) {
+        const double* cur = gE[s & 1];
+        double* nxt = gE[(s + 1) & 1];
+        for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) sA[t2] = __ldcg(cur + t2);
+        __syncthreads();
+        const int ti = tid & 31, tjl = tid >> 5, tj = cta * TJ + tjl;
+        if (tjl < TJ && 4 * ti < n && 4 * tj < n) {
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = 0.0;
+            const double* pa = sA + 4 * ti;
+            const double* pb = sA + (size_t)(4 * tj) * EXPM_LDS;
+            for (int k = 0; k < n; ++k) {
+                const double2 a01 = *reinterpret_cast<const double2*>(pa + (size_t)k * EXPM_LDS);
+                const double2 a23 = *reinterpret_cast<const double2*>(pa + (size_t)k * EXPM_LDS + 2);
+                const double b0 = pb[k], b1 = pb[EXPM_LDS + k], b2 = pb[2 * EXPM_LDS + k], b3 = pb[3 * EXPM_LDS + k];
+                acc[0][0] = fma(a01.x, b0, acc[0][0]); acc[1][0] = fma(a01.y, b0, acc[1][0]);
+                acc[2][0] = fma(a23.x, b0, acc[2][0]); acc[3][0] = fma(a23.y, b0, acc[3][0]);
+                acc[0][1] = fma(a01.x, b1, acc[0][1]); acc[1][1] = fma(a01.y, b1, acc[1][1]);
+                acc[2][1] = fma(a23.x, b1, acc[2][1]); acc[3][1] = fma(a23.y, b1, acc[3][1]);
+                acc[0][2] = fma(a01.x, b2, acc[0][2]); acc[1][2] = fma(a01.y, b2, acc[1][2]);
+                acc[2][2] = fma(a23.x, b2, acc[2][2]); acc[3][2] = fma(a23.y, b2, acc[3][2]);
+                acc[0][3] = fma(a01.x, b3, acc[0][3]); acc[1][3] = fma(a01.y, b3, acc[1][3]);
+                acc[2][3] = fma(a23.x, b3, acc[2][3]); acc[3][3] = fma(a23.y, b3, acc[3][3]);
+            }
+            // the padding rows / columns stay zero: rows >= n of a tile are products of zero rows of E
+#pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int i = 4 * ti + a, j = 4 * tj + b2;
+                    if (i < np && j < np) nxt[(size_t)j * EXPM_LDS + i] = (i < n && j < n) ? acc[a][b2] : 0.0;
+                }
+        }
+        cluster_barrier();
+    }
+    if (cta != 0) return;
+    const double* E = gE[ns & 1];
+    for (int i = tid; i < EXPM_MAXN; i += EXPM_THREADS) res->e[i] = i < n ? __ldcg(E + i) : 0.0;
+    if (full_out)
+        for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) full_out[t2] = __ldcg(E + (size_t)(t2 / n) * EXPM_LDS + t2 % n);
+    if (tid == 0) expm_result(res, 0, ns, n, brk, hnorm, t, ctl);
 }
 
 }  // namespace kfsp

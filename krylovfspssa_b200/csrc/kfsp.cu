@@ -29,7 +29,7 @@ namespace {
 struct GpuBackend {
     Engine& e;
     explicit GpuBackend(Engine& en) : e(en) {}
-    int64_t size() { return e.dist.nranks > 1 ? e.dist.n_global : e.n; }
+    int64_t size() { return (e.dist.nranks > 1 && !e.dist.repl) ? e.dist.n_global : e.n; }
     // phase timers: every timed call ends in a stream synchronisation, so host wall clock is device time + latency
     struct Tick { double& acc; double t0; explicit Tick(double& a) : acc(a), t0(wall_now()) {} ~Tick() { acc += wall_now() - t0; } };
     int onestep() { Tick t(e.phase_s[4]); int st = e.fsp_onestep(); if (st == KFSP_OK) st = e.sync(); return st; }
@@ -43,7 +43,7 @@ struct GpuBackend {
     }
     int norms(double* wsum, double* wssq) {
         Tick t(e.phase_s[1]);
-        k_norms<<<e.wave_grid((const void*)k_norms, e.n), VEC_THREADS, 0, e.stream>>>(e.n, e.d_w, e.next_rd(), e.d_ctl);
+        k_norms<<<e.wave_grid((const void*)k_norms, e.kn()), VEC_THREADS, 0, e.stream>>>(e.kn(), e.d_w + e.kr0(), e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
         { EpiArgs en = Engine::epi_none(); en.kind = RK_NORMS; KFSP_TRY(e.dist_finalize(en, 2)); }
         KFSP_TRY(e.read_ctl());
@@ -56,7 +56,8 @@ struct GpuBackend {
         k_reset_ctl<<<1, 128, 0, e.stream>>>(e.d_ctl);
         KFSP_TRY(e.check_launch());
         KFSP_TRY(e.prof_begin(KFSP_PROF_SCALE_COPY, 16));
-        KFSP_TRY(e.launch_pdl(k_scale_copy, e.wave_grid((const void*)k_scale_copy, e.n), VEC_THREADS, 0, e.n, inv_beta, (const double*)e.d_w, e.d_V));
+        KFSP_TRY(e.launch_pdl(k_scale_copy, e.wave_grid((const void*)k_scale_copy, e.kn()), VEC_THREADS, 0, e.kn(), inv_beta, (const double*)e.d_w + e.kr0(),
+                              e.d_V + e.kr0()));
         KFSP_TRY(e.dist_barrier());        // neighbours gather column 0 straight from this GPU's HBM
         return e.prof_end();
     }
@@ -76,8 +77,8 @@ struct GpuBackend {
     int combine(int mx, double beta, double* wsum, double* wssq) {
         Tick t(e.phase_s[1]);
         KFSP_TRY(e.prof_begin(KFSP_PROF_COMBINE, 8 * (mx + 1)));
-        KFSP_TRY(e.launch_pdl(k_combine, e.wave_grid((const void*)k_combine, e.n), VEC_THREADS, 0, e.n, e.ld, mx, beta, (const double*)e.d_V, (const double*)e.d_res->e, e.d_w,
-                              e.next_rd(), e.d_ctl));
+        KFSP_TRY(e.launch_pdl(k_combine, e.wave_grid((const void*)k_combine, e.kn()), VEC_THREADS, 0, e.kn(), e.ld, mx, beta, (const double*)e.d_V + e.kr0(),
+                              (const double*)e.d_res->e, e.d_w + e.kr0(), e.next_rd(), e.d_ctl));
         { EpiArgs en = Engine::epi_none(); en.kind = RK_NORMS; KFSP_TRY(e.dist_finalize(en, 2)); }
         KFSP_TRY(e.prof_end());
         KFSP_TRY(e.read_ctl());
@@ -86,7 +87,7 @@ struct GpuBackend {
         return KFSP_OK;
     }
     int restore_w(double beta, double* wssq) {
-        k_scale_copy_nrm<<<e.grid_for(e.n), VEC_THREADS, 0, e.stream>>>(e.n, beta, e.d_V, e.d_w, e.next_rd(), e.d_ctl);
+        k_scale_copy_nrm<<<e.grid_for(e.kn()), VEC_THREADS, 0, e.stream>>>(e.kn(), beta, e.d_V + e.kr0(), e.d_w + e.kr0(), e.next_rd(), e.d_ctl);
         KFSP_TRY(e.check_launch());
         { EpiArgs en = Engine::epi_none(); en.kind = RK_NORMS; KFSP_TRY(e.dist_finalize(en, 2)); }
         KFSP_TRY(e.read_ctl());
@@ -120,6 +121,7 @@ int Engine::solve(double T, double fsptol, double krytol, int itrace, kfsp_stats
     GpuBackend be(*this);
     Controller ctl(opt);
     int st = ctl.run(be, R, T, fsptol, krytol, itrace, &local, trace);
+    if (dist.repl && gather_rows(d_w) != KFSP_OK && st == KFSP_OK) st = KFSP_ERR_NCCL;     // every rank ends with the whole vector
     cudaEventRecord(e1, stream);
     cudaEventSynchronize(e1);
     float ms = 0.f;
@@ -355,7 +357,7 @@ int kfsp_fsp_set_vector(kfsp_handle h, const double* v, int64_t cnt) {
     Engine& e = h->e;
     if (e.ld == 0) return KFSP_ERR_BAD_SIZES;
     cudaSetDevice(e.device);
-    if (e.dist.nranks > 1) {                                       // v is the GLOBAL vector: keep rows [lo, hi)
+    if (e.dist.nranks > 1 && !e.dist.repl) {                       // v is the GLOBAL vector: keep rows [lo, hi)
         if (cnt > e.dist.n_global) return KFSP_ERR_BAD_SIZES;
         KFSP_CUDA(cudaMemsetAsync(e.d_w, 0, sizeof(double) * e.ld, e.stream));
         const int64_t a = std::min<int64_t>(cnt, e.dist.lo), b = std::min<int64_t>(cnt, e.dist.hi);
@@ -394,8 +396,9 @@ int kfsp_fsp_get(kfsp_handle h, int32_t* states, int32_t* adj, double* offdiag, 
         }
         return e.sync();
     }
-    if (e.dist.nranks > 1 && adj) return KFSP_ERR_UNSUPPORTED;      // the column form is not kept for partitioned sets
-    const int64_t row0 = e.dist.nranks > 1 ? e.dist.lo : 0;          // this rank's rows
+    const bool part = e.dist.nranks > 1 && !e.dist.repl;             // memory-scaled partition: this rank's rows only
+    if (part && adj) return KFSP_ERR_UNSUPPORTED;                    // the column form is not kept for partitioned sets
+    const int64_t row0 = part ? e.dist.lo : 0;
     if (states) KFSP_CUDA(cudaMemcpyAsync(states, e.d_states + row0 * e.S, sizeof(int32_t) * n * e.S, cudaMemcpyDeviceToHost, e.stream));
     if (diag) KFSP_CUDA(cudaMemcpyAsync(diag, e.d_diag, sizeof(double) * n, cudaMemcpyDeviceToHost, e.stream));
     if (vector) KFSP_CUDA(cudaMemcpyAsync(vector, e.d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, e.stream));
@@ -455,7 +458,8 @@ int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, 
     KFSP_TRY(e.fsp_init(n_in, states_in, /*defer_check=*/true));
     // Partitioned handle (kfsp_dist_init): states_in / p_in are the GLOBAL list and vector on every rank; this rank keeps
     // rows [lo, hi) and returns them (n_out = hi - lo).  fsp_init has zeroed W.
-    const bool part = e.dist.nranks > 1;
+    // An ADAPTIVE handle on several GPUs keeps the whole state space on every rank and returns the whole result on every rank.
+    const bool part = e.dist.nranks > 1 && !e.dist.repl;
     const int64_t lo = part ? e.dist.lo : 0;
     if (n_in > lo) {
         const int64_t cnt = std::min<int64_t>(n_in - lo, e.n);
@@ -508,7 +512,11 @@ int kfsp_matvec(kfsp_handle h, const double* x, double* y) {
     double* dx = (double*)e.d_scratch;
     double* dy = (double*)(e.d_scratch + a);
     KFSP_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * e.n, cudaMemcpyHostToDevice, e.stream));
-    KFSP_TRY(e.spmv<0>(dx, dy));
+    const bool was = e.dist.suspended;
+    if (e.dist.repl) e.dist.suspended = true;                      // adaptive multi-GPU handle: whole vector in and out on every rank
+    const int st = e.spmv<0>(dx, dy);
+    e.dist.suspended = was;
+    KFSP_TRY(st);
     KFSP_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * e.n, cudaMemcpyDeviceToHost, e.stream));
     return e.sync();
 }
@@ -518,7 +526,12 @@ int kfsp_matvec_device(kfsp_handle h, const double* xd, double* yd, int32_t reps
     if (e.n < 1) return KFSP_ERR_BAD_SIZES;
     cudaSetDevice(e.device);
     KFSP_CUDA(cudaEventRecord(e.ev_a, e.stream));
-    for (int r = 0; r < reps; ++r) KFSP_TRY(e.spmv<0>(xd, yd));
+    const bool was = e.dist.suspended;
+    if (e.dist.repl) e.dist.suspended = true;
+    int st = KFSP_OK;
+    for (int r = 0; r < reps && st == KFSP_OK; ++r) st = e.spmv<0>(xd, yd);
+    e.dist.suspended = was;
+    KFSP_TRY(st);
     KFSP_CUDA(cudaEventRecord(e.ev_b, e.stream));
     KFSP_CUDA(cudaEventSynchronize(e.ev_b));
     float ms = 0.f;
@@ -564,8 +577,7 @@ int kfsp_expm(kfsp_handle h, int32_t m, double t, const double* H, int32_t ldh, 
     for (int j = 0; j < m; ++j)
         for (int i = 0; i < m; ++i) Hh[(size_t)j * e.LDH + i] = H[(size_t)j * ldh + i];
     KFSP_CUDA(cudaMemcpyAsync(e.d_H, Hh.data(), sizeof(double) * Hh.size(), cudaMemcpyHostToDevice, e.stream));
-    k_expm<<<1, EXPM_THREADS, EXPM_SMEM, e.stream>>>(e.d_H, e.LDH, m, t, 0, 0.0, -1, (const SweepCtl*)nullptr, e.d_expm_work, e.d_res, e.d_expm_full);
-    KFSP_TRY(e.check_launch());
+    KFSP_TRY(e.launch_expm(m, t, 0, 0.0, -1, (const SweepCtl*)nullptr, e.d_expm_full));
     KFSP_CUDA(cudaMemcpyAsync(e.h_res, e.d_res, sizeof(ExpmResult), cudaMemcpyDeviceToHost, e.stream));
     KFSP_CUDA(cudaMemcpyAsync(out, e.d_expm_full, sizeof(double) * m * m, cudaMemcpyDeviceToHost, e.stream));
     KFSP_TRY(e.sync());

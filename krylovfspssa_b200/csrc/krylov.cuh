@@ -48,6 +48,7 @@ struct DistPeers {
     const int32_t* halo_owner;               // for halo position h: owning rank ...
     const int32_t* halo_lidx;                // ... and row index on the owner
     int32_t* err;
+    int64_t rb[MAX_RANKS + 1];               // replicated-layout partition (adaptive state sets): rank r computes rows [rb[r], rb[r+1])
 };
 struct Reducer {
     double* partials;           // [RED_W * MAX_VEC_BLOCKS]: (hi, lo) planes for up to RED_NV reductions
@@ -319,10 +320,23 @@ __global__ void k_dist_finalize(EpiArgs ea, int nv, const double* __restrict__ r
 //   mode 2: the extra product: ||y||^2 -> AVNORM (:261-263)
 // Algorithmic traffic per row: R*(4+8) matrix + 8 diag + 8 x_i + 8 y_i  = 12R+24 bytes (+8 for g).
 // ---------------------------------------------------------------------------------------
+// HALO 3 / 4: adaptive state sets on several GPUs keep the single-GPU (global) layout on every rank and each rank computes a
+// contiguous slice of the rows (Engine::repartition).  x points at the slice's first row; j is a GLOBAL index.
+//   3: rows outside the slice come from the owner's copy of the same column, same offset, over NVLink (peer memory)
+//   4: the column was completed on this GPU by an all-gather before the launch
 template <int HALO>
 __device__ __forceinline__ double halo_load(const double* __restrict__ x, const double* __restrict__ xh, const DistPeers* __restrict__ dp,
-                                            int32_t j, int64_t nloc, int64_t coloff) {
-    if (HALO == 0 || j < nloc) return x[j];
+                                            int32_t j, int64_t nloc, int64_t coloff, int64_t row0) {
+    if (HALO == 0) return x[j];
+    if (HALO == 4) return x[(int64_t)j - row0];
+    if (HALO == 3) {
+        const int64_t jj = (int64_t)j - row0;
+        if (jj >= 0 && jj < nloc) return x[jj];
+        int r = 0;
+        while ((int64_t)j >= dp->rb[r + 1]) ++r;
+        return __ldcg(dp->V[r] + coloff + jj);
+    }
+    if (j < nloc) return x[j];
     if (HALO == 1) return xh[j - nloc];
     const int64_t h = j - nloc;
     return __ldcg(dp->V[dp->halo_owner[h]] + coloff + dp->halo_lidx[h]);
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
                                                              const double* __restrict__ coef, const double* __restrict__ diag,
                                                              const double* __restrict__ x, double* __restrict__ y,
                                                              const double* __restrict__ g, Reducer rd, SweepCtl* ctl, EpiArgs ea,
-                                                             int cg, const double* __restrict__ xh, int64_t nloc, int64_t coloff) {
+                                                             int cg, const double* __restrict__ xh, int64_t nloc, int64_t coloff, int64_t row0) {
     // HALO 1: gathered index j >= nloc addresses the halo buffer xh filled by the NCCL exchange step;
     // HALO 2: it is loaded straight from the owning GPU's basis column over NVLink (peer memory).
     const int R = RT > 0 ? RT : R_rt;
@@ -373,12 +387,12 @@ __global__ void __launch_bounds__(VEC_THREADS, MINB) k_spmv(int64_t n, int64_t l
                 if (RT > 0) {
 #pragma unroll
                     for (int k = 0; k < RT; ++k)
-                        if (j[u][k] >= 0) sv = fma(a[u][k], halo_load<HALO>(x, xh, rd.peers, j[u][k], nloc, coloff), sv);
+                        if (j[u][k] >= 0) sv = fma(a[u][k], halo_load<HALO>(x, xh, rd.peers, j[u][k], nloc, coloff, row0), sv);
                 } else {
                     for (int k = 0; k < R; ++k) {
                         const int32_t jj = __ldcs(pred + (int64_t)k * ld + i);
                         const double aa = __ldcs(coef + (int64_t)k * ld + i);
-                        if (jj >= 0) sv = fma(aa, halo_load<HALO>(x, xh, rd.peers, jj, nloc, coloff), sv);
+                        if (jj >= 0) sv = fma(aa, halo_load<HALO>(x, xh, rd.peers, jj, nloc, coloff, row0), sv);
                     }
                 }
                 __stcs(y + i, sv);
@@ -437,10 +451,12 @@ __device__ __forceinline__ double fac_term(const FacModel& F, int k, int t, cons
     const int c = (sst[sp * STRIDE] - sgn * (int)F.nu[k][sp]) * (int)F.use[k][t];
     return __ldg(F.tab[k][t] + c);
 }
-template <int STRIDE>
+// GEN = 0: no reaction of the model needs the postfix program -- straight-line code (the shape tests are uniform and
+// guard single instructions), so that the loads of several reactions can be in flight together
+template <int STRIDE, int GEN>
 __device__ __forceinline__ double fac_eval(const FacModel& F, int k, const int32_t* sst, int sgn) {
     const int shp = F.shape[k];
-    if (shp != FAC_GEN) {
+    if (GEN == 0 || shp != FAC_GEN) {
         double a = fac_term<STRIDE>(F, k, 0, sst, sgn);
         if (shp >= FAC_MUL2) a = __dmul_rn(a, fac_term<STRIDE>(F, k, 1, sst, sgn));
         if (shp >= FAC_MUL3) a = __dmul_rn(a, fac_term<STRIDE>(F, k, 2, sst, sgn));
@@ -459,14 +475,18 @@ __device__ __forceinline__ double fac_eval(const FacModel& F, int k, const int32
     }
     return stk[0];
 }
+// RT > 0: reactions unrolled, loads of IDX_GROUP reactions (table entries and gathered x) issued before their FMAs.
+// RT == 0: any R, and the only instantiation that carries the postfix interpreter (models with a FAC_GEN reaction).
+constexpr int IDX_GROUP = 5;
 template <int RT, int ST, int MODE, int HALO, int DREC>
-__global__ void __launch_bounds__(VEC_THREADS) k_spmv_idx(const __grid_constant__ FacModel F, int64_t n, int64_t ld, const int32_t* __restrict__ pred,
+__global__ void __launch_bounds__(VEC_THREADS, MODE == 0 ? 6 : 4) k_spmv_idx(const __grid_constant__ FacModel F, int64_t n, int64_t ld, const int32_t* __restrict__ pred,
                                                           const int32_t* __restrict__ states, const double* __restrict__ diag,
                                                           const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ g,
                                                           Reducer rd, SweepCtl* ctl, EpiArgs ea, int cg, const double* __restrict__ xh,
-                                                          int64_t nloc, int64_t coloff) {
+                                                          int64_t nloc, int64_t coloff, int64_t row0) {
     __shared__ int32_t sstate[KFSP_MAX_SPECIES * VEC_THREADS];
     int32_t* const sst = sstate + threadIdx.x;
+    constexpr int GEN = RT == 0 ? 1 : 0;
     const int R = RT > 0 ? RT : F.R;
     pdl_trigger();
     pdl_wait();
@@ -488,23 +508,39 @@ __global__ void __launch_bounds__(VEC_THREADS) k_spmv_idx(const __grid_constant_
         double d;
         if (DREC) {
             d = 0.0;
+            if (RT > 0) {
 #pragma unroll
-            for (int k = 0; k < (RT > 0 ? RT : 1); ++k) {
-                if (RT > 0) d = __dadd_rn(d, fac_eval<VEC_THREADS>(F, k, sst, 0));
+                for (int k = 0; k < (RT > 0 ? RT : 1); ++k) d = __dadd_rn(d, fac_eval<VEC_THREADS, GEN>(F, k, sst, 0));
+            } else {
+                for (int k = 0; k < R; ++k) d = __dadd_rn(d, fac_eval<VEC_THREADS, GEN>(F, k, sst, 0));
             }
-            if (RT == 0) for (int k = 0; k < R; ++k) d = __dadd_rn(d, fac_eval<VEC_THREADS>(F, k, sst, 0));
         } else {
             d = __ldcs(diag + i);
         }
         double sv = -__dmul_rn(d, xi);
         if (RT > 0) {
 #pragma unroll
-            for (int k = 0; k < RT; ++k)
-                if (j[k] >= 0) sv = fma(fac_eval<VEC_THREADS>(F, k, sst, 1), halo_load<HALO>(x, xh, rd.peers, j[k], nloc, coloff), sv);
+            for (int k0 = 0; k0 < RT; k0 += IDX_GROUP) {
+                double a[IDX_GROUP], xv[IDX_GROUP];
+#pragma unroll
+                for (int q = 0; q < IDX_GROUP; ++q) {
+                    const int k = k0 + q;
+                    if (k < RT) {
+                        const bool ok = j[k] >= 0;
+                        a[q] = ok ? fac_eval<VEC_THREADS, GEN>(F, k, sst, 1) : 0.0;
+                        xv[q] = ok ? halo_load<HALO>(x, xh, rd.peers, j[k], nloc, coloff, row0) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < IDX_GROUP; ++q) {
+                    const int k = k0 + q;
+                    if (k < RT) sv = j[k] >= 0 ? fma(a[q], xv[q], sv) : sv;
+                }
+            }
         } else {
             for (int k = 0; k < R; ++k) {
                 const int32_t jj = __ldcs(pred + (int64_t)k * ld + i);
-                if (jj >= 0) sv = fma(fac_eval<VEC_THREADS>(F, k, sst, 1), halo_load<HALO>(x, xh, rd.peers, jj, nloc, coloff), sv);
+                if (jj >= 0) sv = fma(fac_eval<VEC_THREADS, GEN>(F, k, sst, 1), halo_load<HALO>(x, xh, rd.peers, jj, nloc, coloff, row0), sv);
             }
         }
         __stcs(y + i, sv);
@@ -649,6 +685,24 @@ __device__ __forceinline__ double cta_dd_total(DD v, DD* sh, double* bc) {
     __syncthreads();
     return *bc;
 }
+// three totals at once; `all` = false: only b is needed (a and c come back as 0)
+__device__ __forceinline__ void cta_dd_total3(DD a, DD b, DD c, bool all, DD (*sh3)[32], double* bc3, double* ta, double* tb, double* tc) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    b = warp_sum(b);
+    if (all) { a = warp_sum(a); c = warp_sum(c); }
+    if (lane == 0) { sh3[0][wid] = a; sh3[1][wid] = b; sh3[2][wid] = c; }
+    __syncthreads();
+    if (wid < 3 && (all || wid == 1)) {                   // warps 0, 1, 2 finish one value each
+        DD z; z.hi = 0.0; z.lo = 0.0;
+        DD v = lane < (SWEEP_THREADS >> 5) ? sh3[wid][lane] : z;
+        v = warp_sum(v);
+        if (lane == 0) bc3[wid] = __dadd_rn(v.hi, v.lo);
+    }
+    __syncthreads();
+    *ta = all ? bc3[0] : 0.0;
+    *tb = bc3[1];
+    *tc = all ? bc3[2] : 0.0;
+}
 template <int RT, int IDX>
 __device__ __forceinline__ double spmv_row(int64_t i, int64_t ld, int R, const int32_t* __restrict__ pred, const double* __restrict__ coef,
                                            const double* __restrict__ diag, const double* x, const FacModel& F,
@@ -659,7 +713,7 @@ __device__ __forceinline__ double spmv_row(int64_t i, int64_t ld, int R, const i
     for (int k = 0; k < (RT > 0 ? RT : R); ++k) {
         const int32_t j = pred[(int64_t)k * ld + i];
         if (j >= 0) {
-            const double a = IDX ? fac_eval<SWEEP_THREADS>(F, k, sst, 1) : coef[(int64_t)k * ld + i];
+            const double a = IDX ? fac_eval<SWEEP_THREADS, 1>(F, k, sst, 1) : coef[(int64_t)k * ld + i];
             sv = fma(a, x[j], sv);
         }
     }
@@ -674,7 +728,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
     __shared__ int32_t sstate[IDX ? KFSP_MAX_SPECIES * SWEEP_THREADS : 1];
     int32_t* const sst = sstate + (IDX ? threadIdx.x : 0);
     __shared__ DD sh[32];
+    __shared__ DD sh3[3][32];
     __shared__ double bc;
+    __shared__ double bc3[3];
     __shared__ double cs[MAX_COLS];
     __shared__ int s_brk;
     const int R = RT > 0 ? RT : R_rt;
@@ -704,11 +760,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
                 dd_add_prod(accC, xi, gv);
             }
         }
-        const double dB = cta_dd_total(accB, sh, &bc);
+        // the three inner products of the column with one pair of barriers (same double-double sums, rounded once each)
+        double dA, dB, dC;
+        cta_dd_total3(accA, accB, accC, J >= 2, sh3, bc3, &dA, &dB, &dC);
         double h1 = 0.0, h2 = __dmul_rn(xs, __dmul_rn(xs, dB));
         if (J >= 2) {
-            const double dA = cta_dd_total(accA, sh, &bc);
-            const double dC = cta_dd_total(accC, sh, &bc);
             h1 = __dmul_rn(xs, dA);
             h2 = fma(-h1, __dmul_rn(xs, dC), h2);
             if (tid == 0) hcol[J - 2] = h1;                                  // H(J-1,J)

@@ -22,7 +22,7 @@ for name in sys.argv[1:] or list(RUNS):
         h = k.KrylovFspHandle(examples.driver_model(DRIVERS[name][0]), max_states=cap, seed=12345)
     else:
         t, ftol, ktol, cap = RUNS[name]
-        h, _, x0 = make(name, max_states=cap, seed=12345)
+        h, _, x0 = make(name, max_states=cap, seed=12345, spmv_variant=int(os.environ.get("KFSP_VARIANT", "0")))
     out = h.solve(t, [x0], [1.0], ftol, ktol)
     out = h.solve(t, [x0], [1.0], ftol, ktol)
     st = out["stats"]
