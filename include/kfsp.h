@@ -140,6 +140,10 @@ typedef double (*kfsp_propensity_fn)(const int32_t* state, int32_t reaction, con
 int kfsp_model_set_custom_propensity(kfsp_model m, kfsp_propensity_fn fn, void* ctx);
 /* MODEL%PROPENSITY(STATE, REACTION)  src/model/ModelModule.f90:163-199, evaluated on the host */
 int kfsp_model_propensity(kfsp_model m, const int32_t* state, int32_t reaction, double* out);
+/* The same value computed through the factored form the index-only SpMV (spmv_variant = 2) uses: sub-expressions that read one
+   species each, combined by + - *.  KFSP_ERR_UNSUPPORTED if the propensity has no such form.  nterms / nops (optional): size of
+   the factored form.  Host only (no GPU).  Reference: MODEL%PROPENSITY, ModelModule.f90:163-199. */
+int kfsp_model_propensity_factored(kfsp_model m, const int32_t* state, int32_t reaction, double* out, int32_t* nterms, int32_t* nops);
 
 /* ---- device solver handle ------------------------------------------------------------ */
 int kfsp_create(const kfsp_options* opts, kfsp_handle* out);

@@ -84,6 +84,9 @@ struct Engine {
     Dist dist;                        // multi-GPU row partition (nranks == 1: single GPU)
     int64_t states_cap = 0;           // capacity of d_states / table (global); ld is the capacity of the row arrays
     bool small_sweep = true;          // KFSP_SMALL_SWEEP=0 disables the single-CTA sweep (A/B)
+    bool smem_sweep = true;           // KFSP_SMEM_SWEEP=0 disables its shared-memory-resident form (A/B)
+    static constexpr size_t SWEEP_SMEM_MAX = 220 * 1024;
+    std::vector<const void*> smem_sweep_ready;
     int spmv_tune = 0;                // hoisted loads, one row per iteration, grid = one wave of resident CTAs
 
     // scratch arena (grows on demand)
@@ -181,6 +184,7 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_BD2_AHEAD")) bd2_ahead = std::min(std::max(std::atoi(ev), 0), BD2_L2AHEAD);
         if (const char* ev = std::getenv("KFSP_BD2_SYNC")) { bd2_sync = std::atoi(ev); if (bd2_sync & (bd2_sync - 1)) bd2_sync = 0; }
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_SMEM_SWEEP")) smem_sweep = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_PROP_CACHE_STATES")) pc_budget = std::atoll(ev);
         if (const char* ev = std::getenv("KFSP_DEBUG_REPL")) repl_debug = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_REPL_MIN_ROWS")) dist.repl_min_rows = std::atoll(ev);
@@ -1201,6 +1205,24 @@ struct Engine {
     // columns J = jold..m (1-based) then the extra product (KrylovSolver.f90:236-266). No host sync.
     int arnoldi(int jold, int m) {
         // small state spaces: the whole sweep in one single-CTA launch (bit-identical, see k_sweep_small)
+        // ... and entirely in shared memory when the gather form and three vectors fit (a couple of thousand states)
+        if (!dist_active() && !box && !idx && !profile_spmv && small_sweep && smem_sweep && sweep_smem_bytes(n, R) <= SWEEP_SMEM_MAX) {
+            void (*ks)(int, int64_t, int, const int32_t*, const double*, const double*, double*, double*, int, int, int, SweepCtl*, double);
+            switch (R) {
+            case 4: ks = k_sweep_smem<4>; break;
+            case 6: ks = k_sweep_smem<6>; break;
+            case 10: ks = k_sweep_smem<10>; break;
+            default: ks = k_sweep_smem<0>; break;
+            }
+            bool known = false;
+            for (const void* q : smem_sweep_ready) known = known || q == (const void*)ks;
+            if (!known) {
+                KFSP_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM_MAX));
+                smem_sweep_ready.push_back((const void*)ks);
+            }
+            ks<<<1, SWEEP_THREADS, sweep_smem_bytes(n, R), stream>>>((int)n, ld, R, d_pred, d_coef, d_diag, d_V, d_H, LDH, jold, m, d_ctl, opt.break_tol);
+            return check_launch();
+        }
         if (!dist_active() && !box && !profile_spmv && small_sweep && n * (int64_t)(12 * R + 88) <= (1 << 20)) {
             void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, double*, double*, int, int, int, SweepCtl*, double,
                          const FacModel, const int32_t*);

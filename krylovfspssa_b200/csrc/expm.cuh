@@ -19,6 +19,7 @@ constexpr int EXPM_LDS = EXPM_MAXN;
 constexpr int EXPM_THREADS = 1024;
 constexpr int EXPM_KL = 6;                     // lower bandwidth of q-p when H is tridiagonal (degree-6 Pade)
 constexpr int EXPM_KU = 12;                    // upper bandwidth of U after partial pivoting (kl + ku)
+constexpr int EXPM_TD = 3;                     // tile diagonals |tj - ti| <= EXPM_TD are computed in the banded path (2 would do)
 constexpr size_t EXPM_SMEM = 2 * (size_t)EXPM_LDS * EXPM_MAXN * sizeof(double) + 64 * sizeof(double) +
                              (size_t)EXPM_MAXN * (EXPM_KU + 1 + EXPM_KL) * sizeof(double) + (size_t)EXPM_MAXN * sizeof(int);
 
@@ -43,8 +44,9 @@ __device__ __forceinline__ void expm_load(double* s, const double* __restrict__ 
 // C = sA * sB for the n x n leading blocks; each thread owns a 4x4 tile held in acc.
 // ba / bb: bandwidths of the left / right operand (>= n: dense).  Terms outside the bands are exact zeros, so
 // leaving them out does not change any accumulated value.
-__device__ __forceinline__ void expm_mma(const double* sA, const double* sB, int n, double (&acc)[4][4], int ba = 1 << 20, int bb = 1 << 20) {
-    const int ti = threadIdx.x & 31, tj = threadIdx.x >> 5;
+__device__ __forceinline__ void expm_mma(const double* sA, const double* sB, int n, double (&acc)[4][4], int ba = 1 << 20, int bb = 1 << 20,
+                                         int ti = -1, int tj = -1) {
+    if (ti < 0) { ti = threadIdx.x & 31; tj = threadIdx.x >> 5; }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -72,8 +74,8 @@ __device__ __forceinline__ void expm_mma(const double* sA, const double* sB, int
     }
 }
 // write the register tiles to a column-major matrix with leading dimension ldc (global or shared)
-__device__ __forceinline__ void expm_store(double* C, int ldc, int n, const double (&acc)[4][4], double diag_add) {
-    const int ti = threadIdx.x & 31, tj = threadIdx.x >> 5;
+__device__ __forceinline__ void expm_store(double* C, int ldc, int n, const double (&acc)[4][4], double diag_add, int ti = -1, int tj = -1) {
+    if (ti < 0) { ti = threadIdx.x & 31; tj = threadIdx.x >> 5; }
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -86,8 +88,17 @@ __device__ __forceinline__ void expm_store(double* C, int ldc, int n, const doub
 // Everything of DGPADM up to the squarings, on ONE CTA of 1024 threads: ||H||_inf, ns, the Pade numerator and denominator by
 // Horner, the linear solve, E = I + 2 X.  Returns info (uniform over the CTA); on success E (n x n, zero padded to a multiple
 // of 4) is in sB.  smem: the dynamic shared memory of the kernel (EXPM_SMEM bytes); work: 4 * EXPM_MAXN^2 doubles of global scratch.
+#ifdef KFSP_EXPM_TIMING            // developer build: cycle stamps of the phases, printed by thread 0 (tools/expm_timing.py)
+#define EXPM_STAMP(i) do { if (threadIdx.x == 0) s_stamp[i] = clock64(); } while (0)
+#else
+#define EXPM_STAMP(i) do { } while (0)
+#endif
 __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, int n, double t, double* work, double* smem, int* ns_out,
                                          double* hnorm_out) {
+#ifdef KFSP_EXPM_TIMING
+    __shared__ long long s_stamp[12];
+#endif
+    EXPM_STAMP(0);
     double* sA = smem;
     double* sB = smem + (size_t)EXPM_LDS * EXPM_MAXN;
     double* sx = sB + (size_t)EXPM_LDS * EXPM_MAXN;       // 64 doubles of scratch
@@ -148,6 +159,7 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
         __syncthreads();
     }
     if (s_info != 0) { *ns_out = 0; *hnorm_out = s_hnorm; return s_info; }
+    EXPM_STAMP(1);                                         // H staged, norm, ns
     const double scale = s_scale, scale2 = __dmul_rn(scale, scale);
     double acc[4][4];
     // The Krylov H of IOP-2 is tridiagonal (plus the unit sub-diagonal entry): every Pade factor is banded
@@ -155,7 +167,15 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
     const bool tri = s_kb <= 1 && n > 2 * (EXPM_KL + EXPM_KU);
     const int DENSE = 1 << 20;
     const int bH = tri ? 1 : DENSE, bH2 = tri ? 2 : DENSE;
-    const int ti = tid & 31, tj = tid >> 5;
+    // Tile -> thread.  Dense: tile (ti, tj) = (lane, warp).  Tridiagonal H: every Pade factor has bandwidth <= 6, i.e. only the
+    // tiles with |tj - ti| <= 2 hold anything; with the dense mapping each of 26 warps would run the product loop for ~5 live
+    // lanes (measured: 9.4k cycles per banded product, bound by warp issue), so warp d owns the tile diagonal tj = ti + d - 3
+    // instead: 7 full warps.  Tiles nobody owns are zero in every operand and are never written.
+    int ti = tid & 31, tj = tid >> 5;
+    if (tri) {
+        tj = ti + (tid >> 5) - EXPM_TD;
+        if ((tid >> 5) > 2 * EXPM_TD || tj < 0 || 4 * tj >= n) { ti = 1 << 20; tj = 1 << 20; }     // no tile: every guard below fails
+    }
     // one tile of a polynomial value lives in the registers of the thread that computed it: it goes to shared memory as the
     // left operand of the next product and comes back as that product's accumulator -- nothing of the Horner recurrence
     // passes through global memory (it used to: ~14 round trips of L2 latency per call, a third of the kernel at n = 100)
@@ -170,9 +190,10 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
     // ---- H2 = scale2*H*H (dgpadm.f:270): alpha multiplies the right operand, as DGEMM does ----
     for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) sB[t2] = __dmul_rn(scale2, sA[t2]);     // the padding stays 0
     __syncthreads();
-    expm_mma(sA, sB, n, acc, bH, bH);
+    expm_mma(sA, sB, n, acc, bH, bH, ti, tj);
     __syncthreads();
-    expm_store(sB, EXPM_LDS, n, acc, 0.0);                 // sB <- H2 (stays for both Horner recurrences)
+    expm_store(sB, EXPM_LDS, n, acc, 0.0, ti, tj);                 // sB <- H2 (stays for both Horner recurrences)
+    EXPM_STAMP(2);
     // ---- Horner (dgpadm.f:274-301): q = ((c6 H2 + c4 I) H2 + c2 I) H2 + c0 I and p = ((c5 I) H2 + c3 I) H2 + c1 I are
     // independent of each other: one after the other instead of interleaved, so that a single register tile is live.
     // The first product of each has a diagonal left operand: (c I) H2 = c H2.
@@ -183,9 +204,9 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
     int bQ = tri ? 2 : DENSE;
     for (int k = 2; k >= 0; k -= 2) {                      // q = q*H2 + c2 I ; q = q*H2 + c0 I
         __syncthreads();
-        expm_store(sA, EXPM_LDS, n, acc, 0.0);
+        expm_store(sA, EXPM_LDS, n, acc, 0.0, ti, tj);
         __syncthreads();
-        expm_mma(sA, sB, n, acc, bQ, bH2);
+        expm_mma(sA, sB, n, acc, bQ, bH2, ti, tj);
         if (tri) bQ += 2;
         add_diag(s_coef[k]);
     }
@@ -200,21 +221,22 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
     int bP = tri ? 0 : DENSE;
     for (int k = 3; k >= 1; k -= 2) {                      // p = p*H2 + c3 I ; p = p*H2 + c1 I
         __syncthreads();
-        expm_store(sA, EXPM_LDS, n, acc, 0.0);
+        expm_store(sA, EXPM_LDS, n, acc, 0.0, ti, tj);
         __syncthreads();
-        expm_mma(sA, sB, n, acc, bP, bH2);
+        expm_mma(sA, sB, n, acc, bP, bH2, ti, tj);
         if (tri) bP += 2;
         add_diag(s_coef[k]);
     }
+    EXPM_STAMP(3);                                         // both Horner recurrences
     // p = scale * p * H (dgpadm.f:309-312)
     __syncthreads();
-    expm_store(sA, EXPM_LDS, n, acc, 0.0);
+    expm_store(sA, EXPM_LDS, n, acc, 0.0, ti, tj);
     expm_load(sB, H, ldh, n, np, scale);
     __syncthreads();
-    expm_mma(sA, sB, n, acc, bP, bH);
+    expm_mma(sA, sB, n, acc, bP, bH, ti, tj);
     __syncthreads();
     // ---- sA <- q - p ; sB <- p ; solve (q-p) X = p (dgpadm.f:314-315) ----------------------
-    expm_store(sB, EXPM_LDS, n, acc, 0.0);
+    expm_store(sB, EXPM_LDS, n, acc, 0.0, ti, tj);
 #pragma unroll
     for (int b2 = 0; b2 < 4; ++b2)
 #pragma unroll
@@ -223,56 +245,71 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
             if (i < n && j < n) sA[(size_t)j * EXPM_LDS + i] = __dsub_rn(gQ[(size_t)j * EXPM_LDS + i], acc[a2][b2]);
         }
     __syncthreads();
+    EXPM_STAMP(4);                                         // p*H, q - p
     if (tri) {
         // ---- banded path: q-p has lower bandwidth 6; with partial pivoting U has upper bandwidth 12 ---------
-        // Phase A: ONE warp factors the band in place (no block-wide barriers), keeping compact U rows,
-        // multipliers and pivots.  Every element sees the same operations, in the same order, as in the dense
-        // elimination below (terms with an exactly-zero multiplier or pivot-row entry leave a value unchanged).
+        // Phase A: ONE warp factors the band with the ACTIVE WINDOW IN REGISTERS: at step k the elimination touches rows
+        // k..k+6 of columns k..k+12; lane c holds those 7 entries of column k+c.  The pivot search is seven compares in lane
+        // 0, a row swap is a register exchange in every lane, the multipliers travel by shuffle, and sliding the window one
+        // step is a shuffle from the lane to the right plus ONE shared-memory load per lane (the entry of row k+7, which no
+        // earlier step has touched; everything above it in the incoming column is outside the band of q-p, i.e. zero).
+        // sA is only read.  Every element sees the same operations, in the same order, as in the dense elimination below
+        // (terms with an exactly-zero multiplier or pivot-row entry leave a value unchanged).  Round 1 kept the window in
+        // shared memory behind __syncwarp: 1390 cycles per column against ~350 (profiles/r2_summary.md, section 5).
         if (tid < 32) {
             const int lane = tid;
+            double w[EXPM_KL + 1];
+#pragma unroll
+            for (int r = 0; r <= EXPM_KL; ++r) w[r] = (lane <= EXPM_KU && lane < n && r < n) ? sA[(size_t)lane * EXPM_LDS + r] : 0.0;
+#pragma unroll 1
             for (int k = 0; k < n; ++k) {
-                double best = -1.0; int bi = k;
-                if (lane <= EXPM_KL && k + lane < n) { best = fabs(sA[(size_t)k * EXPM_LDS + k + lane]); bi = k + lane; }
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ob = __shfl_down_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                int pr = 0;
+                double best = fabs(w[0]);
+#pragma unroll
+                for (int r = 1; r <= EXPM_KL; ++r) {
+                    const double v = fabs(w[r]);
+                    if (k + r < n && v > best) { best = v; pr = r; }       // ties: the lowest row, as the reference's IDAMAX
                 }
+                pr = __shfl_sync(0xffffffffu, pr, 0);
                 best = __shfl_sync(0xffffffffu, best, 0);
-                const int p = __shfl_sync(0xffffffffu, bi, 0);
                 if (best == 0.0) { if (lane == 0) s_info = KFSP_ERR_SINGULAR; break; }
-                if (p != k && lane <= EXPM_KU && k + lane < n) {
-                    double* col = sA + (size_t)(k + lane) * EXPM_LDS;
-                    const double tmp = col[k]; col[k] = col[p]; col[p] = tmp;
+#pragma unroll
+                for (int r = 1; r <= EXPM_KL; ++r)
+                    if (r == pr) { const double tmp = w[r]; w[r] = w[0]; w[0] = tmp; }
+                const double inv = 1.0 / w[0];                             // meaningful in lane 0
+                double m[EXPM_KL + 1];
+#pragma unroll
+                for (int r = 1; r <= EXPM_KL; ++r) {
+                    const double mine = k + r < n ? __dmul_rn(w[r], inv) : 0.0;
+                    m[r] = __shfl_sync(0xffffffffu, mine, 0);
                 }
-                __syncwarp();
-                const double inv = 1.0 / sA[(size_t)k * EXPM_LDS + k];
-                __syncwarp();
-                if (lane >= 1 && lane <= EXPM_KL) {
-                    double m = 0.0;
-                    if (k + lane < n) {
-                        m = __dmul_rn(sA[(size_t)k * EXPM_LDS + k + lane], inv);
-                        sA[(size_t)k * EXPM_LDS + k + lane] = m;
-                    }
-                    sL[k * EXPM_KL + lane - 1] = m;
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 1; r <= EXPM_KL; ++r) sL[k * EXPM_KL + r - 1] = m[r];
+                    sPiv[k] = k + pr;
                 }
-                if (lane <= EXPM_KU) sU[k * (EXPM_KU + 1) + lane] = k + lane < n ? sA[(size_t)(k + lane) * EXPM_LDS + k] : 0.0;
-                if (lane == 0) sPiv[k] = p;
-                __syncwarp();
-                for (int e = lane; e < EXPM_KL * EXPM_KU; e += 32) {
-                    const int i = k + 1 + e % EXPM_KL, j = k + 1 + e / EXPM_KL;
-                    if (i < n && j < n) {
-                        double* col = sA + (size_t)j * EXPM_LDS;
-                        col[i] = fma(-sA[(size_t)k * EXPM_LDS + i], col[k], col[i]);
-                    }
+                if (lane <= EXPM_KU) sU[k * (EXPM_KU + 1) + lane] = k + lane < n ? w[0] : 0.0;
+                if (lane >= 1 && lane <= EXPM_KU && k + lane < n) {
+#pragma unroll
+                    for (int r = 1; r <= EXPM_KL; ++r)
+                        if (k + r < n) w[r] = fma(-m[r], w[0], w[r]);
                 }
-                __syncwarp();
+                // slide: rows k+1..k+6 of column k+1+c come from the lane to the right, row k+7 from shared memory
+#pragma unroll
+                for (int r = 0; r < EXPM_KL; ++r) w[r] = __shfl_down_sync(0xffffffffu, w[r + 1], 1);
+                if (lane >= EXPM_KU) {
+#pragma unroll
+                    for (int r = 0; r < EXPM_KL; ++r) w[r] = 0.0;          // the incoming column: above the band
+                }
+                w[EXPM_KL] = (lane <= EXPM_KU && k + 1 + lane < n && k + 1 + EXPM_KL < n) ? sA[(size_t)(k + 1 + lane) * EXPM_LDS + k + 1 + EXPM_KL] : 0.0;
             }
         }
         __syncthreads();
         if (s_info != 0) { *ns_out = s_ns; *hnorm_out = s_hnorm; return s_info; }
+        EXPM_STAMP(5);                                     // banded LU
         // Phase B: the n right-hand sides are independent -> transpose B so that thread j owns column j with
-        // conflict-free shared-memory accesses, then forward and backward substitution without any barrier.
+        // conflict-free shared-memory accesses, then forward and backward substitution without any barrier, the entries
+        // a step touches (7 going down, 13 going up) in a sliding register window.
         for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) {
             const int i = t2 / n, j = t2 % n;
             sA[(size_t)i * EXPM_LDS + j] = sB[(size_t)j * EXPM_LDS + i];
@@ -280,20 +317,31 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
         __syncthreads();
         if (tid < n) {
             double* b = sA + tid;                                  // element i of this column: b[i * EXPM_LDS]
+            double f[EXPM_KL + 1];
+#pragma unroll
+            for (int r = 0; r <= EXPM_KL; ++r) f[r] = r < n ? b[(size_t)r * EXPM_LDS] : 0.0;
+#pragma unroll 1
             for (int k = 0; k < n; ++k) {
-                const int p = sPiv[k];
-                if (p != k) { const double tmp = b[(size_t)k * EXPM_LDS]; b[(size_t)k * EXPM_LDS] = b[(size_t)p * EXPM_LDS]; b[(size_t)p * EXPM_LDS] = tmp; }
-                const double bk = b[(size_t)k * EXPM_LDS];
+                const int pr = sPiv[k] - k;
 #pragma unroll
                 for (int r = 1; r <= EXPM_KL; ++r)
-                    if (k + r < n) b[(size_t)(k + r) * EXPM_LDS] = fma(-sL[k * EXPM_KL + r - 1], bk, b[(size_t)(k + r) * EXPM_LDS]);
+                    if (r == pr) { const double tmp = f[r]; f[r] = f[0]; f[0] = tmp; }
+                const double bk = f[0];
+                b[(size_t)k * EXPM_LDS] = bk;
+#pragma unroll
+                for (int r = 1; r <= EXPM_KL; ++r) f[r - 1] = (k + r < n) ? fma(-sL[k * EXPM_KL + r - 1], bk, f[r]) : 0.0;
+                f[EXPM_KL] = (k + 1 + EXPM_KL < n) ? b[(size_t)(k + 1 + EXPM_KL) * EXPM_LDS] : 0.0;
             }
+            double u[EXPM_KU + 1];
+#pragma unroll
+            for (int c = 0; c <= EXPM_KU; ++c) u[c] = (n - 1 - c >= 0) ? b[(size_t)(n - 1 - c) * EXPM_LDS] : 0.0;
+#pragma unroll 1
             for (int k = n - 1; k >= 0; --k) {
-                const double xk = b[(size_t)k * EXPM_LDS] / sU[k * (EXPM_KU + 1)];
+                const double xk = u[0] / sU[k * (EXPM_KU + 1)];
                 b[(size_t)k * EXPM_LDS] = xk;
 #pragma unroll
-                for (int c = 1; c <= EXPM_KU; ++c)
-                    if (k - c >= 0) b[(size_t)(k - c) * EXPM_LDS] = fma(-xk, sU[(k - c) * (EXPM_KU + 1) + c], b[(size_t)(k - c) * EXPM_LDS]);
+                for (int c = 1; c <= EXPM_KU; ++c) u[c - 1] = (k - c >= 0) ? fma(-xk, sU[(k - c) * (EXPM_KU + 1) + c], u[c]) : 0.0;
+                u[EXPM_KU] = (k - 1 - EXPM_KU >= 0) ? b[(size_t)(k - 1 - EXPM_KU) * EXPM_LDS] : 0.0;
             }
         }
         __syncthreads();
@@ -365,6 +413,13 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
     }
     __syncthreads();
     }   // dense path
+    EXPM_STAMP(6);                                         // substitution, E = I + 2X
+#ifdef KFSP_EXPM_TIMING
+    if (threadIdx.x == 0)
+        printf("expm n=%d ns=%d tri=%d cycles: stage+norm %lld  H2 %lld  horner %lld  pH,q-p %lld  LU %lld  solve %lld\n", n, s_ns, (int)tri,
+               s_stamp[1] - s_stamp[0], s_stamp[2] - s_stamp[1], s_stamp[3] - s_stamp[2], s_stamp[4] - s_stamp[3], s_stamp[5] - s_stamp[4],
+               s_stamp[6] - s_stamp[5]);
+#endif
     *ns_out = s_ns;
     *hnorm_out = s_hnorm;
     return 0;

@@ -293,6 +293,42 @@ int kfsp_model_propensity(kfsp_model m, const int32_t* state, int32_t reaction, 
     return KFSP_OK;
 }
 
+// Host-side view of the factored form the index-only SpMV uses (spmv_variant = 2; model_host.h: factor_program): the
+// propensity evaluated THROUGH its single-species terms, exactly as the device combines the tabulated terms.  No GPU needed.
+int kfsp_model_propensity_factored(kfsp_model m, const int32_t* state, int32_t reaction, double* out, int32_t* nterms, int32_t* nops) {
+    if (!m || !state || !out || reaction < 1 || reaction > m->m.R) return KFSP_ERR_ARG;
+    if (m->m.custom) return KFSP_ERR_UNSUPPORTED;
+    const Program& prog = m->m.programs[reaction - 1];
+    if (prog.empty()) return KFSP_ERR_NO_MODEL;
+    Factored fp;
+    if (!factor_program(prog, m->m.S, fp)) return KFSP_ERR_UNSUPPORTED;
+    if (fp.terms.empty() || (int)fp.terms.size() > FAC_MAX_TERMS || (int)fp.ops.size() > FAC_MAX_OPS) return KFSP_ERR_UNSUPPORTED;   // device structure
+    if (nterms) *nterms = (int32_t)fp.terms.size();
+    if (nops) *nops = (int32_t)fp.ops.size();
+    const int S = m->m.S, P = m->m.P;
+    std::vector<double> val((size_t)S + P, 0.0), stack;
+    for (int i = 0; i < P; ++i) val[S + i] = m->m.params[i];
+    const bool multi = fp.terms.size() > 1;
+    for (int32_t op : fp.ops) {
+        if (op >= 0) {
+            const FactoredTerm& t = fp.terms[op];
+            for (int s2 = 0; s2 < S; ++s2) val[s2] = 0.0;
+            if (t.species >= 0) val[t.species] = (double)state[t.species];     // what the table holds at this count
+            bool ab = false;
+            stack.push_back(evaluate_program_checked(t.prog, val.data(), &ab));
+            if (ab && multi) return KFSP_ERR_UNSUPPORTED;
+        } else if (op == -cNeg) {
+            stack.back() = -stack.back();
+        } else {
+            const double b = stack.back(); stack.pop_back();
+            double& a = stack.back();
+            a = op == -cAdd ? a + b : op == -cSub ? a - b : a * b;
+        }
+    }
+    *out = stack.empty() ? 0.0 : stack[0];
+    return KFSP_OK;
+}
+
 // ------------------------------------------------------------------ handle
 int kfsp_create(const kfsp_options* opts, kfsp_handle* out) {
     if (!out) return KFSP_ERR_ARG;

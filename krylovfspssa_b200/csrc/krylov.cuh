@@ -804,6 +804,120 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
     for (int j = tid; j < MAX_COLS; j += SWEEP_THREADS) ctl->colscale[j] = cs[j];
 }
 
+// The same sweep with EVERYTHING in shared memory, for state sets of a couple of thousand states (BASELINE config 1: the toggle
+// never exceeds 2454): the gather form of the generator (12R+8 bytes per state) is staged once per sweep, the three vectors of
+// the IOP window rotate through three shared buffers, and global memory only receives each finished column (the basis the
+// combination kernel reads later).  In k_sweep_small every phase of a column waits ~700 cycles for L2 (two dependent rounds
+// in the SpMV, one in the finalising pass); here those are ~30-cycle shared-memory accesses.  Same element operations, same
+// double-double sums: bit-identical.  Dynamic shared memory: n * (12R + 32) bytes (sweep_smem_bytes).
+__host__ __device__ inline size_t sweep_smem_bytes(int64_t n, int R) { return (size_t)n * (size_t)(12 * R + 32); }
+template <int RT>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_smem(int n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
+                                                                  const double* __restrict__ coef, const double* __restrict__ diag,
+                                                                  double* V, double* H, int ldh, int jold, int m, SweepCtl* ctl,
+                                                                  double break_tol) {
+    extern __shared__ __align__(16) unsigned char sweep_dyn[];
+    __shared__ DD sh[32];
+    __shared__ DD sh3[3][32];
+    __shared__ double bc;
+    __shared__ double bc3[3];
+    __shared__ double cs[MAX_COLS];
+    __shared__ int s_brk;
+    const int R = RT > 0 ? RT : R_rt;
+    const int tid = threadIdx.x;
+    double* s_coef = reinterpret_cast<double*>(sweep_dyn);               // [k*n + i]
+    double* s_diag = s_coef + (size_t)R * n;
+    double* s_vec = s_diag + n;                                          // three vectors of n
+    int32_t* s_pred = reinterpret_cast<int32_t*>(s_vec + 3 * (size_t)n);  // [k*n + i]
+    for (int j = tid; j < MAX_COLS; j += SWEEP_THREADS) cs[j] = ctl->colscale[j];
+    if (tid == 0) s_brk = ctl->brk;
+    __syncthreads();
+    if (s_brk != 0) return;
+    for (int t = tid; t < R * n; t += SWEEP_THREADS) {
+        const int k = t / n, i = t - k * n;
+        s_pred[t] = pred[(int64_t)k * ld + i];
+        s_coef[t] = coef[(int64_t)k * ld + i];
+    }
+    for (int i = tid; i < n; i += SWEEP_THREADS) {
+        s_diag[i] = diag[i];
+        s_vec[(size_t)((jold - 1) % 3) * n + i] = V[(size_t)(jold - 1) * ld + i];
+        if (jold >= 2) s_vec[(size_t)((jold - 2) % 3) * n + i] = V[(size_t)(jold - 2) * ld + i];
+    }
+    __syncthreads();
+    auto row = [&](int i, const double* x) {
+        double sv = -__dmul_rn(s_diag[i], x[i]);
+#pragma unroll
+        for (int k = 0; k < (RT > 0 ? RT : R); ++k) {
+            const int32_t j = s_pred[k * n + i];
+            if (j >= 0) sv = fma(s_coef[k * n + i], x[j], sv);
+        }
+        return sv;
+    };
+    for (int J = jold; J <= m; ++J) {
+        const double* x = s_vec + (size_t)((J - 1) % 3) * n;
+        double* y = s_vec + (size_t)(J % 3) * n;
+        const double* g = s_vec + (size_t)((J + 1) % 3) * n;              // column J-2
+        const double xs = cs[J - 1];
+        const double gs = J >= 2 ? cs[J - 2] : 0.0;
+        double* hcol = H + (size_t)(J - 1) * ldh;
+        DD accA, accB, accC;
+        accA.hi = accA.lo = accB.hi = accB.lo = accC.hi = accC.lo = 0.0;
+        for (int i = tid; i < n; i += SWEEP_THREADS) {
+            const double sv = row(i, x);
+            y[i] = sv;
+            const double xi = x[i];
+            dd_add_prod(accB, xi, sv);
+            if (J >= 2) {
+                const double gv = __dmul_rn(gs, g[i]);
+                dd_add_prod(accA, gv, sv);
+                dd_add_prod(accC, xi, gv);
+            }
+        }
+        double dA, dB, dC;
+        cta_dd_total3(accA, accB, accC, J >= 2, sh3, bc3, &dA, &dB, &dC);
+        double h1 = 0.0, h2 = __dmul_rn(xs, __dmul_rn(xs, dB));
+        if (J >= 2) {
+            h1 = __dmul_rn(xs, dA);
+            h2 = fma(-h1, __dmul_rn(xs, dC), h2);
+            if (tid == 0) hcol[J - 2] = h1;                                  // H(J-1,J)
+        }
+        if (tid == 0) hcol[J - 1] = h2;                                      // H(J,J)
+        DD acc; acc.hi = 0.0; acc.lo = 0.0;
+        double* yg = V + (size_t)J * ld;
+        for (int i = tid; i < n; i += SWEEP_THREADS) {
+            double inner = __dmul_rn(xs, y[i]);
+            if (J >= 2) inner = fma(-h1, __dmul_rn(gs, g[i]), inner);
+            const double wi = fma(-h2, __dmul_rn(xs, x[i]), inner);
+            y[i] = wi;
+            yg[i] = wi;                                                      // the finished column U_J of the basis
+            dd_add_prod(acc, wi, wi);
+        }
+        const double hn = sqrt(cta_dd_total(acc, sh, &bc));
+        if (hn <= break_tol) {                                               // happy breakdown: uniform over the CTA
+            if (tid == 0) { ctl->scal[SC_HN] = hn; ctl->brk = J; }
+            s_brk = J;
+            break;
+        }
+        if (tid == 0) { hcol[J] = hn; cs[J] = 1.0 / hn; }                    // H(J+1,J), DSCAL factor
+        __syncthreads();
+    }
+    if (s_brk == 0) {
+        const double* x = s_vec + (size_t)(m % 3) * n;
+        double* yg = V + (size_t)(m + 1) * ld;
+        const double xs = cs[m];
+        DD acc; acc.hi = 0.0; acc.lo = 0.0;
+        for (int i = tid; i < n; i += SWEEP_THREADS) {
+            const double sv = row(i, x);
+            yg[i] = sv;
+            dd_add_prod(acc, sv, sv);
+        }
+        const double av = __dmul_rn(xs, sqrt(cta_dd_total(acc, sh, &bc)));
+        if (tid == 0) ctl->scal[SC_AVNORM] = av;
+    }
+    __syncthreads();
+    for (int j = tid; j < MAX_COLS; j += SWEEP_THREADS) ctl->colscale[j] = cs[j];
+}
+
 // Cross-GPU barrier over peer memory (one warp): every rank raises its flag on every peer and waits for all
 // of them.  Needed where a kernel without a reduction (k_scale_copy writing basis column 0) is followed by a
 // SpMV that gathers that column from the neighbours' HBM.

@@ -136,6 +136,13 @@ class CME_MODEL:
         check(lib().kfsp_model_propensity(self._h, _i32(st), reaction, C.byref(out)), "CME_MODEL%PROPENSITY")
         return out.value
 
+    def propensity_factored(self, state, reaction):
+        """(value, nterms, nops): the propensity evaluated through the factored form of the index-only SpMV (spmv_variant = 2)."""
+        st = np.ascontiguousarray(state, dtype=np.int32)
+        out, nt, no = C.c_double(), C.c_int32(), C.c_int32()
+        check(lib().kfsp_model_propensity_factored(self._h, _i32(st), reaction, C.byref(out), C.byref(nt), C.byref(no)), "factor_program")
+        return out.value, nt.value, no.value
+
     def _free(self):
         if self._h:
             lib().kfsp_model_free(self._h)
