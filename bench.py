@@ -359,7 +359,10 @@ def main():
     peak, peak_kind = measured_peak()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if world > 1:
+        h.dist_exchange_stats(reset=True)
     res = timed_solves(h, p0_dev, nloc)
+    xstat = h.dist_exchange_stats() if world > 1 else None
     sampler.stop_flag = True
     sampler.join(timeout=2)
     dev_s = allmax(res["dev_s"])                          # device-timed, max over ranks
@@ -367,6 +370,17 @@ def main():
     units = float(n) * nmult                              # the whole job: all ranks together update N states per SpMV
     value = units / dev_s
     dinfo = h.dist_info() if world > 1 else None
+    if world > 1:
+        # the reduction exchange fused into the tail of every reducing kernel: per rank, mean time from posting its partial to
+        # holding every rank's (NVLink latency + waiting for the slowest rank); the rank that waits least IS the slowest rank,
+        # so the minimum over ranks is the wire latency and the mean over ranks adds the spread of kernel durations
+        xs = [None] * world
+        dist.all_gather_object(xs, xstat)
+        dinfo["exchange_us"] = sum(x["mean_us"] for x in xs) / world
+        dinfo["exchange_us_min_over_ranks"] = min(x["mean_us"] for x in xs)
+        dinfo["exchange_us_max_over_ranks"] = max(x["mean_us"] for x in xs)
+        dinfo["exchange_us_worst_single"] = max(x["max_us"] for x in xs)
+        dinfo["exchanges_per_rank"] = xs[0]["exchanges"]
 
     # plain FMATVEC (mode 0, no fused reduction) on this rank's rows, device-timed: the SURVEY 8d "generator SpMV" number
     plain = None

@@ -228,7 +228,24 @@ int kfsp_dist_owner(int64_t n, int32_t nranks, int64_t row, int32_t* owner);
 int kfsp_lattice_partition(int32_t nz, int32_t nranks, int32_t rank, int32_t* zlo, int32_t* zhi);
 int kfsp_lattice_kernel(int32_t S, int32_t R, const int32_t* stoich /* S*R */, const int32_t* table_species /* R */,
                         int32_t* kind, int32_t* table_mask);
+/* host-side arithmetic of the replicated layout used for ADAPTIVE state sets on several GPUs (no GPU needed): rows [lo,hi) of
+   the Krylov loop computed by `rank` when the set has n rows; whole = 1 while n < min_rows (KFSP_REPL_MIN_ROWS, default 2^22):
+   every rank then computes every row and nothing is exchanged (lo = 0, hi = n).  No reference counterpart (serial code). */
+int kfsp_repl_partition(int64_t n, int32_t nranks, int32_t rank, int64_t min_rows, int64_t* lo, int64_t* hi, int32_t* whole);
 int kfsp_dist_info(kfsp_handle h, int64_t* lo, int64_t* hi, int64_t* n_halo, int64_t* n_send, int64_t* halo_bytes, int64_t* reductions);
+/* How the device path evaluates the propensities of the current model (MODEL%PROPENSITY, ModelModule.f90:163-199):
+   n_tabulated      programs that read one species and hold a transcendental operation: tabulated by the host over the count
+   n_host_evaluated reactions evaluated by the host itself: CUSTOMPROP callbacks, and byte code with a transcendental operation
+                    on several species (the CUDA math library may differ from the host libm by ulps there; KFSP_DEVICE_MATH=1
+                    keeps them on the device)
+   n_device_libm    such programs that DO run on the CUDA math library (only with KFSP_DEVICE_MATH=1): results may then differ
+                    from a host evaluation in the last bits, and with them SSA picks and pruning decisions
+   factored         1 if the index-only SpMV's factored tables are in use (spmv_variant = 2) */
+int kfsp_model_info(kfsp_handle h, int32_t* n_tabulated, int32_t* n_host_evaluated, int32_t* n_device_libm, int32_t* factored);
+/* Peer-memory path: the reduction exchange fused into the tail of every reducing kernel (no reference counterpart; the
+   reference is serial).  exchanges = fused exchanges since the last reset; mean_us / max_us = time between posting this rank's
+   double-double partial to the peers and holding every rank's partial, i.e. NVLink latency plus the wait for the slowest rank. */
+int kfsp_dist_exchange_stats(kfsp_handle h, int64_t* exchanges, double* mean_us, double* max_us, int32_t reset);
 
 /* device memory helpers for hosts without their own CUDA runtime (bench, tests) */
 int kfsp_device_alloc(kfsp_handle h, int64_t bytes, void** ptr);

@@ -89,6 +89,9 @@ SIGNATURES = {
     "kfsp_dist_owner": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _i32p]),
     "kfsp_lattice_partition": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p]),
     "kfsp_lattice_kernel": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p]),
+    "kfsp_model_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p]),
+    "kfsp_repl_partition": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, _i64p, _i64p, _i32p]),
+    "kfsp_dist_exchange_stats": (C.c_int, [_vp, _i64p, _dp, _dp, C.c_int32]),
     "kfsp_dist_info": (C.c_int, [_vp, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p]),
     "kfsp_device_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "kfsp_device_free": (C.c_int, [_vp, _vp]),

@@ -133,6 +133,7 @@ struct Dist {
     void* peer_base[8] = {nullptr};     // opened IPC mappings (for closing)
     void* peer_xbase[8] = {nullptr};
     unsigned long long seq = 0;
+    unsigned long long* d_stat = nullptr;   // exchange statistics written by the reducing kernels (DistPeers::stat)
 #ifdef KFSP_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif

@@ -40,7 +40,7 @@ struct Engine {
     // host-evaluated propensities: CUSTOMPROP callbacks (ModelModule.f90:6-12,188-190), and byte code that holds a
     // transcendental operation on SEVERAL species (not tabulable): the CUDA math library may differ from the host libm by
     // ulps there, which could flip an SSA reaction pick or a DROP decision, so such programs are evaluated by the host
-    // interpreter through the CUSTOMPROP machinery (KFSP_DEVICE_MATH=1 keeps them on the device; kfsp_model_info reports it)
+    // interpreter through the CUSTOMPROP machinery (KFSP_DEVICE_MATH=1 keeps them on the device; kfsp_model_info reports which happened)
     bool host_prop = false;
     HostModel hm;                     // copy of the host model (callback, parameters, programs)
     PropCache pc;                     // device side cache used by SSA walks in host_prop mode
@@ -822,7 +822,7 @@ struct Engine {
         // adds to it (measured: Goutsias, 5e5 states on average, sweep 1.99 s on one GPU, 3.46 s split over two): every
         // rank then computes every row and nothing is exchanged.  W is complete on every rank at both transitions (the
         // caller gathered it before the state set changed).
-        dist.whole = n < dist.repl_min_rows;
+        dist.whole = n < dist.repl_min_rows;                  // (kfsp_repl_partition is the same arithmetic for host-side tests)
         for (int r = 0; r <= dist.nranks; ++r) dist.rb[r] = part_lo(n, dist.nranks, r);
         dist.lo = dist.rb[dist.rank];
         dist.hi = dist.rb[dist.rank + 1];
@@ -1444,6 +1444,11 @@ struct Engine {
         }
         hp.halo_owner = dist.halo_owner; hp.halo_lidx = dist.halo_lidx; hp.err = d_err;
         for (int r = 0; r <= P; ++r) hp.rb[r] = dist.rb[r];
+        if (!dist.d_stat) {
+            KFSP_CUDA(cudaMalloc(&dist.d_stat, 4 * sizeof(unsigned long long)));
+            KFSP_CUDA(cudaMemset(dist.d_stat, 0, 4 * sizeof(unsigned long long)));
+        }
+        hp.stat = dist.d_stat;
         if (!dist.d_peers) KFSP_CUDA(cudaMalloc(&dist.d_peers, sizeof(DistPeers)));
         KFSP_CUDA(cudaMemcpy(dist.d_peers, &hp, sizeof hp, cudaMemcpyHostToDevice));
         if (dist.p2p_red) { rd.peers = dist.d_peers; rd.dist_send = nullptr; }

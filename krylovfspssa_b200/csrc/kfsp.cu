@@ -670,6 +670,15 @@ int kfsp_dist_partition(int64_t n, int32_t nranks, int32_t rank, int64_t* lo, in
     *hi = part_lo(n, nranks, rank + 1);
     return KFSP_OK;
 }
+// host-side arithmetic of the replicated layout of ADAPTIVE sets on several GPUs (Engine::repartition; no GPU needed): the rows
+// `rank` computes in the Krylov loop for a state set of n rows, and whether the set is still kept whole on every rank
+int kfsp_repl_partition(int64_t n, int32_t nranks, int32_t rank, int64_t min_rows, int64_t* lo, int64_t* hi, int32_t* whole) {
+    if (n < 0 || nranks < 1 || rank < 0 || rank >= nranks || !lo || !hi || !whole) return KFSP_ERR_ARG;
+    *whole = (nranks == 1 || n < min_rows) ? 1 : 0;
+    *lo = *whole ? 0 : part_lo(n, nranks, rank);
+    *hi = *whole ? n : part_lo(n, nranks, rank + 1);
+    return KFSP_OK;
+}
 int kfsp_dist_owner(int64_t n, int32_t nranks, int64_t row, int32_t* owner) {
     if (n < nranks || nranks < 1 || row < 0 || row >= n || !owner) return KFSP_ERR_ARG;
     *owner = part_owner(n, nranks, row);
@@ -710,6 +719,33 @@ int kfsp_dist_info(kfsp_handle h, int64_t* lo, int64_t* hi, int64_t* n_halo, int
     if (n_send) *n_send = d.n_send;
     if (halo_bytes) *halo_bytes = d.halo_bytes;
     if (reductions) *reductions = d.reductions;
+    return KFSP_OK;
+}
+
+// How the propensities of the model last given to kfsp_set_model are evaluated (canonical arithmetic)
+int kfsp_model_info(kfsp_handle h, int32_t* n_tabulated, int32_t* n_host_evaluated, int32_t* n_device_libm, int32_t* factored) {
+    if (!h) return KFSP_ERR_ARG;
+    const Engine& e = h->e;
+    if (!e.have_model) return KFSP_ERR_NO_MODEL;
+    if (n_tabulated) *n_tabulated = e.n_tabulated;
+    if (n_host_evaluated) *n_host_evaluated = e.n_host_evaluated;
+    if (n_device_libm) *n_device_libm = e.n_inexact_on_device;
+    if (factored) *factored = e.idx ? 1 : 0;
+    return KFSP_OK;
+}
+int kfsp_dist_exchange_stats(kfsp_handle h, int64_t* exchanges, double* mean_us, double* max_us, int32_t reset) {
+    if (!h) return KFSP_ERR_ARG;
+    Engine& e = h->e;
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (e.dist.d_stat) {
+        cudaSetDevice(e.device);
+        KFSP_CUDA(cudaMemcpyAsync(v, e.dist.d_stat, sizeof v, cudaMemcpyDeviceToHost, e.stream));
+        KFSP_TRY(e.sync());
+        if (reset) KFSP_CUDA(cudaMemsetAsync(e.dist.d_stat, 0, sizeof v, e.stream));
+    }
+    if (exchanges) *exchanges = (int64_t)v[0];
+    if (mean_us) *mean_us = v[0] ? 1e-3 * (double)v[1] / (double)v[0] : 0.0;
+    if (max_us) *max_us = 1e-3 * (double)v[2];
     return KFSP_OK;
 }
 

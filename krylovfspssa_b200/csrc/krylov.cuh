@@ -49,7 +49,14 @@ struct DistPeers {
     const int32_t* halo_lidx;                // ... and row index on the owner
     int32_t* err;
     int64_t rb[MAX_RANKS + 1];               // replicated-layout partition (adaptive state sets): rank r computes rows [rb[r], rb[r+1])
+    unsigned long long* stat;                // [0] fused exchanges done, [1] ns between posting this rank's partial and holding all ranks'
+                                             // (wire latency + waiting for the slowest rank), [2] the largest such wait
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 struct Reducer {
     double* partials;           // [RED_W * MAX_VEC_BLOCKS]: (hi, lo) planes for up to RED_NV reductions
     unsigned int* counter;      // self-resetting ticket
@@ -202,6 +209,7 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
         const int P = dp->nranks, me = dp->rank;
         const int slot = (int)(rd.seq & 1ull);
         __syncthreads();
+        const unsigned long long ns0 = threadIdx.x == 0 ? global_ns() : 0ull;
         if ((int)threadIdx.x < P) {
             const int r = threadIdx.x;
             double* dst = dp->part[r] + ((size_t)slot * P + me) * RED_W;
@@ -219,6 +227,12 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
             __threadfence_system();
         }
         __syncthreads();
+        if (threadIdx.x == 0 && dp->stat) {
+            const unsigned long long dt = global_ns() - ns0;
+            dp->stat[0] += 1ull;
+            dp->stat[1] += dt;
+            if (dt > dp->stat[2]) dp->stat[2] = dt;
+        }
         if ((int)threadIdx.x < NV) {                        // one thread per value merges the P ranks' partials in rank order
             const int q = threadIdx.x;
             DD s; s.hi = 0.0; s.lo = 0.0;

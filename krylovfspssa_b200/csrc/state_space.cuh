@@ -256,7 +256,10 @@ __global__ void k_onestep_fill(FspView f, int64_t n_old, const int32_t* __restri
 // candidate generation: SSA_EXTENDER (StateSpace.f90:571-629).  One thread per start state;
 // the walk is replayed twice (count, then fill) from its own Philox sub-stream.
 // (Measured: persistent lanes with dynamic work fetch were 2x SLOWER on the Goutsias model -- walks are
-// short and the cost is dependent memory latency per walk, not divergence -- so the grid-stride form stays.)
+// short and the cost is dependent memory latency per walk, not divergence -- so the grid-stride form stays.
+// Round 2: a state-major copy {a_1..a_R, DIAG, ADJ_1..ADJ_R} of the column form, one 128-byte record per state instead of
+// 2R+1 sectors per jump, changed nothing either (Goutsias SSA phase 1.535 vs 1.541 s): the kernel lasts as long as its longest
+// walk, and a jump is a serial chain -- Philox, -log(r)/DIAG, the cumulative sum over the reactions, the successor load.)
 // ---------------------------------------------------------------------------------------
 template <bool FILL>
 __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t seed, uint32_t call_no,

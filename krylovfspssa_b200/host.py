@@ -201,6 +201,18 @@ class KrylovFspHandle:
         check(lib().kfsp_dist_info(self._h, *[C.byref(x) for x in v]))
         return dict(zip(("lo", "hi", "n_halo", "n_send", "halo_bytes", "reductions"), [x.value for x in v]))
 
+    def model_info(self):
+        """how the propensities of the current model are evaluated: tabulated / by the host / by the CUDA math library / factored"""
+        v = [C.c_int32() for _ in range(4)]
+        check(lib().kfsp_model_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("n_tabulated", "n_host_evaluated", "n_device_libm", "factored"), [x.value for x in v]))
+
+    def dist_exchange_stats(self, reset=False):
+        """fused reduction exchanges of the peer-memory path: count, mean and max microseconds from posting to holding all partials"""
+        n, mean, mx = C.c_int64(), C.c_double(), C.c_double()
+        check(lib().kfsp_dist_exchange_stats(self._h, C.byref(n), C.byref(mean), C.byref(mx), 1 if reset else 0))
+        return {"exchanges": n.value, "mean_us": mean.value, "max_us": mx.value}
+
     # ---- state space ------------------------------------------------------------------
     def fsp_init(self, states):
         st = np.ascontiguousarray(np.asarray(states, dtype=np.int32).reshape(-1, self.S))

@@ -83,3 +83,34 @@ def test_cme_solve_driver_program():
     assert fsp.index(fsp.state[:, top]) == top + 1                           # FSP%INDEX is 1-based
     assert fsp.probability(fsp.state[:, top]) == w[top]
     assert fsp.index([9999, 9999]) == 0
+
+
+def test_multi_species_transcendental_program_is_evaluated_by_the_host(tmp_path):
+    """a byte-code propensity with a transcendental operation on TWO species (Hill term times a linear one) cannot be tabulated;
+    the CUDA math library may differ from the host libm by ulps, which could flip an SSA pick or a pruning decision, so the
+    library evaluates it on the host through the CUSTOMPROP machinery (kfsp_model_info says so) and the adaptive solve stays
+    bit-identical to the oracle"""
+    import os
+    import numpy as np
+    import krylovfspssa_b200 as k
+    import oracle
+    src = open(os.path.join(k.models_dir(), "toggle.input")).read().splitlines()
+    i = src.index("propensities")
+    src[i + 1] = "(bx + kx/(2.0 + 0.2*Y^2.5))*(1.0 + 0.001*X)"
+    path = tmp_path / "toggle_hill2.input"
+    path.write_text("\n".join(src) + "\n")
+    params = [1.0, 100.0, 1.0, 1.0, 100.0, 1.0]
+    model = k.CME_MODEL().load(str(path))
+    model.reset_parameters(params)
+    h = k.KrylovFspHandle(model, max_states=200000, seed=7)
+    info = h.model_info()
+    assert info["n_host_evaluated"] == 1 and info["n_device_libm"] == 0
+    out = h.solve(3.0, [[0, 0]], [1.0], 1e-4, 1e-10)
+    ref = oracle.solve(oracle.Model.load(str(path), params), [[0, 0]], [1.0], 3.0, 1e-4, 1e-10, reproducible=1, seed=7)
+    assert out["iflag"] == 0
+    assert np.array_equal(out["states"], ref["states"])
+    assert np.array_equal(out["vector"], ref["vector"])
+    h.close()
+    # the same program cannot take the index-only variant together with host evaluation: refused, not switched
+    with pytest.raises(k.KfspError):
+        k.KrylovFspHandle(model, max_states=1000, spmv_variant=2)
