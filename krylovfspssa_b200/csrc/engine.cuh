@@ -185,6 +185,7 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_BD2_SYNC")) { bd2_sync = std::atoi(ev); if (bd2_sync & (bd2_sync - 1)) bd2_sync = 0; }
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_SMEM_SWEEP")) smem_sweep = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_SSA_EMIT")) ssa_emit_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_PROP_CACHE_STATES")) pc_budget = std::atoll(ev);
         if (const char* ev = std::getenv("KFSP_DEBUG_REPL")) repl_debug = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_REPL_MIN_ROWS")) dist.repl_min_rows = std::atoll(ev);
@@ -239,6 +240,7 @@ struct Engine {
         free_prop_cache();
         cudaFree(d_model); cudaFree(d_tables); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
         cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush); cudaFree(hp_dev);
+        cudaFree(emit.tmp); cudaFree(emit.prev); cudaFree(emit.head); cudaFree(emit.cursor);
         cudaFree(d_factabs);
         if (hp_host) cudaFreeHost(hp_host);
         if (h_res) cudaFreeHost(h_res);
@@ -898,9 +900,13 @@ struct Engine {
         int32_t* tb = (int32_t*)p;
         FspView f = view();
         if (ssa) {
-            KFSP_LAUNCH(k_ssa_walk<true>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
-                        (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand, host_prop ? pc : PropCache(),
-                        (int32_t*)nullptr);
+            if (ssa_emit_ready) {                              // the counting pass already holds every candidate: copy them into order
+                KFSP_LAUNCH(k_ssa_gather, grid_for(n_old), VEC_THREADS, 0, n_old, (const int32_t*)off, ncand, emit, S, cand);
+            } else {
+                KFSP_LAUNCH(k_ssa_walk<true>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
+                            (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand, host_prop ? pc : PropCache(),
+                            (int32_t*)nullptr, SsaEmit());
+            }
         } else {
             KFSP_LAUNCH(k_onestep_fill, grid_for(n_old), VEC_THREADS, 0, f, n_old, (const int32_t*)off, cand, d_err);
         }
@@ -917,12 +923,36 @@ struct Engine {
         return commit_candidates(cand, ncand, slot, win, pos, n_new);
     }
 
+    // candidates emitted during the counting pass of the SSA walks (state_space.cuh: SsaEmit); KFSP_SSA_EMIT=0: replay the walks (A/B)
+    SsaEmit emit;
+    size_t emit_states = 0;
+    bool ssa_emit_on = true, emit_armed = false, ssa_emit_ready = false;
+    int prepare_ssa_emit(int64_t n_old) {
+        emit_armed = false;
+        if (!ssa_emit_on) return KFSP_OK;
+        const size_t want = (size_t)std::max<int64_t>(1 << 20, n_old);          // candidates per expansion: a boundary fraction of the set
+        if (want > emit_states || !emit.tmp) {
+            KFSP_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(emit.tmp); cudaFree(emit.prev); cudaFree(emit.head); cudaFree(emit.cursor);
+            emit = SsaEmit();
+            emit_states = std::max(want, 2 * emit_states);
+            KFSP_CUDA(cudaMalloc(&emit.tmp, sizeof(int32_t) * emit_states * S));
+            KFSP_CUDA(cudaMalloc(&emit.prev, sizeof(int32_t) * emit_states));
+            KFSP_CUDA(cudaMalloc(&emit.head, sizeof(int32_t) * emit_states));
+            KFSP_CUDA(cudaMalloc(&emit.cursor, sizeof(int32_t)));
+            emit.cap = (int32_t)std::min<size_t>(emit_states, 2000000000u);
+        }
+        KFSP_CUDA(cudaMemsetAsync(emit.cursor, 0, sizeof(int32_t), stream));
+        return KFSP_OK;
+    }
+
     // ---------------------------------------------------------------- SSA_EXTENDER
     int fsp_ssa_1(double timestep) {
         if (box) return KFSP_ERR_UNSUPPORTED;
         if (n < 1) return KFSP_ERR_BAD_SIZES;
         const int64_t n_old = n;
         ssa_calls += 1;
+        emit_armed = false;
         size_t need0 = align_up(sizeof(int32_t) * n_old) * 2 + align_up(sizeof(int32_t) * scan_buf_ints(n_old));
         const size_t wsave_at = need0;                  // suspended walks of the host-propensity rounds (dead before the scan)
         if (host_prop) need0 += align_up(sizeof(int32_t) * n_old * (size_t)(S + 4));
@@ -955,7 +985,7 @@ struct Engine {
                 if (round > (1 << 24)) return KFSP_ERR_SSA_RUNAWAY;
                 KFSP_CUDA(cudaMemsetAsync(pc.nreq, 0, sizeof(int32_t), stream));
                 KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
-                            (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, pc, wsave);
+                            (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, pc, wsave, SsaEmit());
                 KFSP_CUDA(cudaMemcpyAsync(h_nreq, pc.nreq, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
                 // the request list is small: fetch it with the counter instead of paying a second round trip
                 KFSP_CUDA(cudaMemcpyAsync(h_req, pc.req, sizeof(int32_t) * (size_t)std::min<int64_t>(pc.req_cap, 4096) * S, cudaMemcpyDeviceToHost, stream));
@@ -986,8 +1016,11 @@ struct Engine {
                 pc_n += nu;
             }
         } else {
+            KFSP_TRY(prepare_ssa_emit(n_old));
             KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
-                        (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, PropCache(), (int32_t*)nullptr);
+                        (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, PropCache(), (int32_t*)nullptr,
+                        ssa_emit_on ? emit : SsaEmit());
+            emit_armed = ssa_emit_on;
         }
         int64_t ncand = 0;
         KFSP_TRY(exclusive_scan(cnt, off, n_old, tb0, &ncand));
@@ -996,7 +1029,10 @@ struct Engine {
         if (e) return err_to_status(e);
         if (ncand == 0) return KFSP_OK;
         if (ncand > 2000000000LL - n_old) return KFSP_ERR_OVERFLOW;
-        return expand_with(ncand, n_old, /*ssa=*/true, timestep);
+        ssa_emit_ready = emit_armed && ncand <= emit.cap;       // else: replay the walks to fill the list
+        const int st = expand_with(ncand, n_old, /*ssa=*/true, timestep);
+        ssa_emit_ready = false;
+        return st;
     }
 
     // ---------------------------------------------------------------- FMATVEC

@@ -261,10 +261,34 @@ __global__ void k_onestep_fill(FspView f, int64_t n_old, const int32_t* __restri
 // 2R+1 sectors per jump, changed nothing either (Goutsias SSA phase 1.535 vs 1.541 s): the kernel lasts as long as its longest
 // walk, and a jump is a serial chain -- Philox, -log(r)/DIAG, the cumulative sum over the reactions, the successor load.)
 // ---------------------------------------------------------------------------------------
+// Emission during the counting pass (device-evaluated propensities): the kernel lasts as long as its longest walk, and the
+// walks that leave the projection are the long ones, so replaying them to fill the candidate list cost as much as the counting
+// pass (Goutsias at 8e5 states: 3.5 ms + 2.8 ms per expansion).  Instead a walk appends each candidate to a temporary area
+// (position from one atomicAdd, linked to the walk's previous candidate) and k_ssa_gather copies every walk's chain to its
+// scanned position: same list, same order, one pass of walks.  tmp == nullptr, or more candidates than cap: the replay below.
+struct SsaEmit {
+    int32_t* tmp = nullptr;      // [p*S + s]
+    int32_t* prev = nullptr;     // position of the same walk's previous candidate, -1 for its first
+    int32_t* head = nullptr;     // per start state: position of its LAST candidate, -1 if none
+    int32_t* cursor = nullptr;
+    int32_t cap = 0;
+};
+__global__ void k_ssa_gather(int64_t n_old, const int32_t* __restrict__ off, int64_t ncand, SsaEmit em, int S, int32_t* cand) {
+    for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j0 < n_old; j0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o0 = off[j0];
+        const int64_t c = (j0 + 1 < n_old ? (int64_t)off[j0 + 1] : ncand) - o0;      // candidates of this walk
+        if (c <= 0) continue;
+        int32_t p = em.head[j0];
+        for (int64_t t = c - 1; t >= 0 && p >= 0; --t) {
+            for (int s = 0; s < S; ++s) cand[(o0 + t) * S + s] = em.tmp[(int64_t)p * S + s];
+            p = em.prev[p];
+        }
+    }
+}
 template <bool FILL>
 __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t seed, uint32_t call_no,
                            int32_t* cnt, const int32_t* __restrict__ off, int32_t* cand, int32_t* err, int32_t max_jumps,
-                           int64_t ncand, PropCache pc, int32_t* wsave) {
+                           int64_t ncand, PropCache pc, int32_t* wsave, SsaEmit em) {
     const DeviceModel* __restrict__ m = f.model;
     const int S = f.S, R = f.R;
     for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j0 < n_old; j0 += (int64_t)gridDim.x * blockDim.x) {
@@ -282,6 +306,7 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
         int64_t j = j0;                 // index of the current state, or -1 if it is not (yet) in the projection
         double t = 0.0;
         int32_t emitted = 0;
+        int32_t myhead = -1;
         int64_t o = FILL ? (int64_t)off[j0] : 0;
         uint32_t jump0 = 0;
         if (status == -2) {             // resume where the walk stopped: counter-based RNG, so the draws repeat exactly
@@ -341,7 +366,8 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
             }
             if (neg) break;             // illegal: ADJ(K,J) = -1 and the walk ends (:594-596)
             if (over) { atomicOr(err, DEV_MOLECULE_LIMIT); break; }
-            int32_t nj = j >= 0 ? f.succ[(int64_t)k * f.ld + j] : IDX_ABSENT;
+            int32_t nj = j >= 0 ? f.succ[(int64_t)k * f.ld + j] : IDX_ABSENT;      // (fetching all R successors with the propensities,
+                                                                                     // to save the dependent load, measured 5 % slower)
             if (nj < 0) nj = table_lookup(f, nb);
             for (int s = 0; s < S; ++s) st[s] = nb[s];
             if (nj >= 0) {
@@ -351,6 +377,13 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
                 if (FILL) {
                     for (int s = 0; s < S; ++s) cand[o * S + s] = nb[s];
                     ++o;
+                } else if (em.tmp) {
+                    const int32_t p = atomicAdd(em.cursor, 1);
+                    if (p < em.cap) {
+                        for (int s = 0; s < S; ++s) em.tmp[(int64_t)p * S + s] = nb[s];
+                        em.prev[p] = myhead;
+                        myhead = p;
+                    }
                 }
                 ++emitted;
                 j = -1;
@@ -358,6 +391,7 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
             }
         }
         if (!FILL) cnt[j0] = suspended ? -2 : emitted;
+        if (!FILL && em.tmp) em.head[j0] = myhead;
     }
 }
 
