@@ -60,6 +60,7 @@ SIGNATURES = {
     "kfsp_model_set_custom_propensity": (C.c_int, [_vp, PROPENSITY_FN, _vp]),
     "kfsp_model_propensity": (C.c_int, [_vp, _i32p, C.c_int32, _dp]),
     "kfsp_model_propensity_factored": (C.c_int, [_vp, _i32p, C.c_int32, _dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "kfsp_model_custom_structure": (C.c_int, [_vp, C.c_int32, _i32p, C.POINTER(C.c_int32)]),
     "kfsp_create": (C.c_int, [C.POINTER(Options), C.POINTER(_vp)]),
     "kfsp_destroy": (C.c_int, [_vp]),
     "kfsp_set_model": (C.c_int, [_vp, _vp]),

@@ -186,6 +186,7 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_SMALL_SWEEP")) small_sweep = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_SMEM_SWEEP")) smem_sweep = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_SSA_EMIT")) ssa_emit_on = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_CUSTOM_PROBE")) custom_probe_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_PROP_CACHE_STATES")) pc_budget = std::atoll(ev);
         if (const char* ev = std::getenv("KFSP_DEBUG_REPL")) repl_debug = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_REPL_MIN_ROWS")) dist.repl_min_rows = std::atoll(ev);
@@ -484,8 +485,62 @@ struct Engine {
     // CUSTOMPROP: the propensity is an opaque host function.  Sizes, stoichiometry and parameters go to the
     // device; a_k(x) is evaluated on the host in batches (propensities_host) and, inside SSA walks, served
     // from the device side cache (fsp_ssa_hostprop).
+    // A callback that reads at most one species per reaction (examples/toggle.f90:55-69) is detected by probing, tabulated over
+    // the counts 0..max_molecules and verified bit for bit on random states (model_host.h: probe_custom_single_species); it is
+    // then an ordinary tabulated model on the device: no host round trip, every SpMV variant, every multi-GPU layout.
+    // KFSP_CUSTOM_PROBE=0 keeps the callbacks (A/B).  Callbacks that read several species (examples/transcr6d.f90:63-89) stay on
+    // the host path: explicit matrix, one GPU or the replicated multi-GPU layout (every rank calls its own copy of the function).
+    bool custom_probe_on = true;
+    int set_model_custom_tables(const HostModel& m, const std::vector<int32_t>& species, const std::vector<double>& tables) {
+        DeviceModel dm;
+        std::memset(&dm, 0, sizeof dm);
+        dm.S = m.S; dm.R = m.R; dm.P = m.P; dm.max_molecules = opt.max_molecules;
+        for (int k = 0; k < m.R; ++k)
+            for (int s = 0; s < m.S; ++s) dm.stoich[k * m.S + s] = m.stoich[(size_t)k * m.S + s];
+        for (int i = 0; i < m.P; ++i) dm.params[i] = m.params[i];
+        const int64_t tlen = (int64_t)opt.max_molecules + 1;
+        if (d_tables) { KFSP_CUDA(cudaFree(d_tables)); d_tables = nullptr; }
+        KFSP_CUDA(cudaMalloc(&d_tables, sizeof(double) * tables.size()));
+        KFSP_CUDA(cudaMemcpy(d_tables, tables.data(), sizeof(double) * tables.size(), cudaMemcpyHostToDevice));
+        for (int k = 0; k < m.R; ++k) { dm.table_species[k] = species[k]; dm.table[k] = d_tables + (size_t)k * tlen; }
+        n_tabulated = m.R; n_inexact_on_device = 0; n_host_evaluated = 0;
+        if (opt.spmv_variant == 2) {                        // index-only SpMV: every propensity is one tabulated term
+            FacModel F;
+            std::memset(&F, 0, sizeof F);
+            F.S = m.S; F.R = m.R;
+            for (int k = 0; k < m.R; ++k) {
+                F.shape[k] = FAC_ONE; F.nops[k] = 1; F.ops[k][0] = 0;
+                F.sp[k][0] = (int8_t)species[k]; F.use[k][0] = 1;
+                for (int t = 0; t < FAC_MAX_TERMS; ++t) F.tab[k][t] = dm.table[k];
+                for (int s2 = 0; s2 < m.S; ++s2) {
+                    const int32_t v = m.stoich[(size_t)k * m.S + s2];
+                    if (v < -127 || v > 127) return KFSP_ERR_UNSUPPORTED;
+                    F.nu[k][s2] = (int8_t)v;
+                }
+            }
+            fac = F;
+            idx = true;
+        }
+        KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
+        KFSP_CUDA(cudaStreamSynchronize(stream));
+        h_dm = dm;
+        const bool reshape = !have_model || m.S != S || m.R != R || box;
+        S = m.S; R = m.R;
+        have_model = true;
+        host_prop = false;
+        free_prop_cache();
+        if (reshape) { free_state_space(); }
+        n = 0;
+        return KFSP_OK;
+    }
     int set_model_hostprop(const HostModel& m) {
-        if (dist.nranks > 1 || opt.spmv_variant != 0) return KFSP_ERR_UNSUPPORTED;   // those rows are built from device byte code / tables
+        if (m.custom && custom_probe_on) {
+            std::vector<int32_t> species;
+            std::vector<double> tables;
+            if (probe_custom_single_species(m, opt.max_molecules, species, tables)) return set_model_custom_tables(m, species, tables);
+        }
+        // rows of a memory-scaled partition, the lattice and the index-only variant are built from device byte code / tables
+        if ((dist.nranks > 1 && !dist.repl) || opt.spmv_variant != 0) return KFSP_ERR_UNSUPPORTED;
         DeviceModel dm;
         std::memset(&dm, 0, sizeof dm);
         dm.S = m.S; dm.R = m.R; dm.P = m.P; dm.max_molecules = opt.max_molecules;
@@ -1557,6 +1612,7 @@ struct Engine {
     // full hash table and their own rows, then agree on the halo plan.
     int dist_fsp_init(int64_t n_global, const int32_t* states_host) {
 #ifdef KFSP_WITH_NCCL
+        if (host_prop) return KFSP_ERR_UNSUPPORTED;     // k_dist_build_rows evaluates the propensities of this rank's rows on the device
         KFSP_TRY(ensure_state_space());
         if (n_global < dist.nranks || n_global > opt.max_states) return KFSP_ERR_BAD_SIZES;
         const int P = dist.nranks;

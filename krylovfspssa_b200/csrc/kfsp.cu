@@ -329,6 +329,16 @@ int kfsp_model_propensity_factored(kfsp_model m, const int32_t* state, int32_t r
     return KFSP_OK;
 }
 
+int kfsp_model_custom_structure(kfsp_model m, int32_t max_molecules, int32_t* species_out, int32_t* single_out) {
+    if (!m || !species_out || !single_out || max_molecules < 1) return KFSP_ERR_ARG;
+    if (!m->m.custom) return KFSP_ERR_NO_MODEL;
+    std::vector<int32_t> species;
+    std::vector<double> tables;
+    *single_out = probe_custom_single_species(m->m, max_molecules, species, tables) ? 1 : 0;
+    for (int k = 0; k < m->m.R; ++k) species_out[k] = species[k];
+    return KFSP_OK;
+}
+
 // ------------------------------------------------------------------ handle
 int kfsp_create(const kfsp_options* opts, kfsp_handle* out) {
     if (!out) return KFSP_ERR_ARG;

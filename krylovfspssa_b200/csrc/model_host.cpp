@@ -351,6 +351,82 @@ double HostModel::propensity(const int32_t* state, int reaction1) const {
     return evaluate_program(programs[reaction1 - 1], val);
 }
 
+namespace {
+inline bool same_bits(double a, double b) { return std::memcmp(&a, &b, sizeof a) == 0; }
+// splitmix64: the probe must not depend on the C library's generator (the SSA streams are Philox; this one only picks probe states)
+inline uint64_t probe_next(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+}  // namespace
+
+bool probe_custom_single_species(const HostModel& m, int32_t max_molecules, std::vector<int32_t>& species, std::vector<double>& tables,
+                                 int nverify) {
+    species.assign((size_t)m.R, -2);
+    tables.clear();
+    if (!m.custom || m.S < 1 || m.R < 1 || max_molecules < 1) return false;
+    const int S = m.S, R = m.R;
+    const int64_t tlen = (int64_t)max_molecules + 1;
+    uint64_t rng = 0x6B66737042323030ull;
+    // base states: small counts (where Hill terms and combinatorial factors are most curved), all ones, and a few spread ones
+    std::vector<std::vector<int32_t>> bases;
+    bases.emplace_back((size_t)S, 1);
+    bases.emplace_back((size_t)S, 2);
+    for (int b = 0; b < 6; ++b) {
+        std::vector<int32_t> st((size_t)S);
+        const int32_t range = b < 3 ? std::min<int32_t>(max_molecules, 12) : std::min<int32_t>(max_molecules, 300);
+        for (int s = 0; s < S; ++s) st[s] = 1 + (int32_t)(probe_next(rng) % (uint64_t)range);
+        bases.push_back(st);
+    }
+    std::vector<int32_t> line;
+    for (int32_t c = 0; c <= std::min<int32_t>(max_molecules, 40); ++c) line.push_back(c);
+    for (int q = 0; q < 8; ++q) line.push_back((int32_t)(probe_next(rng) % (uint64_t)tlen));
+    line.push_back(max_molecules);
+    bool all_single = true;
+    std::vector<int32_t> st((size_t)S);
+    for (int k = 0; k < R; ++k) {
+        uint32_t mask = 0;
+        for (const auto& base : bases) {
+            const double a0 = m.custom(base.data(), k + 1, m.params.data(), m.custom_ctx);
+            for (int s = 0; s < S; ++s) {
+                if (mask & (1u << s)) continue;
+                st = base;
+                for (int32_t c : line) {
+                    st[s] = c;
+                    if (!same_bits(m.custom(st.data(), k + 1, m.params.data(), m.custom_ctx), a0)) { mask |= 1u << s; break; }
+                }
+            }
+        }
+        if (mask & (mask - 1)) { species[k] = -2; all_single = false; continue; }
+        int sp = 0;
+        while (mask > 1) { mask >>= 1; ++sp; }
+        species[k] = sp;
+    }
+    if (!all_single) return false;
+    tables.resize((size_t)R * tlen);
+    for (int k = 0; k < R; ++k) {
+        std::fill(st.begin(), st.end(), 0);
+        for (int64_t c = 0; c < tlen; ++c) {
+            st[species[k]] = (int32_t)c;
+            tables[(size_t)k * tlen + c] = m.custom(st.data(), k + 1, m.params.data(), m.custom_ctx);
+        }
+    }
+    // verification: the callback against the tables on states drawn at three scales
+    for (int t = 0; t < nverify; ++t) {
+        const int32_t range = t % 3 == 0 ? std::min<int32_t>(max_molecules, 16) : t % 3 == 1 ? std::min<int32_t>(max_molecules, 400) : max_molecules;
+        for (int s = 0; s < S; ++s) st[s] = (int32_t)(probe_next(rng) % (uint64_t)(range + 1));
+        for (int k = 0; k < R; ++k)
+            if (!same_bits(m.custom(st.data(), k + 1, m.params.data(), m.custom_ctx), tables[(size_t)k * tlen + st[species[k]]])) {
+                species[k] = -2;
+                tables.clear();
+                return false;
+            }
+    }
+    return true;
+}
+
 bool parse_reaction(const std::string& line, const std::vector<std::string>& species, int32_t* vec, std::string& err) {
     std::istringstream is(line);
     std::vector<std::string> terms;

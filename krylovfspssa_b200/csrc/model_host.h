@@ -65,6 +65,16 @@ struct Factored {
 // false if the program is malformed or a multi-species node is not one of + - * neg
 bool factor_program(const Program& p, int S, Factored& out);
 
+// CUSTOMPROP structure by probing (the callback is opaque): for every reaction, vary one species at a time around several
+// base states and record which ones change the value.  If every reaction reads AT MOST ONE species, tabulate it over the
+// counts 0..max_molecules (tables[k*(max_molecules+1) + c], species[k] = that species, 0 for a constant) and verify the
+// tables bit for bit against the callback on `nverify` pseudo-random states; true only if all of that holds.  A model that
+// passes can be served from device tables like a parsed single-species propensity (no host round trips, every SpMV variant,
+// every multi-GPU layout); one that does not stays on the host-callback path.  species[k] = -2 marks a reaction that reads
+// several species (reported even when the function returns false).
+bool probe_custom_single_species(const HostModel& m, int32_t max_molecules, std::vector<int32_t>& species, std::vector<double>& tables,
+                                 int nverify = 16384);
+
 bool load_model_file(const std::string& path, HostModel& m, std::string& err);
 bool parse_reaction(const std::string& line, const std::vector<std::string>& species, int32_t* vec, std::string& err);
 

@@ -129,6 +129,15 @@ class CME_MODEL:
         self.customprop = fn
         check(lib().kfsp_model_set_custom_propensity(self._h, self._cb, None))
 
+    def custom_structure(self, max_molecules=10000):
+        """Structure of the CUSTOMPROP callback found by probing (kfsp_model_custom_structure; host only): (species, single) with
+        species[k] the 0-based species reaction k+1 reads (0: constant, -2: several) and single True when the model can be
+        served from device tables."""
+        sp = np.zeros(self._dims()[1], dtype=np.int32)
+        single = C.c_int32()
+        check(lib().kfsp_model_custom_structure(self._h, int(max_molecules), _i32(sp), C.byref(single)))
+        return sp.tolist(), bool(single.value)
+
     # PROPENSITY(THIS, STATE, REACTION)  ModelModule.f90:163-199
     def propensity(self, state, reaction):
         st = np.ascontiguousarray(state, dtype=np.int32)

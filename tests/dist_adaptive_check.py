@@ -76,6 +76,25 @@ def main():
                        out["stats"]["n_drop"], info["lo"], info["hi"], ok), flush=True)
                 ok_all = ok_all and ok
                 h.close()
+        # CUSTOMPROP (examples/transcr6d.f90: an opaque host function reading two species in reactions 5 and 7) on partitioned
+        # handles: every rank evaluates its own copy of the callback while the state space is expanded identically everywhere.
+        # Must equal the same solve on an unpartitioned handle of this rank's GPU bit for bit.
+        from krylovfspssa_b200 import examples
+        d = examples.DRIVERS["transcr6d"]
+        solo = k.KrylovFspHandle(examples.driver_model("transcr6d"), max_states=400000, seed=4242, device=local)
+        ref = solo.solve(30.0, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
+        solo.close()
+        h = k.KrylovFspHandle(examples.driver_model("transcr6d"), max_states=400000, seed=4242, device=local)
+        h.dist_init(rank, world, new_uid(rank))
+        assert h.model_info()["n_host_evaluated"] == d["R"]
+        out = h.solve(30.0, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
+        ok = out["iflag"] == 0 and ref["iflag"] == 0 and np.array_equal(out["states"], ref["states"])
+        ok = ok and np.array_equal(out["vector"], ref["vector"]) and np.array_equal(out["trace"]["i"], ref["trace"]["i"])
+        print("transcr6d CUSTOMPROP rank %d/%d: N=%d steps=%d expansions=%d host evaluations=%d bit-identical=%s" %
+              (rank, world, len(out["vector"]), out["stats"]["nstep"], out["stats"]["n_expand"],
+               int(h.phase_seconds()["host_propensity_evals"]), ok), flush=True)
+        ok_all = ok_all and ok
+        h.close()
     else:
         db = json.load(open(os.path.join(HERE, "golden", "full_digests.json")))
         for tag, (name, t, ftol, ktol, cap) in sorted(FULL_RUNS.items()):

@@ -139,3 +139,18 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".f90", ".sh")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "kfsp_oracle" not in txt.replace("oracle/kfsp_oracle.cpp", ""), f
+
+
+def test_shim_call_sequence_compiles_as_c_and_fails_loudly_without_a_gpu(tmp_path):
+    """tests/host/shim_sequence.c: the statements of the Fortran shim's CME_SOLVE (krylovfspssa_b200/fortran/kfsp_c_binding.f90,
+    which no compiler here can build) from a compiled C99 host -- include/kfsp.h must be plain C and every entry point the shim
+    binds must link.  Without a GPU the program stops at kfsp_create with KFSP_ERR_NO_DEVICE (the GPU run: test_gpu_shim_sequence.py)."""
+    import subprocess
+    import torch
+    from shim_build import build_shim_sequence
+    exe = build_shim_sequence(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by test_gpu_shim_sequence.py")
+    r = subprocess.run([exe, "bytecode", os.path.join(k.models_dir(), "toggle.input"), "5", "1e-4", "1e-8", "100000", "12345",
+                        str(tmp_path / "o.bin"), "0", "0", "1", "100", "1", "1", "100", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr

@@ -48,3 +48,28 @@ def test_goutsias_stoichiometry_matches_input_file():
     import os
     fm = k.CME_MODEL().load(os.path.join(k.models_dir(), "goutsias.input"))
     assert np.array_equal(fm.stoichiometry, examples.driver_model("transcr6d").stoichiometry)
+
+
+def test_custom_structure_probe_of_the_example_drivers():
+    """kfsp_model_custom_structure (host only): which species each reaction of an opaque callback reads.  toggle.f90 and
+    repressilator.f90 read one species per reaction (-> device tables), transcr6d.f90 reads two in reactions 5 and 7."""
+    sp, single = examples.driver_model("toggle").custom_structure()
+    assert single and sp == [1, 0, 0, 1]
+    sp, single = examples.driver_model("repressilator").custom_structure()
+    assert single and sp == [1, 0, 2, 1, 0, 2]
+    sp, single = examples.driver_model("transcr6d").custom_structure()
+    assert not single and sp == [2, 0, 4, 2, -2, 4, -2, 5, 0, 1]
+
+
+def test_custom_structure_probe_catches_a_coupling_the_axis_probes_miss():
+    """a second species that matters only far from the axes: invisible to the one-species-at-a-time probes, caught by the
+    bit-for-bit verification on random states, so the model keeps the host-callback path"""
+    m = k.CME_MODEL().create(2, 2, 2)
+    m.stoichiometry = np.array([[1, -1], [0, 0]], dtype=np.int32)
+    m.reset_parameters([20.0, 1.0])
+    m.set_customprop(lambda st, r, p: p[0] + (1.0 if (st[0] > 1000 and st[1] > 1000) else 0.0) if r == 1 else p[1] * st[0])
+    sp, single = m.custom_structure(max_molecules=2000)
+    assert not single
+    m.set_customprop(lambda st, r, p: p[0] if r == 1 else p[1] * st[0])
+    sp, single = m.custom_structure(max_molecules=2000)
+    assert single and sp == [0, 0]

@@ -23,8 +23,14 @@ def oracle_model(name):
     return om
 
 
-@pytest.mark.parametrize("name", sorted(examples.DRIVERS))
-def test_fsp_routines_with_host_callback(name):
+# probe "1": callbacks that read one species per reaction (toggle, repressilator) are tabulated and served by the device;
+# probe "0": every callback stays a host function (the path transcr6d always takes)
+PROBE_CASES = [(n, p) for n in sorted(examples.DRIVERS) for p in ("1", "0") if not (n == "transcr6d" and p == "0")]
+
+
+@pytest.mark.parametrize("name,probe", PROBE_CASES)
+def test_fsp_routines_with_host_callback(name, probe, monkeypatch):
+    monkeypatch.setenv("KFSP_CUSTOM_PROBE", probe)
     d = examples.DRIVERS[name]
     h = k.KrylovFspHandle(examples.driver_model(name), max_states=400000, seed=777)
     f = oracle.Fsp(oracle_model(name), max_size=400000, reproducible=1)
@@ -48,12 +54,17 @@ def test_fsp_routines_with_host_callback(name):
     h.close()
 
 
-@pytest.mark.parametrize("name", sorted(examples.DRIVERS))
-def test_solve_with_host_callback_bit_identical(name):
+@pytest.mark.parametrize("name,probe", PROBE_CASES)
+def test_solve_with_host_callback_bit_identical(name, probe, monkeypatch):
+    monkeypatch.setenv("KFSP_CUSTOM_PROBE", probe)
     d = examples.DRIVERS[name]
     t = SHORT_T[name]
     h = k.KrylovFspHandle(examples.driver_model(name), max_states=2000000, seed=12345)
+    tabulated = probe == "1" and name != "transcr6d"
+    info = h.model_info()
+    assert (info["n_tabulated"], info["n_host_evaluated"]) == ((d["R"], 0) if tabulated else (0, d["R"]))
     out = h.solve(t, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
+    assert (h.phase_seconds()["host_propensity_evals"] == 0) == tabulated
     ref = oracle.solve(oracle_model(name), [d["x0"]], [1.0], t, d["fsp_tol"], d["exp_tol"], seed=12345,
                        max_size=2000000, reproducible=1)
     assert out["iflag"] == 0 and ref["iflag"] == 0
@@ -114,3 +125,46 @@ def test_multi_species_transcendental_program_is_evaluated_by_the_host(tmp_path)
     # the same program cannot take the index-only variant together with host evaluation: refused, not switched
     with pytest.raises(k.KfspError):
         k.KrylovFspHandle(model, max_states=1000, spmv_variant=2)
+
+
+EXAMPLE_TOGGLE_AS_STRINGS = ["bx + kx/(1.0 + Y^1.5)", "dx*X", "by + ky/(1.0 + X^3.5)", "dy*Y"]     # examples/toggle.f90:60-74
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_customprop_on_every_spmv_variant(variant, tmp_path):
+    """examples/toggle.f90's CUSTOMPROP model on a fixed 300x200 lattice through the explicit, the matrix-free lattice and the
+    index-only SpMV: the callback is probed, tabulated and verified once, after which the handle is an ordinary tabulated
+    model.  Same bits as the same propensities given as parser strings on the explicit path."""
+    import os
+    d = examples.DRIVERS["toggle"]
+    src = open(os.path.join(k.models_dir(), "toggle.input")).read().splitlines()
+    i = src.index("propensities")
+    src[i + 1:i + 5] = EXAMPLE_TOGGLE_AS_STRINGS
+    path = tmp_path / "toggle_example.input"
+    path.write_text("\n".join(src) + "\n")
+    parsed = k.CME_MODEL().load(str(path))
+    parsed.reset_parameters(d["params"])
+    bx, by = 300, 200
+    yy, xx = np.meshgrid(np.arange(by, dtype=np.int32), np.arange(bx, dtype=np.int32), indexing="ij")
+    states = np.stack([xx.ravel(), yy.ravel()], axis=1)
+    p0 = np.zeros(bx * by)
+    p0[(by // 3) * bx + bx // 4] = 1.0
+    opts = dict(max_states=bx * by + 64, m_max=30, m_min=10, n_init_onestep=0, enable_drop=0, enable_expand=0)
+    ref_h = k.KrylovFspHandle(parsed, spmv_variant=0, **opts)
+    ref = ref_h.solve(0.5, states, p0, 1e-6, 1e-8)
+    h = k.KrylovFspHandle(examples.driver_model("toggle"), spmv_variant=variant, **opts)
+    assert h.model_info()["n_tabulated"] == 4
+    out = h.solve(0.5, states, p0, 1e-6, 1e-8)
+    assert out["iflag"] == 0 and ref["iflag"] == 0
+    assert np.array_equal(out["trace"]["i"], ref["trace"]["i"])
+    assert np.array_equal(out["vector"], ref["vector"])
+    assert h.phase_seconds()["host_propensity_evals"] == 0
+    h.close()
+    ref_h.close()
+
+
+def test_multi_species_callback_keeps_the_explicit_path():
+    """transcr6d.f90's callback reads two species in reactions 5 and 7: the lattice and index-only variants refuse it loudly"""
+    for variant in (1, 2):
+        with pytest.raises(Exception):
+            k.KrylovFspHandle(examples.driver_model("transcr6d"), spmv_variant=variant, max_states=1000)
