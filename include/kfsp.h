@@ -266,6 +266,10 @@ int kfsp_flush_l2(kfsp_handle h);
  * between the sweep's launches); 2: one pair around every launch (per-class table).  The generator SpMV's share is reported
  * in kfsp_stats.spmv_seconds / spmv_launches, everything by class through kfsp_profile_get. */
 int kfsp_set_profiling(kfsp_handle h, int32_t level);
+/* Host waits of this handle sleep on a blocking CUDA event instead of spinning in the driver (default off: lowest latency).
+   For many handles solving concurrently on one GPU from more host threads than cores -- parameter sweeps of small models,
+   krylovfspssa_b200/sweep.py.  No reference counterpart (the reference is a serial CPU code). */
+int kfsp_set_blocking_sync(kfsp_handle h, int32_t on);
 /* FSP%VECTOR(1:n) = src (device pointer), rest zero: device-to-device reset between benchmark steps */
 int kfsp_fsp_set_vector_device(kfsp_handle h, const double* src_device, int64_t n);
 int kfsp_launch_count(kfsp_handle h, int64_t* n);

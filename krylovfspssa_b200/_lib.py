@@ -101,6 +101,7 @@ SIGNATURES = {
     "kfsp_device_vector": (C.c_int, [_vp, C.POINTER(_vp)]),
     "kfsp_flush_l2": (C.c_int, [_vp]),
     "kfsp_set_profiling": (C.c_int, [_vp, C.c_int32]),
+    "kfsp_set_blocking_sync": (C.c_int, [_vp, C.c_int32]),
     "kfsp_fsp_set_vector_device": (C.c_int, [_vp, _vp, C.c_int64]),
     "kfsp_launch_count": (C.c_int, [_vp, _i64p]),
     "kfsp_profile_get": (C.c_int, [_vp, _dp, _i64p, _i64p]),

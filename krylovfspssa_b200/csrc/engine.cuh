@@ -187,6 +187,7 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_SMEM_SWEEP")) smem_sweep = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_SSA_EMIT")) ssa_emit_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_CUSTOM_PROBE")) custom_probe_on = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_BLOCKING_SYNC")) blocking_sync = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_PROP_CACHE_STATES")) pc_budget = std::atoll(ev);
         if (const char* ev = std::getenv("KFSP_DEBUG_REPL")) repl_debug = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_REPL_MIN_ROWS")) dist.repl_min_rows = std::atoll(ev);
@@ -234,6 +235,7 @@ struct Engine {
         cudaSetDevice(device);
         if (repl_debug) std::fprintf(stderr, "libkfsp rank %d: %g gathers of W %.3f s, re-partitions %.3f s\n", dist.rank, repl_s[2], repl_s[0], repl_s[1]);
         if (stream) cudaStreamSynchronize(stream);
+        if (ev_block) cudaEventDestroy(ev_block);
         if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
         if (ev_side) cudaEventDestroy(ev_side);
         cudaFree(d_chk);
@@ -284,8 +286,23 @@ struct Engine {
         if (b > MAX_VEC_BLOCKS) b = MAX_VEC_BLOCKS;
         return (int)b;
     }
+    // Host wait for the solver's stream.  Default: cudaStreamSynchronize (the driver spins: lowest latency, one core per waiting
+    // thread).  blocking_sync (kfsp_set_blocking_sync, KFSP_BLOCKING_SYNC=1): the thread sleeps on an event created with
+    // cudaEventBlockingSync -- for many handles solving concurrently from more host threads than cores (sweep.py: SweepPool).
+    bool blocking_sync = false;
+    cudaEvent_t ev_block = nullptr;
+    cudaError_t wait_stream() {
+        if (!blocking_sync) return cudaStreamSynchronize(stream);
+        if (!ev_block) {
+            const cudaError_t ce = cudaEventCreateWithFlags(&ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+            if (ce != cudaSuccess) return ce;
+        }
+        const cudaError_t ce = cudaEventRecord(ev_block, stream);
+        if (ce != cudaSuccess) return ce;
+        return cudaEventSynchronize(ev_block);
+    }
     int sync() {
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         return KFSP_OK;
     }
     // rows the Krylov kernels of this rank work on: everything, or this rank's slice of the replicated layout
@@ -325,7 +342,7 @@ struct Engine {
 
     int ensure_scratch(size_t bytes) {
         if (bytes <= scratch_bytes) return KFSP_OK;
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         if (d_scratch) KFSP_CUDA(cudaFree(d_scratch));
         size_t want = std::max(bytes, scratch_bytes * 2);
         want = (want + 255) & ~(size_t)255;
@@ -414,7 +431,7 @@ struct Engine {
         }
         if (opt.spmv_variant == 2) KFSP_TRY(build_factored(m));
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         h_dm = dm;
         const bool reshape = !have_model || m.S != S || m.R != R || box;
         S = m.S; R = m.R;
@@ -522,7 +539,7 @@ struct Engine {
             idx = true;
         }
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         h_dm = dm;
         const bool reshape = !have_model || m.S != S || m.R != R || box;
         S = m.S; R = m.R;
@@ -550,7 +567,7 @@ struct Engine {
         for (int k = 0; k < m.R; ++k) { dm.table_species[k] = -1; dm.table[k] = nullptr; }
         n_tabulated = 0; n_inexact_on_device = 0; n_host_evaluated = m.custom ? m.R : 0;
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         const bool reshape = !have_model || m.S != S || m.R != R;
         S = m.S; R = m.R;
         have_model = true;
@@ -572,13 +589,13 @@ struct Engine {
     // pair per expansion cost more than the callbacks themselves)
     int ensure_hp(size_t dev_bytes, size_t host_bytes) {
         if (dev_bytes > hp_dev_bytes) {
-            KFSP_CUDA(cudaStreamSynchronize(stream));
+            KFSP_CUDA(wait_stream());
             if (hp_dev) KFSP_CUDA(cudaFree(hp_dev));
             hp_dev_bytes = align_up(std::max(dev_bytes, 2 * hp_dev_bytes));
             KFSP_CUDA(cudaMalloc(&hp_dev, hp_dev_bytes));
         }
         if (host_bytes > hp_host_bytes) {
-            KFSP_CUDA(cudaStreamSynchronize(stream));
+            KFSP_CUDA(wait_stream());
             if (hp_host) KFSP_CUDA(cudaFreeHost(hp_host));
             hp_host_bytes = align_up(std::max(host_bytes, 2 * hp_host_bytes));
             KFSP_CUDA(cudaMallocHost(&hp_host, hp_host_bytes));
@@ -608,7 +625,7 @@ struct Engine {
             KFSP_CUDA(cudaMemcpyAsync(q.prop, pc.prop, sizeof(double) * pc_n * (R + 1), cudaMemcpyDeviceToDevice, stream));
             KFSP_LAUNCH(k_cache_insert, grid_for(pc_n), VEC_THREADS, 0, q, S, (int64_t)0, pc_n, d_err);
         }
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         const int64_t keep = pc_n;
         free_prop_cache();
         pc = q;
@@ -655,7 +672,7 @@ struct Engine {
             KFSP_CUDA(cudaMemcpyAsync(h_q, d_q, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, stream));
         }
         KFSP_CUDA(cudaMemcpyAsync(h_st, d_states + first * S, sizeof(int32_t) * count * S, cudaMemcpyDeviceToHost, stream));
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         // compact the states the cache did not serve to the front of h_st; h_q becomes their row indices
         int64_t nm = 0;
         for (int64_t t = 0; t < count; ++t) {
@@ -668,7 +685,7 @@ struct Engine {
         KFSP_CUDA(cudaMemcpyAsync(d_q, h_q, sizeof(int32_t) * nm, cudaMemcpyHostToDevice, stream));
         KFSP_CUDA(cudaMemcpyAsync(d_vals, h_vals, sizeof(double) * nm * (R + 1), cudaMemcpyHostToDevice, stream));
         KFSP_LAUNCH(k_scatter_props, grid_for(nm * (R + 1)), VEC_THREADS, 0, f, (const int32_t*)d_q, (const double*)d_vals, nm);
-        KFSP_CUDA(cudaStreamSynchronize(stream));         // the staging buffers are reused by the next call
+        KFSP_CUDA(wait_stream());         // the staging buffers are reused by the next call
         return KFSP_OK;
     }
     int propensities(int64_t first, int64_t count) {
@@ -720,7 +737,7 @@ struct Engine {
     }
     int read_err(int32_t* e) {
         KFSP_CUDA(cudaMemcpyAsync(e, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         if (*e) KFSP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
         return KFSP_OK;
     }
@@ -763,7 +780,7 @@ struct Engine {
         int32_t last_ex = 0, last_in = 0;
         KFSP_CUDA(cudaMemcpyAsync(&last_ex, out + cnt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
         KFSP_CUDA(cudaMemcpyAsync(&last_in, in + cnt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         *total = (int64_t)last_ex + last_in;
         return KFSP_OK;
     }
@@ -941,10 +958,10 @@ struct Engine {
         if (need > scratch_bytes) {
             std::vector<int32_t> keep((size_t)n_old);
             KFSP_CUDA(cudaMemcpyAsync(keep.data(), d_scratch + a_n, sizeof(int32_t) * n_old, cudaMemcpyDeviceToHost, stream));
-            KFSP_CUDA(cudaStreamSynchronize(stream));
+            KFSP_CUDA(wait_stream());
             KFSP_TRY(ensure_scratch(need));
             KFSP_CUDA(cudaMemcpyAsync(d_scratch + a_n, keep.data(), sizeof(int32_t) * n_old, cudaMemcpyHostToDevice, stream));
-            KFSP_CUDA(cudaStreamSynchronize(stream));
+            KFSP_CUDA(wait_stream());
         }
         int32_t* off = (int32_t*)(d_scratch + a_n);
         char* p = d_scratch + 2 * a_n;
@@ -987,7 +1004,7 @@ struct Engine {
         if (!ssa_emit_on) return KFSP_OK;
         const size_t want = (size_t)std::max<int64_t>(1 << 20, n_old);          // candidates per expansion: a boundary fraction of the set
         if (want > emit_states || !emit.tmp) {
-            KFSP_CUDA(cudaStreamSynchronize(stream));
+            KFSP_CUDA(wait_stream());
             cudaFree(emit.tmp); cudaFree(emit.prev); cudaFree(emit.head); cudaFree(emit.cursor);
             emit = SsaEmit();
             emit_states = std::max(want, 2 * emit_states);
@@ -1044,14 +1061,14 @@ struct Engine {
                 KFSP_CUDA(cudaMemcpyAsync(h_nreq, pc.nreq, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
                 // the request list is small: fetch it with the counter instead of paying a second round trip
                 KFSP_CUDA(cudaMemcpyAsync(h_req, pc.req, sizeof(int32_t) * (size_t)std::min<int64_t>(pc.req_cap, 4096) * S, cudaMemcpyDeviceToHost, stream));
-                KFSP_CUDA(cudaStreamSynchronize(stream));
+                KFSP_CUDA(wait_stream());
                 const int32_t nreq = *h_nreq;
                 if (nreq == 0) break;
                 ++host_prop_rounds;
                 const int64_t got = std::min<int64_t>(nreq, pc.req_cap);
                 if (got > 4096) {
                     KFSP_CUDA(cudaMemcpyAsync(h_req + 4096 * S, pc.req + 4096 * S, sizeof(int32_t) * (got - 4096) * S, cudaMemcpyDeviceToHost, stream));
-                    KFSP_CUDA(cudaStreamSynchronize(stream));
+                    KFSP_CUDA(wait_stream());
                 }
                 // several walks may ask for the same state in one round
                 seen.clear();
@@ -1067,7 +1084,7 @@ struct Engine {
                 KFSP_CUDA(cudaMemcpyAsync(pc.states + pc_n * S, h_uniq, sizeof(int32_t) * nu * S, cudaMemcpyHostToDevice, stream));
                 KFSP_CUDA(cudaMemcpyAsync(pc.prop + pc_n * (R + 1), h_vals, sizeof(double) * nu * (R + 1), cudaMemcpyHostToDevice, stream));
                 KFSP_LAUNCH(k_cache_insert, grid_for(nu), VEC_THREADS, 0, pc, S, pc_n, nu, d_err);
-                KFSP_CUDA(cudaStreamSynchronize(stream));        // h_uniq / h_vals are rewritten by the next round
+                KFSP_CUDA(wait_stream());        // h_uniq / h_vals are rewritten by the next round
                 pc_n += nu;
             }
         } else {
@@ -1193,7 +1210,7 @@ struct Engine {
     // sum the bracketed SpMV times recorded since the last call (synchronises)
     int collect_profile() {
         if (!profile_spmv || ev_used == 0) return KFSP_OK;
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         for (size_t i = 0; i + 1 < ev_used; i += 2) {
             float ms = 0.f;
             KFSP_CUDA(cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]));
@@ -1847,7 +1864,7 @@ struct Engine {
         const int64_t cap = ((L.plane * thick + 63) / 64) * 64;          // same leading dimension on every rank
         if (cap != ld || !box || nloc != n) {
             if (dist.nranks > 1 && d_V) return KFSP_ERR_UNSUPPORTED;     // peers hold mappings of this rank's basis
-            KFSP_CUDA(cudaStreamSynchronize(stream));
+            KFSP_CUDA(wait_stream());
             free_state_space();
             KFSP_CUDA(cudaMalloc(&d_w, sizeof(double) * cap));
             ld = cap;
@@ -1920,7 +1937,7 @@ struct Engine {
         int32_t bad = 0;
         KFSP_CUDA(cudaStreamSynchronize(stream2));
         KFSP_CUDA(cudaMemcpyAsync(&bad, d_chk, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        KFSP_CUDA(cudaStreamSynchronize(stream));
+        KFSP_CUDA(wait_stream());
         if (bad) { n = 0; box = false; return KFSP_ERR_UNSUPPORTED; }
         return KFSP_OK;
     }

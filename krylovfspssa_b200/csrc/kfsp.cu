@@ -798,6 +798,11 @@ int kfsp_flush_l2(kfsp_handle h) {
     KFSP_CUDA(cudaMemsetAsync(e.d_flush, 0, e.flush_bytes, e.stream));
     return e.sync();
 }
+int kfsp_set_blocking_sync(kfsp_handle h, int32_t on) {
+    if (!h) return KFSP_ERR_ARG;
+    h->e.blocking_sync = on != 0;
+    return KFSP_OK;
+}
 int kfsp_set_profiling(kfsp_handle h, int32_t on) {
     if (!h) return KFSP_ERR_ARG;
     cudaSetDevice(h->e.device);

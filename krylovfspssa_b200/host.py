@@ -100,6 +100,25 @@ class CME_MODEL:
         self.parameter_val = p.copy()
         return self
 
+    def clone(self):
+        """An independent copy (sizes, stoichiometry, byte code or CUSTOMPROP, current parameter values): concurrent solves of
+        a parameter sweep each RESET_PARAMETERS their own copy."""
+        s, r, p = self._dims()
+        m = CME_MODEL().create(s, r, p)
+        m.stoichiometry = self.stoichiometry
+        if self.customprop is not None:
+            m.set_customprop(self.customprop)
+        else:
+            for k in range(1, r + 1):
+                code, imm = self.bytecode(k)
+                c = np.asarray(code, dtype=np.int32)
+                v = np.asarray(imm if imm else [0.0], dtype=np.float64)
+                check(lib().kfsp_model_set_propensity_bytecode(m._h, k, _i32(c), len(code), _f64(v), len(imm)))
+        if getattr(self, "parameter_val", None) is not None:
+            m.reset_parameters(self.parameter_val)
+        m.loaded = self.loaded
+        return m
+
     def set_propensity(self, reaction, expr):
         """Compile one propensity string as LOAD does (ModelModule.f90:152-155)."""
         check(lib().kfsp_model_set_propensity_string(self._h, reaction, expr.encode()), "EQUATIONPARSER")
@@ -361,6 +380,10 @@ class KrylovFspHandle:
     def set_profiling(self, level=2):
         """0 off, 1 one event pair per Arnoldi sweep, 2 one pair per launch"""
         check(lib().kfsp_set_profiling(self._h, int(level)))
+
+    def set_blocking_sync(self, on=True):
+        """host waits of this handle sleep on a blocking event instead of spinning (many concurrent handles on few cores)"""
+        check(lib().kfsp_set_blocking_sync(self._h, 1 if on else 0))
 
     def phase_seconds(self):
         buf = (C.c_double * 8)()

@@ -24,3 +24,17 @@ def test_sweep_matches_oracle_per_set():
     assert np.array_equal(res[0]["vector"], res[2]["vector"])            # the handle carries nothing over between sets
     summ = sweep.gather_summaries(res, 3)
     assert [s["n"] for s in summ] == [len(res[i]["vector"]) for i in range(3)]
+
+
+def test_concurrent_sweep_is_bit_identical_to_the_sequential_one():
+    """several handles (own stream, buffers, model copy) driven by one host thread each on ONE GPU: same bits per set"""
+    path = os.path.join(k.models_dir(), "toggle.input")
+    rng = np.random.default_rng(3)
+    sets = [[1.0, 60.0 + 40.0 * rng.random(), 1.0, 1.0, 60.0 + 40.0 * rng.random(), 1.0] for _ in range(12)]
+    model = k.CME_MODEL().load(path)
+    seq = sweep.run_share(model, sets, [0, 0], 2.0, 1e-4, 1e-10, max_states=200000, seed=12345, device=0)
+    par = sweep.run_share(model, sets, [0, 0], 2.0, 1e-4, 1e-10, max_states=200000, seed=12345, device=0, concurrency=4)
+    assert sorted(par) == sorted(seq) == list(range(12))
+    for i in range(12):
+        assert np.array_equal(seq[i]["states"], par[i]["states"]) and np.array_equal(seq[i]["vector"], par[i]["vector"]), i
+        assert np.array_equal(seq[i]["trace"]["i"], par[i]["trace"]["i"])

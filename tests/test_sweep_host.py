@@ -22,3 +22,42 @@ def test_two_rank_sweep_gloo():
                        capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "SWEEP HOST OK" in r.stdout
+
+
+def test_concurrent_share_uses_one_handle_and_one_model_copy_per_worker():
+    """concurrency = K on one rank: K handles and K model copies, every set solved exactly once with ITS parameters"""
+    import threading
+
+    import numpy as np
+
+    lock = threading.Lock()
+    made = {"handles": 0, "clones": 0}
+
+    class Model:
+        def reset_parameters(self, p):
+            self.p = np.asarray(p)
+
+        def clone(self):
+            with lock:
+                made["clones"] += 1
+            return Model()
+
+    class Handle:
+        def __init__(self, model, **kw):
+            with lock:
+                made["handles"] += 1
+            self.model = model
+
+        def set_model(self, model):
+            assert model is self.model          # a worker never sees another worker's copy
+
+        def solve(self, t, states, p0, ftol, ktol):
+            return dict(vector=np.full(3, float(self.model.p[0])), iflag=0, stats={})
+
+        def close(self):
+            pass
+
+    sets = [[float(i), 1.0] for i in range(11)]
+    out = sweep.run_share(Model(), sets, [0], 1.0, 1e-4, 1e-8, handle_factory=Handle, concurrency=4)
+    assert sorted(out) == list(range(11)) and made == {"handles": 4, "clones": 4}
+    assert all(out[i]["vector"][0] == float(i) for i in range(11))
