@@ -501,7 +501,9 @@ int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, 
     const double w0 = wall_now();
     if (verbosity) std::printf(" CALLING DGEXPV_FSP\n");                              // KrylovSolver.f90:32
     cudaSetDevice(e.device);
+    static const bool dbg = std::getenv("KFSP_DEBUG_E2E") != nullptr;       // phase stamps of this call on stderr
     KFSP_TRY(e.fsp_init(n_in, states_in, /*defer_check=*/true));
+    const double w1 = dbg ? (e.sync(), wall_now()) : 0.0;
     // Partitioned handle (kfsp_dist_init): states_in / p_in are the GLOBAL list and vector on every rank; this rank keeps
     // rows [lo, hi) and returns them (n_out = hi - lo).  fsp_init has zeroed W.
     // An ADAPTIVE handle on several GPUs keeps the whole state space on every rank and returns the whole result on every rank.
@@ -512,11 +514,14 @@ int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, 
         KFSP_CUDA(cudaMemcpyAsync(e.d_w, p_in + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, e.stream));
     }
     KFSP_TRY(e.box_check_overlap());                       // lattice variant: the state list is uploaded and verified beside the solve
+    const double w2 = dbg ? wall_now() : 0.0;
     int st = e.solve(t, fsp_tol, kry_tol, verbosity, stats);
+    const double w3 = dbg ? wall_now() : 0.0;
     {
         const int chk = e.box_check_finish();               // ... and a list that is not the lattice voids the result
         if (chk != KFSP_OK) { *n_out = 0; return chk; }
     }
+    const double w4 = dbg ? wall_now() : 0.0;
     *n_out = e.n;
     if (st == KFSP_OK || st == KFSP_IFLAG_MXSTEP) {
         if (e.n > max_out) return KFSP_ERR_OUT_TOO_SMALL;
@@ -533,6 +538,10 @@ int kfsp_solve(kfsp_handle h, double t, int64_t n_in, const int32_t* states_in, 
         KFSP_TRY(e.sync());
     }
     if (stats) stats->wall_seconds = wall_now() - w0;
+    if (dbg)
+        std::fprintf(stderr, "kfsp_solve rank %d: init %.2f ms, enqueue uploads %.2f, solve %.2f (device %.2f), list check %.2f, download %.2f, total %.2f\n",
+                     e.dist.rank, 1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w3 - w2), stats ? 1e3 * stats->device_seconds : 0.0, 1e3 * (w4 - w3),
+                     1e3 * (wall_now() - w4), 1e3 * (wall_now() - w0));
     return st;
 }
 int kfsp_trace_length(kfsp_handle h, int64_t* n) {
