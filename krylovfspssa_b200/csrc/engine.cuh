@@ -188,6 +188,8 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_SSA_EMIT")) ssa_emit_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_CUSTOM_PROBE")) custom_probe_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_BLOCKING_SYNC")) blocking_sync = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_COOP_SWEEP")) coop_sweep = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_COOP_MAX_ROWS")) coop_max_rows = std::atoll(ev);
         if (const char* ev = std::getenv("KFSP_PROP_CACHE_STATES")) pc_budget = std::atoll(ev);
         if (const char* ev = std::getenv("KFSP_DEBUG_REPL")) repl_debug = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_REPL_MIN_ROWS")) dist.repl_min_rows = std::atoll(ev);
@@ -244,6 +246,7 @@ struct Engine {
         cudaFree(d_model); cudaFree(d_tables); cudaFree(d_err); cudaFree(d_H); cudaFree(d_expm_work); cudaFree(d_expm_full); cudaFree(d_res);
         cudaFree(d_ctl); cudaFree(rd.partials); cudaFree(rd.counter); cudaFree(d_scratch); cudaFree(d_flush); cudaFree(hp_dev);
         cudaFree(emit.tmp); cudaFree(emit.prev); cudaFree(emit.head); cudaFree(emit.cursor);
+        cudaFree(coop.bar); cudaFree(coop.part);
         cudaFree(d_factabs);
         if (hp_host) cudaFreeHost(hp_host);
         if (h_res) cudaFreeHost(h_res);
@@ -1344,10 +1347,53 @@ struct Engine {
                                                   (const int32_t*)d_states);
             return check_launch();
         }
+        // mid-sized sets: the whole sweep as ONE cooperative launch over all SMs (k_sweep_coop); KFSP_COOP_SWEEP=0 switches it off,
+        // KFSP_COOP_MAX_ROWS moves the upper limit (above it a column is bandwidth, not latency, and the multi-launch kernels win)
+        if (!dist_active() && !box && !profile_spmv && coop_sweep && n <= coop_max_rows) {
+            const int st = arnoldi_coop(jold, m);
+            if (st != KFSP_ERR_UNSUPPORTED) return st;
+        }
         KFSP_TRY(sweep_begin());
         const int st = (box && box_tune < 10 && lattice_bd2_order(lat) >= 0) ? arnoldi_fused(jold, m) : arnoldi_unfused(jold, m);
         KFSP_TRY(sweep_end());
         return st;
+    }
+    bool coop_sweep = true, coop_used = false;
+    int64_t coop_max_rows = 1 << 20;      // measured: 12 % faster at 9e4 rows (repressilator), equal at 8.6e5 (Goutsias: a column is HBM traffic there)
+    CoopBuf coop = {nullptr, nullptr, nullptr};
+    int coop_ok = -1;                                        // device supports cooperative launches
+    int arnoldi_coop(int jold, int m) {
+        if (coop_ok < 0) {
+            int v = 0;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) { cudaGetLastError(); v = 0; }
+            coop_ok = v;
+        }
+        if (!coop_ok) return KFSP_ERR_UNSUPPORTED;
+        void (*kern)(int64_t, int64_t, int, const int32_t*, const double*, const double*, double*, double*, int, int, int, SweepCtl*, double,
+                     const FacModel, const int32_t*, CoopBuf);
+        switch (R) {
+        case 4: kern = idx ? k_sweep_coop<4, 1> : k_sweep_coop<4, 0>; break;
+        case 6: kern = idx ? k_sweep_coop<6, 1> : k_sweep_coop<6, 0>; break;
+        case 10: kern = idx ? k_sweep_coop<10, 1> : k_sweep_coop<10, 0>; break;
+        default: kern = idx ? k_sweep_coop<0, 1> : k_sweep_coop<0, 0>; break;
+        }
+        if (!coop.bar) {
+            KFSP_CUDA(cudaMalloc(&coop.bar, 256));
+            KFSP_CUDA(cudaMalloc(&coop.part, sizeof(double) * 2 * 6 * COOP_MAXG));
+            coop.err = d_err;
+        }
+        int g = wave_grid((const void*)kern, n, SWEEP_THREADS);      // co-resident by construction: SMs x occupancy of this kernel
+        if (g > COOP_MAXG) g = COOP_MAXG;
+        KFSP_CUDA(cudaMemsetAsync(coop.bar, 0, sizeof(unsigned int), stream));
+        int64_t n_ = n, ld_ = ld;
+        int R_ = R, ldh_ = LDH, jold_ = jold, m_ = m;
+        const int32_t* pred_ = d_pred; const double* coef_ = d_coef; const double* diag_ = d_diag;
+        double* V_ = d_V; double* H_ = d_H; SweepCtl* ctl_ = d_ctl; double bt_ = opt.break_tol;
+        FacModel fac_ = fac; const int32_t* st_ = d_states; CoopBuf cb_ = coop;
+        void* args[] = {&n_, &ld_, &R_, &pred_, &coef_, &diag_, &V_, &H_, &ldh_, &jold_, &m_, &ctl_, &bt_, &fac_, &st_, &cb_};
+        KFSP_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)g), dim3(SWEEP_THREADS), args, 0, stream));
+        coop_used = true;
+        return check_launch();
     }
     int arnoldi_unfused(int jold, int m) {
         // Two launches per column: finalise U_c (the two axpys of the previous column + its norm), then the generator product
@@ -1448,6 +1494,15 @@ struct Engine {
         KFSP_TRY(launch_expm(mx_ok, t_ok, use_brk, t_brk, set_one, (const SweepCtl*)d_ctl, nullptr));
         KFSP_TRY(prof_end());
         KFSP_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(ExpmResult), cudaMemcpyDeviceToHost, stream));
+        if (coop_used && dist.nranks == 1) {                   // a cooperative sweep whose CTAs did not all arrive gave up (krylov.cuh)
+            coop_used = false;
+            int32_t e = 0;
+            KFSP_CUDA(cudaMemcpyAsync(&e, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+            KFSP_TRY(sync());
+            if (e & DEV_COOP_TIMEOUT) return KFSP_ERR_CUDA;
+            return h_res->info;
+        }
+        coop_used = false;
         KFSP_TRY(dist.nranks > 1 ? sync_check_peers() : sync());
         return h_res->info;
     }

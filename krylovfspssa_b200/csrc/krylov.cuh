@@ -818,6 +818,199 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_small(int64_t n, int
     for (int j = tid; j < MAX_COLS; j += SWEEP_THREADS) ctl->colscale[j] = cs[j];
 }
 
+// ---------------------------------------------------------------------------------------
+// The same sweep for MID-SIZED state sets (1e4 .. a few 1e6 rows: BASELINE configs 2-4, whose generator sits in the 126 MB
+// L2) as ONE cooperative launch over all SMs: grid-wide barriers instead of kernel boundaries.  In the multi-launch form a
+// column of such a set is two launches whose useful part (a few us of L2 traffic) is shorter than their launch latency,
+// ramp and last-block reduction tail (Goutsias at 6e5 rows: 32 us per column, profiles/r2_summary.md).  Here a column is
+// two phases separated by two barriers; every reduction is written as per-CTA double-double partials that EVERY CTA
+// merges after the barrier (same sums, rounded once: bit-identical to k_sweep_small and to the multi-launch kernels), so
+// no value has to be broadcast and the barrier doubles as the fence between a column's writer and its gatherers.
+// A column is written in iteration J only and first read by other CTAs after that iteration's last barrier, so L1 never
+// holds a stale line of it; the partials (reused every second barrier) are read with ld.cg.
+// ---------------------------------------------------------------------------------------
+constexpr int COOP_MAXG = 1024;                            // CTAs of a cooperative sweep (one or two per SM)
+constexpr int32_t DEV_COOP_TIMEOUT = 64;                   // device error bit (state_space.cuh: DevErr; 32 = a peer GPU stopped responding)
+struct CoopBuf {
+    unsigned int* bar;                                     // arrival counter, zero at launch
+    double* part;                                          // [(buf * 6 + plane) * COOP_MAXG + cta], buf = 0/1, plane = 2*value + (hi|lo)
+    int32_t* err;
+};
+// false: a CTA never arrived (the launch was not co-resident, or a fault): every CTA gives up after ~2 s
+__device__ __forceinline__ bool coop_barrier(const CoopBuf& cb, unsigned int& epoch) {
+    __shared__ int s_ok;
+    __syncthreads();
+    epoch += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(cb.bar, 1u);
+        unsigned int v;
+        const long long t0 = clock64();
+        int ok = 1;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cb.bar) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > 4000000000LL) { ok = 0; atomicOr(cb.err, DEV_COOP_TIMEOUT); break; }
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+template <int NV>
+__device__ __forceinline__ bool coop_total(const DD (&v)[NV], double (&out)[NV], const CoopBuf& cb, int& buf, unsigned int& epoch,
+                                           DD (*sh)[32], double* bc) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* const P = cb.part + (size_t)buf * 6 * COOP_MAXG;
+    DD w[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) w[q] = warp_sum(v[q]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) sh[q][wid] = w[q];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            DD z; z.hi = 0.0; z.lo = 0.0;
+            DD t = lane < nw ? sh[q][lane] : z;
+            t = warp_sum(t);
+            if (lane == 0) {                               // thread 0: the same thread fences and arrives at the barrier
+                __stcg(P + (size_t)(2 * q) * COOP_MAXG + blockIdx.x, t.hi);
+                __stcg(P + (size_t)(2 * q + 1) * COOP_MAXG + blockIdx.x, t.lo);
+            }
+        }
+    }
+    if (!coop_barrier(cb, epoch)) return false;
+    DD s[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) { s[q].hi = 0.0; s[q].lo = 0.0; }
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            DD o;
+            o.hi = __ldcg(P + (size_t)(2 * q) * COOP_MAXG + b);
+            o.lo = __ldcg(P + (size_t)(2 * q + 1) * COOP_MAXG + b);
+            dd_merge(s[q], o);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) s[q] = warp_sum(s[q]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) sh[q][wid] = s[q];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            DD z; z.hi = 0.0; z.lo = 0.0;
+            DD t = lane < nw ? sh[q][lane] : z;
+            t = warp_sum(t);
+            if (lane == 0) bc[q] = __dadd_rn(t.hi, t.lo);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) out[q] = bc[q];
+    buf ^= 1;
+    return true;
+}
+template <int RT, int IDX>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_coop(int64_t n, int64_t ld, int R_rt, const int32_t* __restrict__ pred,
+                                                                  const double* __restrict__ coef, const double* __restrict__ diag,
+                                                                  double* V, double* H, int ldh, int jold, int m, SweepCtl* ctl,
+                                                                  double break_tol, const __grid_constant__ FacModel F,
+                                                                  const int32_t* __restrict__ states, CoopBuf cb) {
+    __shared__ int32_t sstate[IDX ? KFSP_MAX_SPECIES * SWEEP_THREADS : 1];
+    int32_t* const sst = sstate + (IDX ? threadIdx.x : 0);
+    __shared__ DD sh3[3][32];
+    __shared__ double bc3[3];
+    __shared__ double cs[MAX_COLS];
+    const int R = RT > 0 ? RT : R_rt;
+    const int tid = threadIdx.x;
+    const bool lead = blockIdx.x == 0 && tid == 0;
+    const int64_t i0 = (int64_t)blockIdx.x * SWEEP_THREADS + tid, stride = (int64_t)gridDim.x * SWEEP_THREADS;
+    for (int j = tid; j < MAX_COLS; j += SWEEP_THREADS) cs[j] = ctl->colscale[j];
+    const int brk0 = ctl->brk;
+    __syncthreads();
+    if (brk0 != 0) return;                                 // uniform over the grid: written before this launch
+    unsigned int epoch = 0;
+    int buf = 0;
+    int broke = 0;
+    for (int J = jold; J <= m; ++J) {
+        const double* x = V + (size_t)(J - 1) * ld;
+        double* y = V + (size_t)J * ld;
+        const double xs = cs[J - 1];
+        const double* g = J >= 2 ? V + (size_t)(J - 2) * ld : x;
+        const double gs = J >= 2 ? cs[J - 2] : 0.0;
+        double* hcol = H + (size_t)(J - 1) * ldh;
+        DD acc[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { acc[q].hi = 0.0; acc[q].lo = 0.0; }
+        for (int64_t i = i0; i < n; i += stride) {
+            const double sv = spmv_row<RT, IDX>(i, ld, R, pred, coef, diag, x, F, states, sst);
+            y[i] = sv;
+            const double xi = x[i];
+            dd_add_prod(acc[1], xi, sv);
+            if (J >= 2) {
+                const double gv = __dmul_rn(gs, g[i]);
+                dd_add_prod(acc[0], gv, sv);
+                dd_add_prod(acc[2], xi, gv);
+            }
+        }
+        double d3[3];
+        if (!coop_total<3>(acc, d3, cb, buf, epoch, sh3, bc3)) return;
+        double h1 = 0.0, h2 = __dmul_rn(xs, __dmul_rn(xs, d3[1]));
+        if (J >= 2) {
+            h1 = __dmul_rn(xs, d3[0]);
+            h2 = fma(-h1, __dmul_rn(xs, d3[2]), h2);
+            if (lead) hcol[J - 2] = h1;                                      // H(J-1,J)
+        }
+        if (lead) hcol[J - 1] = h2;                                          // H(J,J)
+        DD an[1];
+        an[0].hi = 0.0; an[0].lo = 0.0;
+        for (int64_t i = i0; i < n; i += stride) {
+            double inner = __dmul_rn(xs, y[i]);
+            if (J >= 2) inner = fma(-h1, __dmul_rn(gs, g[i]), inner);
+            const double wi = fma(-h2, __dmul_rn(xs, x[i]), inner);
+            y[i] = wi;
+            dd_add_prod(an[0], wi, wi);
+        }
+        double d1[1];
+        if (!coop_total<1>(an, d1, cb, buf, epoch, sh3, bc3)) return;       // also: column J is complete before anyone gathers from it
+        const double hn = sqrt(d1[0]);
+        if (hn <= break_tol) {                                               // happy breakdown: every CTA holds the same hn
+            if (lead) { ctl->scal[SC_HN] = hn; ctl->brk = J; }
+            broke = J;
+            break;
+        }
+        if (tid == 0) cs[J] = 1.0 / hn;                                      // DSCAL factor (every CTA keeps its own copy)
+        if (lead) hcol[J] = hn;                                              // H(J+1,J)
+        __syncthreads();
+    }
+    if (broke == 0) {
+        const double* x = V + (size_t)m * ld;
+        double* y = V + (size_t)(m + 1) * ld;
+        const double xs = cs[m];
+        DD an[1];
+        an[0].hi = 0.0; an[0].lo = 0.0;
+        for (int64_t i = i0; i < n; i += stride) {
+            const double sv = spmv_row<RT, IDX>(i, ld, R, pred, coef, diag, x, F, states, sst);
+            y[i] = sv;
+            dd_add_prod(an[0], sv, sv);
+        }
+        double d1[1];
+        if (!coop_total<1>(an, d1, cb, buf, epoch, sh3, bc3)) return;
+        const double av = __dmul_rn(xs, sqrt(d1[0]));
+        if (lead) ctl->scal[SC_AVNORM] = av;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int j = tid; j < MAX_COLS; j += SWEEP_THREADS) ctl->colscale[j] = cs[j];
+}
+
 // The same sweep with EVERYTHING in shared memory, for state sets of a couple of thousand states (BASELINE config 1: the toggle
 // never exceeds 2454): the gather form of the generator (12R+8 bytes per state) is staged once per sweep, the three vectors of
 // the IOP window rotate through three shared buffers, and global memory only receives each finished column (the basis the
