@@ -129,3 +129,75 @@ def test_small_krylov_range_option():
     assert np.array_equal(out["states"], ref["states"]) and np.array_equal(out["vector"], ref["vector"])
     assert out["trace"]["i"][:, 0].max() <= 20
     h.close()
+
+
+def _birth_death(params, **kw):
+    path = os.path.join(k.models_dir(), "birth_death.input")
+    model = k.CME_MODEL().load(path)
+    model.reset_parameters(params)
+    return k.KrylovFspHandle(model, max_states=100000, seed=1, **kw), oracle.Model.load(path, params)
+
+
+def test_zero_horizon_returns_the_start_up_expansion_only():
+    """T = 0: the stepping loop of DGEXPV_FSP never runs (KrylovSolver.f90:199); what comes back is the five start-up
+    ONESTEP_EXTENDER rounds (:173-178) around x0 with all the mass still on x0"""
+    h, om = _birth_death([20.0, 1.0])
+    out = h.solve(0.0, [[0]], [1.0], 1e-6, 1e-10)
+    ref = oracle.solve(om, [[0]], [1.0], 0.0, 1e-6, 1e-10, seed=1, reproducible=1)
+    assert out["iflag"] == ref["iflag"] == 0 and out["stats"]["nstep"] == 0
+    assert np.array_equal(out["states"], ref["states"]) and np.array_equal(out["vector"], ref["vector"])
+    assert out["vector"][0] == 1.0 and out["vector"][1:].sum() == 0.0
+    h.close()
+
+
+def test_absorbing_start_state_is_the_reference_error():
+    """no reaction can fire from x0 (k = 0 at X = 0): the generator on the projection is the zero matrix and DGPADM stops with
+    'NULL H IN INPUT OF DGPADM' (dgpadm.f:254); the C ABI returns KFSP_ERR_NULL_H where the reference STOPs, and the handle
+    stays usable"""
+    h, om = _birth_death([0.0, 1.0])
+    ref = oracle.solve(om, [[0]], [1.0], 1.0, 1e-6, 1e-10, seed=1, reproducible=1)
+    assert ref["iflag"] == -4
+    with pytest.raises(k.KfspError) as e:
+        h.solve(1.0, [[0]], [1.0], 1e-6, 1e-10)
+    assert e.value.status == -4
+    out = h.solve(1.0, [[5]], [1.0], 1e-6, 1e-10)                 # pure death from 5: fine, and bit-identical
+    ref = oracle.solve(om, [[5]], [1.0], 1.0, 1e-6, 1e-10, seed=1, reproducible=1)
+    assert out["iflag"] == ref["iflag"] == 0
+    assert np.array_equal(out["states"], ref["states"]) and np.array_equal(out["vector"], ref["vector"])
+    h.close()
+
+
+def test_state_space_overflow_mid_solve_and_recovery():
+    """'FSP SIZE EXCEEDS MEMORY LIMIT' (StateSpace.f90:388-391) raised by an expansion in the middle of a solve comes back as
+    KFSP_ERR_OVERFLOW; the same handle then solves a problem that fits"""
+    path = os.path.join(k.models_dir(), "toggle.input")
+    params = [1.0, 100.0, 1.0, 1.0, 100.0, 1.0]
+    model = k.CME_MODEL().load(path)
+    model.reset_parameters(params)
+    h = k.KrylovFspHandle(model, max_states=300, seed=12345)
+    with pytest.raises(k.KfspError) as e:
+        h.solve(20.0, [[0, 0]], [1.0], 1e-4, 1e-10)
+    assert e.value.status == -10
+    out = h.solve(0.05, [[0, 0]], [1.0], 1e-4, 1e-10)
+    ref = oracle.solve(oracle.Model.load(path, params), [[0, 0]], [1.0], 0.05, 1e-4, 1e-10, seed=12345, reproducible=1, max_size=300)
+    assert out["iflag"] == ref["iflag"] == 0
+    assert np.array_equal(out["states"], ref["states"]) and np.array_equal(out["vector"], ref["vector"])
+    h.close()
+
+
+def test_molecule_limit_is_an_error_not_a_key_collision():
+    """a count above MAXNUMBERMOLECULES aliases hash keys in the reference (HashTable: key arithmetic in base MAXNUMBERMOLECULES);
+    here it is reported (documented deviation)"""
+    path = os.path.join(k.models_dir(), "birth_death.input")
+    model = k.CME_MODEL().load(path)
+    model.reset_parameters([20.0, 1.0])
+    h = k.KrylovFspHandle(model, max_states=1000, max_molecules=50)
+    with pytest.raises(k.KfspError) as e:
+        h.fsp_init([[51]])
+    assert e.value.status in (-11, -12)
+    h.fsp_init([[48]])
+    with pytest.raises(k.KfspError) as e:
+        for _ in range(5):
+            h.onestep()
+    assert e.value.status == -12
+    h.close()
