@@ -64,6 +64,7 @@ struct Engine {
     // index-only SpMV (opt.spmv_variant == 2, krylov.cuh: k_spmv_idx): coef is never stored, a_k(x - nu_k) is recomputed
     // from the row's integer state through the factored propensity tables
     bool idx = false;
+    bool fac_ok = false, ssa_fac_on = true;      // `fac` holds the model's factored tables (any variant)
     FacModel fac{};
     double* d_factabs = nullptr;
 
@@ -188,6 +189,7 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_SSA_EMIT")) ssa_emit_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_CUSTOM_PROBE")) custom_probe_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_BLOCKING_SYNC")) blocking_sync = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_SSA_FAC")) ssa_fac_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_COOP_SWEEP")) coop_sweep = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_COOP_MAX_ROWS")) coop_max_rows = std::atoll(ev);
         if (const char* ev = std::getenv("KFSP_PROP_CACHE_STATES")) pc_budget = std::atoll(ev);
@@ -432,7 +434,13 @@ struct Engine {
             for (size_t q = 0; q < tab_k.size(); ++q) dm.table[tab_k[q]] = d_tables + q * tlen;
             n_tabulated = (int)tab_k.size();
         }
-        if (opt.spmv_variant == 2) KFSP_TRY(build_factored(m));
+        {   // factored single-species tables: required by the index-only SpMV, used by the SSA walks of every variant when the
+            // model has such a form (KFSP_SSA_FAC=0: byte-code interpreter, A/B)
+            fac_ok = false;
+            const int fst = build_factored(m);
+            if (fst == KFSP_OK) fac_ok = true;
+            else if (opt.spmv_variant == 2) return fst;
+        }
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
         KFSP_CUDA(wait_stream());
         h_dm = dm;
@@ -498,7 +506,7 @@ struct Engine {
         for (int k = 0; k < m.R; ++k)
             for (int t = 0; t < FAC_MAX_TERMS; ++t) F.tab[k][t] = d_factabs + off[(size_t)k * FAC_MAX_TERMS + t];
         fac = F;
-        idx = true;
+        idx = opt.spmv_variant == 2;
         return KFSP_OK;
     }
 
@@ -524,6 +532,7 @@ struct Engine {
         KFSP_CUDA(cudaMemcpy(d_tables, tables.data(), sizeof(double) * tables.size(), cudaMemcpyHostToDevice));
         for (int k = 0; k < m.R; ++k) { dm.table_species[k] = species[k]; dm.table[k] = d_tables + (size_t)k * tlen; }
         n_tabulated = m.R; n_inexact_on_device = 0; n_host_evaluated = 0;
+        fac_ok = false;                                     // (eval_propensity is one table load per reaction for such a model)
         if (opt.spmv_variant == 2) {                        // index-only SpMV: every propensity is one tabulated term
             FacModel F;
             std::memset(&F, 0, sizeof F);
@@ -575,6 +584,7 @@ struct Engine {
         S = m.S; R = m.R;
         have_model = true;
         host_prop = true;
+        fac_ok = false;
         hm = m;
         free_prop_cache();
         if (reshape) { free_state_space(); }
@@ -980,7 +990,7 @@ struct Engine {
             } else {
                 KFSP_LAUNCH(k_ssa_walk<true>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
                             (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand, host_prop ? pc : PropCache(),
-                            (int32_t*)nullptr, SsaEmit());
+                            (int32_t*)nullptr, SsaEmit(), fac, ssa_use_fac());
             }
         } else {
             KFSP_LAUNCH(k_onestep_fill, grid_for(n_old), VEC_THREADS, 0, f, n_old, (const int32_t*)off, cand, d_err);
@@ -1021,6 +1031,7 @@ struct Engine {
         return KFSP_OK;
     }
 
+    int ssa_use_fac() const { return (fac_ok && ssa_fac_on && !host_prop) ? 1 : 0; }
     // ---------------------------------------------------------------- SSA_EXTENDER
     int fsp_ssa_1(double timestep) {
         if (box) return KFSP_ERR_UNSUPPORTED;
@@ -1060,7 +1071,7 @@ struct Engine {
                 if (round > (1 << 24)) return KFSP_ERR_SSA_RUNAWAY;
                 KFSP_CUDA(cudaMemsetAsync(pc.nreq, 0, sizeof(int32_t), stream));
                 KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
-                            (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, pc, wsave, SsaEmit());
+                            (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, pc, wsave, SsaEmit(), fac, ssa_use_fac());
                 KFSP_CUDA(cudaMemcpyAsync(h_nreq, pc.nreq, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
                 // the request list is small: fetch it with the counter instead of paying a second round trip
                 KFSP_CUDA(cudaMemcpyAsync(h_req, pc.req, sizeof(int32_t) * (size_t)std::min<int64_t>(pc.req_cap, 4096) * S, cudaMemcpyDeviceToHost, stream));
@@ -1094,7 +1105,7 @@ struct Engine {
             KFSP_TRY(prepare_ssa_emit(n_old));
             KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
                         (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, PropCache(), (int32_t*)nullptr,
-                        ssa_emit_on ? emit : SsaEmit());
+                        ssa_emit_on ? emit : SsaEmit(), fac, ssa_use_fac());
             emit_armed = ssa_emit_on;
         }
         int64_t ncand = 0;

@@ -458,37 +458,7 @@ __device__ __forceinline__ void idx_load_state(const int32_t* __restrict__ state
             if (q < SS) sst[q * STRIDE] = __ldcs(states + row * SS + q);
     }
 }
-// a_k at the row's state (sgn = 0) or at its predecessor x - nu_k (sgn = 1)
-template <int STRIDE>
-__device__ __forceinline__ double fac_term(const FacModel& F, int k, int t, const int32_t* sst, int sgn) {
-    const int sp = F.sp[k][t];
-    const int c = (sst[sp * STRIDE] - sgn * (int)F.nu[k][sp]) * (int)F.use[k][t];
-    return __ldg(F.tab[k][t] + c);
-}
-// GEN = 0: no reaction of the model needs the postfix program -- straight-line code (the shape tests are uniform and
-// guard single instructions), so that the loads of several reactions can be in flight together
-template <int STRIDE, int GEN>
-__device__ __forceinline__ double fac_eval(const FacModel& F, int k, const int32_t* sst, int sgn) {
-    const int shp = F.shape[k];
-    if (GEN == 0 || shp != FAC_GEN) {
-        double a = fac_term<STRIDE>(F, k, 0, sst, sgn);
-        if (shp >= FAC_MUL2) a = __dmul_rn(a, fac_term<STRIDE>(F, k, 1, sst, sgn));
-        if (shp >= FAC_MUL3) a = __dmul_rn(a, fac_term<STRIDE>(F, k, 2, sst, sgn));
-        return a;
-    }
-    double stk[FAC_MAX_OPS];
-    int top = -1;
-    for (int q = 0; q < F.nops[k]; ++q) {
-        const int op = F.ops[k][q];
-        if (op >= 0) stk[++top] = fac_term<STRIDE>(F, k, op, sst, sgn);
-        else if (op == -2) stk[top] = -stk[top];
-        else {
-            const double b = stk[top--];
-            stk[top] = op == -3 ? __dadd_rn(stk[top], b) : op == -4 ? __dsub_rn(stk[top], b) : __dmul_rn(stk[top], b);
-        }
-    }
-    return stk[0];
-}
+// (fac_term / fac_eval: common.cuh)
 // RT > 0: reactions unrolled, loads of IDX_GROUP reactions (table entries and gathered x) issued before their FMAs.
 // RT == 0: any R, and the only instantiation that carries the postfix interpreter (models with a FAC_GEN reaction).
 constexpr int IDX_GROUP = 5;

@@ -288,7 +288,7 @@ __global__ void k_ssa_gather(int64_t n_old, const int32_t* __restrict__ off, int
 template <bool FILL>
 __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t seed, uint32_t call_no,
                            int32_t* cnt, const int32_t* __restrict__ off, int32_t* cand, int32_t* err, int32_t max_jumps,
-                           int64_t ncand, PropCache pc, int32_t* wsave, SsaEmit em) {
+                           int64_t ncand, PropCache pc, int32_t* wsave, SsaEmit em, const __grid_constant__ FacModel F, int use_fac) {
     const DeviceModel* __restrict__ m = f.model;
     const int S = f.S, R = f.R;
     for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j0 < n_old; j0 += (int64_t)gridDim.x * blockDim.x) {
@@ -346,8 +346,16 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
                 dg = row[R];
                 for (int k = 0; k < R; ++k) pr[k] = row[k];
             } else {
+                // a state outside the projection: its propensities are nowhere stored.  The walks that last are exactly those that
+                // stay out there, so this evaluation is the serial chain of the kernel (ncu: the byte-code interpreter's opcode
+                // dispatch held 2/3 of all stall samples, one lane active): the factored tables of the index-only SpMV
+                // (common.cuh, same values bit for bit) replace ~60 interpreted opcodes per jump by 10-20 table loads.
                 dg = 0.0;
-                for (int k = 0; k < R; ++k) { pr[k] = eval_propensity(m, k, st); dg = __dadd_rn(dg, pr[k]); }
+                if (use_fac) {
+                    for (int k = 0; k < R; ++k) { pr[k] = fac_eval<1, 1>(F, k, st, 0); dg = __dadd_rn(dg, pr[k]); }
+                } else {
+                    for (int k = 0; k < R; ++k) { pr[k] = eval_propensity(m, k, st); dg = __dadd_rn(dg, pr[k]); }
+                }
             }
             t = fmin(timestep, __dadd_rn(t, __ddiv_rn(-log(r1), dg)));
             if (!(t <= timestep)) break;
