@@ -347,8 +347,8 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
                 for (int k = 0; k < R; ++k) pr[k] = row[k];
             } else {
                 // a state outside the projection: its propensities are nowhere stored.  The walks that last are exactly those that
-                // stay out there, so this evaluation is the serial chain of the kernel (ncu: the byte-code interpreter's opcode
-                // dispatch held 2/3 of all stall samples, one lane active): the factored tables of the index-only SpMV
+                // stay out there, so this evaluation is the serial chain of the kernel (ncu: half of all stall samples on instructions
+                // issued with one lane active, the hottest the byte-code interpreter's opcode dispatch): the factored tables of the index-only SpMV
                 // (common.cuh, same values bit for bit) replace ~60 interpreted opcodes per jump by 10-20 table loads.
                 dg = 0.0;
                 if (use_fac) {
