@@ -145,11 +145,12 @@ int kfsp_model_propensity(kfsp_model m, const int32_t* state, int32_t reaction, 
    the factored form.  Host only (no GPU).  Reference: MODEL%PROPENSITY, ModelModule.f90:163-199. */
 int kfsp_model_propensity_factored(kfsp_model m, const int32_t* state, int32_t reaction, double* out, int32_t* nterms, int32_t* nops);
 /* Structure of a CUSTOMPROP callback found by probing (host only, no GPU): species_out[k] (R entries) = the 0-based species
-   reaction k+1 reads (0 for a constant), or -2 if it reads several.  *single_out = 1 when every reaction reads at most one
-   species AND the tables built over 0..max_molecules agree with the callback bit for bit on 16384 pseudo-random states: such a
-   model is served from device tables by kfsp_set_model (no host round trips; lattice, index-only and multi-GPU variants
-   included).  Callbacks that read several species keep the host path.  Reference: the CUSTOMPROP models of examples/toggle.f90:55-69
-   (single species) and examples/transcr6d.f90:63-89 (several). */
+   reaction k+1 reads (0 for a constant), or -2 if it reads several.  *single_out = 1: every reaction reads at most one species;
+   2: the rest are bilinear mass action, a = (c * x_a) * x_b in either operand order; 0: neither.  For 1 and 2 the tables built
+   over 0..max_molecules / the bilinear form agree with the callback bit for bit on 16384 pseudo-random states and kfsp_set_model
+   serves the model from the device (no host round trips; lattice, index-only and multi-GPU variants included); for 0 the callback
+   stays a host function.  Reference: the CUSTOMPROP models of examples/toggle.f90:55-69 (single species) and
+   examples/transcr6d.f90:63-89 (reactions 5 and 7 bilinear). */
 int kfsp_model_custom_structure(kfsp_model m, int32_t max_molecules, int32_t* species_out, int32_t* single_out);
 
 /* ---- device solver handle ------------------------------------------------------------ */

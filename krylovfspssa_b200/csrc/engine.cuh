@@ -513,45 +513,77 @@ struct Engine {
     // CUSTOMPROP: the propensity is an opaque host function.  Sizes, stoichiometry and parameters go to the
     // device; a_k(x) is evaluated on the host in batches (propensities_host) and, inside SSA walks, served
     // from the device side cache (fsp_ssa_hostprop).
-    // A callback that reads at most one species per reaction (examples/toggle.f90:55-69) is detected by probing, tabulated over
-    // the counts 0..max_molecules and verified bit for bit on random states (model_host.h: probe_custom_single_species); it is
-    // then an ordinary tabulated model on the device: no host round trip, every SpMV variant, every multi-GPU layout.
-    // KFSP_CUSTOM_PROBE=0 keeps the callbacks (A/B).  Callbacks that read several species (examples/transcr6d.f90:63-89) stay on
-    // the host path: explicit matrix, one GPU or the replicated multi-GPU layout (every rank calls its own copy of the function).
+    // A callback whose reactions each read at most one species (examples/toggle.f90:55-69) or are bilinear mass action
+    // c * x_a * x_b (examples/transcr6d.f90:74,78) is recognised by probing (model_host.h: probe_custom): single-species reactions are
+    // tabulated over the counts 0..max_molecules with the callback's own values, bilinear ones become the three-operation byte code
+    // (c * X_a) * X_b, and everything is verified bit for bit against the callback on random states.  Such a model is then an
+    // ordinary device model: no host round trip, every SpMV variant, every multi-GPU layout.  KFSP_CUSTOM_PROBE=0 keeps the
+    // callbacks (A/B).  Anything else stays on the host path: explicit matrix, one GPU or the replicated multi-GPU layout (every
+    // rank calls its own copy of the function).
     bool custom_probe_on = true;
-    int set_model_custom_tables(const HostModel& m, const std::vector<int32_t>& species, const std::vector<double>& tables) {
+    int set_model_custom_device(const HostModel& m, const CustomProbe& pr) {
         DeviceModel dm;
         std::memset(&dm, 0, sizeof dm);
         dm.S = m.S; dm.R = m.R; dm.P = m.P; dm.max_molecules = opt.max_molecules;
         for (int k = 0; k < m.R; ++k)
-            for (int s = 0; s < m.S; ++s) dm.stoich[k * m.S + s] = m.stoich[(size_t)k * m.S + s];
+            for (int s = 0; s < m.S; ++s) {
+                const int32_t v = m.stoich[(size_t)k * m.S + s];
+                if (v < -127 || v > 127) return KFSP_ERR_UNSUPPORTED;
+                dm.stoich[k * m.S + s] = v;
+            }
         for (int i = 0; i < m.P; ++i) dm.params[i] = m.params[i];
         const int64_t tlen = (int64_t)opt.max_molecules + 1;
-        if (d_tables) { KFSP_CUDA(cudaFree(d_tables)); d_tables = nullptr; }
-        KFSP_CUDA(cudaMalloc(&d_tables, sizeof(double) * tables.size()));
-        KFSP_CUDA(cudaMemcpy(d_tables, tables.data(), sizeof(double) * tables.size(), cudaMemcpyHostToDevice));
-        for (int k = 0; k < m.R; ++k) { dm.table_species[k] = species[k]; dm.table[k] = d_tables + (size_t)k * tlen; }
-        n_tabulated = m.R; n_inexact_on_device = 0; n_host_evaluated = 0;
-        fac_ok = false;                                     // (eval_propensity is one table load per reaction for such a model)
-        if (opt.spmv_variant == 2) {                        // index-only SpMV: every propensity is one tabulated term
-            FacModel F;
-            std::memset(&F, 0, sizeof F);
-            F.S = m.S; F.R = m.R;
-            for (int k = 0; k < m.R; ++k) {
-                F.shape[k] = FAC_ONE; F.nops[k] = 1; F.ops[k][0] = 0;
-                F.sp[k][0] = (int8_t)species[k]; F.use[k][0] = 1;
-                for (int t = 0; t < FAC_MAX_TERMS; ++t) F.tab[k][t] = dm.table[k];
-                for (int s2 = 0; s2 < m.S; ++s2) {
-                    const int32_t v = m.stoich[(size_t)k * m.S + s2];
-                    if (v < -127 || v > 127) return KFSP_ERR_UNSUPPORTED;
-                    F.nu[k][s2] = (int8_t)v;
-                }
+        // device tables: [k] the callback's values of a single-species reaction; then, per bilinear reaction, fl(c * count) for
+        // the factored form; last the identity table (double)count that is the second factor of every bilinear reaction
+        std::vector<double> host(pr.tables);
+        std::vector<size_t> t1((size_t)m.R, 0);
+        int nbil = 0;
+        for (int k = 0; k < m.R; ++k)
+            if (pr.species[k] < 0) {
+                t1[k] = host.size();
+                for (int64_t c = 0; c < tlen; ++c) host.push_back(pr.coef[k] * (double)c);
+                ++nbil;
             }
-            fac = F;
-            idx = true;
+        const size_t ident = host.size();
+        if (nbil > 0)
+            for (int64_t c = 0; c < tlen; ++c) host.push_back((double)c);
+        if (d_tables) { KFSP_CUDA(cudaFree(d_tables)); d_tables = nullptr; }
+        KFSP_CUDA(cudaMalloc(&d_tables, sizeof(double) * host.size()));
+        KFSP_CUDA(cudaMemcpy(d_tables, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
+        FacModel F;
+        std::memset(&F, 0, sizeof F);
+        F.S = m.S; F.R = m.R;
+        int nc = 0, ni = 0;
+        for (int k = 0; k < m.R; ++k) {
+            dm.code_begin[k] = nc; dm.immed_begin[k] = ni;
+            for (int s2 = 0; s2 < m.S; ++s2) F.nu[k][s2] = (int8_t)m.stoich[(size_t)k * m.S + s2];
+            for (int t = 0; t < FAC_MAX_TERMS; ++t) F.tab[k][t] = d_tables;
+            if (pr.species[k] >= 0) {
+                dm.table_species[k] = pr.species[k];
+                dm.table[k] = d_tables + (size_t)k * tlen;
+                F.shape[k] = FAC_ONE; F.nops[k] = 1; F.ops[k][0] = 0;
+                F.sp[k][0] = (int8_t)pr.species[k]; F.use[k][0] = 1;
+                F.tab[k][0] = dm.table[k];
+            } else {
+                // (c * X_a) * X_b in the parser's byte code (FortranParser.f90:52-73): the device interpreter evaluates it with
+                // the very roundings the probe verified against the callback
+                if (nc + 5 > KFSP_MAX_CODE || ni + 1 > KFSP_MAX_IMMED) return KFSP_ERR_UNSUPPORTED;
+                dm.table_species[k] = -1; dm.table[k] = nullptr;
+                dm.code[nc++] = cImmed; dm.code[nc++] = VarBegin + pr.sa[k]; dm.code[nc++] = cMul;
+                dm.code[nc++] = VarBegin + pr.sb[k]; dm.code[nc++] = cMul;
+                dm.immed[ni++] = pr.coef[k];
+                F.shape[k] = FAC_MUL2; F.nops[k] = 3; F.ops[k][0] = 0; F.ops[k][1] = 1; F.ops[k][2] = -cMul;
+                F.sp[k][0] = (int8_t)pr.sa[k]; F.use[k][0] = 1; F.tab[k][0] = d_tables + t1[k];
+                F.sp[k][1] = (int8_t)pr.sb[k]; F.use[k][1] = 1; F.tab[k][1] = d_tables + ident;
+            }
         }
+        dm.code_begin[m.R] = nc; dm.immed_begin[m.R] = ni;
+        n_tabulated = m.R - nbil; n_inexact_on_device = 0; n_host_evaluated = 0;
+        fac = F;
+        fac_ok = true;
+        idx = opt.spmv_variant == 2;
         KFSP_CUDA(cudaMemcpyAsync(d_model, &dm, sizeof dm, cudaMemcpyHostToDevice, stream));
-        KFSP_CUDA(wait_stream());
+        KFSP_CUDA(cudaStreamSynchronize(stream));
         h_dm = dm;
         const bool reshape = !have_model || m.S != S || m.R != R || box;
         S = m.S; R = m.R;
@@ -564,9 +596,8 @@ struct Engine {
     }
     int set_model_hostprop(const HostModel& m) {
         if (m.custom && custom_probe_on) {
-            std::vector<int32_t> species;
-            std::vector<double> tables;
-            if (probe_custom_single_species(m, opt.max_molecules, species, tables)) return set_model_custom_tables(m, species, tables);
+            CustomProbe pr;
+            if (probe_custom(m, opt.max_molecules, pr)) return set_model_custom_device(m, pr);
         }
         // rows of a memory-scaled partition, the lattice and the index-only variant are built from device byte code / tables
         if ((dist.nranks > 1 && !dist.repl) || opt.spmv_variant != 0) return KFSP_ERR_UNSUPPORTED;

@@ -332,10 +332,10 @@ int kfsp_model_propensity_factored(kfsp_model m, const int32_t* state, int32_t r
 int kfsp_model_custom_structure(kfsp_model m, int32_t max_molecules, int32_t* species_out, int32_t* single_out) {
     if (!m || !species_out || !single_out || max_molecules < 1) return KFSP_ERR_ARG;
     if (!m->m.custom) return KFSP_ERR_NO_MODEL;
-    std::vector<int32_t> species;
-    std::vector<double> tables;
-    *single_out = probe_custom_single_species(m->m, max_molecules, species, tables) ? 1 : 0;
-    for (int k = 0; k < m->m.R; ++k) species_out[k] = species[k];
+    CustomProbe pr;
+    const bool ok = probe_custom(m->m, max_molecules, pr);
+    *single_out = ok ? (pr.all_single ? 1 : 2) : 0;
+    for (int k = 0; k < m->m.R; ++k) species_out[k] = pr.species[k];
     return KFSP_OK;
 }
 

@@ -362,14 +362,17 @@ inline uint64_t probe_next(uint64_t& s) {
 }
 }  // namespace
 
-bool probe_custom_single_species(const HostModel& m, int32_t max_molecules, std::vector<int32_t>& species, std::vector<double>& tables,
-                                 int nverify) {
-    species.assign((size_t)m.R, -2);
-    tables.clear();
+bool probe_custom(const HostModel& m, int32_t max_molecules, CustomProbe& out, int nverify) {
+    out = CustomProbe();
+    out.species.assign((size_t)m.R, -2);
+    out.sa.assign((size_t)m.R, -1);
+    out.sb.assign((size_t)m.R, -1);
+    out.coef.assign((size_t)m.R, 0.0);
     if (!m.custom || m.S < 1 || m.R < 1 || max_molecules < 1) return false;
     const int S = m.S, R = m.R;
     const int64_t tlen = (int64_t)max_molecules + 1;
     uint64_t rng = 0x6B66737042323030ull;
+    auto call = [&](const int32_t* st, int k) { return m.custom(st, k + 1, m.params.data(), m.custom_ctx); };
     // base states: small counts (where Hill terms and combinatorial factors are most curved), all ones, and a few spread ones
     std::vector<std::vector<int32_t>> bases;
     bases.emplace_back((size_t)S, 1);
@@ -384,47 +387,96 @@ bool probe_custom_single_species(const HostModel& m, int32_t max_molecules, std:
     for (int32_t c = 0; c <= std::min<int32_t>(max_molecules, 40); ++c) line.push_back(c);
     for (int q = 0; q < 8; ++q) line.push_back((int32_t)(probe_next(rng) % (uint64_t)tlen));
     line.push_back(max_molecules);
-    bool all_single = true;
     std::vector<int32_t> st((size_t)S);
+    std::vector<uint32_t> masks((size_t)R, 0);
+    bool supported = true;
     for (int k = 0; k < R; ++k) {
         uint32_t mask = 0;
         for (const auto& base : bases) {
-            const double a0 = m.custom(base.data(), k + 1, m.params.data(), m.custom_ctx);
+            const double a0 = call(base.data(), k);
             for (int s = 0; s < S; ++s) {
                 if (mask & (1u << s)) continue;
                 st = base;
                 for (int32_t c : line) {
                     st[s] = c;
-                    if (!same_bits(m.custom(st.data(), k + 1, m.params.data(), m.custom_ctx), a0)) { mask |= 1u << s; break; }
+                    if (!same_bits(call(st.data(), k), a0)) { mask |= 1u << s; break; }
                 }
             }
         }
-        if (mask & (mask - 1)) { species[k] = -2; all_single = false; continue; }
-        int sp = 0;
-        while (mask > 1) { mask >>= 1; ++sp; }
-        species[k] = sp;
-    }
-    if (!all_single) return false;
-    tables.resize((size_t)R * tlen);
-    for (int k = 0; k < R; ++k) {
-        std::fill(st.begin(), st.end(), 0);
-        for (int64_t c = 0; c < tlen; ++c) {
-            st[species[k]] = (int32_t)c;
-            tables[(size_t)k * tlen + c] = m.custom(st.data(), k + 1, m.params.data(), m.custom_ctx);
+        masks[k] = mask;
+        const int nsp = __builtin_popcount(mask);
+        if (nsp <= 1) {
+            int sp = 0;
+            while (mask > 1) { mask >>= 1; ++sp; }
+            out.species[k] = sp;
+        } else if (nsp == 2) {
+            out.species[k] = -2;                                   // candidate for the bilinear form, decided below
+        } else {
+            out.species[k] = -2;
+            supported = false;
         }
     }
-    // verification: the callback against the tables on states drawn at three scales
+    out.all_single = true;
+    for (int k = 0; k < R; ++k) out.all_single = out.all_single && out.species[k] >= 0;
+    if (!supported) return false;
+    // tables of the single-species reactions; coefficient and operand order of the two-species ones:
+    // a(x) = fl(fl(c * x_a) * x_b) with c = a(x_a = 1, x_b = 1) -- mass action as a compiler evaluates c*x*y, either operand first
+    out.tables.assign((size_t)R * tlen, 0.0);
+    for (int k = 0; k < R; ++k) {
+        std::fill(st.begin(), st.end(), 0);
+        if (out.species[k] >= 0) {
+            for (int64_t c = 0; c < tlen; ++c) {
+                st[out.species[k]] = (int32_t)c;
+                out.tables[(size_t)k * tlen + c] = call(st.data(), k);
+            }
+            continue;
+        }
+        int p = -1, q = -1;
+        for (int s = 0; s < S; ++s)
+            if (masks[k] & (1u << s)) { if (p < 0) p = s; else q = s; }
+        st[p] = 1; st[q] = 1;
+        const double c = call(st.data(), k);
+        out.coef[k] = c;
+        // which operand is multiplied first: decide on a grid of small counts, then verify on the random states below
+        bool pq = true, qp = true;
+        for (int32_t u = 0; u <= 24 && (pq || qp); ++u)
+            for (int32_t v = 0; v <= 24; ++v) {
+                st[p] = u * 37 % (max_molecules + 1); st[q] = v * 91 % (max_molecules + 1);
+                const double a = call(st.data(), k);
+                pq = pq && same_bits(a, (c * (double)st[p]) * (double)st[q]);
+                qp = qp && same_bits(a, (c * (double)st[q]) * (double)st[p]);
+            }
+        if (pq) { out.sa[k] = p; out.sb[k] = q; }
+        else if (qp) { out.sa[k] = q; out.sb[k] = p; }
+        else return false;                                         // reads two species in some other way: host path
+    }
+    // verification: the callback against the tables / the bilinear form on states drawn at three scales, bit for bit
     for (int t = 0; t < nverify; ++t) {
         const int32_t range = t % 3 == 0 ? std::min<int32_t>(max_molecules, 16) : t % 3 == 1 ? std::min<int32_t>(max_molecules, 400) : max_molecules;
         for (int s = 0; s < S; ++s) st[s] = (int32_t)(probe_next(rng) % (uint64_t)(range + 1));
-        for (int k = 0; k < R; ++k)
-            if (!same_bits(m.custom(st.data(), k + 1, m.params.data(), m.custom_ctx), tables[(size_t)k * tlen + st[species[k]]])) {
-                species[k] = -2;
-                tables.clear();
+        for (int k = 0; k < R; ++k) {
+            const double a = call(st.data(), k);
+            const double e = out.species[k] >= 0 ? out.tables[(size_t)k * tlen + st[out.species[k]]]
+                                                 : (out.coef[k] * (double)st[out.sa[k]]) * (double)st[out.sb[k]];
+            if (!same_bits(a, e)) {
+                if (out.species[k] >= 0) { out.species[k] = -2; out.all_single = false; }
+                out.sa[k] = out.sb[k] = -1;
                 return false;
             }
+        }
     }
+    out.ok = true;
     return true;
+}
+
+bool probe_custom_single_species(const HostModel& m, int32_t max_molecules, std::vector<int32_t>& species, std::vector<double>& tables,
+                                 int nverify) {
+    CustomProbe pr;
+    const bool ok = probe_custom(m, max_molecules, pr, nverify);
+    species = pr.species;
+    tables.clear();
+    if (ok && pr.all_single) { tables = pr.tables; return true; }
+    return false;
 }
 
 bool parse_reaction(const std::string& line, const std::vector<std::string>& species, int32_t* vec, std::string& err) {

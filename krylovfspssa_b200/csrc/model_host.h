@@ -72,6 +72,19 @@ bool factor_program(const Program& p, int S, Factored& out);
 // passes can be served from device tables like a parsed single-species propensity (no host round trips, every SpMV variant,
 // every multi-GPU layout); one that does not stays on the host-callback path.  species[k] = -2 marks a reaction that reads
 // several species (reported even when the function returns false).
+// The general probe: besides single-species reactions it recognises BILINEAR mass action, a(x) = fl(fl(c * x_a) * x_b) with
+// c = a(x_a = 1, x_b = 1) (examples/transcr6d.f90:74,78: parameters(5) * state(DNA) * state(D)), in either operand order, again
+// verified bit for bit on the random states.  ok: every reaction is of one of the two kinds, i.e. the model can be evaluated on
+// the device (tables for the single-species reactions, the three-operation program c * X_a * X_b for the bilinear ones).
+struct CustomProbe {
+    std::vector<int32_t> species;      // per reaction: the species of a single-species reaction (0 for a constant), -2 otherwise
+    std::vector<int32_t> sa, sb;       // bilinear reactions: first and second operand species, else -1
+    std::vector<double> coef;          // bilinear reactions: c
+    std::vector<double> tables;        // [k*(max_molecules+1) + count] for the single-species reactions
+    bool all_single = false;
+    bool ok = false;
+};
+bool probe_custom(const HostModel& m, int32_t max_molecules, CustomProbe& out, int nverify = 16384);
 bool probe_custom_single_species(const HostModel& m, int32_t max_molecules, std::vector<int32_t>& species, std::vector<double>& tables,
                                  int nverify = 16384);
 

@@ -149,13 +149,13 @@ class CME_MODEL:
         check(lib().kfsp_model_set_custom_propensity(self._h, self._cb, None))
 
     def custom_structure(self, max_molecules=10000):
-        """Structure of the CUSTOMPROP callback found by probing (kfsp_model_custom_structure; host only): (species, single) with
-        species[k] the 0-based species reaction k+1 reads (0: constant, -2: several) and single True when the model can be
-        served from device tables."""
+        """Structure of the CUSTOMPROP callback found by probing (kfsp_model_custom_structure; host only): (species, kind) with
+        species[k] the 0-based species reaction k+1 reads (0: constant, -2: several) and kind 1 (all single-species: device
+        tables), 2 (single-species + bilinear mass action: device tables and byte code) or 0 (host callbacks)."""
         sp = np.zeros(self._dims()[1], dtype=np.int32)
-        single = C.c_int32()
-        check(lib().kfsp_model_custom_structure(self._h, int(max_molecules), _i32(sp), C.byref(single)))
-        return sp.tolist(), bool(single.value)
+        kind = C.c_int32()
+        check(lib().kfsp_model_custom_structure(self._h, int(max_molecules), _i32(sp), C.byref(kind)))
+        return sp.tolist(), int(kind.value)
 
     # PROPENSITY(THIS, STATE, REACTION)  ModelModule.f90:163-199
     def propensity(self, state, reaction):

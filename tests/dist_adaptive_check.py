@@ -81,20 +81,24 @@ def main():
         # Must equal the same solve on an unpartitioned handle of this rank's GPU bit for bit.
         from krylovfspssa_b200 import examples
         d = examples.DRIVERS["transcr6d"]
+        os.environ["KFSP_CUSTOM_PROBE"] = "0"               # the callbacks stay host functions (read when a handle is created)
         solo = k.KrylovFspHandle(examples.driver_model("transcr6d"), max_states=400000, seed=4242, device=local)
         ref = solo.solve(30.0, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
         solo.close()
-        h = k.KrylovFspHandle(examples.driver_model("transcr6d"), max_states=400000, seed=4242, device=local)
-        h.dist_init(rank, world, new_uid(rank))
-        assert h.model_info()["n_host_evaluated"] == d["R"]
-        out = h.solve(30.0, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
-        ok = out["iflag"] == 0 and ref["iflag"] == 0 and np.array_equal(out["states"], ref["states"])
-        ok = ok and np.array_equal(out["vector"], ref["vector"]) and np.array_equal(out["trace"]["i"], ref["trace"]["i"])
-        print("transcr6d CUSTOMPROP rank %d/%d: N=%d steps=%d expansions=%d host evaluations=%d bit-identical=%s" %
-              (rank, world, len(out["vector"]), out["stats"]["nstep"], out["stats"]["n_expand"],
-               int(h.phase_seconds()["host_propensity_evals"]), ok), flush=True)
-        ok_all = ok_all and ok
-        h.close()
+        for probe in ("0", "1"):                            # "1": the probed model is evaluated on the device -- same bits
+            os.environ["KFSP_CUSTOM_PROBE"] = probe
+            h = k.KrylovFspHandle(examples.driver_model("transcr6d"), max_states=400000, seed=4242, device=local)
+            h.dist_init(rank, world, new_uid(rank))
+            assert h.model_info()["n_host_evaluated"] == (d["R"] if probe == "0" else 0)
+            out = h.solve(30.0, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
+            ok = out["iflag"] == 0 and ref["iflag"] == 0 and np.array_equal(out["states"], ref["states"])
+            ok = ok and np.array_equal(out["vector"], ref["vector"]) and np.array_equal(out["trace"]["i"], ref["trace"]["i"])
+            print("transcr6d CUSTOMPROP probe=%s rank %d/%d: N=%d steps=%d expansions=%d host evaluations=%d bit-identical=%s" %
+                  (probe, rank, world, len(out["vector"]), out["stats"]["nstep"], out["stats"]["n_expand"],
+                   int(h.phase_seconds()["host_propensity_evals"]), ok), flush=True)
+            ok_all = ok_all and ok
+            h.close()
+        del os.environ["KFSP_CUSTOM_PROBE"]
     else:
         db = json.load(open(os.path.join(HERE, "golden", "full_digests.json")))
         for tag, (name, t, ftol, ktol, cap) in sorted(FULL_RUNS.items()):

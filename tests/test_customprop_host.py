@@ -52,24 +52,35 @@ def test_goutsias_stoichiometry_matches_input_file():
 
 def test_custom_structure_probe_of_the_example_drivers():
     """kfsp_model_custom_structure (host only): which species each reaction of an opaque callback reads.  toggle.f90 and
-    repressilator.f90 read one species per reaction (-> device tables), transcr6d.f90 reads two in reactions 5 and 7."""
-    sp, single = examples.driver_model("toggle").custom_structure()
-    assert single and sp == [1, 0, 0, 1]
-    sp, single = examples.driver_model("repressilator").custom_structure()
-    assert single and sp == [1, 0, 2, 1, 0, 2]
-    sp, single = examples.driver_model("transcr6d").custom_structure()
-    assert not single and sp == [2, 0, 4, 2, -2, 4, -2, 5, 0, 1]
+    repressilator.f90 read one species per reaction (kind 1: device tables); transcr6d.f90 reads two in reactions 5 and 7, as
+    bilinear mass action (c * x_a) * x_b (kind 2: tables + three-operation byte code)."""
+    sp, kind = examples.driver_model("toggle").custom_structure()
+    assert kind == 1 and sp == [1, 0, 0, 1]
+    sp, kind = examples.driver_model("repressilator").custom_structure()
+    assert kind == 1 and sp == [1, 0, 2, 1, 0, 2]
+    sp, kind = examples.driver_model("transcr6d").custom_structure()
+    assert kind == 2 and sp == [2, 0, 4, 2, -2, 4, -2, 5, 0, 1]
 
 
-def test_custom_structure_probe_catches_a_coupling_the_axis_probes_miss():
-    """a second species that matters only far from the axes: invisible to the one-species-at-a-time probes, caught by the
-    bit-for-bit verification on random states, so the model keeps the host-callback path"""
+def test_custom_structure_probe_rejects_what_it_cannot_reproduce_bit_for_bit():
     m = k.CME_MODEL().create(2, 2, 2)
     m.stoichiometry = np.array([[1, -1], [0, 0]], dtype=np.int32)
     m.reset_parameters([20.0, 1.0])
+    # a second species that matters only far from the axes: invisible to the one-species-at-a-time probes, caught by the
+    # bit-for-bit verification on random states
     m.set_customprop(lambda st, r, p: p[0] + (1.0 if (st[0] > 1000 and st[1] > 1000) else 0.0) if r == 1 else p[1] * st[0])
-    sp, single = m.custom_structure(max_molecules=2000)
-    assert not single
+    assert m.custom_structure(max_molecules=2000)[1] == 0
+    # two species, but not (c * x_a) * x_b: a Hill-type coupling, and mass action evaluated as c * (x_a * x_b) with a coefficient
+    # for which the two roundings differ
+    m.set_customprop(lambda st, r, p: p[0] * st[0] / (1.0 + st[1]) if r == 1 else p[1] * st[0])
+    assert m.custom_structure(max_molecules=2000)[1] == 0
+    m.set_customprop(lambda st, r, p: 0.1 * (float(st[0]) * float(st[1])) if r == 1 else p[1] * st[0])
+    sp, kind = m.custom_structure(max_molecules=2000)
+    assert kind == 0 and sp[0] == -2
+    # the same product the way a compiler evaluates c*x*y, either operand first: recognised
+    m.set_customprop(lambda st, r, p: (0.1 * float(st[1])) * float(st[0]) if r == 1 else p[1] * st[0])
+    sp, kind = m.custom_structure(max_molecules=2000)
+    assert kind == 2 and sp == [-2, 0]
     m.set_customprop(lambda st, r, p: p[0] if r == 1 else p[1] * st[0])
-    sp, single = m.custom_structure(max_molecules=2000)
-    assert single and sp == [0, 0]
+    sp, kind = m.custom_structure(max_molecules=2000)
+    assert kind == 1 and sp == [0, 0]

@@ -23,9 +23,10 @@ def oracle_model(name):
     return om
 
 
-# probe "1": callbacks that read one species per reaction (toggle, repressilator) are tabulated and served by the device;
-# probe "0": every callback stays a host function (the path transcr6d always takes)
-PROBE_CASES = [(n, p) for n in sorted(examples.DRIVERS) for p in ("1", "0") if not (n == "transcr6d" and p == "0")]
+# probe "1": the callback's structure is found by probing -- single-species reactions are tabulated, bilinear mass action
+# (transcr6d, reactions 5 and 7) becomes byte code -- and the model is served by the device;
+# probe "0": every callback stays a host function
+PROBE_CASES = [(n, p) for n in sorted(examples.DRIVERS) for p in ("1", "0")]
 
 
 @pytest.mark.parametrize("name,probe", PROBE_CASES)
@@ -60,11 +61,12 @@ def test_solve_with_host_callback_bit_identical(name, probe, monkeypatch):
     d = examples.DRIVERS[name]
     t = SHORT_T[name]
     h = k.KrylovFspHandle(examples.driver_model(name), max_states=2000000, seed=12345)
-    tabulated = probe == "1" and name != "transcr6d"
+    on_device = probe == "1"
     info = h.model_info()
-    assert (info["n_tabulated"], info["n_host_evaluated"]) == ((d["R"], 0) if tabulated else (0, d["R"]))
+    n_tab = d["R"] - (2 if name == "transcr6d" else 0)
+    assert (info["n_tabulated"], info["n_host_evaluated"]) == ((n_tab, 0) if on_device else (0, d["R"]))
     out = h.solve(t, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
-    assert (h.phase_seconds()["host_propensity_evals"] == 0) == tabulated
+    assert (h.phase_seconds()["host_propensity_evals"] == 0) == on_device
     ref = oracle.solve(oracle_model(name), [d["x0"]], [1.0], t, d["fsp_tol"], d["exp_tol"], seed=12345,
                        max_size=2000000, reproducible=1)
     assert out["iflag"] == 0 and ref["iflag"] == 0
@@ -163,8 +165,37 @@ def test_customprop_on_every_spmv_variant(variant, tmp_path):
     ref_h.close()
 
 
-def test_multi_species_callback_keeps_the_explicit_path():
-    """transcr6d.f90's callback reads two species in reactions 5 and 7: the lattice and index-only variants refuse it loudly"""
+def test_transcr6d_callback_on_the_index_only_variant():
+    """examples/transcr6d.f90's CUSTOMPROP (two species in reactions 5 and 7, bilinear) through the index-only SpMV: possible
+    because the probed model has a factored form; bit-identical to the oracle that calls its own restatement of the function"""
+    d = examples.DRIVERS["transcr6d"]
+    h = k.KrylovFspHandle(examples.driver_model("transcr6d"), max_states=2000000, seed=12345, spmv_variant=2)
+    assert h.model_info()["factored"] == 1
+    out = h.solve(60.0, [d["x0"]], [1.0], d["fsp_tol"], d["exp_tol"])
+    ref = oracle.solve(oracle_model("transcr6d"), [d["x0"]], [1.0], 60.0, d["fsp_tol"], d["exp_tol"], seed=12345,
+                       max_size=2000000, reproducible=1)
+    assert out["iflag"] == 0 and ref["iflag"] == 0
+    assert np.array_equal(out["states"], ref["states"]) and np.array_equal(out["vector"], ref["vector"])
+    assert h.phase_seconds()["host_propensity_evals"] == 0
+    h.close()
+
+
+def test_unrecognised_callback_keeps_the_explicit_path():
+    """a callback the probe cannot reproduce (Hill-type coupling of two species) stays a host function: explicit matrix only, the
+    lattice and index-only variants refuse it loudly"""
+    def make():
+        m = k.CME_MODEL().create(2, 4, 2)
+        m.stoichiometry = np.array([[1, -1, 0, 0], [0, 0, 1, -1]], dtype=np.int32)
+        m.reset_parameters([30.0, 1.0])
+        m.set_customprop(lambda st, r, p: (p[0] / (1.0 + 0.1 * st[1]) * (1.0 + 0.01 * st[0]), p[1] * st[0],
+                                           p[0] / (1.0 + 0.1 * st[0]), p[1] * st[1])[r - 1])
+        return m
+    assert make().custom_structure(max_molecules=2000)[1] == 0
     for variant in (1, 2):
-        with pytest.raises(Exception):
-            k.KrylovFspHandle(examples.driver_model("transcr6d"), spmv_variant=variant, max_states=1000)
+        with pytest.raises(k.KfspError):
+            k.KrylovFspHandle(make(), spmv_variant=variant, max_states=1000, max_molecules=2000)
+    h = k.KrylovFspHandle(make(), max_states=20000, max_molecules=2000, seed=5)
+    assert h.model_info()["n_host_evaluated"] == 4
+    out = h.solve(0.5, [[0, 0]], [1.0], 1e-4, 1e-8)
+    assert out["iflag"] == 0 and abs(out["vector"].sum() - 1.0) < 1e-3 and h.phase_seconds()["host_propensity_evals"] > 0
+    h.close()
