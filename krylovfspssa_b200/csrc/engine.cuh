@@ -1391,7 +1391,8 @@ struct Engine {
         }
         // mid-sized sets: the whole sweep as ONE cooperative launch over all SMs (k_sweep_coop); KFSP_COOP_SWEEP=0 switches it off,
         // KFSP_COOP_MAX_ROWS moves the upper limit (above it a column is bandwidth, not latency, and the multi-launch kernels win)
-        if (!dist_active() && !box && !profile_spmv && coop_sweep && n <= coop_max_rows) {
+        // (not for the index-only variant: at 1024 threads per CTA its row evaluation spills, measured 1.96 vs 1.75 s on Goutsias)
+        if (!dist_active() && !box && !idx && !profile_spmv && coop_sweep && n <= coop_max_rows) {
             const int st = arnoldi_coop(jold, m);
             if (st != KFSP_ERR_UNSUPPORTED) return st;
         }
