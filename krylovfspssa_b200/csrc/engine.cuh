@@ -326,6 +326,17 @@ struct Engine {
         KFSP_TRY(check_launch());                              \
     } while (0)
 
+    // k_ssa_walk with the number of reactions at compile time for the shipped model shapes (R = 4, 6, 10), any R otherwise
+#define KFSP_LAUNCH_SSA(FILL, grid, block, smem, ...)                                        \
+    do {                                                                                     \
+        switch (R) {                                                                         \
+        case 4: k_ssa_walk<FILL, 4><<<(grid), (block), (smem), stream>>>(__VA_ARGS__); break;  \
+        case 6: k_ssa_walk<FILL, 6><<<(grid), (block), (smem), stream>>>(__VA_ARGS__); break;  \
+        case 10: k_ssa_walk<FILL, 10><<<(grid), (block), (smem), stream>>>(__VA_ARGS__); break; \
+        default: k_ssa_walk<FILL, 0><<<(grid), (block), (smem), stream>>>(__VA_ARGS__); break; \
+        }                                                                                    \
+        KFSP_TRY(check_launch());                                                            \
+    } while (0)
     // Launch with programmatic stream serialization (KFSP_PDL=0 switches it off): the kernel may be scheduled while its
     // predecessor drains; it calls pdl_wait() before touching anything the predecessor wrote (krylov.cuh).
     bool use_pdl = true;
@@ -1019,7 +1030,7 @@ struct Engine {
             if (ssa_emit_ready) {                              // the counting pass already holds every candidate: copy them into order
                 KFSP_LAUNCH(k_ssa_gather, grid_for(n_old), VEC_THREADS, 0, n_old, (const int32_t*)off, ncand, emit, S, cand);
             } else {
-                KFSP_LAUNCH(k_ssa_walk<true>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
+                KFSP_LAUNCH_SSA(true, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls,
                             (int32_t*)nullptr, (const int32_t*)off, cand, d_err, (int32_t)(1 << 24), ncand, host_prop ? pc : PropCache(),
                             (int32_t*)nullptr, SsaEmit(), fac, ssa_use_fac());
             }
@@ -1101,7 +1112,7 @@ struct Engine {
             for (int64_t round = 0;; ++round) {
                 if (round > (1 << 24)) return KFSP_ERR_SSA_RUNAWAY;
                 KFSP_CUDA(cudaMemsetAsync(pc.nreq, 0, sizeof(int32_t), stream));
-                KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
+                KFSP_LAUNCH_SSA(false, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
                             (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, pc, wsave, SsaEmit(), fac, ssa_use_fac());
                 KFSP_CUDA(cudaMemcpyAsync(h_nreq, pc.nreq, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
                 // the request list is small: fetch it with the counter instead of paying a second round trip
@@ -1134,7 +1145,7 @@ struct Engine {
             }
         } else {
             KFSP_TRY(prepare_ssa_emit(n_old));
-            KFSP_LAUNCH(k_ssa_walk<false>, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
+            KFSP_LAUNCH_SSA(false, grid_for(n_old, 128), 128, 0, f, n_old, timestep, (uint64_t)opt.seed, ssa_calls, cnt,
                         (const int32_t*)nullptr, (int32_t*)nullptr, d_err, (int32_t)(1 << 24), (int64_t)0, PropCache(), (int32_t*)nullptr,
                         ssa_emit_on ? emit : SsaEmit(), fac, ssa_use_fac());
             emit_armed = ssa_emit_on;

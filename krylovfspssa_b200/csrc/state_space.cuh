@@ -285,12 +285,15 @@ __global__ void k_ssa_gather(int64_t n_old, const int32_t* __restrict__ off, int
         }
     }
 }
-template <bool FILL>
+// RT > 0: the number of reactions at compile time -- the propensities of the current state stay in registers and the search
+// for the firing reaction is an unrolled chain (with a run-time R the array is indexed dynamically, i.e. lives in local memory:
+// after the factored tables went in, ncu had 25 % of the stall samples on its STL / LDL and the DADD of the cumulative sum).
+template <bool FILL, int RT>
 __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t seed, uint32_t call_no,
                            int32_t* cnt, const int32_t* __restrict__ off, int32_t* cand, int32_t* err, int32_t max_jumps,
                            int64_t ncand, PropCache pc, int32_t* wsave, SsaEmit em, const __grid_constant__ FacModel F, int use_fac) {
     const DeviceModel* __restrict__ m = f.model;
-    const int S = f.S, R = f.R;
+    const int S = f.S, R = RT > 0 ? RT : f.R;
     for (int64_t j0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j0 < n_old; j0 += (int64_t)gridDim.x * blockDim.x) {
         // host-propensity rounds: cnt >= 0 walk completed, -1 not started, -2 suspended (state saved in wsave)
         const int32_t status = (!FILL && pc.table) ? cnt[j0] : -1;
@@ -323,11 +326,16 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
             philox_uniform2(seed, call_no, (uint32_t)(j0 + 1), jump, &r1, &r2);
             // all R propensities of the current state at once: independent loads (one memory latency instead of
             // a dependent chain through the cumulative sum), and a single byte-code evaluation for unknown states
-            double pr[KFSP_MAX_REACTIONS];
+            double pr[RT > 0 ? RT : KFSP_MAX_REACTIONS];
             double dg;
             if (j >= 0) {
                 dg = f.diag[j];
-                for (int k = 0; k < R; ++k) pr[k] = f.prop[(int64_t)k * f.ld + j];
+                if constexpr (RT > 0) {
+#pragma unroll
+                    for (int k = 0; k < RT; ++k) pr[k] = f.prop[(int64_t)k * f.ld + j];
+                } else {
+                    for (int k = 0; k < R; ++k) pr[k] = f.prop[(int64_t)k * f.ld + j];
+                }
             } else if (pc.table) {
                 const int32_t q = cache_lookup(pc, st, S);
                 if (q < 0) {
@@ -344,17 +352,32 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
                 }
                 const double* __restrict__ row = pc.prop + (int64_t)q * (R + 1);
                 dg = row[R];
-                for (int k = 0; k < R; ++k) pr[k] = row[k];
+                if constexpr (RT > 0) {
+#pragma unroll
+                    for (int k = 0; k < RT; ++k) pr[k] = row[k];
+                } else {
+                    for (int k = 0; k < R; ++k) pr[k] = row[k];
+                }
             } else {
                 // a state outside the projection: its propensities are nowhere stored.  The walks that last are exactly those that
                 // stay out there, so this evaluation is the serial chain of the kernel (ncu: half of all stall samples on instructions
                 // issued with one lane active, the hottest the byte-code interpreter's opcode dispatch): the factored tables of the index-only SpMV
                 // (common.cuh, same values bit for bit) replace ~60 interpreted opcodes per jump by 10-20 table loads.
                 dg = 0.0;
-                if (use_fac) {
-                    for (int k = 0; k < R; ++k) { pr[k] = fac_eval<1, 1>(F, k, st, 0); dg = __dadd_rn(dg, pr[k]); }
+                if constexpr (RT > 0) {
+                    if (use_fac) {
+#pragma unroll
+                        for (int k = 0; k < RT; ++k) { pr[k] = fac_eval<1, 1>(F, k, st, 0); dg = __dadd_rn(dg, pr[k]); }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < RT; ++k) { pr[k] = eval_propensity(m, k, st); dg = __dadd_rn(dg, pr[k]); }
+                    }
                 } else {
-                    for (int k = 0; k < R; ++k) { pr[k] = eval_propensity(m, k, st); dg = __dadd_rn(dg, pr[k]); }
+                    if (use_fac) {
+                        for (int k = 0; k < R; ++k) { pr[k] = fac_eval<1, 1>(F, k, st, 0); dg = __dadd_rn(dg, pr[k]); }
+                    } else {
+                        for (int k = 0; k < R; ++k) { pr[k] = eval_propensity(m, k, st); dg = __dadd_rn(dg, pr[k]); }
+                    }
                 }
             }
             t = fmin(timestep, __dadd_rn(t, __ddiv_rn(-log(r1), dg)));
@@ -362,9 +385,18 @@ __global__ void k_ssa_walk(FspView f, int64_t n_old, double timestep, uint64_t s
             const double r2a = fmin(__dmul_rn(r2, dg), dg);
             int k = 0;
             double tmp = pr[0];
-            while (tmp < r2a && k < R - 1) {
-                ++k;
-                tmp = __dadd_rn(tmp, pr[k]);
+            if (RT > 0) {               // while (tmp < r2a && k < R - 1) { ++k; tmp += pr[k]; } without indexing pr at run time
+                bool go = true;
+#pragma unroll
+                for (int q = 1; q < (RT > 0 ? RT : 1); ++q) {
+                    go = go && tmp < r2a;
+                    if (go) { k = q; tmp = __dadd_rn(tmp, pr[q]); }
+                }
+            } else {
+                while (tmp < r2a && k < R - 1) {
+                    ++k;
+                    tmp = __dadd_rn(tmp, pr[k]);
+                }
             }
             bool neg = false, over = false;
             for (int s = 0; s < S; ++s) {
