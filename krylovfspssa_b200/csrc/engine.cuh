@@ -1660,6 +1660,8 @@ struct Engine {
             return KFSP_OK;
         }
         hp.halo_owner = dist.halo_owner; hp.halo_lidx = dist.halo_lidx; hp.err = d_err;
+        hp.ll = 1;
+        if (const char* ev = std::getenv("KFSP_DIST_LL")) hp.ll = std::atoi(ev) != 0;      // 0: data, system fence, flag (A/B)
         for (int r = 0; r <= P; ++r) hp.rb[r] = dist.rb[r];
         if (!dist.d_stat) {
             KFSP_CUDA(cudaMalloc(&dist.d_stat, 4 * sizeof(unsigned long long)));

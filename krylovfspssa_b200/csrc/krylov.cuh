@@ -49,6 +49,7 @@ struct DistPeers {
     const int32_t* halo_lidx;                // ... and row index on the owner
     int32_t* err;
     int64_t rb[MAX_RANKS + 1];               // replicated-layout partition (adaptive state sets): rank r computes rows [rb[r], rb[r+1])
+    int ll;                                  // 1: partials travel as 8-byte {half, tag} words (no fence between data and flag), 0: data, fence, flag
     unsigned long long* stat;                // [0] fused exchanges done, [1] ns between posting this rank's partial and holding all ranks'
                                              // (wire latency + waiting for the slowest rank), [2] the largest such wait
 };
@@ -210,6 +211,58 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
         const int slot = (int)(rd.seq & 1ull);
         __syncthreads();
         const unsigned long long ns0 = threadIdx.x == 0 ? global_ns() : 0ull;
+        if (dp->ll) {
+            // Low-latency form: every 4-byte half of this rank's (hi,lo) partials is stored to every peer as ONE 8-byte word
+            // {half, tag} (tag = this reduction's sequence number): an 8-byte store arrives whole, so the word is its own
+            // arrival flag and nothing waits for a fence between data and flag -- one one-way NVLink latency instead of
+            // store + system fence (a round trip) + flag store.  The system fence BEFORE the words orders everything this
+            // GPU wrote in this kernel (the columns the peers' next launch reads over NVLink) ahead of them.
+            // Word w of source r: ll[(slot*P + r)*16 + w], w = 4*q + 2*(lo?) + (upper half?), in the exchange area at +1 MiB.
+            __shared__ unsigned int recv[MAX_RANKS][4 * RED_NV];
+            const unsigned int tag = (unsigned int)(rd.seq & 0x7fffffffull) + 1u;
+            if (threadIdx.x == 0) __threadfence_system();
+            __syncthreads();
+            for (int t = threadIdx.x; t < 16 * P; t += blockDim.x) {
+                const int r = t >> 4, w = t & 15;
+                if (w >= 4 * NV) continue;
+                const double val = mine[w >> 1];
+                const unsigned int half = (w & 1) ? (unsigned int)__double2hiint(val) : (unsigned int)__double2loint(val);
+                unsigned long long* dst = (unsigned long long*)((char*)dp->part[r] + (1 << 20)) + ((size_t)slot * P + me) * 16 + w;
+                const unsigned long long word = ((unsigned long long)tag << 32) | (unsigned long long)half;
+                asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+                const unsigned long long* src = (const unsigned long long*)((const char*)dp->part[me] + (1 << 20)) + ((size_t)slot * P + r) * 16 + w;
+                const long long t0 = clock64();
+                const volatile int32_t* gone = dp->err;
+                unsigned long long got = 0ull;
+                for (unsigned int spin = 0;; ++spin) {
+                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+                    if ((unsigned int)(got >> 32) == tag) break;
+                    if ((spin & 63u) != 63u) continue;                                        // the slow checks every 64th poll only
+                    if (*gone & 32) break;                                                    // a peer timed out earlier: do not spin again
+                    if (clock64() - t0 > 8000000000LL) { atomicOr(dp->err, 32); break; }      // ~4 s: a rank is gone
+                }
+                recv[r][w] = (unsigned int)got;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) __threadfence_system();
+            if (threadIdx.x == 0 && dp->stat) {
+                const unsigned long long dt = global_ns() - ns0;
+                dp->stat[0] += 1ull;
+                dp->stat[1] += dt;
+                if (dt > dp->stat[2]) dp->stat[2] = dt;
+            }
+            if ((int)threadIdx.x < NV) {                        // one thread per value merges the P ranks' partials in rank order
+                const int q = threadIdx.x;
+                DD s2; s2.hi = 0.0; s2.lo = 0.0;
+                for (int r2 = 0; r2 < P; ++r2) {
+                    DD o;
+                    o.hi = __hiloint2double((int)recv[r2][4 * q + 1], (int)recv[r2][4 * q]);
+                    o.lo = __hiloint2double((int)recv[r2][4 * q + 3], (int)recv[r2][4 * q + 2]);
+                    dd_merge(s2, o);
+                }
+                tot[q] = __dadd_rn(s2.hi, s2.lo);
+            }
+        } else {
         if ((int)threadIdx.x < P) {
             const int r = threadIdx.x;
             double* dst = dp->part[r] + ((size_t)slot * P + me) * RED_W;
@@ -243,6 +296,7 @@ __device__ __forceinline__ bool grid_reduce(const DD (&v)[NV], double (&out)[NV]
             }
             tot[q] = __dadd_rn(s.hi, s.lo);
         }
+        }   // fence / flag form
     } else if (rd.dist_send) {
         return false;                        // uniform: totals are combined across ranks by NCCL first
     }
