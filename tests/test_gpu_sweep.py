@@ -38,3 +38,18 @@ def test_concurrent_sweep_is_bit_identical_to_the_sequential_one():
     for i in range(12):
         assert np.array_equal(seq[i]["states"], par[i]["states"]) and np.array_equal(seq[i]["vector"], par[i]["vector"]), i
         assert np.array_equal(seq[i]["trace"]["i"], par[i]["trace"]["i"])
+
+
+def test_blocking_host_waits_change_nothing_but_the_wait():
+    """kfsp_set_blocking_sync: the host thread sleeps on a blocking event instead of spinning in the driver; same bits"""
+    path = os.path.join(k.models_dir(), "toggle.input")
+    model = k.CME_MODEL().load(path)
+    model.reset_parameters([1.0, 100.0, 1.0, 1.0, 100.0, 1.0])
+    a = k.KrylovFspHandle(model, max_states=200000, seed=12345)
+    ra = a.solve(2.0, [[0, 0]], [1.0], 1e-4, 1e-10)
+    a.close()
+    b = k.KrylovFspHandle(model, max_states=200000, seed=12345)
+    b.set_blocking_sync(True)
+    rb = b.solve(2.0, [[0, 0]], [1.0], 1e-4, 1e-10)
+    b.close()
+    assert np.array_equal(ra["states"], rb["states"]) and np.array_equal(ra["vector"], rb["vector"])
