@@ -190,6 +190,7 @@ struct Engine {
         if (const char* ev = std::getenv("KFSP_CUSTOM_PROBE")) custom_probe_on = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_BLOCKING_SYNC")) blocking_sync = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_SSA_FAC")) ssa_fac_on = std::atoi(ev) != 0;
+        if (const char* ev = std::getenv("KFSP_EXPM_SMALL_THREADS")) expm_small_threads = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_COOP_SWEEP")) coop_sweep = std::atoi(ev) != 0;
         if (const char* ev = std::getenv("KFSP_COOP_MAX_ROWS")) coop_max_rows = std::atoll(ev);
         if (const char* ev = std::getenv("KFSP_PROP_CACHE_STATES")) pc_budget = std::atoll(ev);
@@ -1524,9 +1525,13 @@ struct Engine {
     }
     // orders >= expm_cluster_from run the squarings on a cluster of 8 CTAs (expm.cuh); KFSP_EXPM_CLUSTER=1000 keeps everything on one CTA (A/B)
     int expm_cluster_from = 36;
+    bool expm_small_threads = true;
     int launch_expm(int mx_ok, double t_ok, int use_brk, double t_brk, int set_one, const SweepCtl* ctl, double* full_out) {
         if (mx_ok < expm_cluster_from) {
-            KFSP_LAUNCH(k_expm, 1, EXPM_THREADS, EXPM_SMEM, d_H, LDH, mx_ok, t_ok, use_brk, t_brk, set_one, ctl, d_expm_work, d_res, full_out);
+            // orders up to 32 are 8x8 tiles of 4x4: 8 warps own them all, and every block-wide barrier of the Pade / LU / squaring
+            // chain is cheaper with 8 warps than with 32 (same element operations: bit-identical; KFSP_EXPM_SMALL_THREADS=0 for A/B)
+            const int threads = (mx_ok <= 32 && expm_small_threads) ? 256 : EXPM_THREADS;
+            KFSP_LAUNCH(k_expm, 1, threads, EXPM_SMEM, d_H, LDH, mx_ok, t_ok, use_brk, t_brk, set_one, ctl, d_expm_work, d_res, full_out);
             return KFSP_OK;
         }
         cudaLaunchConfig_t cfg = {};

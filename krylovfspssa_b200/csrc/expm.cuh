@@ -36,7 +36,7 @@ struct ExpmResult {
 
 // load an n x n column-major matrix (ld = lda) into shared memory, scaled by alpha, zero padded to np rows/cols
 __device__ __forceinline__ void expm_load(double* s, const double* __restrict__ g, int lda, int n, int np, double alpha) {
-    for (int t = threadIdx.x; t < np * EXPM_LDS; t += EXPM_THREADS) {
+    for (int t = threadIdx.x; t < np * EXPM_LDS; t += (int)blockDim.x) {
         const int j = t / EXPM_LDS, i = t % EXPM_LDS;
         s[t] = (i < n && j < n) ? __dmul_rn(alpha, g[(size_t)j * lda + i]) : 0.0;
     }
@@ -134,7 +134,7 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
         __syncthreads();
         if (tid == 0) {
             double mxv = 0.0;
-            for (int w = 0; w < EXPM_THREADS / 32; ++w) mxv = fmax(mxv, sx[w]);
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mxv = fmax(mxv, sx[w]);
             const double hnorm = fabs(t * mxv);
             s_hnorm = hnorm;
             int ns = 0;
@@ -188,7 +188,7 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
     };
 
     // ---- H2 = scale2*H*H (dgpadm.f:270): alpha multiplies the right operand, as DGEMM does ----
-    for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) sB[t2] = __dmul_rn(scale2, sA[t2]);     // the padding stays 0
+    for (int t2 = tid; t2 < np * EXPM_LDS; t2 += (int)blockDim.x) sB[t2] = __dmul_rn(scale2, sA[t2]);     // the padding stays 0
     __syncthreads();
     expm_mma(sA, sB, n, acc, bH, bH, ti, tj);
     __syncthreads();
@@ -310,7 +310,7 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
         // Phase B: the n right-hand sides are independent -> transpose B so that thread j owns column j with
         // conflict-free shared-memory accesses, then forward and backward substitution without any barrier, the entries
         // a step touches (7 going down, 13 going up) in a sliding register window.
-        for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) {
+        for (int t2 = tid; t2 < n * n; t2 += (int)blockDim.x) {
             const int i = t2 / n, j = t2 % n;
             sA[(size_t)i * EXPM_LDS + j] = sB[(size_t)j * EXPM_LDS + i];
         }
@@ -346,7 +346,7 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
         }
         __syncthreads();
         // back to the column-major operand layout, fused with E = I + 2 X
-        for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) {
+        for (int t2 = tid; t2 < np * EXPM_LDS; t2 += (int)blockDim.x) {
             const int j = t2 / EXPM_LDS, i = t2 % EXPM_LDS;
             sB[t2] = (i < n && j < n) ? __dadd_rn(__dmul_rn(2.0, sA[(size_t)i * EXPM_LDS + j]), (i == j ? 1.0 : 0.0)) : 0.0;
         }
@@ -371,7 +371,7 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
         if (s_info != 0) break;
         const int p = s_piv;
         if (p != k) {
-            for (int j = tid; j < 2 * n; j += EXPM_THREADS) {
+            for (int j = tid; j < 2 * n; j += (int)blockDim.x) {
                 double* col = (j < n ? sA + (size_t)j * EXPM_LDS : sB + (size_t)(j - n) * EXPM_LDS);
                 const double tmp = col[k]; col[k] = col[p]; col[p] = tmp;
             }
@@ -379,13 +379,13 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
         }
         const double inv = 1.0 / sA[(size_t)k * EXPM_LDS + k];
         __syncthreads();
-        for (int i = k + 1 + tid; i < n; i += EXPM_THREADS) sA[(size_t)k * EXPM_LDS + i] = __dmul_rn(sA[(size_t)k * EXPM_LDS + i], inv);
+        for (int i = k + 1 + tid; i < n; i += (int)blockDim.x) sA[(size_t)k * EXPM_LDS + i] = __dmul_rn(sA[(size_t)k * EXPM_LDS + i], inv);
         __syncthreads();
         const int rows = n - k - 1;
         if (rows > 0) {
             const int colsA = n - k - 1;
             const int total = rows * (colsA + n);
-            for (int t2 = tid; t2 < total; t2 += EXPM_THREADS) {
+            for (int t2 = tid; t2 < total; t2 += (int)blockDim.x) {
                 const int i = k + 1 + t2 % rows, c = t2 / rows;
                 double* col = c < colsA ? sA + (size_t)(k + 1 + c) * EXPM_LDS : sB + (size_t)(c - colsA) * EXPM_LDS;
                 col[i] = fma(-sA[(size_t)k * EXPM_LDS + i], col[k], col[i]);
@@ -397,17 +397,17 @@ __device__ __forceinline__ int expm_pade(const double* __restrict__ H, int ldh, 
     // back substitution U X = Y, column oriented
     for (int k = n - 1; k >= 0; --k) {
         const double ukk = sA[(size_t)k * EXPM_LDS + k];
-        for (int j = tid; j < n; j += EXPM_THREADS) sB[(size_t)j * EXPM_LDS + k] /= ukk;
+        for (int j = tid; j < n; j += (int)blockDim.x) sB[(size_t)j * EXPM_LDS + k] /= ukk;
         __syncthreads();
         const int total = k * n;
-        for (int t2 = tid; t2 < total; t2 += EXPM_THREADS) {
+        for (int t2 = tid; t2 < total; t2 += (int)blockDim.x) {
             const int i = t2 % k, j = t2 / k;
             sB[(size_t)j * EXPM_LDS + i] = fma(-sB[(size_t)j * EXPM_LDS + k], sA[(size_t)k * EXPM_LDS + i], sB[(size_t)j * EXPM_LDS + i]);
         }
         __syncthreads();
     }
     // ---- E = I + 2 X (dgpadm.f:317-320); iodd == 0 so no sign flip (:322-325) -----------------
-    for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) {
+    for (int t2 = tid; t2 < np * EXPM_LDS; t2 += (int)blockDim.x) {
         const int j = t2 / EXPM_LDS, i = t2 % EXPM_LDS;
         sB[t2] = (i < n && j < n) ? __dadd_rn(__dmul_rn(2.0, sB[t2]), (i == j ? 1.0 : 0.0)) : 0.0;
     }
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
     double acc[4][4];
     // ---- squarings (dgpadm.f:329-336) ------------------------------------------------------
     for (int s = 0; s < ns; ++s) {
-        for (int t2 = tid; t2 < np * EXPM_LDS; t2 += EXPM_THREADS) sA[t2] = sB[t2];
+        for (int t2 = tid; t2 < np * EXPM_LDS; t2 += (int)blockDim.x) sA[t2] = sB[t2];
         __syncthreads();
         expm_mma(sA, sB, n, acc);
         __syncthreads();
@@ -468,9 +468,9 @@ __global__ void __launch_bounds__(EXPM_THREADS, 1) k_expm(double* H, int ldh, in
         __syncthreads();
     }
     // ---- results -----------------------------------------------------------------------------
-    for (int i = tid; i < EXPM_MAXN; i += EXPM_THREADS) res->e[i] = i < n ? sB[i] : 0.0;
+    for (int i = tid; i < EXPM_MAXN; i += (int)blockDim.x) res->e[i] = i < n ? sB[i] : 0.0;
     if (full_out)
-        for (int t2 = tid; t2 < n * n; t2 += EXPM_THREADS) full_out[t2] = sB[(size_t)(t2 / n) * EXPM_LDS + t2 % n];
+        for (int t2 = tid; t2 < n * n; t2 += (int)blockDim.x) full_out[t2] = sB[(size_t)(t2 / n) * EXPM_LDS + t2 % n];
     if (tid == 0) expm_result(res, 0, ns, n, brk, hnorm, t, ctl);
 }
 
