@@ -3,6 +3,8 @@ the GPUs of a box.  This is what `RESET_PARAMETERS` (src/model/Mod
 reference, where the sets would be solved one after the other on one core.  One process per GPU; parameter set `i` goes to
 rank `i mod world` (the sets are independent: no data-path collective, weak scaling); every rank keeps ONE solver handle
 and re-ships only the model's parameter values between solves."""
+import os
+
 import numpy as np
 
 
@@ -67,10 +69,11 @@ class SweepPool:
 
 def run_share(model, param_sets, x0, t, fsptol, krytol, rank=0, world=1, handle_factory=None, concurrency=1, **opt_kw):
     """Solve this rank's share.  Returns {index: result dict of KrylovFspHandle.solve}.
-    `handle_factory(model, **opt_kw)` creates the solver (default: KrylovFspHandle on device `rank`).
+    `handle_factory(model, **opt_kw)` creates the solver (default: KrylovFspHandle on device LOCAL_RANK when torchrun set
+    it, else `rank`: the two differ as soon as the sweep spans more than one box).
     `concurrency` > 1: that many handles solve at the same time on this rank's GPU (SweepPool)."""
     if handle_factory is None:
-        opt_kw.setdefault("device", rank)
+        opt_kw.setdefault("device", int(os.environ.get("LOCAL_RANK", rank)))
     idx = my_share(len(param_sets), rank, world)
     pool = SweepPool(model, min(max(1, int(concurrency)), max(1, len(idx))), handle_factory, **opt_kw)
     try:
