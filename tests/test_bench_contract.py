@@ -52,7 +52,9 @@ def test_roofline_is_consistent(n):
     d = _line(n)
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s"
-    assert r["peak"] == _peak() and r["peak_kind"] == "measured"
+    # the measured copy bandwidth of the pool's B200s (MEASURED_PEAKS.json is re-written by the driver per pod, so the committed
+    # line is only required to sit within 5 % of the file's current value)
+    assert r["peak_kind"] == "measured" and r["peak"] == pytest.approx(_peak(), rel=0.05)
     assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-12)
     assert 0.0 < r["frac"] < 1.0
     # achieved = algorithmic bytes per launch / measured launch time
